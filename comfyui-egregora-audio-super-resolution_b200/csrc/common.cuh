@@ -1,0 +1,85 @@
+// common.cuh — shared host/device helpers for libegregora_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include "../../include/egregora_b200.h"
+
+#define EGR_OK 0
+#define EGR_ERR_ARG -1
+#define EGR_ERR_CUDA -2
+#define EGR_ERR_UNSUPPORTED -3
+#define EGR_ERR_STATE -4
+
+namespace egr {
+
+// thread-local last-error text, exposed through egr_last_error()
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+
+#define EGR_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return egr::fail(EGR_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                       __FILE__, __LINE__);                                                     \
+  } while (0)
+
+#define EGR_CHECK_LAUNCH(what)                                                                  \
+  do {                                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess)                                                                     \
+      return egr::fail(EGR_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e__)); \
+  } while (0)
+
+struct DeviceInfo {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  bool inited = false;
+};
+DeviceInfo& devinfo();
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// resolved pointers of a plan
+struct Spaces {
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+  const char* wt = nullptr;
+  size_t wt_bytes = 0;
+};
+
+inline void* resolve(const Spaces& s, uint64_t addr) {
+  uint64_t space = addr >> 60, off = addr & 0x0FFFFFFFFFFFFFFFull;
+  switch (space) {
+    case EGR_SPACE_WS: return s.ws + off;
+    case EGR_SPACE_WT: return const_cast<char*>(s.wt) + off;
+    case EGR_SPACE_ABS: return reinterpret_cast<void*>(off);
+    default: return nullptr;
+  }
+}
+
+}  // namespace egr
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ float egr_silu(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

@@ -1,0 +1,145 @@
+// wola.cu — path A driver kernels: span gather (slice + right zero-pad) and Hann weighted overlap-add.
+// Semantics follow /root/reference egregora_audio_super_resolution.py:411-416 (gather) and :227-251
+// (_wola_stitch).  Both are pure HBM streaming kernels: every chunk sample is read once, every output
+// sample written once (algorithmic bytes = 4*(n*C*L + C*total), DESIGN.md "K9").
+#include "common.cuh"
+
+using namespace egr;
+
+// ------------------------------------------------------------------------------------------------
+// gather: chunks[k][c][j] = j < L_k ? in[c][s_k + j] : 0
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) chunk_gather_kernel(const float* __restrict__ in, int C, int64_t total,
+                                                            const int64_t* __restrict__ starts,
+                                                            const int32_t* __restrict__ lens, int win,
+                                                            float* __restrict__ chunks) {
+  const int k = blockIdx.z, c = blockIdx.y;
+  const int64_t s = starts[k];
+  const int L = min(lens[k], win);
+  const float* src = in + (int64_t)c * total + s;
+  float* dst = chunks + ((int64_t)k * C + c) * win;
+  const bool vec = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0;
+  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int jstride = gridDim.x * blockDim.x * 4;
+  for (int j = j0; j < win; j += jstride) {
+    if (vec && j + 4 <= L) {
+      *reinterpret_cast<float4*>(dst + j) = __ldg(reinterpret_cast<const float4*>(src + j));
+    } else if (vec && j >= L && j + 4 <= win) {
+      *reinterpret_cast<float4*>(dst + j) = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + u < win) dst[j + u] = (j + u < L) ? src[j + u] : 0.f;
+    }
+  }
+}
+
+extern "C" int egr_chunk_gather(const float* d_in, int C, int64_t total, const int64_t* d_starts,
+                                const int32_t* d_lens, int n_spans, int win, float* d_chunks, void* stream) {
+  if (n_spans == 0) return EGR_OK;
+  if (!d_in || !d_starts || !d_lens || !d_chunks || C <= 0 || win <= 0 || n_spans < 0 || total < 0)
+    return fail(EGR_ERR_ARG, "egr_chunk_gather: bad arguments");
+  if (C > 65535 || n_spans > 65535) return fail(EGR_ERR_ARG, "egr_chunk_gather: C and n_spans must be <= 65535");
+  int bx = ceil_div(win, 256 * 4 * 4);
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, C, n_spans);
+  chunk_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_in, C, total, d_starts, d_lens, win, d_chunks);
+  EGR_CHECK_LAUNCH("chunk_gather_kernel");
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WOLA stitch, output-centric (no atomics): each thread owns 4 consecutive output samples of every
+// channel, finds the spans that cover them by binary search over the sorted starts, and accumulates in
+// span order with separately rounded multiply and add so the result is bit-identical to numpy's
+//   acc[:, s:s+L] += y[:, :L] * w[None, :];  wsum[s:s+L] += w;  out = acc / where(wsum==0, 1, wsum)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wola_stitch_kernel(const float* __restrict__ chunks, int l_pred,
+                                                           const int64_t* __restrict__ starts,
+                                                           const int32_t* __restrict__ lens, int n_spans, int C,
+                                                           int64_t total, int win,
+                                                           const float* __restrict__ window,
+                                                           float* __restrict__ out) {
+  const int64_t t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (t0 >= total) return;
+  const int64_t tlast = min(t0 + 3, total - 1);
+  // khi = last span with start <= tlast
+  int lo = 0, hi = n_spans;  // first index with start > tlast
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (starts[mid] <= tlast) lo = mid + 1; else hi = mid;
+  }
+  const int khi = lo - 1;
+  int klo = khi;
+  while (klo > 0 && starts[klo - 1] > t0 - win) --klo;
+  if (klo < 0) klo = 0;
+
+  float wsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = klo; k <= khi; ++k) {
+    const int64_t s = starts[k];
+    const int L = min(min(lens[k], l_pred), win);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t j = t0 + u - s;
+      if (j >= 0 && j < L) wsum[u] = __fadd_rn(wsum[u], window[j]);
+    }
+  }
+  const bool out_vec = (t0 + 4 <= total) && ((total & 3) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  for (int c = 0; c < C; ++c) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = klo; k <= khi; ++k) {
+      const int64_t s = starts[k];
+      const int L = min(min(lens[k], l_pred), win);
+      const float* y = chunks + ((int64_t)k * C + c) * l_pred;
+      const int64_t j0 = t0 - s;
+      if (j0 >= 0 && j0 + 4 <= L && ((j0 & 3) == 0) && ((l_pred & 3) == 0) &&
+          ((reinterpret_cast<uintptr_t>(chunks) | reinterpret_cast<uintptr_t>(window)) & 15) == 0) {
+        const float4 yv = __ldg(reinterpret_cast<const float4*>(y + j0));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(window + j0));
+        acc[0] = __fadd_rn(acc[0], __fmul_rn(yv.x, wv.x));
+        acc[1] = __fadd_rn(acc[1], __fmul_rn(yv.y, wv.y));
+        acc[2] = __fadd_rn(acc[2], __fmul_rn(yv.z, wv.z));
+        acc[3] = __fadd_rn(acc[3], __fmul_rn(yv.w, wv.w));
+      } else {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t j = j0 + u;
+          if (j >= 0 && j < L) acc[u] = __fadd_rn(acc[u], __fmul_rn(y[j], window[j]));
+        }
+      }
+    }
+    float r[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) r[u] = __fdiv_rn(acc[u], wsum[u] == 0.f ? 1.0f : wsum[u]);
+    float* o = out + (int64_t)c * total + t0;
+    if (out_vec) {
+      *reinterpret_cast<float4*>(o) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (t0 + u < total) o[u] = r[u];
+    }
+  }
+}
+
+extern "C" int egr_wola_stitch(const float* d_chunks, int l_pred, const int64_t* d_starts, const int32_t* d_lens,
+                               int n_spans, int C, int64_t total, int win, const float* d_window, float* d_out,
+                               void* stream) {
+  if (total <= 0) return EGR_OK;
+  if (!d_out || C <= 0 || win <= 0 || n_spans < 0) return fail(EGR_ERR_ARG, "egr_wola_stitch: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_spans == 0) {  // reference returns zeros for an empty span list
+    EGR_CUDA(cudaMemsetAsync(d_out, 0, sizeof(float) * (size_t)C * (size_t)total, st));
+    return EGR_OK;
+  }
+  if (!d_chunks || !d_starts || !d_lens || !d_window || l_pred <= 0)
+    return fail(EGR_ERR_ARG, "egr_wola_stitch: null pointer / bad l_pred");
+  int64_t threads = (total + 3) / 4;
+  int64_t blocks = (threads + 255) / 256;
+  if (blocks > 0x7fffffffLL) return fail(EGR_ERR_ARG, "egr_wola_stitch: total too large");
+  wola_stitch_kernel<<<(unsigned)blocks, 256, 0, st>>>(d_chunks, l_pred, d_starts, d_lens, n_spans, C, total, win,
+                                                       d_window, d_out);
+  EGR_CHECK_LAUNCH("wola_stitch_kernel");
+  return EGR_OK;
+}

@@ -1,0 +1,249 @@
+"""🎧 Audio Super Resolution (FlashSR) — B200-native drop-in for the reference node of the same ID.
+
+Mirrors /root/reference/egregora_audio_super_resolution.py:372-431 (`EgregoraAudioSuperResolution`):
+same INPUT_TYPES / RETURN_TYPES / FUNCTION / CATEGORY / OUTPUT_NODE, same AUDIO dict in and out, same
+RuntimeError messages.  What differs is where the work happens:
+
+  reference                                   here
+  ---------                                   ----
+  numpy slice + pad per span (:411-416)       one egr_chunk_gather launch for all spans, on device
+  sequential model call per span (:417)       all chunk-channels batched through the CUDA plan
+  numpy Hann WOLA (:227-251)                  egr_wola_stitch (bit-identical, one HBM pass)
+  model rebuilt on every run() (:393)         process-level engine cache
+
+With torch.distributed initialised (world_size > 1) the span list is sharded contiguously across ranks
+and the per-rank chunk outputs are joined by ONE all_gather before the stitch.
+Host code here is plumbing only; all arithmetic is in libegregora_b200.so.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi
+
+FUNCTION = "run"
+CATEGORY = "Egregora/Audio"
+
+REQ_SR = 48000
+CHUNK_S = 5.12
+OVERLAP_S = 0.50
+CHUNK_SAMPLES = int(REQ_SR * CHUNK_S)  # 245760, reference :258
+
+
+# ------------------------------------------------------------------------------------------ AUDIO
+def _make_audio(sr: int, samples_cs) -> Dict[str, Any]:
+    """[C,T] (device or host tensor / ndarray) -> ComfyUI AUDIO dict with a fresh CPU f32 [1,C,T] (ref :116-123)."""
+    t = samples_cs if isinstance(samples_cs, torch.Tensor) else torch.from_numpy(np.asarray(samples_cs, np.float32))
+    if t.dim() == 1:
+        t = t[None, :]
+    t = t.detach().to(device="cpu", dtype=torch.float32)
+    return {"waveform": t.unsqueeze(0).contiguous(), "sample_rate": int(sr)}
+
+
+def _from_audio_dict(AUDIO: Any) -> Tuple[torch.Tensor, int]:
+    """AUDIO dict or (array, sr) -> ([C,T] f32 tensor, sr).  Shape rules and messages follow ref :125-156;
+    the tensor is left on whatever device it already lives on (the engine moves it once)."""
+    if isinstance(AUDIO, dict) and "waveform" in AUDIO and "sample_rate" in AUDIO:
+        wf = AUDIO["waveform"]
+        if not isinstance(wf, torch.Tensor):
+            wf = torch.as_tensor(np.asarray(wf))
+        if wf.dim() == 3:
+            wf = wf[0]  # batch items > 0 are dropped, as in the reference
+        if wf.dim() != 2:
+            raise RuntimeError(f"Unexpected AUDIO tensor shape {tuple(wf.shape)}; expected [C, T].")
+        return wf.detach().float(), int(AUDIO["sample_rate"])
+    if isinstance(AUDIO, (list, tuple)) and len(AUDIO) == 2:
+        arr, sr = AUDIO
+        arr = np.asarray(arr, dtype=np.float32)
+        if arr.ndim == 1:
+            cs = arr[None, :]
+        elif arr.ndim == 2:
+            frames_first = arr.shape[0] >= arr.shape[1] and arr.shape[1] <= 8
+            cs = arr.T if frames_first else arr
+        else:
+            cs = arr.reshape(1, -1)
+        return torch.from_numpy(np.ascontiguousarray(cs, dtype=np.float32)), int(sr)
+    raise RuntimeError("No valid AUDIO provided.")
+
+
+# --------------------------------------------------------------------------------- resample (host)
+def _resample_hq(x_cs: torch.Tensor, src_sr: int, dst_sr: int) -> torch.Tensor:
+    """Sample-rate conversion either side of the hot path (ref :159-207, scipy polyphase branch).
+    SURVEY.md §8(f) rank 2 — a "next" row: still host-side scipy here, to be replaced by the polyphase
+    CUDA kernel; it is not exercised by any BASELINE config (all are 48 kHz in, 48 kHz out)."""
+    if src_sr == dst_sr:
+        return x_cs.float()
+    from math import gcd
+    from scipy.signal import resample_poly  # the reference's branch when soxr is absent
+    g = gcd(src_sr, dst_sr)
+    x = x_cs.detach().cpu().float().numpy()
+    chans = [resample_poly(x[c], up=dst_sr // g, down=src_sr // g).astype(np.float32) for c in range(x.shape[0])]
+    n = min(len(c) for c in chans)
+    return torch.from_numpy(np.stack([c[:n] for c in chans], axis=0))
+
+
+# --------------------------------------------------------------------------------- spans and WOLA
+def _hann(L: int) -> np.ndarray:
+    return np.hanning(L).astype(np.float32)  # symmetric, f64 -> f32, ref :210-211
+
+
+def _iter_chunks(total_samples: int, win: int, hop: int) -> List[Tuple[int, int]]:
+    """(start, length) spans covering [0,total) — same sequence as ref :213-225, closed form."""
+    if total_samples <= 0:
+        return []
+    if total_samples <= win:
+        return [(0, total_samples)]
+    n = 1 + -(-(total_samples - win) // hop)  # 1 + ceil((total-win)/hop)
+    return [(k * hop, min(win, total_samples - k * hop)) for k in range(n)]
+
+
+def _win_hop() -> Tuple[int, int]:
+    win = CHUNK_SAMPLES
+    hop = int((CHUNK_S - OVERLAP_S) * REQ_SR)
+    if hop <= 0 or hop >= win:
+        hop = win // 2
+    return win, hop
+
+
+_WINDOW_CACHE: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def _device_window(win: int, device: torch.device) -> torch.Tensor:
+    key = (win, str(device))
+    if key not in _WINDOW_CACHE:
+        _WINDOW_CACHE[key] = torch.from_numpy(_hann(win)).to(device)
+    return _WINDOW_CACHE[key]
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def gather_chunks(x_dev: torch.Tensor, spans, win: int) -> torch.Tensor:
+    """[C,total] device f32 -> [n,C,win] (slice + right zero pad of every span in one launch)."""
+    lib = _abi.init(x_dev.device.index or 0)
+    C, total = x_dev.shape
+    n = len(spans)
+    out = torch.empty((n, C, win), dtype=torch.float32, device=x_dev.device)
+    if n == 0:
+        return out
+    starts = torch.tensor([s for s, _ in spans], dtype=torch.int64).to(x_dev.device, non_blocking=True)
+    lens = torch.tensor([l for _, l in spans], dtype=torch.int32).to(x_dev.device, non_blocking=True)
+    x_dev = x_dev.contiguous()
+    _abi.check(lib.egr_chunk_gather(x_dev.data_ptr(), C, total, starts.data_ptr(), lens.data_ptr(), n, win,
+                                    out.data_ptr(), _stream_ptr()), "egr_chunk_gather")
+    return out
+
+
+def wola_stitch(preds_dev: torch.Tensor, spans, total: int, win: int) -> torch.Tensor:
+    """[n,C,L_pred] device f32 + spans -> [C,total] (Hann WOLA with weight-sum normalisation, ref :227-251)."""
+    if len(spans) == 0:
+        return torch.zeros((1, max(1, total)), dtype=torch.float32, device=preds_dev.device)
+    lib = _abi.init(preds_dev.device.index or 0)
+    n, C, l_pred = preds_dev.shape
+    out = torch.empty((C, total), dtype=torch.float32, device=preds_dev.device)
+    starts = torch.tensor([s for s, _ in spans], dtype=torch.int64).to(preds_dev.device, non_blocking=True)
+    lens = torch.tensor([l for _, l in spans], dtype=torch.int32).to(preds_dev.device, non_blocking=True)
+    w = _device_window(win, preds_dev.device)
+    preds_dev = preds_dev.contiguous()
+    _abi.check(lib.egr_wola_stitch(preds_dev.data_ptr(), l_pred, starts.data_ptr(), lens.data_ptr(), n, C, total,
+                                   win, w.data_ptr(), out.data_ptr(), _stream_ptr()), "egr_wola_stitch")
+    return out
+
+
+# ------------------------------------------------------------------------------------ engine cache
+_ENGINES: Dict[Tuple[int, str], Any] = {}
+
+
+def _require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "CUDA GPU not detected. The B200-native FlashSR path has no CPU fallback (sm_100a kernels only).")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def get_engine(device: Optional[torch.device] = None):
+    """Process-level FlashSR engine (the reference rebuilds its runner on every run(), ref :393)."""
+    from .flashsr_engine import FlashSREngine
+    device = device or _require_cuda()
+    key = (device.index or 0, os.environ.get("EGREGORA_FLASHSR_WEIGHTS", ""))
+    if key not in _ENGINES:
+        _ENGINES[key] = FlashSREngine(device)
+    return _ENGINES[key]
+
+
+def upscale_48k(x_dev: torch.Tensor, chunk_model, *, shard: bool = True) -> torch.Tensor:
+    """The hot loop of run(): spans -> gather -> model on every chunk-channel -> WOLA.
+    `chunk_model([N,win] device f32) -> [N,L_pred]`.  Sharded over ranks when torch.distributed is up."""
+    win, hop = _win_hop()
+    C, total = x_dev.shape
+    spans = _iter_chunks(total, win, hop)
+    n = len(spans)
+    import torch.distributed as dist
+    world = dist.get_world_size() if (shard and dist.is_available() and dist.is_initialized()) else 1
+    if world == 1 or n == 0:
+        chunks = gather_chunks(x_dev, spans, win)
+        preds = chunk_model(chunks.view(n * C, win)) if n else chunks
+        preds = preds.view(n, C, -1) if n else preds
+        return wola_stitch(preds, spans, total, win)
+    # contiguous blocks of ceil(n/world) spans per rank; pad the tail ranks so one all_gather suffices
+    rank = dist.get_rank()
+    per = -(-n // world)
+    lo, hi = min(rank * per, n), min((rank + 1) * per, n)
+    mine = spans[lo:hi]
+    chunks = gather_chunks(x_dev, mine, win)
+    local = torch.zeros((per, C, win), dtype=torch.float32, device=x_dev.device)
+    if hi > lo:
+        y = chunk_model(chunks.view((hi - lo) * C, win)).view(hi - lo, C, -1)
+        if y.shape[-1] != win:
+            raise RuntimeError("sharded stitch needs the chunk model to return full windows")
+        local[: hi - lo] = y
+    gathered = torch.empty((world * per, C, win), dtype=torch.float32, device=x_dev.device)
+    dist.all_gather_into_tensor(gathered, local)
+    return wola_stitch(gathered[:n], spans, total, win)
+
+
+# --------------------------------------------------------------------------------------------- node
+class EgregoraAudioSuperResolution:
+    @classmethod
+    def INPUT_TYPES(cls):
+        return {
+            "required": {
+                "audio": ("AUDIO",),
+                "lowpass_input": ("BOOLEAN", {"default": False}),
+                "output_sr": (["48000", "44100", "96000"], {"default": "48000"}),
+            }
+        }
+
+    RETURN_TYPES = ("AUDIO",)
+    FUNCTION = FUNCTION
+    CATEGORY = CATEGORY
+    OUTPUT_NODE = False
+
+    # Knobs BASELINE.json's configs name but the reference surface does not expose:
+    # kept off INPUT_TYPES so existing graphs and the surface snapshot stay identical.
+    NUM_STEPS = int(os.environ.get("EGREGORA_FLASHSR_STEPS", "1"))
+    SEED = int(os.environ.get("EGREGORA_FLASHSR_SEED", "4321"))
+
+    def run(self, audio=None, lowpass_input=False, output_sr="48000"):
+        in_cs, in_sr = _from_audio_dict(audio)
+        device = _require_cuda()
+        engine = get_engine(device)
+        if in_sr != REQ_SR:
+            in_cs = _resample_hq(in_cs, in_sr, REQ_SR)
+            in_sr = REQ_SR
+        x_dev = in_cs.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        steps, seed, lp = int(self.NUM_STEPS), int(self.SEED), bool(lowpass_input)
+        out_48k = upscale_48k(x_dev, lambda chunks: engine.infer(chunks, lowpass=lp, steps=steps, seed=seed))
+        tgt_sr = int(output_sr)
+        if tgt_sr != in_sr:
+            return (_make_audio(tgt_sr, _resample_hq(out_48k, in_sr, tgt_sr)),)
+        return (_make_audio(in_sr, out_48k),)
+
+
+NODE_CLASS_MAPPINGS = {"EgregoraAudioUpscaler": EgregoraAudioSuperResolution}
+NODE_DISPLAY_NAME_MAPPINGS = {"EgregoraAudioUpscaler": "🎧 Audio Super Resolution (FlashSR)"}

@@ -1,0 +1,112 @@
+"""Pin the path-A driver oracle (oracle/driver_oracle.py) and the host-side mirror against vectors produced
+by the reference itself (tests/golden/driver_golden.npz)."""
+import hashlib
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import driver_oracle as O
+
+WIN, HOP = 245760, 221760
+TOTALS = [0, 1, 1000, 221760, 245759, 245760, 245761, 443520, 467520, 480000, 8640000, 14400000, 28800000]
+
+
+def test_win_hop():
+    assert O.win_hop() == (WIN, HOP)
+
+
+@pytest.mark.parametrize("total", TOTALS)
+def test_spans_oracle_and_host(total, golden, pkg):
+    from egregora_b200 import egregora_audio_super_resolution as N
+    want = golden[f"spans_{total}"].reshape(-1, 2)
+    assert np.array_equal(np.asarray(O.iter_chunks(total, WIN, HOP), np.int64).reshape(-1, 2), want)
+    assert np.array_equal(np.asarray(N._iter_chunks(total, WIN, HOP), np.int64).reshape(-1, 2), want)
+
+
+def test_span_counts_survey():
+    # SURVEY.md §8 a6
+    assert len(O.iter_chunks(28_800_000, WIN, HOP)) == 130
+    assert O.iter_chunks(28_800_000, WIN, HOP)[-1] == (28_607_040, 192_960)
+    assert len(O.iter_chunks(14_400_000, WIN, HOP)) == 65
+    assert len(O.iter_chunks(28_800_000, WIN, WIN // 2)) == 234
+
+
+def test_small_spans(golden, pkg):
+    from egregora_b200 import egregora_audio_super_resolution as N
+    for key, args in (("spans_small_1000_64_48", (1000, 64, 48)), ("spans_small_halfhop_1000_64", (1000, 64, 32))):
+        assert np.array_equal(np.asarray(O.iter_chunks(*args), np.int64), golden[key])
+        assert np.array_equal(np.asarray(N._iter_chunks(*args), np.int64), golden[key])
+
+
+def test_hann(golden):
+    h = O.hann(WIN)
+    assert np.array_equal(h[golden["hann_probe_idx"]], golden["hann_probe_val"])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(h.tobytes()).digest(), np.uint8), golden["hann_sha256"])
+    assert h[0] == 0 and h[-1] == 0 and h[1] == np.float32(1.6341084e-10)
+    assert np.array_equal(O.hann(64), golden["hann_64"])
+
+
+@pytest.mark.parametrize("case", list("abcdef"))
+def test_wola_oracle(case, golden):
+    total, w, hp, C, lpred = golden[f"wola_{case}_meta"]
+    spans = golden[f"wola_{case}_spans"]
+    preds = golden[f"wola_{case}_preds"]
+    out = O.wola_stitch([(preds[k], int(s), int(L)) for k, (s, L) in enumerate(spans)], int(total), int(w))
+    assert out.dtype == np.float32 and np.array_equal(out, golden[f"wola_{case}_out"])
+
+
+def test_wola_empty(golden):
+    assert np.array_equal(O.wola_stitch([], 5, 64), golden["wola_empty"])
+
+
+@pytest.mark.parametrize("model", ["identity", "gain_roll", "short"])
+def test_driver_oracle(model, golden):
+    rng = np.random.default_rng(1234)
+    # replay make_golden.py's rng stream up to the driver input
+    for total, w, hp, C, lpred in [(1000, 64, 48, 2, 64), (777, 64, 48, 1, 64), (500, 64, 32, 3, 64),
+                                   (300, 64, 48, 2, 50), (64, 64, 48, 2, 64), (10, 64, 48, 1, 64)]:
+        for _ in O.iter_chunks(total, w, hp):
+            rng.standard_normal((C, lpred))
+    x = (rng.standard_normal((2, 480000)) * 0.1).astype(np.float32)
+    assert np.array_equal(x[:, ::997], golden["driver_in"])
+    fn = {"identity": lambda c: c, "gain_roll": lambda c: (0.5 * np.roll(c, 3, axis=1)).astype(np.float32),
+          "short": lambda c: c[:, :200000]}[model]
+    y, sr = O.run_driver(x, 48000, fn)
+    assert sr == 48000
+    assert np.array_equal(y[:, golden["driver_probe_idx"]], golden[f"driver_{model}_probe"])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(y.tobytes()).digest(), np.uint8), golden[f"driver_{model}_sha256"])
+    if model == "identity":  # SURVEY.md KAT: identity model reproduces the input except sample 0 (hann[0] = 0)
+        assert np.all(y[:, 0] == 0) and np.max(np.abs(y[:, 1:] - x[:, 1:])) < 1e-7
+
+
+def test_coercions(golden, pkg):
+    from egregora_b200 import egregora_audio_super_resolution as N
+    from egregora_b200 import egregora_fat_llama_gpu as F
+    for fn in (O.to_cs, F._to_cs):
+        assert np.array_equal(fn(golden["to_cs_in_frames_first"]), golden["to_cs_out_frames_first"])
+        assert np.array_equal(fn(golden["to_cs_in_cs"]), golden["to_cs_out_cs"])
+        assert np.array_equal(fn(golden["to_cs_in_cs"][0]), golden["to_cs_out_1d"])
+    assert np.array_equal(O.from_audio_array(golden["to_cs_in_frames_first"]), golden["from_tuple_out"])
+    cs, sr = N._from_audio_dict((golden["to_cs_in_frames_first"], 8000))
+    assert sr == 8000 and np.array_equal(cs.numpy(), golden["from_tuple_out"])
+    cs, sr = N._from_audio_dict({"waveform": torch.zeros(3, 2, 2), "sample_rate": 7})
+    assert tuple(cs.shape) == tuple(golden["from_dict_b3_shape"])
+    err = json.loads((GOLDEN / "errors.json").read_text())["from_audio_dict_1d"]
+    with pytest.raises(RuntimeError) as e:
+        N._from_audio_dict({"waveform": torch.zeros(5), "sample_rate": 7})
+    assert str(e.value) == err
+    with pytest.raises(RuntimeError, match="No valid AUDIO provided."):
+        N._from_audio_dict(None)
+
+
+def test_resample_branch(golden, pkg):
+    from egregora_b200 import egregora_audio_super_resolution as N
+    rng = np.random.default_rng(7)
+    x = (rng.standard_normal((1, 16000)) * 0.1).astype(np.float32)
+    a = O.resample_poly_ref(x, 16000, 48000)
+    b = N._resample_hq(torch.from_numpy(x), 16000, 48000).numpy()
+    assert a.shape == (1, 48000) and np.array_equal(a, b)
+    assert tuple(golden["driver_16k_shape"]) == (1, 441000) and int(golden["driver_16k_sr"][0]) == 44100
