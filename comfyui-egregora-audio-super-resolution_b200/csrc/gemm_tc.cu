@@ -1,0 +1,404 @@
+// gemm_tc.cu — the dense contraction of the FlashSR plan on 5th-gen tensor cores (sm_100a):
+//
+//     out[pix, n] = act(alpha * sum_tap sum_k A[pix + tap, k] * B[tap|batch, n, k] + bias[n] + rowbias[b,n]) + resid
+//
+// One kernel covers 3x3 / 1x1 / strided 2-D convs, dilated 1-D convs, transposed convs (as 2-tap GEMMs with
+// N = stride*Cout), linears and the two attention GEMMs: the A operand is a channels-last f16 activation viewed
+// through a rank-5 TMA tensor map, so every tap is just a shifted box load and zero padding is TMA's
+// out-of-bounds fill — no im2col buffer ever exists in HBM.
+//
+// CTA = 128 output pixels x BLOCK_N channels, 192 threads, warp-specialised:
+//   warp 0      TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier expect_tx)          [UTMALDG]
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 f16)   [UTCHMMA]
+//   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> bias/act/residual -> vector stores   [LDTM]
+// smem ring of S stages x (16 KB A + BLOCK_N*128 B of B); accumulator 128 lanes x BLOCK_N f32 columns in TMEM.
+#include <cuda.h>
+#include "ops.cuh"
+
+namespace egr {
+
+static constexpr int TILE_M = 128;
+static constexpr int KBLK = 64;  // f16 elements per smem row = 128 B = one swizzle span
+static constexpr int A_STAGE_BYTES = TILE_M * KBLK * 2;
+
+struct TcPrepared {
+  CUtensorMap tmA, tmB;
+  GemmArgs g;
+  Taps taps;
+  int a_rank;
+  int stages, tmem_cols, smem_bytes;
+  dim3 grid;
+  int vec_ok;
+  char name[48];
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encode = nullptr;
+
+}  // namespace egr
+
+using namespace egr;
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
+// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+struct TcKernelArgs {
+  GemmArgs g;
+  Taps taps;
+  int stages, tmem_cols, kchunks, vec_ok;
+};
+
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmB,
+                                                          const __grid_constant__ TcKernelArgs ka) {
+  extern __shared__ uint8_t smem_raw[];
+  const GemmArgs& g = ka.g;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = g.block_n;
+  const int b_stage_bytes = BN * KBLK * 2;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)ka.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + ka.stages;
+  uint64_t* accum_bar = empty_bar + ka.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int tiles_w = (g.Wo + g.bw - 1) / g.bw, tiles_h = (g.Ho + g.bh - 1) / g.bh;
+  int mt = blockIdx.x;
+  const int w0 = (mt % tiles_w) * g.bw; mt /= tiles_w;
+  const int h0 = (mt % tiles_h) * g.bh; mt /= tiles_h;
+  const int b0 = mt * g.bb;
+  const int n0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ka.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)ka.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int iters = g.ntaps * ka.kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      const uint32_t tx_bytes = (uint32_t)stage_bytes;
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % ka.stages;
+        const uint32_t ph = (uint32_t)(it / ka.stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int tap = it / ka.kchunks, kc = it - tap * ka.kchunks;
+        int c[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) c[d] = ka.taps.t[tap][d];
+        c[0] += kc * KBLK;
+        c[g.dimW] += w0; c[g.dimH] += h0; c[g.dimB] += b0;
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full_bar[s], tx_bytes);
+        tma_load_5d(sa, &tmA, &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
+        tma_load_3d(sa + A_STAGE_BYTES, &tmB, &full_bar[s], kc * KBLK, n0, g.wz_batch ? b0 : tap);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % ka.stages;
+        const uint32_t ph = (uint32_t)(it / ka.stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+#pragma unroll
+        for (int k = 0; k < KBLK / 16; ++k) {
+          // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
+          tc_mma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(accum_bar);
+    }
+  } else {
+    // epilogue warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    const int wl = row % g.bw, hl = (row / g.bw) % g.bh, bl = row / (g.bw * g.bh);
+    const int w = w0 + wl, h = h0 + hl, b = b0 + bl;
+    const bool row_ok = (w < g.Wo) && (h < g.Ho) && (b < g.Bo);
+    const long long pix = (long long)h * g.Wo + w;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    for (int cb = 0; cb < BN; cb += 32) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cb;
+      const int ncols = min(32, BN - cb);  // BN is a multiple of 16
+      if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
+      tc_wait_ld();
+      const int nb = n0 + cb;
+      if (!row_ok) {
+        // nothing to store for padded rows
+      } else if (g.transposed) {
+        for (int j = 0; j < ncols; ++j) {
+          const int n = nb + j;
+          if (n >= g.N) break;
+          float v = __uint_as_float(r[j]) * g.alpha;
+          if (g.bias) v += g.bias[n];
+          if (g.rowbias) v += g.rowbias[(long long)b * g.rowbias_stride + n];
+          v = egr_apply_act(v, g.act);
+          const long long idx = (long long)b * g.out_batch_stride + (long long)n * g.out_n_stride + pix + g.out_offset;
+          if (g.resid) v += g.resid[idx];
+          if (g.out32) g.out32[idx] = v;
+          if (g.out16) g.out16[idx] = __float2half_rn(v);
+        }
+      } else {
+      const long long flat0 = pix * g.out_pix_stride + g.out_offset + nb;
+      const long long base = (long long)b * g.out_batch_stride + flat0;
+      const float* rb = g.rowbias ? g.rowbias + (long long)b * g.rowbias_stride + nb : nullptr;
+      if (ka.vec_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j >= ncols || nb + j >= g.N) break;
+          const long long fl = flat0 + j;
+          if (fl < g.out_lo || fl >= g.out_hi) continue;
+          float v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(r[j + u]) * g.alpha;
+          if (g.bias) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
+            v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+          }
+          if (rb) {
+            const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + j));
+            v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+          }
+          if (g.act) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = egr_apply_act(v[u], g.act);
+          }
+          if (g.resid) {
+            const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid + base + j));
+            v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+          }
+          if (g.out32) *reinterpret_cast<float4*>(g.out32 + base + j) = make_float4(v[0], v[1], v[2], v[3]);
+          if (g.out16) {
+            __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned*>(&h0);
+            pk.y = *reinterpret_cast<unsigned*>(&h1);
+            *reinterpret_cast<uint2*>(g.out16 + base + j) = pk;
+          }
+        }
+      } else {
+        for (int j = 0; j < ncols; ++j) {
+          const int n = nb + j;
+          if (n >= g.N) break;
+          const long long fl = flat0 + j;
+          if (fl < g.out_lo || fl >= g.out_hi) continue;
+          float v = __uint_as_float(r[j]) * g.alpha;
+          if (g.bias) v += g.bias[n];
+          if (rb) v += rb[j];
+          v = egr_apply_act(v, g.act);
+          if (g.resid) v += g.resid[base + j];
+          if (g.out32) g.out32[base + j] = v;
+          if (g.out16) g.out16[base + j] = __float2half_rn(v);
+        }
+      }
+      }
+      __syncwarp();  // reconverge before the next .sync.aligned TMEM load
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)ka.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+int egr::tc_global_init() {
+  if (g_encode) return EGR_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess)
+    return fail(EGR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+  g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  EGR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  return EGR_OK;
+}
+
+static int encode_map(CUtensorMap* tm, void* base, int rank, const long long* dim, const long long* stride_elems,
+                      const int* box, const char* what) {
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int d = 0; d < rank; ++d) {
+    gdim[d] = (cuuint64_t)dim[d];
+    bx[d] = (cuuint32_t)box[d];
+    es[d] = 1;
+    if (d > 0) gstr[d - 1] = (cuuint64_t)stride_elems[d] * 2;  // f16
+    if (box[d] < 1 || box[d] > 256) return fail(EGR_ERR_ARG, "%s: TMA box[%d]=%d out of range", what, d, box[d]);
+    if (d > 0 && ((stride_elems[d] * 2) % 16 != 0 || stride_elems[d] <= 0))
+      return fail(EGR_ERR_ARG, "%s: TMA stride[%d]=%lld elements is not a positive multiple of 16 bytes", what, d, stride_elems[d]);
+  }
+  if (reinterpret_cast<uintptr_t>(base) % 16) return fail(EGR_ERR_ARG, "%s: TMA base not 16-byte aligned", what);
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, gdim, gstr, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(EGR_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed with CUresult %d", what, (int)r);
+  return EGR_OK;
+}
+
+int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
+  int rc = tc_global_init();
+  if (rc) return rc;
+  TcPrepared* p = new TcPrepared();
+  View a;
+  rc = gemm_args_from_op(s, op, &p->g, &p->taps, &a);
+  if (rc) { delete p; return rc; }
+  GemmArgs& g = p->g;
+  snprintf(p->name, sizeof(p->name), "%s", op.name);
+  auto bail = [&](int code) { delete p; return code; };
+  if (a.elem != 1) return bail(fail(EGR_ERR_ARG, "%s: tensor-core path needs an f16 A operand", op.name));
+  if (g.block_n < 16 || g.block_n > 256 || g.block_n % 16) return bail(fail(EGR_ERR_ARG, "%s: BLOCK_N=%d must be a multiple of 16 in [16,256]", op.name, g.block_n));
+  if (op.i[EGR_I_KBLOCK] && op.i[EGR_I_KBLOCK] != KBLK) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: only K block 64 is built", op.name));
+  // A map: always rank 5 (missing dims are size 1 with a harmless stride)
+  long long dim[5], str[5]; int box[5];
+  long long span = 0;
+  for (int d = 0; d < 5; ++d) {
+    dim[d] = a.dim[d]; str[d] = a.stride[d];
+    if (d < a.rank) span = span > a.dim[d] * a.stride[d] ? span : a.dim[d] * a.stride[d];
+  }
+  for (int d = a.rank; d < 5; ++d) { dim[d] = 1; str[d] = dim[d - 1] * str[d - 1]; }
+  for (int d = 0; d < 5; ++d) box[d] = 1;
+  box[0] = KBLK; box[g.dimW] = g.bw; box[g.dimH] = g.bh; box[g.dimB] = g.bb;
+  if (g.dimW == g.dimH || g.dimW == g.dimB || g.dimH == g.dimB)
+    return bail(fail(EGR_ERR_ARG, "%s: tile dims must be distinct A dims", op.name));
+  rc = encode_map(&p->tmA, const_cast<void*>(a.p), 5, dim, str, box, op.name);
+  if (rc) return bail(rc);
+  // B map: [K, N, Z]
+  long long bdim[3] = {g.K, g.N, g.wz_batch ? (long long)g.Bo : (long long)g.ntaps};
+  long long bstr[3] = {1, g.wstride_n, g.wstride_z > 0 ? g.wstride_z : g.wstride_n * g.N};
+  int bbox[3] = {KBLK, g.block_n, 1};
+  rc = encode_map(&p->tmB, const_cast<void*>(g.W), 3, bdim, bstr, bbox, op.name);
+  if (rc) return bail(rc);
+  if (g.wz_batch && g.bb != 1) return bail(fail(EGR_ERR_ARG, "%s: batch-indexed B operand needs BB == 1", op.name));
+
+  const int stage_bytes = A_STAGE_BYTES + g.block_n * KBLK * 2;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  p->stages = stages;
+  p->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 16;
+  int cols = 32;
+  while (cols < g.block_n) cols <<= 1;
+  p->tmem_cols = cols;
+  const int tiles = ceil_div(g.Wo, g.bw) * ceil_div(g.Ho, g.bh) * ceil_div(g.Bo, g.bb);
+  p->grid = dim3(tiles, ceil_div(g.N, g.block_n), 1);
+  // vector epilogue needs 16-byte aligned rows of 4
+  bool vec = !g.transposed && (g.N % 4 == 0) && (g.out_pix_stride % 4 == 0) && (g.out_batch_stride % 4 == 0) &&
+             (g.out_offset % 4 == 0) && (g.out_lo % 4 == 0) && (g.out_hi % 4 == 0) && (g.rowbias_stride % 4 == 0);
+  auto al = [](const void* q, int a) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % a == 0; };
+  vec = vec && al(g.out32, 16) && al(g.out16, 8) && al(g.resid, 16) && al(g.bias, 16) && al(g.rowbias, 16);
+  p->vec_ok = vec ? 1 : 0;
+  *out = p;
+  return EGR_OK;
+}
+
+int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
+  TcKernelArgs ka;
+  ka.g = p->g;
+  ka.taps = p->taps;
+  ka.stages = p->stages;
+  ka.tmem_cols = p->tmem_cols;
+  ka.kchunks = ceil_div(p->g.K, KBLK);
+  ka.vec_ok = p->vec_ok;
+  gemm_tc_kernel<<<p->grid, 192, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
+  EGR_CHECK_LAUNCH(p->name);
+  return EGR_OK;
+}
+
+void egr::tc_free(TcPrepared* p) { delete p; }

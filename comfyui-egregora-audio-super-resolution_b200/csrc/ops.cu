@@ -1,0 +1,697 @@
+// ops.cu — CUDA-core ops of the FlashSR plan: SIMT tap-GEMM (tiny-K / tiny-N layers and the in-library
+// cross-check of the tcgen05 path), GroupNorm, LayerNorm, softmax, short-sequence attention, GEGLU,
+// element-wise glue, anti-aliased SnakeBeta, time embedding.  All are HBM-bound streaming kernels:
+// coalesced float4 / half2 accesses with channels innermost, warp-shuffle reductions, f64 accumulators
+// where cancellation matters (GroupNorm moments).
+#include "ops.cuh"
+
+namespace egr {
+
+int gemm_args_from_op(const Spaces& s, const egr_op& op, GemmArgs* g, Taps* taps, View* a) {
+  *a = make_view(s, op.x0);
+  if (!a->p) return fail(EGR_ERR_ARG, "%s: null A operand", op.name);
+  if (a->stride[0] != 1) return fail(EGR_ERR_ARG, "%s: A stride[0] must be 1", op.name);
+  g->dimW = (int)op.i[EGR_I_DIMW]; g->dimH = (int)op.i[EGR_I_DIMH]; g->dimB = (int)op.i[EGR_I_DIMB];
+  g->bw = (int)op.i[EGR_I_BW]; g->bh = (int)op.i[EGR_I_BH]; g->bb = (int)op.i[EGR_I_BB];
+  g->Wo = (int)op.i[EGR_I_WO]; g->Ho = (int)op.i[EGR_I_HO]; g->Bo = (int)op.i[EGR_I_BO];
+  g->ntaps = (int)op.i[EGR_I_NTAPS]; g->K = (int)op.i[EGR_I_K]; g->N = (int)op.i[EGR_I_N];
+  g->block_n = (int)op.i[EGR_I_BLOCKN];
+  g->wstride_n = op.i[EGR_I_WSTRIDE_N]; g->wstride_z = op.i[EGR_I_WSTRIDE_Z];
+  g->wz_batch = (int)op.i[EGR_I_WZ_BATCH];
+  g->W = resolve(s, op.ptr[EGR_P_W]);
+  g->bias = (const float*)resolve(s, op.ptr[EGR_P_BIAS]);
+  g->rowbias = (const float*)resolve(s, op.ptr[EGR_P_ROWBIAS]);
+  g->rowbias_stride = op.i[EGR_I_ROWBIAS_STRIDE];
+  g->resid = (const float*)resolve(s, op.ptr[EGR_P_RESID]);
+  g->out32 = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
+  g->out16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
+  g->out_pix_stride = op.i[EGR_I_OUT_PIX_STRIDE]; g->out_batch_stride = op.i[EGR_I_OUT_BATCH_STRIDE];
+  g->out_offset = op.i[EGR_I_OUT_OFFSET]; g->out_lo = op.i[EGR_I_OUT_LO]; g->out_hi = op.i[EGR_I_OUT_HI];
+  g->out_n_stride = op.i[EGR_I_OUT_N_STRIDE];
+  g->transposed = (int)op.i[EGR_I_TRANSPOSED]; g->act = (int)op.i[EGR_I_ACT];
+  g->alpha = (float)op.f[EGR_F_ALPHA];
+  if (g->ntaps < 1 || g->ntaps > EGR_MAX_TAPS) return fail(EGR_ERR_ARG, "%s: ntaps=%d out of range", op.name, g->ntaps);
+  if (g->bw * g->bh * g->bb != 128) return fail(EGR_ERR_ARG, "%s: tile %dx%dx%d != 128 rows", op.name, g->bw, g->bh, g->bb);
+  if (!g->W || (!g->out32 && !g->out16)) return fail(EGR_ERR_ARG, "%s: missing weights or output", op.name);
+  if (g->K < 1 || g->N < 1) return fail(EGR_ERR_ARG, "%s: bad K/N", op.name);
+  for (int d : {g->dimW, g->dimH, g->dimB})
+    if (d < 1 || d > 4) return fail(EGR_ERR_ARG, "%s: tile dims must index A dims 1..4", op.name);
+  memcpy(taps->t, op.tap, sizeof(taps->t));
+  return EGR_OK;
+}
+
+}  // namespace egr
+
+using namespace egr;
+
+// ------------------------------------------------------------------------------------------------
+// shared scalar epilogue: out = act(alpha*acc + bias + rowbias) + resid, with the transposed-conv crop
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_store(const GemmArgs& g, int b, long long pix, int n, float acc) {
+  float v = acc * g.alpha;
+  if (g.bias) v += g.bias[n];
+  if (g.rowbias) v += g.rowbias[(long long)b * g.rowbias_stride + n];
+  v = egr_apply_act(v, g.act);
+  long long idx;
+  if (g.transposed) {
+    idx = (long long)b * g.out_batch_stride + (long long)n * g.out_n_stride + pix + g.out_offset;
+  } else {
+    long long flat = pix * g.out_pix_stride + g.out_offset + n;
+    if (flat < g.out_lo || flat >= g.out_hi) return;
+    idx = (long long)b * g.out_batch_stride + flat;
+  }
+  if (g.resid) v += g.resid[idx];
+  if (g.out32) g.out32[idx] = v;
+  if (g.out16) g.out16[idx] = __float2half_rn(v);
+}
+
+__device__ __forceinline__ float load_view(const View& a, const long long c[5]) {
+  long long off = 0;
+#pragma unroll
+  for (int d = 0; d < 5; ++d) {
+    if (c[d] < 0 || c[d] >= a.dim[d]) return 0.f;
+    off += c[d] * a.stride[d];
+  }
+  return a.elem ? __half2float(reinterpret_cast<const __half*>(a.p)[off]) : reinterpret_cast<const float*>(a.p)[off];
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT tap-GEMM, general tile: 32 pixels x 32 outputs per block, reduction index r = tap*K + k in chunks
+// of 32 through shared memory.  W is f32 [Z][N][K].
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_simt_kernel(View a, GemmArgs g, Taps taps) {
+  __shared__ float As[32][33];
+  __shared__ float Ws[32][33];
+  __shared__ int pw[32], ph[32], pb[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long npix = (long long)g.Wo * g.Ho * g.Bo;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int n0 = blockIdx.y * 32;
+  if (threadIdx.x < 32) {
+    long long p = p0 + threadIdx.x;
+    if (p < npix) {
+      pw[threadIdx.x] = (int)(p % g.Wo);
+      ph[threadIdx.x] = (int)((p / g.Wo) % g.Ho);
+      pb[threadIdx.x] = (int)(p / ((long long)g.Wo * g.Ho));
+    } else {
+      pw[threadIdx.x] = -1; ph[threadIdx.x] = 0; pb[threadIdx.x] = 0;
+    }
+  }
+  __syncthreads();
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int R = g.ntaps * g.K;
+  const float* W = reinterpret_cast<const float*>(g.W);
+  for (int r0 = 0; r0 < R; r0 += 32) {
+    const int r = r0 + tx;
+    const int tap = r < R ? r / g.K : 0, k = r < R ? r % g.K : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int px = ty + 8 * i;
+      float av = 0.f;
+      if (r < R && pw[px] >= 0) {
+        long long c[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) c[d] = taps.t[tap][d];
+        c[0] += k;
+        c[g.dimW] += pw[px];
+        c[g.dimH] += ph[px];
+        c[g.dimB] += pb[px];
+        av = load_view(a, c);
+      }
+      As[px][tx] = av;
+      const int n = n0 + px;  // reuse the same (row, col) pattern for the weight tile: row = output n
+      float wv = 0.f;
+      if (r < R && n < g.N) {
+        // z = tap for weights; batch-indexed B operands (attention) are not supported on this path
+        wv = W[(long long)tap * g.wstride_z + (long long)n * g.wstride_n + k];
+      }
+      Ws[px][tx] = wv;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; ++kk) {
+      const float w = Ws[tx][kk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(As[ty + 8 * i][kk], w, acc[i]);
+    }
+    __syncthreads();
+  }
+  const int n = n0 + tx;
+  if (n < g.N) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int px = ty + 8 * i;
+      if (pw[px] >= 0) epilogue_store(g, pb[px], (long long)ph[px] * g.Wo + pw[px], n, acc[i]);
+    }
+  }
+}
+
+// SIMT tap-GEMM for N <= 4: one warp per pixel, lanes stride the channel dimension (coalesced), shuffle reduce.
+__global__ void __launch_bounds__(256) gemm_simt_smalln_kernel(View a, GemmArgs g, Taps taps) {
+  const int lane = threadIdx.x & 31;
+  const long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const long long npix = (long long)g.Wo * g.Ho * g.Bo;
+  if (p >= npix) return;
+  const int w = (int)(p % g.Wo), h = (int)((p / g.Wo) % g.Ho), b = (int)(p / ((long long)g.Wo * g.Ho));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* W = reinterpret_cast<const float*>(g.W);
+  for (int tap = 0; tap < g.ntaps; ++tap) {
+    long long c[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) c[d] = taps.t[tap][d];
+    c[g.dimW] += w; c[g.dimH] += h; c[g.dimB] += b;
+    const long long c0 = c[0];
+    for (int k = lane; k < g.K; k += 32) {
+      c[0] = c0 + k;
+      const float av = load_view(a, c);
+      for (int n = 0; n < g.N; ++n) acc[n] = fmaf(av, W[(long long)tap * g.wstride_z + (long long)n * g.wstride_n + k], acc[n]);
+    }
+  }
+  for (int n = 0; n < g.N; ++n) {
+    const float v = warp_sum(acc[n]);
+    if (lane == 0) epilogue_store(g, b, (long long)h * g.Wo + w, n, v);
+  }
+}
+
+int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  GemmArgs g; Taps taps; View a;
+  int rc = gemm_args_from_op(s, op, &g, &taps, &a);
+  if (rc) return rc;
+  if (g.wz_batch) return fail(EGR_ERR_UNSUPPORTED, "%s: batch-indexed B operand needs the tensor-core path", op.name);
+  const long long npix = (long long)g.Wo * g.Ho * g.Bo;
+  if (g.N <= 4) {
+    gemm_simt_smalln_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, st>>>(a, g, taps);
+  } else {
+    dim3 grid((unsigned)((npix + 31) / 32), (unsigned)((g.N + 31) / 32));
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(a, g, taps);
+  }
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm.  Input is a virtual channel-concat of x0 (C0 channels) and x1 (C1 channels), f32, channels
+// innermost, pixels contiguous per batch item: element (b,p,c) at base + (b*P + p)*Cx + c.
+// stats: f64 [B][G][2] = (sum, sumsq), must be zeroed first (EGR_OP_ZERO).
+// ------------------------------------------------------------------------------------------------
+struct CatArgs {
+  const float* x0; const float* x1;
+  int C0, C1, G, B;
+  long long P;  // pixels per batch item
+};
+
+__global__ void __launch_bounds__(256) gn_stats_kernel(CatArgs a, double* __restrict__ stats, int slab) {
+  extern __shared__ double sh[];  // [G][2]
+  const int C = a.C0 + a.C1, C4 = C >> 2, cpg = C / a.G;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) sh[i] = 0.0;
+  __syncthreads();
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long p_lo = (long long)blockIdx.x * slab, p_hi = min(p_lo + slab, a.P);
+  for (int q = tx; q < C4; q += 32) {
+    const int c = q << 2;
+    const float* base; int cc, Cx;
+    if (c < a.C0) { base = a.x0; cc = c; Cx = a.C0; } else { base = a.x1; cc = c - a.C0; Cx = a.C1; }
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long long p = p_lo + ty; p < p_hi; p += 8) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((long long)b * a.P + p) * Cx + cc));
+      s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
+      s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
+      s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
+      s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
+    }
+    if ((cpg & 3) == 0) {
+      const int gi = c / cpg;
+      atomicAdd(&sh[2 * gi], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
+      atomicAdd(&sh[2 * gi + 1], (double)ss[0] + (double)ss[1] + (double)ss[2] + (double)ss[3]);
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int gi = (c + u) / cpg;
+        atomicAdd(&sh[2 * gi], (double)s[u]);
+        atomicAdd(&sh[2 * gi + 1], (double)ss[u]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) atomicAdd(&stats[(long long)b * 2 * a.G + i], sh[i]);
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* __restrict__ stats,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, int silu, float* __restrict__ out32,
+                                                        __half* __restrict__ out16, int slab) {
+  extern __shared__ float shf[];  // scale[C], shift[C]
+  const int C = a.C0 + a.C1, C4 = C >> 2, cpg = C / a.G;
+  const int b = blockIdx.y;
+  float* scale = shf; float* shift = shf + C;
+  const double cnt = (double)cpg * (double)a.P;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int gi = c / cpg;
+    const double sum = stats[((long long)b * a.G + gi) * 2], sq = stats[((long long)b * a.G + gi) * 2 + 1];
+    const double mean = sum / cnt;
+    double var = sq / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = rstd * gamma[c];
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+  }
+  __syncthreads();
+  const long long p_lo = (long long)blockIdx.x * slab, p_hi = min(p_lo + slab, a.P);
+  const long long total = (p_hi - p_lo) * C4;
+  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+    const long long p = p_lo + i / C4;
+    const int c = (int)(i % C4) << 2;
+    const float* src = c < a.C0 ? a.x0 + ((long long)b * a.P + p) * a.C0 + c
+                                : a.x1 + ((long long)b * a.P + p) * a.C1 + (c - a.C0);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src));
+    float r[4] = {fmaf(v.x, scale[c], shift[c]), fmaf(v.y, scale[c + 1], shift[c + 1]),
+                  fmaf(v.z, scale[c + 2], shift[c + 2]), fmaf(v.w, scale[c + 3], shift[c + 3])};
+    if (silu) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = egr_silu(r[u]);
+    }
+    const long long o = ((long long)b * a.P + p) * C + c;
+    if (out32) *reinterpret_cast<float4*>(out32 + o) = make_float4(r[0], r[1], r[2], r[3]);
+    if (out16) {
+      __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<unsigned*>(&h0);
+      pk.y = *reinterpret_cast<unsigned*>(&h1);
+      *reinterpret_cast<uint2*>(out16 + o) = pk;
+    }
+  }
+}
+
+static int cat_args(const Spaces& s, const egr_op& op, CatArgs* a) {
+  a->x0 = (const float*)resolve(s, op.x0.addr);
+  a->x1 = (const float*)resolve(s, op.x1.addr);
+  a->C0 = (int)op.i[EGR_I_C0]; a->C1 = (int)op.i[EGR_I_C1];
+  a->G = (int)op.i[EGR_I_GROUPS]; a->B = (int)op.i[EGR_I_BATCH];
+  a->P = op.i[EGR_I_ROWS];
+  const int C = a->C0 + a->C1;
+  if (!a->x0 || a->C0 <= 0 || (a->C1 > 0 && !a->x1)) return fail(EGR_ERR_ARG, "%s: bad inputs", op.name);
+  if ((a->C0 & 3) || (a->C1 & 3)) return fail(EGR_ERR_ARG, "%s: channel counts must be multiples of 4", op.name);
+  if (a->G <= 0 || C % a->G) return fail(EGR_ERR_ARG, "%s: C=%d not divisible by groups=%d", op.name, C, a->G);
+  if (a->B <= 0 || a->B > 65535 || a->P <= 0) return fail(EGR_ERR_ARG, "%s: bad batch/pixels", op.name);
+  return EGR_OK;
+}
+
+static int slab_for(long long P, int B, int* nslabs) {
+  // enough blocks to fill the machine (~8 per SM) without making slabs tiny
+  int sms = devinfo().sm_count ? devinfo().sm_count : 148;
+  long long want = ((long long)sms * 8 + B - 1) / B;
+  long long slab = (P + want - 1) / want;
+  if (slab < 64) slab = 64;
+  if (slab > P) slab = P;
+  *nslabs = (int)((P + slab - 1) / slab);
+  return (int)slab;
+}
+
+int egr::launch_gn_stats(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  CatArgs a;
+  int rc = cat_args(s, op, &a);
+  if (rc) return rc;
+  double* stats = (double*)resolve(s, op.ptr[EGR_P_STATS]);
+  if (!stats) return fail(EGR_ERR_ARG, "%s: null stats", op.name);
+  int ns; int slab = slab_for(a.P, a.B, &ns);
+  gn_stats_kernel<<<dim3(ns, a.B), 256, 2 * a.G * sizeof(double), st>>>(a, stats, slab);
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+int egr::launch_gn_apply(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  CatArgs a;
+  int rc = cat_args(s, op, &a);
+  if (rc) return rc;
+  const double* stats = (const double*)resolve(s, op.ptr[EGR_P_STATS]);
+  const float* gamma = (const float*)resolve(s, op.ptr[EGR_P_GAMMA]);
+  const float* beta = (const float*)resolve(s, op.ptr[EGR_P_BETA]);
+  float* o32 = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
+  __half* o16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
+  if (!stats || !gamma || !beta || (!o32 && !o16)) return fail(EGR_ERR_ARG, "%s: null pointer", op.name);
+  int ns; int slab = slab_for(a.P, a.B, &ns);
+  const int C = a.C0 + a.C1;
+  gn_apply_kernel<<<dim3(ns, a.B), 256, 2 * C * sizeof(float), st>>>(a, stats, gamma, beta, (float)op.f[EGR_F_EPS],
+                                                                     (int)op.i[EGR_I_MODE], o32, o16, slab);
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over the channel dimension: one warp per token row, f32 in -> f16 out.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         float eps, __half* __restrict__ out16, float* __restrict__ out32) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+  const float rstd = rsqrtf(warp_sum(v) / C + eps);
+  for (int c = lane; c < C; c += 32) {
+    const float y = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+    if (out16) out16[row * C + c] = __float2half_rn(y);
+    if (out32) out32[row * C + c] = y;
+  }
+}
+
+int egr::launch_layernorm(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  const float* x = (const float*)resolve(s, op.x0.addr);
+  const long long rows = op.i[EGR_I_ROWS];
+  const int C = (int)op.i[EGR_I_COLS];
+  const float* gamma = (const float*)resolve(s, op.ptr[EGR_P_GAMMA]);
+  const float* beta = (const float*)resolve(s, op.ptr[EGR_P_BETA]);
+  __half* o16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
+  float* o32 = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
+  if (!x || !gamma || !beta || (!o16 && !o32) || rows <= 0 || C <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, C, gamma, beta, (float)op.f[EGR_F_EPS], o16, o32);
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// row softmax(scale * x): f32 [rows, cols] -> f16, one warp per row (cols up to a few thousand).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ x, long long rows, int cols, float scale,
+                                                       __half* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * cols;
+  float m = -INFINITY;
+  for (int c = lane; c < cols; c += 32) m = fmaxf(m, xr[c] * scale);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < cols; c += 32) s += __expf(xr[c] * scale - m);
+  const float inv = 1.0f / warp_sum(s);
+  for (int c = lane; c < cols; c += 32) out[row * cols + c] = __float2half_rn(__expf(xr[c] * scale - m) * inv);
+}
+
+int egr::launch_softmax(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  const float* x = (const float*)resolve(s, op.x0.addr);
+  __half* o = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
+  const long long rows = op.i[EGR_I_ROWS];
+  const int cols = (int)op.i[EGR_I_COLS];
+  if (!x || !o || rows <= 0 || cols <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  softmax_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, rows, cols, (float)op.f[EGR_F_ALPHA], o);
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Short-sequence multi-head self-attention (UNet transformers: S <= 512, head_dim <= 64).
+// q,k,v f16 [B,S,heads*hd]; K and V of one (b, head) are staged in shared memory, each warp owns query
+// rows: lanes split the keys for QK^T + softmax, then split head_dim for PV.  f32 math throughout.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) attn_small_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                          const __half* __restrict__ v, __half* __restrict__ out, int S,
+                                                          int heads, int hd, float scale) {
+  extern __shared__ unsigned char smraw[];
+  const int C = heads * hd;
+  const int kst = hd + 2;  // padded row stride (halves) -> conflict-free column walks
+  __half* Ks = reinterpret_cast<__half*>(smraw);
+  __half* Vs = Ks + (size_t)S * kst;
+  float* probs = reinterpret_cast<float*>(Vs + (size_t)S * kst);  // [8 warps][S]
+  float* qrow = probs + 8 * S;                                     // [8 warps][hd]
+  const int b = blockIdx.z, h = blockIdx.y;
+  const long long base = (long long)b * S * C + (long long)h * hd;
+  for (int i = threadIdx.x; i < S * hd; i += blockDim.x) {
+    const int j = i / hd, d = i % hd;
+    Ks[j * kst + d] = k[base + (long long)j * C + d];
+    Vs[j * kst + d] = v[base + (long long)j * C + d];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* pr = probs + warp * S;
+  float* qr = qrow + warp * hd;
+  const int rows_per_block = (S + gridDim.x - 1) / gridDim.x;
+  const int r_lo = blockIdx.x * rows_per_block, r_hi = min(S, r_lo + rows_per_block);
+  for (int r = r_lo + warp; r < r_hi; r += 8) {
+    for (int d = lane; d < hd; d += 32) qr[d] = __half2float(q[base + (long long)r * C + d]) * scale;
+    __syncwarp();
+    float m = -INFINITY;
+    for (int j = lane; j < S; j += 32) {
+      float dot = 0.f;
+      for (int d = 0; d < hd; ++d) dot = fmaf(qr[d], __half2float(Ks[j * kst + d]), dot);
+      pr[j] = dot;
+      m = fmaxf(m, dot);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) { const float e = __expf(pr[j] - m); pr[j] = e; sum += e; }
+    const float inv = 1.0f / warp_sum(sum);
+    __syncwarp();
+    for (int d = lane; d < hd; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < S; ++j) o = fmaf(pr[j], __half2float(Vs[j * kst + d]), o);
+      out[base + (long long)r * C + d] = __float2half_rn(o * inv);
+    }
+    __syncwarp();
+  }
+}
+
+int egr::launch_attn_small(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  const __half* q = (const __half*)resolve(s, op.x0.addr);
+  const __half* k = (const __half*)resolve(s, op.x1.addr);
+  const __half* v = (const __half*)resolve(s, op.ptr[EGR_P_AUX]);
+  __half* o = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
+  const int S = (int)op.i[EGR_I_SEQ], heads = (int)op.i[EGR_I_HEADS], hd = (int)op.i[EGR_I_HEADDIM], B = (int)op.i[EGR_I_BATCH];
+  if (!q || !k || !v || !o || S <= 0 || heads <= 0 || hd <= 0 || B <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  size_t smem = (size_t)2 * S * (hd + 2) * sizeof(__half) + (size_t)8 * S * sizeof(float) + 8 * hd * sizeof(float);
+  if (smem > 200 * 1024) return fail(EGR_ERR_UNSUPPORTED, "%s: S=%d hd=%d needs %zu B smem; use the GEMM attention path", op.name, S, hd, smem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    EGR_CUDA(cudaFuncSetAttribute(attn_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  int qblocks = (S + 63) / 64;  // 64 query rows per block: K/V re-staged per block, fine for S <= 512
+  attn_small_kernel<<<dim3(qblocks, heads, B), 256, smem, st>>>(q, k, v, o, S, heads, hd, (float)op.f[EGR_F_ALPHA]);
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEGLU: x f32 [rows, 2D] -> f16 [rows, D] = x[:, :D] * gelu(x[:, D:])   (exact erf gelu, torch default)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) geglu_kernel(const float* __restrict__ x, long long rows, int D, __half* __restrict__ out) {
+  const long long total = rows * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D; const int d = (int)(i % D);
+    const float a = x[r * 2 * D + d], g = x[r * 2 * D + D + d];
+    out[i] = __float2half_rn(a * (0.5f * g * (1.0f + erff(g * 0.70710678118654752f))));
+  }
+}
+
+static unsigned grid1d(long long n, int per_block = 256) {
+  int sms = devinfo().sm_count ? devinfo().sm_count : 148;
+  long long b = (n + per_block - 1) / per_block;
+  if (b > (long long)sms * 32) b = (long long)sms * 32;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
+int egr::launch_geglu(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  const float* x = (const float*)resolve(s, op.x0.addr);
+  __half* o = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
+  const long long rows = op.i[EGR_I_ROWS]; const int D = (int)op.i[EGR_I_COLS];
+  if (!x || !o || rows <= 0 || D <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  geglu_kernel<<<grid1d(rows * D), 256, 0, st>>>(x, rows, D, o);
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise glue.  All operate on channels-innermost f32 tensors of `rows` pixels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) elt_cat_kernel(const float* __restrict__ x0, const float* __restrict__ x1, int C0,
+                                                       int C1, long long rows, long long ld0, long long ld1,
+                                                       float* __restrict__ o32, __half* __restrict__ o16) {
+  const int C = C0 + C1;
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C; const int c = (int)(i % C);
+    const float v = c < C0 ? x0[r * ld0 + c] : x1[r * ld1 + (c - C0)];
+    if (o32) o32[i] = v;
+    if (o16) o16[i] = __float2half_rn(v);
+  }
+}
+
+__global__ void __launch_bounds__(256) elt_axpby_kernel(const float* __restrict__ x, const float* __restrict__ y, float a,
+                                                         float b, long long n, float* __restrict__ o32, __half* __restrict__ o16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = y ? fmaf(a, x[i], b * y[i]) : fmaf(a, x[i], b);
+    if (o32) o32[i] = v;
+    if (o16) o16[i] = __float2half_rn(v);
+  }
+}
+
+// nearest 2x upsample of [B,H,W,C] f32 -> [B,2H,2W,C] f16 (and/or f32)
+__global__ void __launch_bounds__(256) elt_up2x_kernel(const float* __restrict__ x, int B, int H, int W, int C,
+                                                        float* __restrict__ o32, __half* __restrict__ o16) {
+  const long long total = (long long)B * 2 * H * 2 * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long p = i / C;
+    const int w2 = (int)(p % (2 * W)); p /= 2 * W;
+    const int h2 = (int)(p % (2 * H)); const int b = (int)(p / (2 * H));
+    const float v = x[(((long long)b * H + (h2 >> 1)) * W + (w2 >> 1)) * C + c];
+    if (o32) o32[i] = v;
+    if (o16) o16[i] = __float2half_rn(v);
+  }
+}
+
+int egr::launch_eltwise(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  const float* x0 = (const float*)resolve(s, op.x0.addr);
+  const float* x1 = (const float*)resolve(s, op.x1.addr);
+  float* o32 = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
+  __half* o16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
+  const int mode = (int)op.i[EGR_I_MODE];
+  if (!x0 || (!o32 && !o16)) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  switch (mode) {
+    case EGR_ELT_CAST16:
+    case EGR_ELT_COPY32: {
+      const int C0 = (int)op.i[EGR_I_C0], C1 = (int)op.i[EGR_I_C1];
+      const long long rows = op.i[EGR_I_ROWS];
+      const long long ld0 = op.i[EGR_I_AUX0] ? op.i[EGR_I_AUX0] : C0, ld1 = op.i[EGR_I_AUX1] ? op.i[EGR_I_AUX1] : C1;
+      if (C1 > 0 && !x1) return fail(EGR_ERR_ARG, "%s: null x1", op.name);
+      elt_cat_kernel<<<grid1d(rows * (C0 + C1)), 256, 0, st>>>(x0, x1, C0, C1, rows, ld0, ld1, o32, o16);
+      break;
+    }
+    case EGR_ELT_AXPBY:
+      if (!x1) return fail(EGR_ERR_ARG, "%s: null x1", op.name);
+      elt_axpby_kernel<<<grid1d(op.i[EGR_I_ROWS]), 256, 0, st>>>(x0, x1, (float)op.f[EGR_F_A], (float)op.f[EGR_F_B],
+                                                                 op.i[EGR_I_ROWS], o32, o16);
+      break;
+    case EGR_ELT_SCALE_SHIFT:
+      elt_axpby_kernel<<<grid1d(op.i[EGR_I_ROWS]), 256, 0, st>>>(x0, nullptr, (float)op.f[EGR_F_A], (float)op.f[EGR_F_B],
+                                                                 op.i[EGR_I_ROWS], o32, o16);
+      break;
+    case EGR_ELT_UPSAMPLE2X: {
+      const int B = (int)op.i[EGR_I_BATCH], H = (int)op.i[EGR_I_AUX0], W = (int)op.i[EGR_I_AUX1], C = (int)op.i[EGR_I_C0];
+      elt_up2x_kernel<<<grid1d((long long)B * 4 * H * W * C), 256, 0, st>>>(x0, B, H, W, C, o32, o16);
+      break;
+    }
+    default:
+      return fail(EGR_ERR_ARG, "%s: unknown eltwise mode %d", op.name, mode);
+  }
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Anti-aliased SnakeBeta (BigVGAN Activation1d): y = down2(snake(up2(x))), 12-tap Kaiser-sinc FIRs with
+// replicate padding.  x f32 [B,T,C] -> f16 (and/or f32).  Thread = (channel, run of TT outputs): lanes walk
+// channels (coalesced 128 B per time step), each thread slides a register window along time so every
+// up-sampled/activated sample is computed exactly once: 1 load, 2 snake evaluations, 24 FMAs per output.
+//   u[2m]   = 2*sum_r x[m-3+r]*f[11-2r],  u[2m+1] = 2*sum_r x[m-2+r]*f[10-2r]        (r = 0..5)
+//   s[n]    = u[n] + inv_beta*sin^2(alpha*u[n])
+//   y[t]    = sum_j s[clamp(2t+j-5, 0, 2T-1)]*f[j]                                    (j = 0..11)
+// ------------------------------------------------------------------------------------------------
+#define SNAKE_TT 32
+
+__device__ __forceinline__ float snake_eval(float u, float alpha, float inv_beta) {
+  const float sn = sinf(u * alpha);
+  return fmaf(inv_beta * sn, sn, u);
+}
+
+__global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__ x, int T, int C,
+                                                        const float* __restrict__ log_alpha,
+                                                        const float* __restrict__ log_beta,
+                                                        const float* __restrict__ filt, float* __restrict__ o32,
+                                                        __half* __restrict__ o16) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int trun = blockIdx.y * 4 + (threadIdx.x >> 5);
+  const int b = blockIdx.z;
+  const int t0 = trun * SNAKE_TT;
+  if (c >= C || t0 >= T) return;
+  const float alpha = __expf(log_alpha[c]);
+  const float inv_beta = 1.0f / (__expf(log_beta[c]) + 1e-9f);
+  const float* xb = x + (long long)b * T * C + c;
+  float f[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) f[j] = __ldg(filt + j);
+  const int n_last = 2 * T - 1;
+  // s window: s[2t-5 .. 2t+6] for the current t.  xw[i] = x[clamp(m0-3+i)] for the 7 inputs around m.
+  auto xat = [&](int m) { m = m < 0 ? 0 : (m >= T ? T - 1 : m); return __ldg(xb + (long long)m * C); };
+  auto s_at = [&](int n) {  // activated up-sampled sample n (clamped = replicate padding of s)
+    n = n < 0 ? 0 : (n > n_last ? n_last : n);
+    const int m = n >> 1;
+    float u = 0.f;
+    if (n & 1) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) u = fmaf(xat(m - 2 + r), f[10 - 2 * r], u);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) u = fmaf(xat(m - 3 + r), f[11 - 2 * r], u);
+    }
+    return snake_eval(2.0f * u, alpha, inv_beta);
+  };
+  float sw[12];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) sw[j + 2] = s_at(2 * t0 - 5 + j);  // slots 2..11 hold s[2t0-5 .. 2t0+4]
+  const int t_end = min(T, t0 + SNAKE_TT);
+  // rolling input window for the fast interior path: xin[i] = x[m+i-3], m = t+2 .. needs x[t-1 .. t+5]
+  for (int t = t0; t < t_end; ++t) {
+#pragma unroll
+    for (int j = 0; j < 10; ++j) sw[j] = sw[j + 2];
+    sw[10] = s_at(2 * t + 5);
+    sw[11] = s_at(2 * t + 6);
+    float y = 0.f;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
+    const long long o = ((long long)b * T + t) * C + c;
+    if (o32) o32[o] = y;
+    if (o16) o16[o] = __float2half_rn(y);
+  }
+}
+
+int egr::launch_snake_aa(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  const float* x = (const float*)resolve(s, op.x0.addr);
+  const float* la = (const float*)resolve(s, op.ptr[EGR_P_GAMMA]);
+  const float* lb = (const float*)resolve(s, op.ptr[EGR_P_BETA]);
+  const float* filt = (const float*)resolve(s, op.ptr[EGR_P_AUX]);
+  float* o32 = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
+  __half* o16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
+  const int B = (int)op.i[EGR_I_BATCH], T = (int)op.i[EGR_I_ROWS], C = (int)op.i[EGR_I_COLS];
+  if (!x || !la || !lb || !filt || (!o32 && !o16) || B <= 0 || T <= 0 || C <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  if (op.i[EGR_I_AUX0] != 12) return fail(EGR_ERR_UNSUPPORTED, "%s: only the 12-tap anti-alias filter is built", op.name);
+  dim3 grid((C + 31) / 32, (T + SNAKE_TT * 4 - 1) / (SNAKE_TT * 4), B);
+  snake_aa_kernel<<<grid, 128, 0, st>>>(x, T, C, la, lb, filt, o32, o16);
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sinusoidal timestep embedding: out[0:half] = cos(t*f_i), out[half:] = sin(t*f_i), f_i = 10000^(-i/half)
+// ------------------------------------------------------------------------------------------------
+__global__ void time_embed_kernel(float t, int dim, float* __restrict__ out) {
+  const int half = dim / 2;
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float fr = expf(-9.210340371976184f * (float)i / (float)half);
+    const float a = t * fr;
+    out[i] = cosf(a);
+    out[half + i] = sinf(a);
+  }
+}
+
+int egr::launch_time_embed(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  float* o = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
+  const int dim = (int)op.i[EGR_I_COLS];
+  if (!o || dim <= 0 || (dim & 1)) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  time_embed_kernel<<<1, 128, 0, st>>>((float)op.f[EGR_F_A], dim, o);
+  EGR_CHECK_LAUNCH(op.name);
+  return EGR_OK;
+}
+
+int egr::launch_zero(const Spaces& s, const egr_op& op, cudaStream_t st) {
+  void* p = resolve(s, op.ptr[EGR_P_OUT32]);
+  if (!p || op.i[EGR_I_ROWS] < 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  EGR_CUDA(cudaMemsetAsync(p, 0, (size_t)op.i[EGR_I_ROWS], st));
+  return EGR_OK;
+}

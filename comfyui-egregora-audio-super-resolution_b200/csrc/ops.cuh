@@ -1,0 +1,78 @@
+// ops.cuh — launch entry points of the plan's ops (one function per EGR_OP_* code).
+#pragma once
+#include "common.cuh"
+
+namespace egr {
+
+// device-side strided 5-D view (resolved pointer)
+struct View {
+  const void* p;
+  int rank, elem;  // elem: 0 f32, 1 f16
+  long long dim[5];
+  long long stride[5];
+};
+
+inline View make_view(const Spaces& s, const egr_tensor& t) {
+  View v;
+  v.p = resolve(s, t.addr);
+  v.rank = t.rank;
+  v.elem = t.elem;
+  for (int i = 0; i < 5; ++i) {
+    v.dim[i] = i < t.rank ? t.dim[i] : 1;
+    v.stride[i] = i < t.rank ? t.stride[i] : 0;
+  }
+  return v;
+}
+
+struct Taps {
+  short t[EGR_MAX_TAPS][5];
+};
+
+// Everything the GEMM-family kernels need besides the operand views.
+struct GemmArgs {
+  int dimW, dimH, dimB, bw, bh, bb, Wo, Ho, Bo, ntaps, K, N, block_n;
+  long long wstride_n, wstride_z;
+  int wz_batch;
+  const void* W;
+  const float* bias;
+  const float* rowbias;
+  long long rowbias_stride;
+  const float* resid;
+  float* out32;
+  __half* out16;
+  long long out_pix_stride, out_batch_stride, out_offset, out_lo, out_hi, out_n_stride;
+  int transposed, act;
+  float alpha;
+};
+
+int gemm_args_from_op(const Spaces& s, const egr_op& op, GemmArgs* g, Taps* taps, View* a);
+
+int launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_gn_stats(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_gn_apply(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_layernorm(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_softmax(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_attn_small(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_geglu(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_eltwise(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_snake_aa(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_stft_mel(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_lowpass(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_time_embed(const Spaces& s, const egr_op& op, cudaStream_t st);
+int launch_zero(const Spaces& s, const egr_op& op, cudaStream_t st);
+
+// tcgen05 path (gemm_tc.cu)
+struct TcPrepared;  // tensor maps + launch geometry, built once per op at plan creation
+int  tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out);
+int  tc_launch(const TcPrepared* p, cudaStream_t st);
+void tc_free(TcPrepared* p);
+int  tc_global_init();
+
+}  // namespace egr
+
+// shared epilogue math
+__device__ __forceinline__ float egr_apply_act(float v, int act) {
+  if (act == EGR_ACT_SILU) return v / (1.0f + __expf(-v));
+  if (act == EGR_ACT_TANH) return tanhf(v);
+  return v;
+}

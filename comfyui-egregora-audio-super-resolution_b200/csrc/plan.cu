@@ -1,0 +1,97 @@
+// plan.cu — the FlashSR plan executor: a straight-line list of egr_op over one workspace and one weight
+// blob.  Creation validates every op and encodes the TMA tensor maps of the tensor-core GEMMs once; run just
+// enqueues kernels on the caller's stream (no allocation, no synchronisation), so a whole forward pass can be
+// captured into a CUDA graph by the host.
+#include <vector>
+#include "ops.cuh"
+
+using namespace egr;
+
+struct egr_plan {
+  std::vector<egr_op> ops;
+  std::vector<TcPrepared*> tc;  // per op, nullptr unless GEMM_TC
+  Spaces sp;
+};
+
+static int run_op(const egr_plan* p, int i, cudaStream_t st) {
+  const egr_op& op = p->ops[i];
+  switch (op.code) {
+    case EGR_OP_GEMM_TC: return tc_launch(p->tc[i], st);
+    case EGR_OP_GEMM_SIMT: return launch_gemm_simt(p->sp, op, st);
+    case EGR_OP_GN_STATS: return launch_gn_stats(p->sp, op, st);
+    case EGR_OP_GN_APPLY: return launch_gn_apply(p->sp, op, st);
+    case EGR_OP_LAYERNORM: return launch_layernorm(p->sp, op, st);
+    case EGR_OP_SOFTMAX: return launch_softmax(p->sp, op, st);
+    case EGR_OP_ATTN_SMALL: return launch_attn_small(p->sp, op, st);
+    case EGR_OP_GEGLU: return launch_geglu(p->sp, op, st);
+    case EGR_OP_ELTWISE: return launch_eltwise(p->sp, op, st);
+    case EGR_OP_SNAKE_AA: return launch_snake_aa(p->sp, op, st);
+    case EGR_OP_STFT_MEL: return launch_stft_mel(p->sp, op, st);
+    case EGR_OP_LOWPASS: return launch_lowpass(p->sp, op, st);
+    case EGR_OP_TIME_EMBED: return launch_time_embed(p->sp, op, st);
+    case EGR_OP_ZERO: return launch_zero(p->sp, op, st);
+    default: return fail(EGR_ERR_ARG, "op %d (%s): unknown code %d", i, op.name, op.code);
+  }
+}
+
+extern "C" int egr_plan_create(const egr_op* h_ops, int n_ops, void* d_workspace, size_t ws_bytes,
+                               const void* d_weights, size_t wt_bytes, egr_plan** out) {
+  if (!h_ops || n_ops <= 0 || !out) return fail(EGR_ERR_ARG, "egr_plan_create: bad arguments");
+  if (!devinfo().inited) return fail(EGR_ERR_STATE, "egr_plan_create: call egr_init first");
+  egr_plan* p = new egr_plan();
+  p->sp.ws = (char*)d_workspace; p->sp.ws_bytes = ws_bytes;
+  p->sp.wt = (const char*)d_weights; p->sp.wt_bytes = wt_bytes;
+  p->ops.assign(h_ops, h_ops + n_ops);
+  p->tc.assign(n_ops, nullptr);
+  for (int i = 0; i < n_ops; ++i) {
+    egr_op& op = p->ops[i];
+    op.name[sizeof(op.name) - 1] = 0;
+    // bounds-check every address against its space
+    auto chk = [&](uint64_t a) -> bool {
+      uint64_t space = a >> 60, off = a & 0x0FFFFFFFFFFFFFFFull;
+      if (space == EGR_SPACE_WS) return off < ws_bytes;
+      if (space == EGR_SPACE_WT) return off < wt_bytes;
+      return true;
+    };
+    bool ok = chk(op.x0.addr) && chk(op.x1.addr);
+    for (int k = 0; k < 10; ++k) ok = ok && chk(op.ptr[k]);
+    if (!ok) {
+      int rc = fail(EGR_ERR_ARG, "op %d (%s): address outside its workspace/weights space", i, op.name);
+      egr_plan_destroy(p);
+      return rc;
+    }
+    if (op.code == EGR_OP_GEMM_TC) {
+      int rc = tc_prepare(p->sp, op, &p->tc[i]);
+      if (rc) { egr_plan_destroy(p); return rc; }
+    }
+  }
+  *out = p;
+  return EGR_OK;
+}
+
+extern "C" int egr_plan_run(egr_plan* plan, int first, int last, void* stream) {
+  if (!plan) return fail(EGR_ERR_ARG, "egr_plan_run: null plan");
+  const int n = (int)plan->ops.size();
+  if (first < 0) first = 0;
+  if (last < 0 || last > n) last = n;
+  for (int i = first; i < last; ++i) {
+    int rc = run_op(plan, i, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return EGR_OK;
+}
+
+extern "C" int egr_plan_num_launches(const egr_plan* plan, int first, int last) {
+  if (!plan) return 0;
+  const int n = (int)plan->ops.size();
+  if (first < 0) first = 0;
+  if (last < 0 || last > n) last = n;
+  return last > first ? last - first : 0;
+}
+
+extern "C" void egr_plan_destroy(egr_plan* plan) {
+  if (!plan) return;
+  for (TcPrepared* t : plan->tc)
+    if (t) tc_free(t);
+  delete plan;
+}

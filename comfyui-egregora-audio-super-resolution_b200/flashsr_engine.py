@@ -1,0 +1,122 @@
+"""FlashSR engine: owns the device weight blob, the workspace and one compiled plan per (batch, steps, lowpass).
+
+Replaces `_FlashSRRunner` of the reference (egregora_audio_super_resolution.py:254-369): `infer` keeps its
+contract — [N, 245760] f32 at 48 kHz in, same shape out — but takes every chunk-channel of a clip at once
+and runs them through libegregora_b200.so in sub-batches.  Host code is plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _abi
+from . import flashsr_model as M
+from .flashsr_plan import PlanBackend, WeightBlob, build_plan
+
+
+class FlashSREngine:
+    def __init__(self, device: torch.device, spec: Optional[dict] = None, weights: Optional[Dict[str, torch.Tensor]] = None,
+                 seed: int = 0, max_batch: Optional[int] = None, debug: bool = False):
+        if device.type != "cuda":
+            raise RuntimeError("FlashSREngine needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = device
+        self.lib = _abi.init(device.index or 0)
+        self.spec = spec or M.default_spec()
+        # No checkpoint exists in this environment: seeded random weights of the spec'd architecture.
+        self.weights = weights if weights is not None else M.init_weights(self.spec, seed)
+        self.max_batch = int(max_batch or os.environ.get("EGREGORA_FLASHSR_BATCH", "8"))
+        self.debug = debug
+        self.blob = WeightBlob()
+        # one dry walk (batch 1, lowpass on) packs every weight/constant the graph can touch
+        build_plan(self.spec, self.weights, self.blob, 1, 1, True)
+        self.blob.frozen = True
+        raw = self.blob.tobytes()
+        self.d_weights = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.ws: Optional[torch.Tensor] = None
+        self.plans: Dict[Tuple[int, int, bool], Tuple[PlanBackend, int]] = {}
+        self.launches_last = 0
+
+    # ------------------------------------------------------------------ plans
+    def _create(self, be: PlanBackend) -> int:
+        ops = be.build_ops()
+        handle = C.c_void_p()
+        _abi.check(self.lib.egr_plan_create(ops, len(be.ops), self.ws.data_ptr(), self.ws.numel(), self.d_weights.data_ptr(),
+                                            self.d_weights.numel(), C.byref(handle)), "egr_plan_create")
+        return handle.value
+
+    def plan(self, batch: int, steps: int, lowpass: bool) -> Tuple[PlanBackend, int]:
+        key = (int(batch), int(steps), bool(lowpass))
+        if key in self.plans:
+            return self.plans[key]
+        be = build_plan(self.spec, self.weights, self.blob, batch, steps, lowpass, debug=self.debug)
+        need = be.ws_bytes + 4096
+        if self.ws is None or self.ws.numel() < need:
+            torch.cuda.synchronize(self.device)
+            for _, h in self.plans.values():
+                self.lib.egr_plan_destroy(h)
+            self.ws = None
+            self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            rebuilt = {}
+            for k, (obe, _) in self.plans.items():
+                rebuilt[k] = (obe, self._create(obe))
+            self.plans = rebuilt
+        self.plans[key] = (be, self._create(be))
+        return self.plans[key]
+
+    def view(self, buf, dtype, shape) -> torch.Tensor:
+        n = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+        return self.ws[buf.offset: buf.offset + n].view(dtype).view(*shape)
+
+    def read(self, be: PlanBackend, name: str) -> torch.Tensor:
+        """debug: fetch a named intermediate as NCHW / [B,C,T] float32 on the CPU."""
+        t = be.named[name]
+        if t.f32 is not None:
+            x = self.view(t.f32, torch.float32, (t.B, t.H, t.W, t.C)).float()
+        elif t.f16_transposed:
+            return self.view(t.f16, torch.float16, (t.B, t.C, t.H, t.W)).float().cpu()
+        else:
+            x = self.view(t.f16, torch.float16, (t.B, t.H, t.W, t.C)).float()
+        return x.permute(0, 3, 1, 2).contiguous().cpu()
+
+    # ------------------------------------------------------------------ inference
+    def make_noise(self, n: int, seed: int) -> torch.Tensor:
+        """x_T [n, z, T/8, F/8] from a CPU generator, so the oracle can be fed the same tensor."""
+        s = self.spec
+        g = torch.Generator().manual_seed(int(seed))
+        fr = s["chunk"] // s["mel"]["hop"]
+        return torch.randn((n, s["vae"]["embed_dim"], fr // 8, s["mel"]["n_mels"] // 8), generator=g)
+
+    def infer(self, x: torch.Tensor, lowpass: bool = False, steps: int = 1, seed: int = 4321,
+              noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """x [N, chunk] f32 on the engine's device -> [N, chunk]."""
+        if x.dim() != 2 or x.shape[1] != self.spec["chunk"]:
+            raise RuntimeError(f"FlashSR expects [N, {self.spec['chunk']}] chunks, got {tuple(x.shape)}")
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        N = x.shape[0]
+        if noise is None:
+            noise = self.make_noise(N, seed)
+        noise = noise.to(self.device, torch.float32).permute(0, 2, 3, 1).contiguous()  # NHWC
+        out = torch.empty_like(x)
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        self.launches_last = 0
+        i = 0
+        while i < N:
+            b = min(self.max_batch, N - i)
+            be, h = self.plan(b, steps, lowpass)
+            wav_in, nz_in = be.inputs["wav"], be.inputs["noise"]
+            self.view(wav_in.f32, torch.float32, (b, x.shape[1])).copy_(x[i:i + b])
+            self.view(nz_in.f32, torch.float32, tuple(noise[i:i + b].shape)).copy_(noise[i:i + b])
+            _abi.check(self.lib.egr_plan_run(h, 0, -1, st), "egr_plan_run")
+            self.launches_last += len(be.ops)
+            out[i:i + b].copy_(self.view(be.output.f32, torch.float32, (b, x.shape[1])))
+            i += b
+        return out
+
+    def close(self):
+        for _, h in self.plans.values():
+            self.lib.egr_plan_destroy(h)
+        self.plans = {}

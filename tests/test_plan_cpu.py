@@ -1,0 +1,71 @@
+"""CPU-side check of everything the plan builder decides (views, taps, packed weights, crops, buffer reuse):
+the op list is executed by the torch interpreter in tests/plan_interp.py and compared with the fp32 oracle."""
+import numpy as np
+import torch
+
+from conftest import load_pkg
+
+load_pkg()
+from egregora_b200 import _abi, flashsr_model as M, flashsr_plan as P  # noqa: E402
+from oracle import flashsr_oracle as O  # noqa: E402
+from plan_interp import Interp  # noqa: E402
+
+
+def _inputs(spec, B, seed=5):
+    g = torch.Generator().manual_seed(seed)
+    wav = (0.1 * torch.randn(B, spec["chunk"], generator=g)).cumsum(1) * 0.05
+    wav = wav - wav.mean(1, keepdim=True)
+    wav = wav / wav.abs().max() * 0.5
+    fr = spec["chunk"] // spec["mel"]["hop"]
+    noise = torch.randn(B, spec["vae"]["embed_dim"], fr // 8, spec["mel"]["n_mels"] // 8, generator=g)
+    return wav, noise
+
+
+def test_tiny_plan_matches_oracle_through_interpreter():
+    spec = M.tiny_spec()
+    W = M.init_weights(spec, 0)
+    B, steps, lp = 1, 1, True
+    blob = P.WeightBlob()
+    be = P.build_plan(spec, W, blob, B, steps, lp)
+    it = Interp(_abi.K, be.build_ops(), be.ws_bytes, blob.tobytes())
+    wav, noise = _inputs(spec, B)
+
+    def view(buf, dt, shape):
+        n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        return it.ws[buf.offset: buf.offset + n].view(dt).view(*shape)
+
+    view(be.inputs["wav"].f32, torch.float32, wav.shape).copy_(wav)
+    view(be.inputs["noise"].f32, torch.float32, noise.permute(0, 2, 3, 1).shape).copy_(noise.permute(0, 2, 3, 1))
+    it.run()
+    y = view(be.output.f32, torch.float32, wav.shape).clone()
+    yo, obe = O.run_flashsr(spec, W, wav, noise, steps=steps, lowpass=lp)
+    assert not torch.isnan(y).any()
+    rms = float((y - yo).pow(2).mean().sqrt())
+    assert rms < 1e-3, rms  # north_star tolerance: FlashSR waveform within 1e-3 RMS
+    assert 0.02 < float(yo.pow(2).mean().sqrt()) < 0.5  # the synthetic model is not degenerate / saturated
+    assert list(view(be.cutoff_buf, torch.int32, (B,))) == list(obe.cutoff_bins)
+
+
+def test_param_shapes_cover_all_weights():
+    spec = M.tiny_spec()
+    shapes = M.param_shapes(spec)
+    W = M.init_weights(spec, 0)
+    assert list(shapes) == list(W)
+    full = M.param_shapes(M.default_spec())
+    n = sum(int(np.prod(s)) for s, _ in full.values())
+    assert 4e8 < n < 7e8  # ~0.5 B parameters: AudioSR-class VAE + UNet + BigVGAN-class vocoder
+
+
+def test_ddim_schedule():
+    s1 = M.ddim_schedule(1000, 0.008, 1)
+    assert len(s1) == 1 and s1[0][0] == 999 and s1[0][2] == 1.0
+    s4 = M.ddim_schedule(1000, 0.008, 4)
+    assert [t for t, _, _ in s4] == [999, 749, 500, 250] and s4[-1][2] == 1.0
+    assert all(s4[i][2] == s4[i + 1][1] for i in range(3))
+
+
+def test_tile_geometry_and_block_n():
+    for (w, h, b) in [(256, 512, 1), (32, 64, 8), (4, 8, 3), (3072, 1, 2), (513, 1, 1), (1, 1, 1)]:
+        bw, bh, bb = P.tile_geometry(w, h, b)
+        assert bw * bh * bb == 128
+    assert [P.pick_block_n(n) for n in (16, 48, 96, 128, 384, 640, 1024, 1920, 4608, 5120)] == [16, 48, 96, 128, 192, 160, 256, 240, 256, 256]
