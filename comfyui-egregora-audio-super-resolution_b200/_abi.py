@@ -104,6 +104,8 @@ def load() -> C.CDLL:
         "egr_plan_create": (C.c_int, [C.POINTER(Op), i32, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
         "egr_plan_run": (C.c_int, [vp, i32, i32, vp]),
         "egr_plan_num_launches": (C.c_int, [vp, i32, i32]),
+        "egr_plan_run_code": (C.c_int, [vp, i32, vp]),
+        "egr_plan_count_code": (C.c_int, [vp, i32]),
         "egr_plan_destroy": (None, [vp]),
         "egr_fft_plan_create": (C.c_int, [i64, i32, C.POINTER(vp)]),
         "egr_fft_plan_workspace_bytes": (C.c_size_t, [vp]),

@@ -89,6 +89,23 @@ extern "C" int egr_plan_num_launches(const egr_plan* plan, int first, int last) 
   return last > first ? last - first : 0;
 }
 
+extern "C" int egr_plan_run_code(egr_plan* plan, int code, void* stream) {
+  if (!plan) return fail(EGR_ERR_ARG, "egr_plan_run_code: null plan");
+  for (int i = 0; i < (int)plan->ops.size(); ++i) {
+    if (plan->ops[i].code != code) continue;
+    int rc = run_op(plan, i, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return EGR_OK;
+}
+
+extern "C" int egr_plan_count_code(const egr_plan* plan, int code) {
+  if (!plan) return 0;
+  int n = 0;
+  for (const egr_op& op : plan->ops) n += (op.code == code);
+  return n;
+}
+
 extern "C" void egr_plan_destroy(egr_plan* plan) {
   if (!plan) return;
   for (TcPrepared* t : plan->tc)
