@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — real-time factor of the FlashSR hot path (BASELINE.json `metric`) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "c2"): 5.12 s mono chunks @ 48 kHz, 1 diffusion step, lowpass_input=True.
+One step = one pass of the whole node path (span gather -> FlashSR plan on every chunk-channel -> [all-gather]
+-> Hann WOLA) over a clip of N chunks (N = number of GPUs, weak scaling: one chunk-channel per GPU; at N=1 this is
+exactly c2's single chunk).  Random-init weights of the spec'd architecture and synthetic band-limited audio
+ — there is no checkpoint and no dataset in this environment.
+
+  value     : sec of 48 kHz audio / sec, inputs already resident in HBM, device-timed (CUDA events, max over ranks)
+  e2e       : same through the reference-facing node call EgregoraAudioSuperResolution.run() with HOST (pinned)
+              buffers: H2D of the clip and D2H of the result inside the timed region
+  roofline  : the tcgen05 tap-GEMM (dominant kernel): algorithmic FLOPs of every GEMM_TC launch of one pass / the
+              device time of exactly those launches (egr_plan_run_code, CUDA events on the launching stream)
+  cpu_baseline / --impl reference : the fp32 oracle port of the same path on the host cores (the upstream
+              FlashSR_Inference package and its weights cannot be installed here) — baseline only.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+PKG_DIR = ROOT / "comfyui-egregora-audio-super-resolution_b200"
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = "real-time factor (sec 48 kHz audio / sec wall) FlashSR"
+UNIT = "x real-time"
+WORKLOAD = "c2: FlashSR 5.12 s mono chunk @48 kHz, 1 diffusion step, lowpass_input=True (one chunk-channel per GPU)"
+
+
+def load_pkg():
+    if "egregora_b200" in sys.modules:
+        return sys.modules["egregora_b200"]
+    spec = importlib.util.spec_from_file_location("egregora_b200", PKG_DIR / "__init__.py",
+                                                  submodule_search_locations=[str(PKG_DIR)])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["egregora_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def synth_audio(total: int, channels: int = 1, sr: int = 48000, seed: int = 1234):
+    """white noise x0.1 low-passed at 4 kHz + 5 partials of 220 Hz, peak 0.5, float32 [C,total]."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = 0.1 * torch.randn(channels, total, generator=g)
+    X = torch.fft.rfft(x)
+    f = torch.fft.rfftfreq(total, 1.0 / sr)
+    X[:, f > 4000.0] = 0
+    x = torch.fft.irfft(X, n=total)
+    t = torch.arange(total, dtype=torch.float64) / sr
+    for h in (1, 2, 3, 5, 7):
+        x = x + 0.05 * torch.sin(2 * math.pi * 220.0 * h * t).float()[None]
+    x = x / x.abs().max() * 0.5
+    return x.float().contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of B200_PROFILING.md, sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            p = [s.strip() for s in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks() -> dict:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return {"bf16_burst": d.get("bf16_tflops"), "bf16_sustained": d.get("bf16_tflops_sustained"), "hbm": d.get("hbm_gbs"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------ oracle leg
+def oracle_chunk_seconds(spec, weights, frac: int, threads: int):
+    """Time ONE pass of the fp32 oracle port over a [1, chunk/frac] sample on the host cores -> (sec, audio_sec)."""
+    import torch
+    from oracle import flashsr_oracle as O
+    torch.set_num_threads(threads)
+    s = dict(spec)
+    s["chunk"] = spec["chunk"] // frac
+    wav = synth_audio(s["chunk"], 1)
+    fr = s["chunk"] // s["mel"]["hop"]
+    noise = torch.randn(1, s["vae"]["embed_dim"], fr // 8, s["mel"]["n_mels"] // 8, generator=torch.Generator().manual_seed(4321))
+    t0 = time.perf_counter()
+    O.run_flashsr(s, weights, wav, noise, steps=1, lowpass=True)
+    return time.perf_counter() - t0, s["chunk"] / spec["sr"]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    load_pkg()
+    from egregora_b200 import flashsr_model as M
+    import torch
+    spec = M.default_spec()
+    W = M.init_weights(spec, 0)
+    threads = os.cpu_count() or 1
+    # bounded sample: shrink the chunk (the graph is length-agnostic) until warmup+steps fit in ~4 minutes
+    frac, budget = 1, 240.0
+    t1, a1 = oracle_chunk_seconds(spec, W, frac, threads)
+    while (args.steps + max(args.warmup - 1, 0)) * t1 > budget and frac < 8:
+        frac *= 2
+        t1, a1 = oracle_chunk_seconds(spec, W, frac, threads)
+    for _ in range(max(args.warmup - 1, 0)):
+        oracle_chunk_seconds(spec, W, frac, threads)
+    tot = 0.0
+    for _ in range(args.steps):
+        t, a = oracle_chunk_seconds(spec, W, frac, threads)
+        tot += t
+    v = args.steps * a1 / tot
+    sample = f"{args.steps} x one {a1:.2f} s mono chunk (chunk/{frac}), 1 step, lowpass on, fp32 torch oracle port on {threads} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic band-limited audio, random-init weights",
+        "config": {"workload": WORKLOAD, "note": "upstream FlashSR_Inference + weights are not installable here; "
+                   "this arm is the fp32 oracle port of the same graph on the host cores"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    load_pkg()
+    from egregora_b200 import _abi, egregora_audio_super_resolution as N
+    K = _abi.K
+
+    os.environ["EGREGORA_FLASHSR_STEPS"] = "1"
+    N.EgregoraAudioSuperResolution.NUM_STEPS = 1
+    engine = N.get_engine(dev)
+    node = N.EgregoraAudioSuperResolution()
+    win, hop = N._win_hop()
+    total = win + (world - 1) * hop
+    audio_s = total / N.REQ_SR
+    x_host = synth_audio(total, 1).pin_memory()
+    x_dev = x_host.to(dev)
+    chunk_model = lambda c: engine.infer(c, lowpass=True, steps=1, seed=4321)  # noqa: E731
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_dev():
+        return N.upscale_48k(x_dev, chunk_model)
+
+    def step_e2e():
+        (res,) = node.run(audio={"waveform": x_host[None], "sample_rate": N.REQ_SR}, lowpass_input=True, output_sr="48000")
+        return res
+
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    be, handle = engine.plan(1, 1, True)
+    n_memsets = sum(1 for o in be.ops if o.code == K["EGR_OP_ZERO"])
+    launches_per_step = (len(be.ops) - n_memsets) + 2  # plan kernels + chunk gather + WOLA
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    # ---- device-resident timing
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_dev()
+    e1.record()
+    sync_all()
+    t_dev = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+    # ---- end-to-end timing through the node (host buffers)
+    for _ in range(2):
+        step_e2e()
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        res = step_e2e()
+    e1.record()
+    sync_all()
+    t_e2e = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    t_dev, t_e2e = float(t_dev.item()), float(t_e2e.item())
+    assert res["waveform"].shape == (1, 1, total) and bool(torch.isfinite(res["waveform"]).all())
+
+    if rank == 0:
+        pk = peaks()
+        lib = engine.lib
+        st = torch.cuda.current_stream(dev).cuda_stream
+        # ---- roofline of the dominant kernel: every GEMM_TC launch of one pass, timed alone on its stream
+        n_tc = lib.egr_plan_count_code(handle, K["EGR_OP_GEMM_TC"])
+        for _ in range(3):
+            _abi.check(lib.egr_plan_run_code(handle, K["EGR_OP_GEMM_TC"], st))
+        torch.cuda.synchronize(dev)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            _abi.check(lib.egr_plan_run_code(handle, K["EGR_OP_GEMM_TC"], st))
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t_tc = e0.elapsed_time(e1) / 1e3 / reps
+        # whole plan alone (no host plumbing) for the share of the step
+        e0.record()
+        for _ in range(reps):
+            _abi.check(lib.egr_plan_run(handle, 0, -1, st))
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t_plan = e0.elapsed_time(e1) / 1e3 / reps
+        achieved = be.tc_flops / t_tc / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 tap-GEMM, f16 operands, f32 TMEM accumulate)",
+                "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long pass)", "traffic": None,
+                "launches_per_pass": n_tc, "flops_per_pass": be.tc_flops, "avg_launch_us": 1e6 * t_tc / max(n_tc, 1),
+                "gemm_share_of_plan": t_tc / t_plan, "plan_ms": 1e3 * t_plan}
+        # ---- batched throughput (c3's per-GPU share: 33 chunk-channels, 4 steps), extra information
+        extra = None
+        if os.environ.get("EGR_BENCH_BATCHED", "1") == "1":
+            try:
+                nb = 33
+                xb = x_dev[:, :win].expand(nb, win).contiguous()
+                engine.infer(xb[:8], lowpass=False, steps=4)
+                torch.cuda.synchronize(dev)
+                e0.record()
+                engine.infer(xb, lowpass=False, steps=4)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                tb = e0.elapsed_time(e1) / 1e3
+                extra = {"workload": "c3 per-GPU share: 33 chunk-channels x 5.12 s, 4 diffusion steps, batch 8",
+                         "chunk_channels_per_s": nb / tb, "rtf_mono_equiv": nb * win / N.REQ_SR / tb, "seconds": tb}
+            except Exception as e:  # pragma: no cover
+                extra = {"error": str(e)[:200]}
+        # ---- CPU baseline beside it (N=1 only): the oracle port on a bounded sample
+        cpu = None
+        if world == 1 and os.environ.get("EGR_BENCH_CPU", "1") == "1":
+            from egregora_b200 import flashsr_model as M
+            threads = os.cpu_count() or 1
+            frac = 4
+            tc_, a_ = oracle_chunk_seconds(engine.spec, engine.weights, frac, threads)
+            if tc_ < 8.0:
+                frac = 1
+                tc_, a_ = oracle_chunk_seconds(engine.spec, engine.weights, frac, threads)
+            cpu = {"value": a_ / tc_, "unit": UNIT, "cores": threads, "kind": "port",
+                   "sample": f"one {a_:.2f} s mono chunk (chunk/{frac}), 1 step, lowpass on, fp32 torch oracle port, {tc_:.1f} s"}
+        ws_mb = be.ws_bytes / 1e6
+        out = {
+            "metric": METRIC, "value": args.steps * audio_s / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (f32 activations between layers)",
+            "data": "synthetic band-limited 48 kHz audio (SURVEY.md 8d); random-init weights of the spec'd architecture",
+            "config": {"workload": WORKLOAD, "clip_samples": total, "chunks": world, "chunk_channels_per_gpu": 1, "steps_diffusion": 1,
+                       "lowpass_input": True, "parallelism": f"chunk-sharded dp{world}" + (" + 1 NCCL all-gather" if world > 1 else ""),
+                       "l2": f"no explicit flush: per-step working set (weights {engine.d_weights.numel() / 1e6:.0f} MB + "
+                             f"workspace {ws_mb:.0f} MB) exceeds the 126 MB L2"},
+            "e2e": {"value": args.steps * audio_s / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "h2d_bytes_per_step": int(x_host.numel() * 4) + world * (int(engine.make_noise(1, 0).numel()) * 4 + 24),
+                    "d2h_bytes_per_step": int(total * 4)},
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "batched": extra,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
