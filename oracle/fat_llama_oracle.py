@@ -23,7 +23,7 @@ Restated upstream algorithm (per channel, float32 on integer-scaled samples):
     repeat max_iterations times:                        (iterative_soft_thresholding)
         X = fft(x); X = where(|X| > thr, X, 0); x = ifft(X).real
     y = expanded + x
-    autoscale : y *= max|channel_in| / max|y|           (scale_amplitude, per channel)
+    autoscale : y = (y / max|y|) * max|channel_in|      (scale_amplitude, per channel)
     normalize : y /= max|y| over all channels           (normalize_signal)
     U = max(1, round(target_bitrate / source_bitrate)),  output sample rate = sr * U.
 Anything here that later proves to differ from the real packages is a one-line change in both this file and
@@ -83,12 +83,11 @@ def upscale(samples_sc: np.ndarray, U: int, max_iterations: int, threshold_value
     if x.ndim == 1:
         x = x[:, None]
     y = upscale_channels(x, U, max_iterations, threshold_value, dtype)
-    if toggle_autoscale:
+    if toggle_autoscale:                                   # scale_amplitude, per channel
         cols = []
         for c in range(x.shape[1]):
-            peak_in = np.max(np.abs(x[:, c]))
-            peak_out = np.max(np.abs(y[:, c]))
-            cols.append(y[:, c] * (peak_in / peak_out))
+            normalized = (y[:, c] / np.max(np.abs(y[:, c]))).astype(dtype)
+            cols.append((normalized * np.max(np.abs(x[:, c]))).astype(dtype))
         y = np.stack(cols, axis=1).astype(dtype)
     if toggle_normalize:
         y = (y / np.max(np.abs(y))).astype(dtype)

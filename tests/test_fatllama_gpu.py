@@ -1,0 +1,137 @@
+"""GPU parity of path B (egr_fatllama_run + the PCM-16 wire kernels, through the node and through the C ABI)
+against the CPU restatement in oracle/fat_llama_oracle.py.
+
+Tolerances (BASELINE.json north_star: within 1e-5 per sample of the CPU path): the float32 loop is compared
+PRE-quantisation against the oracle evaluated in float64 (the exact-arithmetic answer both float32
+implementations approximate) at 1e-5 of full scale, and POST-quantisation (the node output, after the PCM-16
+wire format) sample for sample: at most 1 LSB (1/32768) away, and equal for all but a small fraction."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_pkg
+
+load_pkg()
+from egregora_b200 import _abi, egregora_fat_llama_gpu as G  # noqa: E402
+from oracle import fat_llama_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+LSB = 1.0 / 32768.0
+
+
+def _audio(C, S, seed, sr=16000):
+    rng = np.random.default_rng(seed)
+    t = np.arange(S) / sr
+    x = 0.05 * rng.standard_normal((C, S))
+    for h, a in ((220.0, 0.3), (440.0, 0.15), (1760.0, 0.05)):
+        x += a * np.sin(2 * np.pi * h * t + rng.uniform(0, 6.28, (C, 1)))
+    return np.clip(x, -1, 1).astype(np.float32)
+
+
+def _run_abi(samples_cs: np.ndarray, U, iters, thr, normalize=True, autoscale=True):
+    lib = _abi.init(0)
+    C, n = samples_cs.shape
+    d_in = torch.from_numpy(np.ascontiguousarray(samples_cs, np.float32)).cuda()
+    d_out = torch.empty((C, n * U), dtype=torch.float32, device="cuda")
+    wb = lib.egr_fatllama_workspace_bytes(C, n, U)
+    w = torch.empty(wb, dtype=torch.uint8, device="cuda")
+    flags = (_abi.K["EGR_FL_NORMALIZE"] if normalize else 0) | (_abi.K["EGR_FL_AUTOSCALE"] if autoscale else 0)
+    _abi.check(lib.egr_fatllama_run(d_in.data_ptr(), d_out.data_ptr(), C, n, U, iters, thr, flags, w.data_ptr(), wb, 0))
+    torch.cuda.synchronize()
+    return d_out.cpu().numpy()
+
+
+@pytest.mark.parametrize("C,S,U,iters,thr", [
+    (1, 160000, 1, 50, 0.5),     # BASELINE config c1: 10 s mono 16 kHz, 50 iterations, threshold 0.5
+    (2, 44100, 1, 20, 0.6),      # stereo, N/2 = 22050 = 2*3^2*5^2*7^2
+    (1, 8000, 2, 10, 0.6),       # upscale factor 2
+    (2, 2, 1, 3, 0.6),           # smallest even length
+    (1, 4096, 3, 5, 0.6),        # U = 3, single-level transform
+    (2, 30030, 1, 5, 0.6),       # 11 and 13 as radices
+])
+def test_loop_matches_oracle_fast_path(C, S, U, iters, thr, cuda_dev):
+    x = _audio(C, S, seed=S + C)
+    samples = O.pcm16_write(x.T).astype(np.float32)          # [S,C] integer-scaled, as upstream read_audio yields
+    want = O.upscale(samples, U, iters, thr, True, True, dtype=np.float64).T
+    got = _run_abi(samples.T.copy(), U, iters, thr)
+    assert got.shape == want.shape
+    assert np.max(np.abs(got - want)) < TOL
+
+
+@pytest.mark.parametrize("C,S,iters", [(1, 10007, 4), (2, 4801, 3), (1, 1, 2), (1, 19 * 4, 3)])
+def test_loop_matches_oracle_general_path(C, S, iters, cuda_dev):
+    """odd / non-smooth lengths go through the complex (Bluestein) transforms"""
+    x = _audio(C, S, seed=S)
+    samples = O.pcm16_write(x.T).astype(np.float32)
+    want = O.upscale(samples, 1, iters, 0.6, True, True, dtype=np.float64).T
+    got = _run_abi(samples.T.copy(), 1, iters, 0.6)
+    assert np.max(np.abs(got - want)) < 3 * TOL
+
+
+@pytest.mark.parametrize("thr", [40.0, 400.0, 4000.0])
+def test_gate_removes_bins(thr, cuda_dev):
+    """thresholds (through the ABI; the node clamps to [0,1]) that zero a real fraction of samples and bins, so the
+    Hermitian split / re-pack path with mixed gates is exercised; no scaling flags so magnitudes are comparable."""
+    S = 48000
+    x = _audio(1, S, seed=3)
+    samples = O.pcm16_write(x.T).astype(np.float32) * np.float32(0.01)   # small integer-ish scale: many bins near thr
+    want = O.upscale(samples, 1, 3, thr, False, False, dtype=np.float64).T
+    got = _run_abi(samples.T.copy(), 1, 3, thr, normalize=False, autoscale=False)
+    assert np.sqrt(np.mean((want - 2 * samples.T) ** 2)) > 1e-3 * np.sqrt(np.mean(samples ** 2))  # the gates did something
+    scale = max(1.0, float(np.max(np.abs(want))))
+    # a bin whose magnitude sits within rounding of thr may flip in float32: allow a small relative L2 budget
+    rel = np.sqrt(np.mean((got - want) ** 2)) / (np.sqrt(np.mean(want ** 2)) + 1e-30)
+    assert rel < 2e-3 and np.max(np.abs(got - want)) < 0.05 * scale
+
+
+def test_flags(cuda_dev):
+    x = _audio(2, 24000, seed=9)
+    x[1] *= 0.25
+    samples = O.pcm16_write(x.T).astype(np.float32)
+    for norm, auto in ((False, False), (True, False), (False, True)):
+        want = O.upscale(samples, 1, 4, 0.6, norm, auto, dtype=np.float64).T
+        got = _run_abi(samples.T.copy(), 1, 4, 0.6, normalize=norm, autoscale=auto)
+        assert np.max(np.abs(got - want)) < TOL * max(1.0, float(np.max(np.abs(want))))
+
+
+def test_node_matches_oracle_node(cuda_dev):
+    """EgregoraFatLlamaGPU.run (AUDIO dict in, AUDIO dict out) vs the oracle's node_run, after the PCM-16 wire."""
+    x = _audio(2, 88200, seed=21, sr=44100)
+    node = G.EgregoraFatLlamaGPU()
+    (res,) = node.run("wav", 30, 0.6, 1411, True, True, AUDIO={"waveform": torch.from_numpy(x)[None], "sample_rate": 44100})
+    want, sr = O.node_run(x, 44100, 30, 0.6, 1411, True, True, dtype=np.float64)
+    got = res["waveform"][0].numpy()
+    assert res["sample_rate"] == sr == 44100 and got.shape == want.shape and res["waveform"].dtype == torch.float32
+    diff = np.abs(got - want)
+    assert np.max(diff) <= LSB * 1.0001
+    assert np.mean(diff > 0) < 0.02
+    # the float32 oracle is equally close to the float64 one
+    want32, _ = O.node_run(x, 44100, 30, 0.6, 1411, True, True, dtype=np.float32)
+    assert np.max(np.abs(want32 - want)) <= LSB * 1.0001
+
+
+def test_cpu_node_id_uses_same_kernels(cuda_dev):
+    from egregora_b200 import egregora_fat_llama_cpu as Cn
+    x = _audio(1, 16000, seed=2)
+    (res,) = Cn.EgregoraFatLlamaCPU().run("wav", 10, 0.5, 256, AUDIO={"waveform": torch.from_numpy(x)[None], "sample_rate": 16000})
+    want, sr = O.node_run(x, 16000, 10, 0.5, 256, True, True, dtype=np.float64)
+    assert res["sample_rate"] == sr
+    assert np.max(np.abs(res["waveform"][0].numpy() - want)) <= LSB * 1.0001
+
+
+def test_full_size_c4_properties(cuda_dev):
+    """BASELINE config c4 (3 min stereo 44.1 kHz, 300 iterations, thr 0.6, autoscale on) at full size.  With
+    integer-scaled samples every non-zero sample and bin passes the 0.6 gate, so the loop is a projection that
+    keeps the signal: y = 2x up to float32 rounding of 300 round trips, and the node output is x / max|x|
+    re-quantised (size-independent properties; the numpy oracle needs ~4 minutes at this size)."""
+    S = 7938000
+    x = _audio(2, S, seed=44, sr=44100)
+    xq = O.pcm16_read(O.pcm16_write(x))
+    out, sr, pre = G.fat_llama_device(torch.from_numpy(x).cuda(), 44100, 300, 0.6, 1411, True, True, return_prequant=True)
+    torch.cuda.synchronize()
+    assert sr == 44100 and out.shape == (2, S)
+    pre = pre.cpu().numpy()
+    want = xq / np.max(np.abs(xq))         # autoscale restores each channel's own peak, normalise divides by the global one
+    assert np.max(np.abs(pre - want)) < 5e-5
+    assert float(np.max(np.abs(out.cpu().numpy()))) <= 1.0

@@ -8,3 +8,5 @@ run ops_simt tests/test_ops_gpu.py -k "simt or groupnorm or layernorm or attenti
 run ops_tc_basic tests/test_ops_gpu.py -k "conv2d_tc"
 run ops_tc_rest tests/test_ops_gpu.py -k "stride2 or transposed or conv1d or conv_transpose or attention_gemm"
 run flashsr_tiny tests/test_flashsr_gpu.py -k "tiny"
+run fft tests/test_fft_gpu.py
+run fatllama tests/test_fatllama_gpu.py
