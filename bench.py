@@ -178,6 +178,68 @@ def run_reference(args):
     }), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------------------ path B leg
+def bench_fatllama(dev, pk):
+    """BASELINE config c4: Fat-Llama spectral enhance, 3 min 44.1 kHz stereo, 300 iterations, thr 0.6, autoscale on."""
+    import numpy as np
+    import torch
+    from egregora_b200 import _abi, egregora_fat_llama_gpu as G
+    from oracle import fat_llama_oracle as O
+    C, S, sr, iters, thr = 2, 7938000, 44100, 300, 0.6
+    x_host = synth_audio(S, C, sr=sr, seed=77).pin_memory()
+    x_dev = x_host.to(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    G.fat_llama_device(x_dev, sr, iters, thr, 1411, True, True)
+    torch.cuda.synchronize(dev)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        G.fat_llama_device(x_dev, sr, iters, thr, 1411, True, True)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t_dev = e0.elapsed_time(e1) / 1e3 / reps
+    node = G.EgregoraFatLlamaGPU()
+    e0.record()
+    for _ in range(reps):
+        (res,) = node.run("wav", iters, thr, 1411, True, True, AUDIO={"waveform": x_host[None], "sample_rate": sr})
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t_e2e = e0.elapsed_time(e1) / 1e3 / reps
+    # the loop alone (egr_fatllama_run): 2 kernels per iteration, 16*N algorithmic bytes per iteration and channel
+    lib = _abi.init(dev.index or 0)
+    samples = (x_dev * 32767.0).round()
+    y = torch.empty_like(samples)
+    wb = lib.egr_fatllama_workspace_bytes(C, S, 1)
+    w = torch.empty(wb, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    flags = _abi.K["EGR_FL_NORMALIZE"] | _abi.K["EGR_FL_AUTOSCALE"]
+    _abi.check(lib.egr_fatllama_run(samples.data_ptr(), y.data_ptr(), C, S, 1, iters, thr, flags, w.data_ptr(), wb, st))
+    torch.cuda.synchronize(dev)
+    e0.record()
+    _abi.check(lib.egr_fatllama_run(samples.data_ptr(), y.data_ptr(), C, S, 1, iters, thr, flags, w.data_ptr(), wb, st))
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t_loop = e0.elapsed_time(e1) / 1e3
+    alg_bytes = 16.0 * S * C * iters
+    ach = alg_bytes / t_loop / 1e9
+    # CPU port on a bounded sample: 1 channel, 4 iterations at the full length, scaled to C x iters
+    cs = O.pcm16_write(x_host[:1].numpy().T).astype(np.float32)
+    k = 4
+    t0 = time.perf_counter()
+    O.upscale(cs, 1, k, thr, True, True, dtype=np.float32)
+    t_cpu = (time.perf_counter() - t0) / k * iters * C
+    audio_s = S / sr
+    return {"workload": "c4: Fat-Llama 3 min 44.1 kHz stereo, 300 iterations, thr 0.6, normalize+autoscale on",
+            "metric": "sec audio / sec", "value": audio_s / t_dev, "ms": 1e3 * t_dev,
+            "e2e": {"value": audio_s / t_e2e, "ms": 1e3 * t_e2e, "h2d_bytes": int(x_host.numel() * 4), "d2h_bytes": int(res["waveform"].numel() * 4)},
+            "gpu_launches": 2 * iters + 2 + 6,
+            "roofline": {"bound": "hbm", "kernel": "fl_row_kernel + fl_col_kernel (2 per iteration)", "achieved": ach, "peak": pk["hbm"],
+                         "unit": "GB/s", "frac": ach / pk["hbm"], "algorithmic_bytes": alg_bytes, "loop_ms": 1e3 * t_loop,
+                         "note": "16*N bytes per iteration and channel; the 63.5 MB of work arrays are L2-resident, so DRAM traffic is lower"},
+            "cpu_baseline": {"value": audio_s / t_cpu, "unit": "sec audio / sec", "cores": 1, "kind": "port",
+                             "sample": f"numpy/scipy.fft float32 port, 1 channel x {k} iterations at N={S}, scaled to {C} ch x {iters} it"}}
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch
@@ -222,8 +284,8 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step_dev()
     be, handle = engine.plan(1, 1, True)
-    n_memsets = sum(1 for o in be.ops if o.code == K["EGR_OP_ZERO"])
-    launches_per_step = (len(be.ops) - n_memsets) + 2  # plan kernels + chunk gather + WOLA
+    per_op = {K["EGR_OP_ZERO"]: 0, K["EGR_OP_GN_STATS"]: 2}  # memset node / partial + finalize kernels
+    launches_per_step = sum(per_op.get(o.code, 1) for o in be.ops) + 2  # plan kernels + chunk gather + WOLA
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -312,6 +374,12 @@ def run_b200(args):
                 tc_, a_ = oracle_chunk_seconds(engine.spec, engine.weights, frac, threads)
             cpu = {"value": a_ / tc_, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"one {a_:.2f} s mono chunk (chunk/{frac}), 1 step, lowpass on, fp32 torch oracle port, {tc_:.1f} s"}
+        path_b = None
+        if world == 1 and os.environ.get("EGR_BENCH_PATHB", "1") == "1":
+            try:
+                path_b = bench_fatllama(dev, pk)
+            except Exception as e:  # pragma: no cover
+                path_b = {"error": str(e)[:300]}
         ws_mb = be.ws_bytes / 1e6
         out = {
             "metric": METRIC, "value": args.steps * audio_s / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -326,7 +394,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": int(x_host.numel() * 4) + world * (int(engine.make_noise(1, 0).numel()) * 4 + 24),
                     "d2h_bytes_per_step": int(total * 4)},
             "gpu_launches": launches_per_step * args.steps,
-            "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "batched": extra,
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "batched": extra, "path_b": path_b,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

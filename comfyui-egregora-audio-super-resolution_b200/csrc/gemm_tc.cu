@@ -7,12 +7,19 @@
 // through a rank-5 TMA tensor map, so every tap is just a shifted box load and zero padding is TMA's
 // out-of-bounds fill — no im2col buffer ever exists in HBM.
 //
-// CTA = 128 output pixels x BLOCK_N channels, 192 threads, warp-specialised:
+// CTA = MT x 128 output pixels (MT = 1 or 2 sub-tiles sharing every B load) x BLOCK_N channels, 192 threads:
 //   warp 0      TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier expect_tx)          [UTMALDG]
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 f16)   [UTCHMMA]
 //   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> bias/act/residual -> vector stores   [LDTM]
-// smem ring of S stages x (16 KB A + BLOCK_N*128 B of B); accumulator 128 lanes x BLOCK_N f32 columns in TMEM.
+// Two shared-memory rings, A and B, each with its own full/empty mbarriers:
+//   normal mode : one A stage (MT boxes of 128 rows x 64 ch) and one B stage (BLOCK_N x 64) per (tap, k-chunk)
+//   halo mode   : (taps along one axis, 1-D convs) the A stage is a super-tile of MT*128 + tap-span rows loaded
+//                 ONCE per k-chunk; every tap multiplies a row-shifted window of it (the UMMA descriptor start
+//                 address moves by whole 128-byte rows), so A traffic from L2 drops by the tap count and the
+//                 loop streams only the per-tap weight tiles.
+// Accumulators: MT x 128 lanes x BLOCK_N f32 columns in TMEM.
 #include <cuda.h>
+#include <cstdlib>
 #include "ops.cuh"
 
 namespace egr {
@@ -26,7 +33,8 @@ struct TcPrepared {
   GemmArgs g;
   Taps taps;
   int a_rank;
-  int stages, tmem_cols, smem_bytes;
+  int mt, halo, n_outer, n_inner, kchunks, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin, tiles, tiles_w;
+  int tmem_cols, smem_bytes;
   dim3 grid;
   int vec_ok;
   char name[48];
@@ -104,8 +112,9 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
 // descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int base_off_mode) {
   uint64_t d = 0;
+  if (base_off_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;  // start not on a 1024-byte swizzle repeat
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
@@ -118,8 +127,28 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 struct TcKernelArgs {
   GemmArgs g;
   Taps taps;
-  int stages, tmem_cols, kchunks, vec_ok;
+  int mt, halo, n_outer, n_inner, kchunks, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin, tiles, tiles_w;
+  int tmem_cols, vec_ok, base_off_mode;
 };
+
+static constexpr int HALO_BOX_ROWS = 64;
+
+__device__ __forceinline__ void tile_origin(const GemmArgs& g, const TcKernelArgs& ka, int sub, int& w0, int& h0, int& b0, bool& valid) {
+  const int tiles_h = (g.Ho + g.bh - 1) / g.bh;
+  if (ka.halo) {  // CTA tile = mt*128 consecutive positions along W inside one (h, b) row
+    int mt_ = blockIdx.x;
+    w0 = (mt_ % ka.tiles_w) * (128 * ka.mt) + 128 * sub; mt_ /= ka.tiles_w;
+    h0 = (mt_ % tiles_h) * g.bh; mt_ /= tiles_h;
+    b0 = mt_ * g.bb;
+    valid = w0 < g.Wo;
+  } else {
+    int mt_ = blockIdx.x * ka.mt + sub;
+    valid = mt_ < ka.tiles;
+    w0 = (mt_ % ka.tiles_w) * g.bw; mt_ /= ka.tiles_w;
+    h0 = (mt_ % tiles_h) * g.bh; mt_ /= tiles_h;
+    b0 = mt_ * g.bb;
+  }
+}
 
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB,
@@ -128,25 +157,21 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   const GemmArgs& g = ka.g;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.block_n;
-  const int b_stage_bytes = BN * KBLK * 2;
-  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)ka.stages * stage_bytes);
-  uint64_t* empty_bar = full_bar + ka.stages;
-  uint64_t* accum_bar = empty_bar + ka.stages;
+  uint8_t* ringA = smem;
+  uint8_t* ringB = smem + (size_t)ka.SA * ka.a_stage_bytes;
+  uint64_t* fullA = reinterpret_cast<uint64_t*>(ringB + (size_t)ka.SB * ka.b_stage_bytes);
+  uint64_t* emptyA = fullA + ka.SA;
+  uint64_t* fullB = emptyA + ka.SA;
+  uint64_t* emptyB = fullB + ka.SB;
+  uint64_t* accum_bar = emptyB + ka.SB;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int tiles_w = (g.Wo + g.bw - 1) / g.bw, tiles_h = (g.Ho + g.bh - 1) / g.bh;
-  int mt = blockIdx.x;
-  const int w0 = (mt % tiles_w) * g.bw; mt /= tiles_w;
-  const int h0 = (mt % tiles_h) * g.bh; mt /= tiles_h;
-  const int b0 = mt * g.bb;
   const int n0 = blockIdx.y * BN;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ka.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < ka.SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
+    for (int s = 0; s < ka.SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
     mbar_init(accum_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -159,46 +184,83 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int iters = g.ntaps * ka.kchunks;
+
+  // valid sub-tiles of this CTA (the second one may fall off the end of the tile list)
+  int w0s[2], h0s[2], b0s[2];
+  int mt_eff = 0;
+  for (int m = 0; m < ka.mt; ++m) {
+    bool v;
+    tile_origin(g, ka, m, w0s[m], h0s[m], b0s[m], v);
+    if (v) mt_eff = m + 1;
+  }
 
   if (warp == 0) {
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      const uint32_t tx_bytes = (uint32_t)stage_bytes;
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % ka.stages;
-        const uint32_t ph = (uint32_t)(it / ka.stages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tap = it / ka.kchunks, kc = it - tap * ka.kchunks;
-        int c[5];
+      const int nA = ka.halo ? ka.nboxA : mt_eff;
+      for (int io = 0; io < ka.n_outer; ++io) {
+        const int sa = io % ka.SA;
+        mbar_wait(&emptyA[sa], (((uint32_t)(io / ka.SA)) & 1u) ^ 1u);
+        uint8_t* dstA = ringA + (size_t)sa * ka.a_stage_bytes;
+        mbar_expect_tx(&fullA[sa], (uint32_t)(nA * ka.boxA_bytes));
+        int tap = 0, kc = io;
+        if (!ka.halo) { tap = io / ka.kchunks; kc = io - tap * ka.kchunks; }
+        for (int bx = 0; bx < nA; ++bx) {
+          int c[5];
+          if (ka.halo) {
 #pragma unroll
-        for (int d = 0; d < 5; ++d) c[d] = ka.taps.t[tap][d];
-        c[0] += kc * KBLK;
-        c[g.dimW] += w0; c[g.dimH] += h0; c[g.dimB] += b0;
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        mbar_expect_tx(&full_bar[s], tx_bytes);
-        tma_load_5d(sa, &tmA, &full_bar[s], c[0], c[1], c[2], c[3], c[4]);
-        tma_load_3d(sa + A_STAGE_BYTES, &tmB, &full_bar[s], kc * KBLK, n0, g.wz_batch ? b0 : tap);
+            for (int d = 0; d < 5; ++d) c[d] = 0;
+            c[0] = kc * KBLK;
+            c[g.dimW] = w0s[0] + ka.tmin + bx * HALO_BOX_ROWS;
+            c[g.dimH] += h0s[0]; c[g.dimB] += b0s[0];
+          } else {
+#pragma unroll
+            for (int d = 0; d < 5; ++d) c[d] = ka.taps.t[tap][d];
+            c[0] += kc * KBLK;
+            c[g.dimW] += w0s[bx]; c[g.dimH] += h0s[bx]; c[g.dimB] += b0s[bx];
+          }
+          tma_load_5d(dstA + (size_t)bx * ka.boxA_bytes, &tmA, &fullA[sa], c[0], c[1], c[2], c[3], c[4]);
+        }
+        for (int ii = 0; ii < ka.n_inner; ++ii) {
+          const int ib = io * ka.n_inner + ii;
+          const int sb = ib % ka.SB;
+          mbar_wait(&emptyB[sb], (((uint32_t)(ib / ka.SB)) & 1u) ^ 1u);
+          mbar_expect_tx(&fullB[sb], (uint32_t)ka.b_stage_bytes);
+          const int z = g.wz_batch ? b0s[0] : (ka.halo ? ii : tap);
+          tma_load_3d(ringB + (size_t)sb * ka.b_stage_bytes, &tmB, &fullB[sb], kc * KBLK, n0, z);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % ka.stages;
-        const uint32_t ph = (uint32_t)(it / ka.stages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      for (int io = 0; io < ka.n_outer; ++io) {
+        const int sa = io % ka.SA;
+        mbar_wait(&fullA[sa], ((uint32_t)(io / ka.SA)) & 1u);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + A_STAGE_BYTES);
+        const uint32_t aBase = smem_u32(ringA + (size_t)sa * ka.a_stage_bytes);
+        for (int ii = 0; ii < ka.n_inner; ++ii) {
+          const int ib = io * ka.n_inner + ii;
+          const int sb = ib % ka.SB;
+          mbar_wait(&fullB[sb], ((uint32_t)(ib / ka.SB)) & 1u);
+          tc_fence_after();
+          const uint64_t bdesc = make_smem_desc(smem_u32(ringB + (size_t)sb * ka.b_stage_bytes), 0);
+          for (int m = 0; m < mt_eff; ++m) {
+            const uint32_t aoff = ka.halo ? (uint32_t)((m * TILE_M + ka.taps.t[ii][g.dimW] - ka.tmin) * 128)
+                                          : (uint32_t)(m * A_STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(aBase + aoff, ka.base_off_mode);
 #pragma unroll
-        for (int k = 0; k < KBLK / 16; ++k) {
-          // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
-          tc_mma_f16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) ? 1u : 0u);
+            for (int k = 0; k < KBLK / 16; ++k) {
+              // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
+              tc_mma_f16(tmem_base + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                         (io | ii | k) ? 1u : 0u);
+            }
+          }
+          tc_commit(&emptyB[sb]);
         }
-        tc_commit(&empty_bar[s]);
+        tc_commit(&emptyA[sa]);
       }
       tc_commit(accum_bar);
     }
@@ -206,15 +268,20 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     // epilogue warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
-    const int wl = row % g.bw, hl = (row / g.bw) % g.bh, bl = row / (g.bw * g.bh);
-    const int w = w0 + wl, h = h0 + hl, b = b0 + bl;
-    const bool row_ok = (w < g.Wo) && (h < g.Ho) && (b < g.Bo);
-    const long long pix = (long long)h * g.Wo + w;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    for (int m = 0; m < mt_eff; ++m) {
+    int w, h, b;
+    if (ka.halo) { w = w0s[m] + row; h = h0s[m]; b = b0s[m]; }
+    else {
+      const int wl = row % g.bw, hl = (row / g.bw) % g.bh, bl = row / (g.bw * g.bh);
+      w = w0s[m] + wl; h = h0s[m] + hl; b = b0s[m] + bl;
+    }
+    const bool row_ok = (w < g.Wo) && (h < g.Ho) && (b < g.Bo);
+    const long long pix = (long long)h * g.Wo + w;
     for (int cb = 0; cb < BN; cb += 32) {
       uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)cb;
+      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(m * BN + cb);
       const int ncols = min(32, BN - cb);  // BN is a multiple of 16
       if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
       tc_wait_ld();
@@ -290,6 +357,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
       }
       __syncwarp();  // reconverge before the next .sync.aligned TMEM load
     }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -345,16 +413,47 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   if (a.elem != 1) return bail(fail(EGR_ERR_ARG, "%s: tensor-core path needs an f16 A operand", op.name));
   if (g.block_n < 16 || g.block_n > 256 || g.block_n % 16) return bail(fail(EGR_ERR_ARG, "%s: BLOCK_N=%d must be a multiple of 16 in [16,256]", op.name, g.block_n));
   if (op.i[EGR_I_KBLOCK] && op.i[EGR_I_KBLOCK] != KBLK) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: only K block 64 is built", op.name));
+  // halo mode: every tap moves along dimW only and the tile is 128 consecutive W positions
+  const int kchunks = ceil_div(g.K, KBLK);
+  bool halo = g.ntaps > 1 && !g.wz_batch && g.bw == 128 && g.bh == 1 && g.bb == 1 && getenv("EGR_TC_NO_HALO") == nullptr;
+  int tmin = 0, tmax = 0;
+  for (int t = 0; t < g.ntaps && halo; ++t) {
+    for (int d = 0; d < 5; ++d)
+      if (d != g.dimW && p->taps.t[t][d] != 0) halo = false;
+    const int o = p->taps.t[t][g.dimW];
+    tmin = o < tmin ? o : tmin; tmax = o > tmax ? o : tmax;
+  }
+  if (halo && tmax - tmin > 128) halo = false;
+  const int tiles_w128 = ceil_div(g.Wo, g.bw), tiles_h = ceil_div(g.Ho, g.bh), tiles_b = ceil_div(g.Bo, g.bb);
+  const int tiles1 = tiles_w128 * tiles_h * tiles_b;
+  const int ntn = ceil_div(g.N, g.block_n);
+  const int sms = devinfo().sm_count ? devinfo().sm_count : 148;
+  // two sub-tiles per CTA (shared B loads) when that still leaves at least ~a wave of CTAs
+  int mt = 1;
+  if (!g.wz_batch && g.block_n <= 256 && getenv("EGR_TC_NO_MT2") == nullptr) {
+    const long long ctas2 = halo ? (long long)ceil_div(g.Wo, 256) * tiles_h * tiles_b * ntn : (long long)ceil_div(tiles1, 2) * ntn;
+    if (ctas2 >= sms) mt = 2;
+  }
+  p->mt = mt; p->halo = halo ? 1 : 0; p->kchunks = kchunks; p->tmin = tmin;
+  p->tiles = tiles1;
+  p->tiles_w = halo ? ceil_div(g.Wo, 128 * mt) : tiles_w128;
+  if (halo) {
+    p->n_outer = kchunks; p->n_inner = g.ntaps;
+    p->boxA_bytes = HALO_BOX_ROWS * KBLK * 2;
+    p->nboxA = ceil_div(128 * mt + (tmax - tmin), HALO_BOX_ROWS);
+  } else {
+    p->n_outer = g.ntaps * kchunks; p->n_inner = 1;
+    p->boxA_bytes = A_STAGE_BYTES;
+    p->nboxA = mt;
+  }
+  p->a_stage_bytes = p->nboxA * p->boxA_bytes;
+  p->b_stage_bytes = g.block_n * KBLK * 2;
   // A map: always rank 5 (missing dims are size 1 with a harmless stride)
   long long dim[5], str[5]; int box[5];
-  long long span = 0;
-  for (int d = 0; d < 5; ++d) {
-    dim[d] = a.dim[d]; str[d] = a.stride[d];
-    if (d < a.rank) span = span > a.dim[d] * a.stride[d] ? span : a.dim[d] * a.stride[d];
-  }
+  for (int d = 0; d < 5; ++d) { dim[d] = a.dim[d]; str[d] = a.stride[d]; }
   for (int d = a.rank; d < 5; ++d) { dim[d] = 1; str[d] = dim[d - 1] * str[d - 1]; }
   for (int d = 0; d < 5; ++d) box[d] = 1;
-  box[0] = KBLK; box[g.dimW] = g.bw; box[g.dimH] = g.bh; box[g.dimB] = g.bb;
+  box[0] = KBLK; box[g.dimW] = halo ? HALO_BOX_ROWS : g.bw; box[g.dimH] = g.bh; box[g.dimB] = g.bb;
   if (g.dimW == g.dimH || g.dimW == g.dimB || g.dimH == g.dimB)
     return bail(fail(EGR_ERR_ARG, "%s: tile dims must be distinct A dims", op.name));
   rc = encode_map(&p->tmA, const_cast<void*>(a.p), 5, dim, str, box, op.name);
@@ -367,17 +466,26 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   if (rc) return bail(rc);
   if (g.wz_batch && g.bb != 1) return bail(fail(EGR_ERR_ARG, "%s: batch-indexed B operand needs BB == 1", op.name));
 
-  const int stage_bytes = A_STAGE_BYTES + g.block_n * KBLK * 2;
-  int stages = (200 * 1024) / stage_bytes;
-  if (stages > 8) stages = 8;
-  if (stages < 2) stages = 2;
-  p->stages = stages;
-  p->smem_bytes = stages * stage_bytes + 1024 /*align slack*/ + (2 * stages + 1) * 8 + 16;
+  // ring depths inside ~200 KB: B first (it is the stream in halo mode), the rest to A
+  const int budget = 200 * 1024;
+  int SB, SA;
+  if (halo) {
+    SB = (96 * 1024) / p->b_stage_bytes; if (SB > 6) SB = 6; if (SB < 2) SB = 2;
+    SA = (budget - SB * p->b_stage_bytes) / p->a_stage_bytes; if (SA > 3) SA = 3;
+    if (SA < 2) { SA = 2; SB = (budget - 2 * p->a_stage_bytes) / p->b_stage_bytes; }
+    if (SB < 2) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: halo tile does not fit shared memory", op.name));
+  } else {
+    SA = budget / (p->a_stage_bytes + p->b_stage_bytes); if (SA > 8) SA = 8; if (SA < 2) SA = 2;
+    SB = SA;
+  }
+  p->SA = SA; p->SB = SB;
+  p->smem_bytes = SA * p->a_stage_bytes + SB * p->b_stage_bytes + 1024 /*align slack*/ + (2 * SA + 2 * SB + 1) * 8 + 16;
+  if (p->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: %d B of shared memory needed", op.name, p->smem_bytes));
   int cols = 32;
-  while (cols < g.block_n) cols <<= 1;
+  while (cols < mt * g.block_n) cols <<= 1;
   p->tmem_cols = cols;
-  const int tiles = ceil_div(g.Wo, g.bw) * ceil_div(g.Ho, g.bh) * ceil_div(g.Bo, g.bb);
-  p->grid = dim3(tiles, ceil_div(g.N, g.block_n), 1);
+  const int ctas_m = halo ? p->tiles_w * tiles_h * tiles_b : ceil_div(tiles1, mt);
+  p->grid = dim3(ctas_m, ntn, 1);
   // vector epilogue needs 16-byte aligned rows of 4
   bool vec = !g.transposed && (g.N % 4 == 0) && (g.out_pix_stride % 4 == 0) && (g.out_batch_stride % 4 == 0) &&
              (g.out_offset % 4 == 0) && (g.out_lo % 4 == 0) && (g.out_hi % 4 == 0) && (g.rowbias_stride % 4 == 0);
@@ -392,10 +500,13 @@ int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
   TcKernelArgs ka;
   ka.g = p->g;
   ka.taps = p->taps;
-  ka.stages = p->stages;
+  ka.mt = p->mt; ka.halo = p->halo; ka.n_outer = p->n_outer; ka.n_inner = p->n_inner; ka.kchunks = p->kchunks;
+  ka.nboxA = p->nboxA; ka.boxA_bytes = p->boxA_bytes; ka.a_stage_bytes = p->a_stage_bytes; ka.b_stage_bytes = p->b_stage_bytes;
+  ka.SA = p->SA; ka.SB = p->SB; ka.tmin = p->tmin; ka.tiles = p->tiles; ka.tiles_w = p->tiles_w;
   ka.tmem_cols = p->tmem_cols;
-  ka.kchunks = ceil_div(p->g.K, KBLK);
   ka.vec_ok = p->vec_ok;
+  static const int base_off_mode = getenv("EGR_TC_BASEOFF") ? atoi(getenv("EGR_TC_BASEOFF")) : 1;
+  ka.base_off_mode = base_off_mode;
   gemm_tc_kernel<<<p->grid, 192, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
   EGR_CHECK_LAUNCH(p->name);
   return EGR_OK;

@@ -200,41 +200,62 @@ struct CatArgs {
   long long P;  // pixels per batch item
 };
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(CatArgs a, double* __restrict__ stats, int slab) {
-  extern __shared__ double sh[];  // [G][2]
+// Deterministic (no atomics, fixed summation order) and independent of the batch size: block (slab, b) reduces its
+// slab of pixels to per-group f64 partial sums; gn_finalize_kernel adds the slabs in index order.
+__global__ void __launch_bounds__(256) gn_stats_kernel(CatArgs a, double* __restrict__ partials, int slab, int nslabs) {
+  extern __shared__ double sh[];  // [C][2]
   const int C = a.C0 + a.C1, C4 = C >> 2, cpg = C / a.G;
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) sh[i] = 0.0;
-  __syncthreads();
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long p_lo = (long long)blockIdx.x * slab, p_hi = min(p_lo + slab, a.P);
-  for (int q = tx; q < C4; q += 32) {
-    const int c = q << 2;
-    const float* base; int cc, Cx;
-    if (c < a.C0) { base = a.x0; cc = c; Cx = a.C0; } else { base = a.x1; cc = c - a.C0; Cx = a.C1; }
+  for (int q0 = 0; q0 < C4; q0 += 32) {
+    const int q = q0 + tx;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
-    for (long long p = p_lo + ty; p < p_hi; p += 8) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((long long)b * a.P + p) * Cx + cc));
-      s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
-      s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
-      s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
-      s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
-    }
-    if ((cpg & 3) == 0) {
-      const int gi = c / cpg;
-      atomicAdd(&sh[2 * gi], (double)s[0] + (double)s[1] + (double)s[2] + (double)s[3]);
-      atomicAdd(&sh[2 * gi + 1], (double)ss[0] + (double)ss[1] + (double)ss[2] + (double)ss[3]);
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int gi = (c + u) / cpg;
-        atomicAdd(&sh[2 * gi], (double)s[u]);
-        atomicAdd(&sh[2 * gi + 1], (double)ss[u]);
+    const int c = q << 2;
+    if (q < C4) {
+      const float* base; int cc, Cx;
+      if (c < a.C0) { base = a.x0; cc = c; Cx = a.C0; } else { base = a.x1; cc = c - a.C0; Cx = a.C1; }
+      for (long long p = p_lo + ty; p < p_hi; p += 8) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(base + ((long long)b * a.P + p) * Cx + cc));
+        s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
+        s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
+        s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
+        s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
       }
     }
+    // warps add their partials into sh in warp order (each lane owns its 4 channels: no conflicts)
+    for (int w = 0; w < 8; ++w) {
+      if (ty == w && q < C4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (w == 0) { sh[2 * (c + u)] = (double)s[u]; sh[2 * (c + u) + 1] = (double)ss[u]; }
+          else { sh[2 * (c + u)] += (double)s[u]; sh[2 * (c + u) + 1] += (double)ss[u]; }
+        }
+      }
+      __syncthreads();
+    }
   }
+  for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) {
+    const int gi = i >> 1, st = i & 1;
+    double acc = 0.0;
+    for (int cc = 0; cc < cpg; ++cc) acc += sh[2 * (gi * cpg + cc) + st];
+    partials[(((long long)b * nslabs + blockIdx.x) * a.G + gi) * 2 + st] = acc;
+  }
+}
+
+// stats[b][g][2] = sum over slabs (fixed order: 8 strided lanes, then lane order)
+__global__ void gn_finalize_kernel(const double* __restrict__ partials, double* __restrict__ stats, int G2, int nslabs) {
+  extern __shared__ double shf64[];  // [8][G2]
+  const int b = blockIdx.x, i = threadIdx.x, y = threadIdx.y;
+  double acc = 0.0;
+  for (int sl = y; sl < nslabs; sl += 8) acc += partials[((long long)b * nslabs + sl) * G2 + i];
+  shf64[y * G2 + i] = acc;
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) atomicAdd(&stats[(long long)b * 2 * a.G + i], sh[i]);
+  if (y == 0) {
+    double t = 0.0;
+    for (int k = 0; k < 8; ++k) t += shf64[k * G2 + i];
+    stats[(long long)b * G2 + i] = t;
+  }
 }
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* __restrict__ stats,
@@ -298,11 +319,9 @@ static int cat_args(const Spaces& s, const egr_op& op, CatArgs* a) {
   return EGR_OK;
 }
 
-static int slab_for(long long P, int B, int* nslabs) {
-  // enough blocks to fill the machine (~8 per SM) without making slabs tiny
-  int sms = devinfo().sm_count ? devinfo().sm_count : 148;
-  long long want = ((long long)sms * 8 + B - 1) / B;
-  long long slab = (P + want - 1) / want;
+static int slab_for(long long P, int* nslabs) {
+  // ~1184 slabs for the largest maps (8 per SM at batch 1); a function of P only, so results do not depend on B
+  long long slab = (P + 1183) / 1184;
   if (slab < 64) slab = 64;
   if (slab > P) slab = P;
   *nslabs = (int)((P + slab - 1) / slab);
@@ -315,8 +334,16 @@ int egr::launch_gn_stats(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (rc) return rc;
   double* stats = (double*)resolve(s, op.ptr[EGR_P_STATS]);
   if (!stats) return fail(EGR_ERR_ARG, "%s: null stats", op.name);
-  int ns; int slab = slab_for(a.P, a.B, &ns);
-  gn_stats_kernel<<<dim3(ns, a.B), 256, 2 * a.G * sizeof(double), st>>>(a, stats, slab);
+  int ns; int slab = slab_for(a.P, &ns);
+  if (op.i[EGR_I_AUX1] != ns) return fail(EGR_ERR_ARG, "%s: plan was built for %lld slabs, kernel wants %d", op.name, (long long)op.i[EGR_I_AUX1], ns);
+  const int C = a.C0 + a.C1, G2 = 2 * a.G;
+  double* partials = stats + (long long)a.B * G2;
+  const size_t smem = (size_t)C * 2 * sizeof(double);
+  if (smem > 48 * 1024) return fail(EGR_ERR_UNSUPPORTED, "%s: C=%d too wide for the GroupNorm reduction", op.name, C);
+  if (G2 > 128) return fail(EGR_ERR_UNSUPPORTED, "%s: at most 64 groups", op.name);
+  gn_stats_kernel<<<dim3(ns, a.B), 256, smem, st>>>(a, partials, slab, ns);
+  EGR_CHECK_LAUNCH(op.name);
+  gn_finalize_kernel<<<a.B, dim3(G2, 8), (size_t)8 * G2 * sizeof(double), st>>>(partials, stats, G2, ns);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }
@@ -331,7 +358,7 @@ int egr::launch_gn_apply(const Spaces& s, const egr_op& op, cudaStream_t st) {
   float* o32 = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
   __half* o16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
   if (!stats || !gamma || !beta || (!o32 && !o16)) return fail(EGR_ERR_ARG, "%s: null pointer", op.name);
-  int ns; int slab = slab_for(a.P, a.B, &ns);
+  int ns; int slab = slab_for(a.P, &ns);
   const int C = a.C0 + a.C1;
   gn_apply_kernel<<<dim3(ns, a.B), 256, 2 * C * sizeof(float), st>>>(a, stats, gamma, beta, (float)op.f[EGR_F_EPS],
                                                                      (int)op.i[EGR_I_MODE], o32, o16, slab);
@@ -593,23 +620,34 @@ int egr::launch_eltwise(const Spaces& s, const egr_op& op, cudaStream_t st) {
 //   s[n]    = u[n] + inv_beta*sin^2(alpha*u[n])
 //   y[t]    = sum_j s[clamp(2t+j-5, 0, 2T-1)]*f[j]                                    (j = 0..11)
 // ------------------------------------------------------------------------------------------------
-#define SNAKE_TT 32
+#define SNAKE_TT 64
 
+// sin with an exact two-constant range reduction to [-pi, pi] followed by the SFU approximation (abs err ~4e-7)
+__device__ __forceinline__ float snake_sin(float a) {
+  const float k = rintf(a * 0.15915494309189535f);
+  a = fmaf(k, -6.2831854820251465f, a);
+  a = fmaf(k, 1.7484555e-7f, a);
+  return __sinf(a);
+}
 __device__ __forceinline__ float snake_eval(float u, float alpha, float inv_beta) {
-  const float sn = sinf(u * alpha);
+  const float sn = snake_sin(u * alpha);
   return fmaf(inv_beta * sn, sn, u);
 }
 
-__global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__ x, int T, int C,
+// Thread = (channel, run of SNAKE_TT outputs), linear over (run, channel) so every lane is busy for any C and
+// consecutive lanes read consecutive channels (coalesced).  Both the 6-sample input window and the 12-sample
+// activated window slide in registers: per output 1 load, 12 FMAs (two up-sampling phases), 2 snake evaluations,
+// 12 FMAs (down-sampling), 1 store.
+__global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__ x, int T, int C, int nruns,
                                                         const float* __restrict__ log_alpha,
                                                         const float* __restrict__ log_beta,
                                                         const float* __restrict__ filt, float* __restrict__ o32,
                                                         __half* __restrict__ o16) {
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int trun = blockIdx.y * 4 + (threadIdx.x >> 5);
-  const int b = blockIdx.z;
-  const int t0 = trun * SNAKE_TT;
-  if (c >= C || t0 >= T) return;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nruns * C) return;
+  const int c = (int)(idx % C);
+  const int t0 = (int)(idx / C) * SNAKE_TT;
+  const int b = blockIdx.y;
   const float alpha = __expf(log_alpha[c]);
   const float inv_beta = 1.0f / (__expf(log_beta[c]) + 1e-9f);
   const float* xb = x + (long long)b * T * C + c;
@@ -617,9 +655,8 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
 #pragma unroll
   for (int j = 0; j < 12; ++j) f[j] = __ldg(filt + j);
   const int n_last = 2 * T - 1;
-  // s window: s[2t-5 .. 2t+6] for the current t.  xw[i] = x[clamp(m0-3+i)] for the 7 inputs around m.
   auto xat = [&](int m) { m = m < 0 ? 0 : (m >= T ? T - 1 : m); return __ldg(xb + (long long)m * C); };
-  auto s_at = [&](int n) {  // activated up-sampled sample n (clamped = replicate padding of s)
+  auto s_at = [&](int n) {  // activated up-sampled sample n (clamped = replicate padding of s); warm-up only
     n = n < 0 ? 0 : (n > n_last ? n_last : n);
     const int m = n >> 1;
     float u = 0.f;
@@ -635,13 +672,27 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
   float sw[12];
 #pragma unroll
   for (int j = 0; j < 10; ++j) sw[j + 2] = s_at(2 * t0 - 5 + j);  // slots 2..11 hold s[2t0-5 .. 2t0+4]
+  float xw[6];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) xw[r + 1] = xat(t0 + r);  // slots 1..5 hold x[t0 .. t0+4]
   const int t_end = min(T, t0 + SNAKE_TT);
-  // rolling input window for the fast interior path: xin[i] = x[m+i-3], m = t+2 .. needs x[t-1 .. t+5]
+#pragma unroll 4
   for (int t = t0; t < t_end; ++t) {
 #pragma unroll
     for (int j = 0; j < 10; ++j) sw[j] = sw[j + 2];
-    sw[10] = s_at(2 * t + 5);
-    sw[11] = s_at(2 * t + 6);
+#pragma unroll
+    for (int r = 0; r < 5; ++r) xw[r] = xw[r + 1];
+    xw[5] = xat(t + 5);
+    // s[2t+5] (odd phase of m = t+2) and s[2t+6] (even phase of m = t+3) both read x[t .. t+5]
+    float uo = 0.f, ue = 0.f;
+#pragma unroll
+    for (int r = 0; r < 6; ++r) {
+      uo = fmaf(xw[r], f[10 - 2 * r], uo);
+      ue = fmaf(xw[r], f[11 - 2 * r], ue);
+    }
+    const float so = snake_eval(2.0f * uo, alpha, inv_beta), se = snake_eval(2.0f * ue, alpha, inv_beta);
+    sw[10] = (2 * t + 5 <= n_last) ? so : sw[9];
+    sw[11] = (2 * t + 6 <= n_last) ? se : sw[10];
     float y = 0.f;
 #pragma unroll
     for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
@@ -661,8 +712,9 @@ int egr::launch_snake_aa(const Spaces& s, const egr_op& op, cudaStream_t st) {
   const int B = (int)op.i[EGR_I_BATCH], T = (int)op.i[EGR_I_ROWS], C = (int)op.i[EGR_I_COLS];
   if (!x || !la || !lb || !filt || (!o32 && !o16) || B <= 0 || T <= 0 || C <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
   if (op.i[EGR_I_AUX0] != 12) return fail(EGR_ERR_UNSUPPORTED, "%s: only the 12-tap anti-alias filter is built", op.name);
-  dim3 grid((C + 31) / 32, (T + SNAKE_TT * 4 - 1) / (SNAKE_TT * 4), B);
-  snake_aa_kernel<<<grid, 128, 0, st>>>(x, T, C, la, lb, filt, o32, o16);
+  const int nruns = (T + SNAKE_TT - 1) / SNAKE_TT;
+  dim3 grid((unsigned)(((long long)nruns * C + 127) / 128), B);
+  snake_aa_kernel<<<grid, 128, 0, st>>>(x, T, C, nruns, la, lb, filt, o32, o16);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }

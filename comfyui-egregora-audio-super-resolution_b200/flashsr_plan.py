@@ -107,6 +107,13 @@ def tile_geometry(Wo: int, Ho: int, Bo: int) -> Tuple[int, int, int]:
     return bw, bh, bb
 
 
+def gn_slabs(P: int) -> Tuple[int, int]:
+    """(slab, n_slabs) of the GroupNorm reduction — must match slab_for() in csrc/ops.cu; a function of the pixel
+    count only, so results are bit-identical for any batch size."""
+    slab = min(max((P + 1183) // 1184, 64), P)
+    return slab, (P + slab - 1) // slab
+
+
 def pick_block_n(N: int) -> int:
     best = 0
     for bn in range(16, 257, 16):
@@ -353,12 +360,10 @@ class PlanBackend:
         assert x.C == c
         a, b = x.parts if x.parts else (x, None)
         assert a.f32 is not None and a.ld == a.C and (b is None or (b.f32 is not None and b.ld == b.C))
-        stats = self.buf(x.B * groups * 2 * 8, name + ".stats")
-        z = RawOp(K["EGR_OP_ZERO"], name + ".zero")
-        z.i = {"ROWS": x.B * groups * 16}
-        self._ws(z, "OUT32", stats, write=True)
-        self.emit(z)
-        common = {"C0": a.C, "C1": b.C if b else 0, "GROUPS": groups, "BATCH": x.B, "ROWS": x.P}
+        slab, ns = gn_slabs(x.P)
+        # [B][G][2] f64 totals followed by [B][ns][G][2] per-slab partials (deterministic two-stage reduction)
+        stats = self.buf(x.B * groups * 2 * 8 * (1 + ns), name + ".stats")
+        common = {"C0": a.C, "C1": b.C if b else 0, "GROUPS": groups, "BATCH": x.B, "ROWS": x.P, "AUX0": slab, "AUX1": ns}
         st = RawOp(K["EGR_OP_GN_STATS"], name + ".stats")
         st.i = dict(common)
         st.x0 = (a.f32, 0, 1, 0, [a.C], [1]); st.reads.append(a.f32)

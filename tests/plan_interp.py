@@ -127,8 +127,8 @@ class Interp:
         G = self.i(op, "GROUPS")
         xg = x.view(B, P, G, Cc // G)
         st = self.p(op, "STATS", torch.float64, B * G * 2).view(B, G, 2)
-        st[:, :, 0] += xg.sum((1, 3))
-        st[:, :, 1] += (xg * xg).sum((1, 3))
+        st[:, :, 0] = xg.sum((1, 3))
+        st[:, :, 1] = (xg * xg).sum((1, 3))
 
     def gn_apply(self, op):
         x = self._cat(op)
