@@ -112,9 +112,11 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
 // descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int base_off_mode) {
+// The 128-byte swizzle XOR is applied by the hardware to the ABSOLUTE shared-memory address (bits 4-6 ^= bits 7-9),
+// exactly as TMA wrote it, so a start address moved by whole 128-byte rows (halo mode) or by 32 bytes inside the
+// span (k advance) needs no "base offset" field — measured on B200: setting it breaks the row-shifted reads.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
-  if (base_off_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;  // start not on a 1024-byte swizzle repeat
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)(1024 >> 4) << 32;
@@ -128,7 +130,7 @@ struct TcKernelArgs {
   GemmArgs g;
   Taps taps;
   int mt, halo, n_outer, n_inner, kchunks, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin, tiles, tiles_w;
-  int tmem_cols, vec_ok, base_off_mode;
+  int tmem_cols, vec_ok;
 };
 
 static constexpr int HALO_BOX_ROWS = 64;
@@ -246,11 +248,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           const int sb = ib % ka.SB;
           mbar_wait(&fullB[sb], ((uint32_t)(ib / ka.SB)) & 1u);
           tc_fence_after();
-          const uint64_t bdesc = make_smem_desc(smem_u32(ringB + (size_t)sb * ka.b_stage_bytes), 0);
+          const uint64_t bdesc = make_smem_desc(smem_u32(ringB + (size_t)sb * ka.b_stage_bytes));
           for (int m = 0; m < mt_eff; ++m) {
             const uint32_t aoff = ka.halo ? (uint32_t)((m * TILE_M + ka.taps.t[ii][g.dimW] - ka.tmin) * 128)
                                           : (uint32_t)(m * A_STAGE_BYTES);
-            const uint64_t adesc = make_smem_desc(aBase + aoff, ka.base_off_mode);
+            const uint64_t adesc = make_smem_desc(aBase + aoff);
 #pragma unroll
             for (int k = 0; k < KBLK / 16; ++k) {
               // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
@@ -505,8 +507,6 @@ int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
   ka.SA = p->SA; ka.SB = p->SB; ka.tmin = p->tmin; ka.tiles = p->tiles; ka.tiles_w = p->tiles_w;
   ka.tmem_cols = p->tmem_cols;
   ka.vec_ok = p->vec_ok;
-  static const int base_off_mode = getenv("EGR_TC_BASEOFF") ? atoi(getenv("EGR_TC_BASEOFF")) : 1;
-  ka.base_off_mode = base_off_mode;
   gemm_tc_kernel<<<p->grid, 192, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
   EGR_CHECK_LAUNCH(p->name);
   return EGR_OK;
