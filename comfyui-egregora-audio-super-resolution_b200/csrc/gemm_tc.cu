@@ -7,17 +7,27 @@
 // through a rank-5 TMA tensor map, so every tap is just a shifted box load and zero padding is TMA's
 // out-of-bounds fill — no im2col buffer ever exists in HBM.
 //
-// CTA = MT x 128 output pixels (MT = 1 or 2 sub-tiles sharing every B load) x BLOCK_N channels, 192 threads:
-//   warp 0      TMA producer  (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier expect_tx)          [UTMALDG]
+// PERSISTENT, warp-specialised CTA (one per SM, 224 threads) looping over work items (m-tile, n-tile, k-split):
+//   warp 0 / 6  TMA producers of the A / B rings (cp.async.bulk.tensor, SWIZZLE_128B, expect_tx)  [UTMALDG]
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 f16)   [UTCHMMA]
-//   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> bias/act/residual -> vector stores   [LDTM]
+//   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> shared-memory transpose -> bias/act/residual ->
+//               row-contiguous (coalesced) vector stores                                         [LDTM]
+// The accumulator is double-buffered in TMEM (2 x MT x BLOCK_N f32 columns of the 512), so the epilogue of
+// work item i drains buffer i&1 while the tensor pipe already fills the other one with item i+1.
 // Two shared-memory rings, A and B, each with its own full/empty mbarriers:
 //   normal mode : one A stage (MT boxes of 128 rows x 64 ch) and one B stage (BLOCK_N x 64) per (tap, k-chunk)
 //   halo mode   : (taps along one axis, 1-D convs) the A stage is a super-tile of MT*128 + tap-span rows loaded
 //                 ONCE per k-chunk; every tap multiplies a row-shifted window of it (the UMMA descriptor start
 //                 address moves by whole 128-byte rows), so A traffic from L2 drops by the tap count and the
 //                 loop streams only the per-tap weight tiles.
-// Accumulators: MT x 128 lanes x BLOCK_N f32 columns in TMEM.
+// Split-K: layers with few output tiles (the UNet at 8x4 .. 64x32 latent pixels) would leave most SMs idle while a
+// handful of CTAs stream megabytes of weights; their reduction range is cut into `splits` work items, each CTA
+// writes its raw f32 partial tile to a library-owned workspace and the LAST one to arrive (one atomic counter per
+// output tile) sums the partials in split order — deterministic — and applies the epilogue.  `splits` depends only
+// on the per-item geometry, never on the batch size, so results are identical alone or inside a batch.
+//
+// The single-thread producer / issuer loops are kept free of integer divisions and of dynamically indexed local
+// arrays: a clock trace of the previous version showed ~1400 cycles per k-step spent in exactly that scalar code.
 #include <cuda.h>
 #include <cstdlib>
 #include "ops.cuh"
@@ -26,17 +36,32 @@ namespace egr {
 
 static constexpr int TILE_M = 128;
 static constexpr int KBLK = 64;  // f16 elements per smem row = 128 B = one swizzle span
-static constexpr int A_STAGE_BYTES = TILE_M * KBLK * 2;
+static constexpr int A_BOX_BYTES = TILE_M * KBLK * 2;
+static constexpr int HALO_BOX_ROWS = 64;
+static constexpr int STAGE_LD = 36;  // floats per row of the epilogue staging tile (16-byte aligned, conflict-free)
+static constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_LD * 4;
+static constexpr int MAX_SPLITS = 16;
+
+struct TcKernelArgs {
+  GemmArgs g;
+  Taps taps;
+  short tapw[EGR_MAX_TAPS];  // tap offset along dimW (halo mode)
+  int mt, halo, kchunks, n_outer, n_inner, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin;
+  int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
+  int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (<= 256)
+  int vec_ok;
+  float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
+  unsigned int* counters;  // one per output tile, zero between launches
+  unsigned long long* trace;  // debug: clock64() stamps of CTA 0 when non-null
+};
 
 struct TcPrepared {
   CUtensorMap tmA, tmB;
-  GemmArgs g;
-  Taps taps;
-  int a_rank;
-  int mt, halo, n_outer, n_inner, kchunks, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin, tiles, tiles_w;
-  int tmem_cols, smem_bytes;
-  dim3 grid;
-  int vec_ok;
+  TcKernelArgs ka;
+  int smem_bytes;
+  int grid;
+  size_t partial_bytes;
+  int n_counters;
   char name[48];
 };
 
@@ -55,32 +80,35 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
       "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -109,6 +137,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// one lane of a fully converged warp; the surrounding code stays warp-uniform so that descriptors and addresses live
+// in uniform registers (a lane==0 guard around the whole loop makes ptxas wrap every UTCHMMA / UTMALDG in a
+// per-lane "waterfall" loop of R2UR moves, ~100 cycles per instruction)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
 // descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
@@ -125,34 +162,114 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
-// ------------------------------------------------------------------------------------------------ the kernel
-struct TcKernelArgs {
-  GemmArgs g;
-  Taps taps;
-  int mt, halo, n_outer, n_inner, kchunks, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin, tiles, tiles_w;
-  int tmem_cols, vec_ok;
+// ------------------------------------------------------------------------------------------------ work decoding
+struct WorkItem {
+  int tm, tn, ks;
+  int o_begin, o_end;  // outer-step range of this split
+  int mt_eff;          // valid sub-tiles
+  int w0[2], h0[2], b0[2];
 };
 
-static constexpr int HALO_BOX_ROWS = 64;
-
-__device__ __forceinline__ void tile_origin(const GemmArgs& g, const TcKernelArgs& ka, int sub, int& w0, int& h0, int& b0, bool& valid) {
-  const int tiles_h = (g.Ho + g.bh - 1) / g.bh;
-  if (ka.halo) {  // CTA tile = mt*128 consecutive positions along W inside one (h, b) row
-    int mt_ = blockIdx.x;
-    w0 = (mt_ % ka.tiles_w) * (128 * ka.mt) + 128 * sub; mt_ /= ka.tiles_w;
-    h0 = (mt_ % tiles_h) * g.bh; mt_ /= tiles_h;
-    b0 = mt_ * g.bb;
-    valid = w0 < g.Wo;
-  } else {
-    int mt_ = blockIdx.x * ka.mt + sub;
-    valid = mt_ < ka.tiles;
-    w0 = (mt_ % ka.tiles_w) * g.bw; mt_ /= ka.tiles_w;
-    h0 = (mt_ % tiles_h) * g.bh; mt_ /= tiles_h;
-    b0 = mt_ * g.bb;
+__device__ __forceinline__ void decode_work(const TcKernelArgs& ka, int w, WorkItem& wi) {
+  const GemmArgs& g = ka.g;
+  wi.ks = w % ka.splits;
+  int t = w / ka.splits;
+  wi.tn = t % ka.tiles_n;
+  wi.tm = t / ka.tiles_n;
+  wi.o_begin = wi.ks * ka.outer_per_split;
+  wi.o_end = min(ka.n_outer, wi.o_begin + ka.outer_per_split);
+  wi.mt_eff = 0;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    wi.w0[m] = wi.h0[m] = wi.b0[m] = 0;
+    if (m >= ka.mt) continue;
+    bool valid;
+    int q;
+    if (ka.halo) {  // CTA tile = mt*128 consecutive positions along W inside one (h, b) row
+      q = wi.tm;
+      wi.w0[m] = (q % ka.tiles_w) * (TILE_M * ka.mt) + TILE_M * m; q /= ka.tiles_w;
+      valid = wi.w0[m] < g.Wo;
+    } else {
+      q = wi.tm * ka.mt + m;
+      valid = q < ka.tiles1;
+      wi.w0[m] = (q % ka.tiles_w) * g.bw; q /= ka.tiles_w;
+    }
+    wi.h0[m] = (q % ka.tiles_h) * g.bh; q /= ka.tiles_h;
+    wi.b0[m] = q * g.bb;
+    if (valid) wi.mt_eff = m + 1;
   }
 }
 
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+// ------------------------------------------------------------------------------------------------ epilogue math
+struct RowInfo {
+  long long base;   // output index of column 0 of this row (non-transposed) / of n = 0 (transposed)
+  long long flat0;  // in-batch flat index of column 0 (crop test)
+  int b;
+  int ok;
+};
+
+__device__ __forceinline__ RowInfo row_info(const TcKernelArgs& ka, const WorkItem& wi, int m, int row) {
+  const GemmArgs& g = ka.g;
+  int w, h, b;
+  if (ka.halo) { w = wi.w0[m] + row; h = wi.h0[m]; b = wi.b0[m]; }
+  else {
+    const int wl = row % g.bw, t = row / g.bw;
+    w = wi.w0[m] + wl; h = wi.h0[m] + t % g.bh; b = wi.b0[m] + t / g.bh;
+  }
+  RowInfo r;
+  r.ok = (w < g.Wo) && (h < g.Ho) && (b < g.Bo);
+  r.b = b;
+  const long long pix = (long long)h * g.Wo + w;
+  if (g.transposed) {
+    r.flat0 = 0;
+    r.base = (long long)b * g.out_batch_stride + pix + g.out_offset;
+  } else {
+    r.flat0 = pix * g.out_pix_stride + g.out_offset;
+    r.base = (long long)b * g.out_batch_stride + r.flat0;
+  }
+  return r;
+}
+
+// final value of 4 consecutive columns n..n+3 of one row (vector path: alignment checked on the host)
+__device__ __forceinline__ void finish4(const GemmArgs& g, float4 acc, long long idx, int n, const float* rb) {
+  float v[4] = {acc.x * g.alpha, acc.y * g.alpha, acc.z * g.alpha, acc.w * g.alpha};
+  if (g.bias) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+    v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+  }
+  if (rb) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + n));
+    v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+  }
+  if (g.act) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = egr_apply_act(v[u], g.act);
+  }
+  if (g.resid) {
+    const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid + idx));
+    v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+  }
+  if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  if (g.out16) {
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned*>(&h0);
+    pk.y = *reinterpret_cast<unsigned*>(&h1);
+    *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
+  }
+}
+__device__ __forceinline__ void finish1(const GemmArgs& g, float acc, long long idx, int n, const float* rb) {
+  float v = acc * g.alpha;
+  if (g.bias) v += g.bias[n];
+  if (rb) v += rb[n];
+  v = egr_apply_act(v, g.act);
+  if (g.resid) v += g.resid[idx];
+  if (g.out32) g.out32[idx] = v;
+  if (g.out16) g.out16[idx] = __float2half_rn(v);
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(224, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB,
                                                           const __grid_constant__ TcKernelArgs ka) {
   extern __shared__ uint8_t smem_raw[];
@@ -160,211 +277,399 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = g.block_n;
   uint8_t* ringA = smem;
-  uint8_t* ringB = smem + (size_t)ka.SA * ka.a_stage_bytes;
-  uint64_t* fullA = reinterpret_cast<uint64_t*>(ringB + (size_t)ka.SB * ka.b_stage_bytes);
+  uint8_t* ringB = ringA + (size_t)ka.SA * ka.a_stage_bytes;
+  float* stage_all = reinterpret_cast<float*>(ringB + (size_t)ka.SB * ka.b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_all) + 4 * STAGE_BYTES_PER_WARP);
+  uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + ka.SA;
   uint64_t* fullB = emptyA + ka.SA;
   uint64_t* emptyB = fullB + ka.SB;
-  uint64_t* accum_bar = emptyB + ka.SB;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+  uint64_t* acc_full = emptyB + ka.SB;   // [2]
+  uint64_t* acc_empty = acc_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint32_t* last_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BN;
+  unsigned long long* tr = (ka.trace && blockIdx.x == 0) ? ka.trace : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
+  if (ka.trace && threadIdx.x == 0 && blockIdx.x < 148) {  // per-CTA wall-clock start (ns)
+    unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    ka.trace[1100 + 2 * blockIdx.x] = gt;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ka.SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
     for (int s = 0; s < ka.SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    mbar_init(accum_bar, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)ka.tmem_cols) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  // valid sub-tiles of this CTA (the second one may fall off the end of the tile list)
-  int w0s[2], h0s[2], b0s[2];
-  int mt_eff = 0;
-  for (int m = 0; m < ka.mt; ++m) {
-    bool v;
-    tile_origin(g, ka, m, w0s[m], h0s[m], b0s[m], v);
-    if (v) mt_eff = m + 1;
-  }
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 0) {
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      const int nA = ka.halo ? ka.nboxA : mt_eff;
-      for (int io = 0; io < ka.n_outer; ++io) {
-        const int sa = io % ka.SA;
-        mbar_wait(&emptyA[sa], (((uint32_t)(io / ka.SA)) & 1u) ^ 1u);
-        uint8_t* dstA = ringA + (size_t)sa * ka.a_stage_bytes;
-        mbar_expect_tx(&fullA[sa], (uint32_t)(nA * ka.boxA_bytes));
-        int tap = 0, kc = io;
-        if (!ka.halo) { tap = io / ka.kchunks; kc = io - tap * ka.kchunks; }
-        for (int bx = 0; bx < nA; ++bx) {
-          int c[5];
+    // ============================================================ A producer (whole warp, one elected lane issues)
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    __syncwarp();
+    const uint32_t ringA_u = smem_u32(ringA), fullA_u = smem_u32(fullA), emptyA_u = smem_u32(emptyA);
+    int sa = 0;
+    uint32_t pa = 0;  // ring phase
+    int tcount = 0;
+    for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x) {
+      WorkItem wi;
+      decode_work(ka, w, wi);
+      const int nA = ka.halo ? ka.nboxA : wi.mt_eff;
+      // per-sub-tile base coordinates, selected without dynamic register indexing
+      int cb[2][5];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int d = 0; d < 5; ++d)
+          cb[m][d] = (g.dimW == d ? wi.w0[m] : 0) + (g.dimH == d ? wi.h0[m] : 0) + (g.dimB == d ? wi.b0[m] : 0);
+      int tap = 0, kc = wi.o_begin;
+      if (!ka.halo) { tap = wi.o_begin / ka.kchunks; kc = wi.o_begin - tap * ka.kchunks; }
+      for (int io = wi.o_begin; io < wi.o_end; ++io) {
+        mbar_wait(emptyA_u + 8 * sa, pa ^ 1u);
+        const uint32_t dstA = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
+        if (elect_one()) {
+          if (tr && tcount < 250) tr[16 + 2 * tcount] = clock64();
+          mbar_expect_tx(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
           if (ka.halo) {
+            int c[5];
 #pragma unroll
-            for (int d = 0; d < 5; ++d) c[d] = 0;
+            for (int d = 0; d < 5; ++d) c[d] = cb[0][d] + (g.dimW == d ? ka.tmin : 0);
             c[0] = kc * KBLK;
-            c[g.dimW] = w0s[0] + ka.tmin + bx * HALO_BOX_ROWS;
-            c[g.dimH] += h0s[0]; c[g.dimB] += b0s[0];
+            for (int bx = 0; bx < nA; ++bx) {
+              const int sh = bx * HALO_BOX_ROWS;
+              tma_load_5d(dstA + (uint32_t)bx * (uint32_t)ka.boxA_bytes, &tmA, fullA_u + 8 * sa, c[0],
+                          c[1] + (g.dimW == 1 ? sh : 0), c[2] + (g.dimW == 2 ? sh : 0), c[3] + (g.dimW == 3 ? sh : 0),
+                          c[4] + (g.dimW == 4 ? sh : 0));
+            }
           } else {
+            int t[5];
 #pragma unroll
-            for (int d = 0; d < 5; ++d) c[d] = ka.taps.t[tap][d];
-            c[0] += kc * KBLK;
-            c[g.dimW] += w0s[bx]; c[g.dimH] += h0s[bx]; c[g.dimB] += b0s[bx];
+            for (int d = 0; d < 5; ++d) t[d] = ka.taps.t[tap][d];
+            t[0] += kc * KBLK;
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              if (m < nA)
+                tma_load_5d(dstA + (uint32_t)m * A_BOX_BYTES, &tmA, fullA_u + 8 * sa, t[0] + cb[m][0], t[1] + cb[m][1],
+                            t[2] + cb[m][2], t[3] + cb[m][3], t[4] + cb[m][4]);
+            }
           }
-          tma_load_5d(dstA + (size_t)bx * ka.boxA_bytes, &tmA, &fullA[sa], c[0], c[1], c[2], c[3], c[4]);
+          if (tr && tcount < 250) tr[16 + 2 * tcount + 1] = clock64();
         }
+        __syncwarp();
+        ++tcount;
+        if (++sa == ka.SA) { sa = 0; pa ^= 1u; }
+        if (++kc == ka.kchunks && !ka.halo) { kc = 0; ++tap; }
+      }
+    }
+  } else if (warp == 6) {
+    // ============================================================ B producer (weights / batch-indexed operand)
+    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    __syncwarp();
+    const uint32_t ringB_u = smem_u32(ringB), fullB_u = smem_u32(fullB), emptyB_u = smem_u32(emptyB);
+    int sb = 0;
+    uint32_t pb = 0;
+    for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x) {
+      WorkItem wi;
+      decode_work(ka, w, wi);
+      const int n0 = wi.tn * BN;
+      int tap = 0, kc = wi.o_begin;
+      if (!ka.halo) { tap = wi.o_begin / ka.kchunks; kc = wi.o_begin - tap * ka.kchunks; }
+      for (int io = wi.o_begin; io < wi.o_end; ++io) {
         for (int ii = 0; ii < ka.n_inner; ++ii) {
-          const int ib = io * ka.n_inner + ii;
-          const int sb = ib % ka.SB;
-          mbar_wait(&emptyB[sb], (((uint32_t)(ib / ka.SB)) & 1u) ^ 1u);
-          mbar_expect_tx(&fullB[sb], (uint32_t)ka.b_stage_bytes);
-          const int z = g.wz_batch ? b0s[0] : (ka.halo ? ii : tap);
-          tma_load_3d(ringB + (size_t)sb * ka.b_stage_bytes, &tmB, &fullB[sb], kc * KBLK, n0, z);
+          mbar_wait(emptyB_u + 8 * sb, pb ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(fullB_u + 8 * sb, (uint32_t)ka.b_stage_bytes);
+            const int z = g.wz_batch ? wi.b0[0] : (ka.halo ? ii : tap);
+            tma_load_3d(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, &tmB, fullB_u + 8 * sb, kc * KBLK, n0, z);
+          }
+          __syncwarp();
+          if (++sb == ka.SB) { sb = 0; pb ^= 1u; }
         }
+        if (++kc == ka.kchunks && !ka.halo) { kc = 0; ++tap; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ============================================================ MMA issuer (whole warp, one elected lane issues)
+    {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-      for (int io = 0; io < ka.n_outer; ++io) {
-        const int sa = io % ka.SA;
-        mbar_wait(&fullA[sa], ((uint32_t)(io / ka.SA)) & 1u);
+      const uint32_t ringA_u = smem_u32(ringA), ringB_u = smem_u32(ringB);
+      const uint32_t fullA_u = smem_u32(fullA), emptyA_u = smem_u32(emptyA), fullB_u = smem_u32(fullB), emptyB_u = smem_u32(emptyB);
+      const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      int it = 0, tcount = 0;
+      for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
+        WorkItem wi;
+        decode_work(ka, w, wi);
+        const int buf = it & 1;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * ka.acc_cols);
+        mbar_wait(accE_u + 8 * buf, (((uint32_t)(it >> 1)) & 1u) ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
-        const uint32_t aBase = smem_u32(ringA + (size_t)sa * ka.a_stage_bytes);
-        for (int ii = 0; ii < ka.n_inner; ++ii) {
-          const int ib = io * ka.n_inner + ii;
-          const int sb = ib % ka.SB;
-          mbar_wait(&fullB[sb], ((uint32_t)(ib / ka.SB)) & 1u);
-          tc_fence_after();
-          const uint64_t bdesc = make_smem_desc(smem_u32(ringB + (size_t)sb * ka.b_stage_bytes));
-          for (int m = 0; m < mt_eff; ++m) {
-            const uint32_t aoff = ka.halo ? (uint32_t)((m * TILE_M + ka.taps.t[ii][g.dimW] - ka.tmin) * 128)
-                                          : (uint32_t)(m * A_STAGE_BYTES);
-            const uint64_t adesc = make_smem_desc(aBase + aoff);
+        uint32_t first = 0;  // 0 until the first MMA of this item has been issued (accumulate flag)
+        for (int io = wi.o_begin; io < wi.o_end; ++io) {
+          mbar_wait(fullA_u + 8 * sa, pa);
+          const uint32_t aBase = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
+          for (int ii = 0; ii < ka.n_inner; ++ii) {
+            mbar_wait(fullB_u + 8 * sb, pb);
+            tc_fence_after();
+            const uint64_t bdesc = make_smem_desc(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes);
+            const uint32_t shift = ka.halo ? (uint32_t)((ka.tapw[ii] - ka.tmin) * 128) : 0u;
+            const bool lastB = (ii == ka.n_inner - 1);
+            if (elect_one()) {
+              if (tr && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
 #pragma unroll
-            for (int k = 0; k < KBLK / 16; ++k) {
-              // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
-              tc_mma_f16(tmem_base + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                         (io | ii | k) ? 1u : 0u);
+              for (int m = 0; m < 2; ++m) {
+                if (m < wi.mt_eff) {
+                  const uint64_t adesc = make_smem_desc(aBase + shift + (uint32_t)m * A_BOX_BYTES);
+#pragma unroll
+                  for (int k = 0; k < KBLK / 16; ++k) {
+                    // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
+                    tc_mma_f16(acc + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                  }
+                }
+              }
+              tc_commit(emptyB_u + 8 * sb);
+              if (lastB) {
+                tc_commit(emptyA_u + 8 * sa);
+                if (io == wi.o_end - 1) tc_commit(accF_u + 8 * buf);
+                if (tr && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
+              }
             }
+            __syncwarp();
+            first = 1;
+            if (++sb == ka.SB) { sb = 0; pb ^= 1u; }
           }
-          tc_commit(&emptyB[sb]);
+          ++tcount;
+          if (++sa == ka.SA) { sa = 0; pa ^= 1u; }
         }
-        tc_commit(&emptyA[sa]);
       }
-      tc_commit(accum_bar);
     }
   } else {
-    // epilogue warps 2..5; a warp may only touch TMEM lanes 32*(warp%4) .. +31
+    // ============================================================ epilogue warps 2..5 (TMEM lanes 32*(warp%4) ..)
     const int lg = warp & 3;
-    const int row = lg * 32 + lane;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-    for (int m = 0; m < mt_eff; ++m) {
-    int w, h, b;
-    if (ka.halo) { w = w0s[m] + row; h = h0s[m]; b = b0s[m]; }
-    else {
-      const int wl = row % g.bw, hl = (row / g.bw) % g.bh, bl = row / (g.bw * g.bh);
-      w = w0s[m] + wl; h = h0s[m] + hl; b = b0s[m] + bl;
-    }
-    const bool row_ok = (w < g.Wo) && (h < g.Ho) && (b < g.Bo);
-    const long long pix = (long long)h * g.Wo + w;
-    for (int cb = 0; cb < BN; cb += 32) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(m * BN + cb);
-      const int ncols = min(32, BN - cb);  // BN is a multiple of 16
-      if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
-      tc_wait_ld();
-      const int nb = n0 + cb;
-      if (!row_ok) {
-        // nothing to store for padded rows
-      } else if (g.transposed) {
-        for (int j = 0; j < ncols; ++j) {
-          const int n = nb + j;
-          if (n >= g.N) break;
-          float v = __uint_as_float(r[j]) * g.alpha;
-          if (g.bias) v += g.bias[n];
-          if (g.rowbias) v += g.rowbias[(long long)b * g.rowbias_stride + n];
-          v = egr_apply_act(v, g.act);
-          const long long idx = (long long)b * g.out_batch_stride + (long long)n * g.out_n_stride + pix + g.out_offset;
-          if (g.resid) v += g.resid[idx];
-          if (g.out32) g.out32[idx] = v;
-          if (g.out16) g.out16[idx] = __float2half_rn(v);
-        }
-      } else {
-      const long long flat0 = pix * g.out_pix_stride + g.out_offset + nb;
-      const long long base = (long long)b * g.out_batch_stride + flat0;
-      const float* rb = g.rowbias ? g.rowbias + (long long)b * g.rowbias_stride + nb : nullptr;
-      if (ka.vec_ok) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (j >= ncols || nb + j >= g.N) break;
-          const long long fl = flat0 + j;
-          if (fl < g.out_lo || fl >= g.out_hi) continue;
-          float v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = __uint_as_float(r[j + u]) * g.alpha;
-          if (g.bias) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + nb + j));
-            v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+    float* stg = stage_all + (size_t)(warp - 2) * (32 * STAGE_LD);
+    const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // vector pass: 4 rows x 8 float4 per instruction
+    int it = 0;
+    for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
+      WorkItem wi;
+      decode_work(ka, w, wi);
+      const int buf = it & 1;
+      const int n0 = wi.tn * BN;
+      if (g.resid && ka.splits == 1 && !g.transposed) {
+        // the mainloop of this item is still running: pull the residual tile into L2 meanwhile, so that the loads of
+        // the store pass below pay an L2 hit instead of a DRAM round trip per 32x32 block
+        for (int m = 0; m < wi.mt_eff; ++m) {
+          const RowInfo rp = row_info(ka, wi, m, lg * 32 + lane);
+          if (rp.ok) {
+            const float* q = g.resid + rp.base + n0;
+            for (int c = 0; c < BN; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
           }
-          if (rb) {
-            const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + j));
-            v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
-          }
-          if (g.act) {
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = egr_apply_act(v[u], g.act);
-          }
-          if (g.resid) {
-            const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid + base + j));
-            v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
-          }
-          if (g.out32) *reinterpret_cast<float4*>(g.out32 + base + j) = make_float4(v[0], v[1], v[2], v[3]);
-          if (g.out16) {
-            __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-            uint2 pk;
-            pk.x = *reinterpret_cast<unsigned*>(&h0);
-            pk.y = *reinterpret_cast<unsigned*>(&h1);
-            *reinterpret_cast<uint2*>(g.out16 + base + j) = pk;
-          }
-        }
-      } else {
-        for (int j = 0; j < ncols; ++j) {
-          const int n = nb + j;
-          if (n >= g.N) break;
-          const long long fl = flat0 + j;
-          if (fl < g.out_lo || fl >= g.out_hi) continue;
-          float v = __uint_as_float(r[j]) * g.alpha;
-          if (g.bias) v += g.bias[n];
-          if (rb) v += rb[j];
-          v = egr_apply_act(v, g.act);
-          if (g.resid) v += g.resid[base + j];
-          if (g.out32) g.out32[base + j] = v;
-          if (g.out16) g.out16[base + j] = __float2half_rn(v);
         }
       }
+      mbar_wait(accF_u + 8 * buf, ((uint32_t)(it >> 1)) & 1u);
+      tc_fence_after();
+      if (tr && threadIdx.x == 64 && it < 6) tr[2 + 2 * it] = clock64();
+      const int tile_id = wi.tm * ka.tiles_n + wi.tn;
+      const size_t pstride = (size_t)ka.mt * TILE_M * BN;
+      float* part = ka.splits > 1 ? ka.partial + ((size_t)tile_id * ka.splits + wi.ks) * pstride : nullptr;
+      for (int m = 0; m < wi.mt_eff; ++m) {
+        const RowInfo ri = row_info(ka, wi, m, lg * 32 + lane);  // this thread's own row
+        const uint32_t any_ok = __ballot_sync(0xffffffffu, ri.ok);
+        for (int cb = 0; cb < BN; cb += 32) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ka.acc_cols + m * BN + cb);
+          const int ncols = min(32, BN - cb);  // BN is a multiple of 16
+          if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
+          tc_wait_ld();
+          if (m == wi.mt_eff - 1 && cb + 32 >= BN) {  // last TMEM read of this buffer: hand it back to the MMA warp
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(accE_u + 8 * buf);
+          }
+          if (!any_ok) continue;
+          const int nb = n0 + cb;
+          if (g.transposed && !part) {
+            // out[b][n][pix]: consecutive rows are consecutive addresses -> already coalesced per column
+            if (ri.ok) {
+              const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
+              for (int j = 0; j < ncols; ++j) {
+                const int n = nb + j;
+                if (n >= g.N) break;
+                finish1(g, __uint_as_float(r[j]), ri.base + (long long)n * g.out_n_stride, n, rb);
+              }
+            }
+            continue;
+          }
+          // transpose through shared memory: thread = row  ->  lane = column group
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (j < ncols)
+              *reinterpret_cast<float4*>(stg + lane * STAGE_LD + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          __syncwarp();
+          if (part) {
+            // raw partial sums, row-major [mt*128][BN]
+            if (c4 < ncols) {
+#pragma unroll
+              for (int r0 = 0; r0 < 32; r0 += 4) {
+                const int rr = r0 + rsub;
+                if ((any_ok >> rr) & 1u)
+                  __stcg(reinterpret_cast<float4*>(part + ((size_t)(m * TILE_M + lg * 32 + rr)) * BN + cb + c4),
+                         *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4));
+              }
+            }
+          } else if (ka.vec_ok) {
+            // 4 rows x 8 float4 per pass; all residual / row-bias loads of the 8 passes are issued before the first
+            // store so one memory latency covers the whole 32x32 block (stores may alias the residual for ptxas)
+            const int n = nb + c4;
+            const bool col_ok = c4 < ncols && n < g.N;
+            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (col_ok && g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+            long long idx[8];
+            float4 rv[8];
+            int bbs[8];
+            uint32_t okm = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + rsub;
+              const long long base = __shfl_sync(0xffffffffu, ri.base, rr);
+              const long long fl = __shfl_sync(0xffffffffu, ri.flat0, rr) + n;
+              const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
+              const bool ok = col_ok && ((any_ok >> rr) & 1u) && fl >= g.out_lo && fl < g.out_hi;
+              idx[i] = base + n;
+              bbs[i] = bb;
+              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok) {
+                okm |= 1u << i;
+                if (g.resid) rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + idx[i]));
+                if (g.rowbias) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bb * g.rowbias_stride + n));
+                  // the row bias is added before the activation, the residual after it: keep them apart
+                  if (!g.act) { rv[i].x += b4.x; rv[i].y += b4.y; rv[i].z += b4.z; rv[i].w += b4.w; }
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (!((okm >> i) & 1u)) continue;
+              const int rr = 4 * i + rsub;
+              const float4 a = *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4);
+              float v[4] = {fmaf(a.x, g.alpha, bias4.x), fmaf(a.y, g.alpha, bias4.y), fmaf(a.z, g.alpha, bias4.z), fmaf(a.w, g.alpha, bias4.w)};
+              if (g.act) {
+                if (g.rowbias) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bbs[i] * g.rowbias_stride + n));
+                  v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = egr_apply_act(v[u], g.act);
+              }
+              v[0] += rv[i].x; v[1] += rv[i].y; v[2] += rv[i].z; v[3] += rv[i].w;
+              if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx[i]) = make_float4(v[0], v[1], v[2], v[3]);
+              if (g.out16) {
+                __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                uint2 pk;
+                pk.x = *reinterpret_cast<unsigned*>(&h0);
+                pk.y = *reinterpret_cast<unsigned*>(&h1);
+                *reinterpret_cast<uint2*>(g.out16 + idx[i]) = pk;
+              }
+            }
+          } else {
+            for (int rr = 0; rr < 32; ++rr) {
+              const long long base = __shfl_sync(0xffffffffu, ri.base, rr);
+              const long long fl0 = __shfl_sync(0xffffffffu, ri.flat0, rr);
+              const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
+              const int n = nb + lane;
+              const long long fl = fl0 + n;
+              if (((any_ok >> rr) & 1u) && lane < ncols && n < g.N && fl >= g.out_lo && fl < g.out_hi) {
+                const float* rb = g.rowbias ? g.rowbias + (long long)bb * g.rowbias_stride : nullptr;
+                finish1(g, stg[rr * STAGE_LD + lane], base + n, n, rb);
+              }
+            }
+          }
+          __syncwarp();
+        }
       }
-      __syncwarp();  // reconverge before the next .sync.aligned TMEM load
-    }
+      if (part) {
+        // split-K: the last CTA to finish this output tile reduces all partials in split order
+        __threadfence();
+        epi_bar_sync();
+        if (threadIdx.x == 64) {
+          const unsigned int old = atomicAdd(ka.counters + tile_id, 1u);
+          const unsigned int last = (old == (unsigned int)(ka.splits - 1)) ? 1u : 0u;
+          if (last) ka.counters[tile_id] = 0u;  // ready for the next launch
+          *last_flag = last;
+        }
+        epi_bar_sync();
+        const bool is_last = *last_flag != 0u;
+        epi_bar_sync();  // everyone has read the flag before a later item may overwrite it
+        if (is_last) {
+          __threadfence();
+          // all 128 epilogue threads share the valid elements, whatever TMEM lane group produced them
+          const float* pt = ka.partial + (size_t)tile_id * ka.splits * pstride;
+          const int c4n = BN >> 2;
+          const int total = wi.mt_eff * TILE_M * c4n;
+          for (int e = (int)threadIdx.x - 64; e < total; e += 128) {
+            const int row = e / c4n, c = (e - row * c4n) * 4;
+            const int m = row >> 7;
+            const RowInfo ri = row_info(ka, wi, m, row & 127);
+            const int n = n0 + c;
+            if (!ri.ok || n >= g.N) continue;
+            const float* pe = pt + (size_t)row * BN + c;
+            float4 acc = __ldcg(reinterpret_cast<const float4*>(pe));
+            int sidx = 1;
+            for (; sidx + 4 <= ka.splits; sidx += 4) {  // four independent loads in flight, summed in split order
+              const float4 v0 = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)sidx * pstride));
+              const float4 v1 = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)(sidx + 1) * pstride));
+              const float4 v2 = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)(sidx + 2) * pstride));
+              const float4 v3 = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)(sidx + 3) * pstride));
+              acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
+              acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
+              acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
+              acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
+            }
+            for (; sidx < ka.splits; ++sidx) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)sidx * pstride));
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
+            const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+            if (g.transposed) {
+              for (int u = 0; u < 4 && n + u < g.N; ++u) finish1(g, a4[u], ri.base + (long long)(n + u) * g.out_n_stride, n + u, rb);
+            } else if (ka.vec_ok) {
+              const long long fl = ri.flat0 + n;
+              if (fl >= g.out_lo && fl < g.out_hi) finish4(g, acc, ri.base + n, n, rb);
+            } else {
+              for (int u = 0; u < 4 && n + u < g.N; ++u) {
+                const long long fl = ri.flat0 + n + u;
+                if (fl >= g.out_lo && fl < g.out_hi) finish1(g, a4[u], ri.base + n + u, n + u, rb);
+              }
+            }
+          }
+        }
+      }
+      if (tr && threadIdx.x == 64 && it < 6) tr[3 + 2 * it] = clock64();
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (ka.trace && threadIdx.x == 64 && blockIdx.x < 148) {  // per-CTA wall-clock end (ns), after the barrier released
+    unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    ka.trace[1100 + 2 * blockIdx.x + 1] = gt;
+  }
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)ka.tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -402,114 +707,190 @@ static int encode_map(CUtensorMap* tm, void* base, int rank, const long long* di
   return EGR_OK;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   int rc = tc_global_init();
   if (rc) return rc;
   TcPrepared* p = new TcPrepared();
+  memset(&p->ka, 0, sizeof(p->ka));
+  TcKernelArgs& ka = p->ka;
   View a;
-  rc = gemm_args_from_op(s, op, &p->g, &p->taps, &a);
+  rc = gemm_args_from_op(s, op, &ka.g, &ka.taps, &a);
   if (rc) { delete p; return rc; }
-  GemmArgs& g = p->g;
+  GemmArgs& g = ka.g;
   snprintf(p->name, sizeof(p->name), "%s", op.name);
   auto bail = [&](int code) { delete p; return code; };
   if (a.elem != 1) return bail(fail(EGR_ERR_ARG, "%s: tensor-core path needs an f16 A operand", op.name));
-  if (g.block_n < 16 || g.block_n > 256 || g.block_n % 16) return bail(fail(EGR_ERR_ARG, "%s: BLOCK_N=%d must be a multiple of 16 in [16,256]", op.name, g.block_n));
+  if (g.N % 16) return bail(fail(EGR_ERR_ARG, "%s: N=%d must be a multiple of 16", op.name, g.N));
   if (op.i[EGR_I_KBLOCK] && op.i[EGR_I_KBLOCK] != KBLK) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: only K block 64 is built", op.name));
-  // halo mode: every tap moves along dimW only and the tile is 128 consecutive W positions
+  if (g.dimW == g.dimH || g.dimW == g.dimB || g.dimH == g.dimB)
+    return bail(fail(EGR_ERR_ARG, "%s: tile dims must be distinct A dims", op.name));
+  if (g.wz_batch && g.bb != 1) return bail(fail(EGR_ERR_ARG, "%s: batch-indexed B operand needs BB == 1", op.name));
+  const int sms = devinfo().sm_count ? devinfo().sm_count : 148;
   const int kchunks = ceil_div(g.K, KBLK);
-  bool halo = g.ntaps > 1 && !g.wz_batch && g.bw == 128 && g.bh == 1 && g.bb == 1 && getenv("EGR_TC_NO_HALO") == nullptr;
+
+  // ---- halo mode: every tap moves along dimW only and the tile is 128 consecutive W positions
+  bool halo = g.ntaps > 1 && !g.wz_batch && g.bw == 128 && g.bh == 1 && g.bb == 1 && env_int("EGR_TC_NO_HALO", 0) == 0;
   int tmin = 0, tmax = 0;
-  for (int t = 0; t < g.ntaps && halo; ++t) {
+  for (int t = 0; t < g.ntaps; ++t) {
     for (int d = 0; d < 5; ++d)
-      if (d != g.dimW && p->taps.t[t][d] != 0) halo = false;
-    const int o = p->taps.t[t][g.dimW];
+      if (d != g.dimW && ka.taps.t[t][d] != 0) halo = false;
+    const int o = ka.taps.t[t][g.dimW];
+    ka.tapw[t] = (short)o;
     tmin = o < tmin ? o : tmin; tmax = o > tmax ? o : tmax;
   }
   if (halo && tmax - tmin > 128) halo = false;
+  if (!halo) { tmin = 0; tmax = 0; }
   const int tiles_w128 = ceil_div(g.Wo, g.bw), tiles_h = ceil_div(g.Ho, g.bh), tiles_b = ceil_div(g.Bo, g.bb);
   const int tiles1 = tiles_w128 * tiles_h * tiles_b;
-  const int ntn = ceil_div(g.N, g.block_n);
-  const int sms = devinfo().sm_count ? devinfo().sm_count : 148;
-  // two sub-tiles per CTA (shared B loads) when that still leaves at least ~a wave of CTAs
-  int mt = 1;
-  if (!g.wz_batch && g.block_n <= 256 && getenv("EGR_TC_NO_MT2") == nullptr) {
-    const long long ctas2 = halo ? (long long)ceil_div(g.Wo, 256) * tiles_h * tiles_b * ntn : (long long)ceil_div(tiles1, 2) * ntn;
-    if (ctas2 >= sms) mt = 2;
+  const int n_outer = halo ? kchunks : g.ntaps * kchunks;
+  const int n_inner = halo ? g.ntaps : 1;
+
+  // ---- split-K: a function of the per-item geometry only (batch-invariant results)
+  const long long pix_item = (long long)g.Wo * g.Ho;
+  const int units = ceil_div(pix_item, TILE_M) * ceil_div(g.N, 128);  // 128x128 output blocks of one batch item
+  int splits = 1;
+  if (!g.wz_batch && env_int("EGR_TC_NO_SPLITK", 0) == 0) {
+    splits = sms / (units > 0 ? units : 1);
+    if (splits > MAX_SPLITS) splits = MAX_SPLITS;
+    if (splits > n_outer / 3) splits = n_outer / 3;  // at least three outer steps per split
+    if (splits < 1) splits = 1;
   }
-  p->mt = mt; p->halo = halo ? 1 : 0; p->kchunks = kchunks; p->tmin = tmin;
-  p->tiles = tiles1;
-  p->tiles_w = halo ? ceil_div(g.Wo, 128 * mt) : tiles_w128;
+  if (env_int("EGR_TC_SPLITS", 0) > 0) splits = env_int("EGR_TC_SPLITS", 0) > n_outer ? n_outer : env_int("EGR_TC_SPLITS", 0);
+  const int ops = ceil_div(n_outer, splits);
+  splits = ceil_div(n_outer, ops);  // no empty split
+
+  // ---- BLOCK_N and sub-tiles per CTA: cheapest (waves x per-item cycles) under a coarse cost model
+  int bn = 0, mt = 1;
+  {
+    const int cands[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
+    double best = 1e30;
+    for (int c : cands) {
+      if (g.N % c) continue;
+      for (int m = 1; m <= 2; ++m) {
+        if (m * c > 256) continue;
+        if (m == 2 && (g.wz_batch || env_int("EGR_TC_NO_MT2", 0))) continue;
+        if (splits > 1 && (m == 2 || c > 128)) continue;  // bounded partial-tile workspace
+        const long long tiles_m = halo ? (long long)ceil_div(g.Wo, TILE_M * m) * tiles_h * tiles_b : ceil_div(tiles1, m);
+        const long long ctas = tiles_m * (g.N / c) * splits;
+        const long long waves = (ctas + sms - 1) / sms;
+        // per k-step: MMA pace (N < 64 still costs a 64-column pass) vs the L2->SM stream at ~48 B/clk/SM
+        const double a_bytes = halo ? (double)(TILE_M * m + (tmax - tmin)) * 128.0 / n_inner : (double)m * A_BOX_BYTES;
+        const double step_mma = (double)m * 4.0 * (c > 64 ? c : 64) / 2.0;
+        const double step_mem = (a_bytes + c * 128.0) / 48.0;
+        const double step = step_mma > step_mem ? step_mma : step_mem;
+        const double epi = 600.0 + (double)m * c * 14.0;
+        const double item = (double)ops * n_inner * step + 1500.0;
+        const double cost = (double)waves * (item > epi ? item : epi) + epi;
+        if (cost < best) { best = cost; bn = c; mt = m; }
+      }
+    }
+    if (bn == 0) return bail(fail(EGR_ERR_ARG, "%s: no BLOCK_N fits N=%d", op.name, g.N));
+  }
+  if (env_int("EGR_TC_BN", 0) > 0 && g.N % env_int("EGR_TC_BN", 0) == 0) { bn = env_int("EGR_TC_BN", 0); if (mt * bn > 256) mt = 1; }
+  g.block_n = bn;
+
+  ka.mt = mt; ka.halo = halo ? 1 : 0; ka.kchunks = kchunks; ka.tmin = tmin;
+  ka.n_outer = n_outer; ka.n_inner = n_inner;
+  ka.tiles1 = tiles1;
+  ka.tiles_w = halo ? ceil_div(g.Wo, TILE_M * mt) : tiles_w128;
+  ka.tiles_h = tiles_h;
+  ka.tiles_m = halo ? ka.tiles_w * tiles_h * tiles_b : ceil_div(tiles1, mt);
+  ka.tiles_n = g.N / bn;
+  ka.splits = splits; ka.outer_per_split = ops;
+  ka.n_work = ka.tiles_m * ka.tiles_n * splits;
+  ka.acc_cols = mt * bn;
   if (halo) {
-    p->n_outer = kchunks; p->n_inner = g.ntaps;
-    p->boxA_bytes = HALO_BOX_ROWS * KBLK * 2;
-    p->nboxA = ceil_div(128 * mt + (tmax - tmin), HALO_BOX_ROWS);
+    ka.boxA_bytes = HALO_BOX_ROWS * KBLK * 2;
+    ka.nboxA = ceil_div(TILE_M * mt + (tmax - tmin), HALO_BOX_ROWS);
   } else {
-    p->n_outer = g.ntaps * kchunks; p->n_inner = 1;
-    p->boxA_bytes = A_STAGE_BYTES;
-    p->nboxA = mt;
+    ka.boxA_bytes = A_BOX_BYTES;
+    ka.nboxA = mt;
   }
-  p->a_stage_bytes = p->nboxA * p->boxA_bytes;
-  p->b_stage_bytes = g.block_n * KBLK * 2;
+  ka.a_stage_bytes = ka.nboxA * ka.boxA_bytes;
+  ka.b_stage_bytes = bn * KBLK * 2;
   // A map: always rank 5 (missing dims are size 1 with a harmless stride)
   long long dim[5], str[5]; int box[5];
   for (int d = 0; d < 5; ++d) { dim[d] = a.dim[d]; str[d] = a.stride[d]; }
   for (int d = a.rank; d < 5; ++d) { dim[d] = 1; str[d] = dim[d - 1] * str[d - 1]; }
   for (int d = 0; d < 5; ++d) box[d] = 1;
   box[0] = KBLK; box[g.dimW] = halo ? HALO_BOX_ROWS : g.bw; box[g.dimH] = g.bh; box[g.dimB] = g.bb;
-  if (g.dimW == g.dimH || g.dimW == g.dimB || g.dimH == g.dimB)
-    return bail(fail(EGR_ERR_ARG, "%s: tile dims must be distinct A dims", op.name));
   rc = encode_map(&p->tmA, const_cast<void*>(a.p), 5, dim, str, box, op.name);
   if (rc) return bail(rc);
   // B map: [K, N, Z]
   long long bdim[3] = {g.K, g.N, g.wz_batch ? (long long)g.Bo : (long long)g.ntaps};
   long long bstr[3] = {1, g.wstride_n, g.wstride_z > 0 ? g.wstride_z : g.wstride_n * g.N};
-  int bbox[3] = {KBLK, g.block_n, 1};
+  int bbox[3] = {KBLK, bn, 1};
   rc = encode_map(&p->tmB, const_cast<void*>(g.W), 3, bdim, bstr, bbox, op.name);
   if (rc) return bail(rc);
-  if (g.wz_batch && g.bb != 1) return bail(fail(EGR_ERR_ARG, "%s: batch-indexed B operand needs BB == 1", op.name));
 
-  // ring depths inside ~200 KB: B first (it is the stream in halo mode), the rest to A
-  const int budget = 200 * 1024;
+  // ---- ring depths: ~195 KB of the 227 KB for the two rings (the rest: epilogue staging, barriers, alignment slack)
+  const int budget = 195 * 1024;
   int SB, SA;
   if (halo) {
-    SB = (96 * 1024) / p->b_stage_bytes; if (SB > 6) SB = 6; if (SB < 2) SB = 2;
-    SA = (budget - SB * p->b_stage_bytes) / p->a_stage_bytes; if (SA > 3) SA = 3;
-    if (SA < 2) { SA = 2; SB = (budget - 2 * p->a_stage_bytes) / p->b_stage_bytes; }
+    SB = (96 * 1024) / ka.b_stage_bytes; if (SB > 8) SB = 8; if (SB < 2) SB = 2;
+    SA = (budget - SB * ka.b_stage_bytes) / ka.a_stage_bytes; if (SA > 3) SA = 3;
+    if (SA < 2) { SA = 2; SB = (budget - 2 * ka.a_stage_bytes) / ka.b_stage_bytes; if (SB > 8) SB = 8; }
     if (SB < 2) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: halo tile does not fit shared memory", op.name));
   } else {
-    SA = budget / (p->a_stage_bytes + p->b_stage_bytes); if (SA > 8) SA = 8; if (SA < 2) SA = 2;
+    SA = budget / (ka.a_stage_bytes + ka.b_stage_bytes); if (SA > 10) SA = 10; if (SA < 2) SA = 2;
     SB = SA;
   }
-  p->SA = SA; p->SB = SB;
-  p->smem_bytes = SA * p->a_stage_bytes + SB * p->b_stage_bytes + 1024 /*align slack*/ + (2 * SA + 2 * SB + 1) * 8 + 16;
+  ka.SA = SA; ka.SB = SB;
+  p->smem_bytes = SA * ka.a_stage_bytes + SB * ka.b_stage_bytes + 4 * STAGE_BYTES_PER_WARP + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
   if (p->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: %d B of shared memory needed", op.name, p->smem_bytes));
-  int cols = 32;
-  while (cols < mt * g.block_n) cols <<= 1;
-  p->tmem_cols = cols;
-  const int ctas_m = halo ? p->tiles_w * tiles_h * tiles_b : ceil_div(tiles1, mt);
-  p->grid = dim3(ctas_m, ntn, 1);
-  // vector epilogue needs 16-byte aligned rows of 4
+  p->grid = ka.n_work < sms ? ka.n_work : sms;
+  p->partial_bytes = splits > 1 ? (size_t)ka.tiles_m * ka.tiles_n * splits * mt * TILE_M * bn * sizeof(float) : 0;
+  p->n_counters = splits > 1 ? ka.tiles_m * ka.tiles_n : 0;
+  // vector epilogue needs 16-byte aligned groups of 4 columns
   bool vec = !g.transposed && (g.N % 4 == 0) && (g.out_pix_stride % 4 == 0) && (g.out_batch_stride % 4 == 0) &&
              (g.out_offset % 4 == 0) && (g.out_lo % 4 == 0) && (g.out_hi % 4 == 0) && (g.rowbias_stride % 4 == 0);
   auto al = [](const void* q, int a) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % a == 0; };
   vec = vec && al(g.out32, 16) && al(g.out16, 8) && al(g.resid, 16) && al(g.bias, 16) && al(g.rowbias, 16);
-  p->vec_ok = vec ? 1 : 0;
+  ka.vec_ok = vec ? 1 : 0;
   *out = p;
   return EGR_OK;
 }
 
+size_t egr::tc_partial_bytes(const TcPrepared* p) { return p->partial_bytes; }
+int egr::tc_num_counters(const TcPrepared* p) { return p->n_counters; }
+void egr::tc_bind_scratch(TcPrepared* p, float* partial, unsigned int* counters) {
+  p->ka.partial = partial;
+  p->ka.counters = counters;
+}
+
+static unsigned long long* g_trace_dev = nullptr;
+// debug hook (not part of the public header): first call enables the per-launch clock trace of CTA 0, later calls
+// read it back and clear it
+extern "C" int egr_debug_tc_trace(unsigned long long* h_out, int n) {
+  if (!g_trace_dev) {
+    if (cudaMalloc(&g_trace_dev, 1400 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+    cudaMemset(g_trace_dev, 0, 1400 * sizeof(unsigned long long));
+    return 0;
+  }
+  cudaDeviceSynchronize();
+  if (h_out && n > 0) cudaMemcpy(h_out, g_trace_dev, sizeof(unsigned long long) * (n > 1400 ? 1400 : n), cudaMemcpyDeviceToHost);
+  cudaMemset(g_trace_dev, 0, 1400 * sizeof(unsigned long long));
+  return 0;
+}
+
 int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
-  TcKernelArgs ka;
-  ka.g = p->g;
-  ka.taps = p->taps;
-  ka.mt = p->mt; ka.halo = p->halo; ka.n_outer = p->n_outer; ka.n_inner = p->n_inner; ka.kchunks = p->kchunks;
-  ka.nboxA = p->nboxA; ka.boxA_bytes = p->boxA_bytes; ka.a_stage_bytes = p->a_stage_bytes; ka.b_stage_bytes = p->b_stage_bytes;
-  ka.SA = p->SA; ka.SB = p->SB; ka.tmin = p->tmin; ka.tiles = p->tiles; ka.tiles_w = p->tiles_w;
-  ka.tmem_cols = p->tmem_cols;
-  ka.vec_ok = p->vec_ok;
-  gemm_tc_kernel<<<p->grid, 192, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
+  if (p->ka.splits > 1 && (!p->ka.partial || !p->ka.counters))
+    return fail(EGR_ERR_STATE, "%s: split-K scratch not bound", p->name);
+  TcKernelArgs ka = p->ka;
+  ka.trace = g_trace_dev;
+  gemm_tc_kernel<<<p->grid, 224, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
   EGR_CHECK_LAUNCH(p->name);
   return EGR_OK;
+}
+
+void egr::tc_describe(const TcPrepared* p, int* o) {
+  o[0] = p->ka.g.block_n; o[1] = p->ka.mt; o[2] = p->ka.splits; o[3] = p->ka.halo; o[4] = p->ka.n_work; o[5] = p->grid;
+  o[6] = p->ka.SA; o[7] = p->ka.SB;
 }
 
 void egr::tc_free(TcPrepared* p) { delete p; }

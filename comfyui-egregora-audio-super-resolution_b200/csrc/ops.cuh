@@ -66,6 +66,11 @@ struct TcPrepared;  // tensor maps + launch geometry, built once per op at plan 
 int  tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out);
 int  tc_launch(const TcPrepared* p, cudaStream_t st);
 void tc_free(TcPrepared* p);
+// split-K scratch (library-owned, shared by all ops of a plan: they run in stream order)
+size_t tc_partial_bytes(const TcPrepared* p);
+int    tc_num_counters(const TcPrepared* p);
+void   tc_bind_scratch(TcPrepared* p, float* partial, unsigned int* counters);
+void   tc_describe(const TcPrepared* p, int* out8);  // block_n, mt, splits, halo, n_work, grid, SA, SB
 int  tc_global_init();
 
 }  // namespace egr

@@ -11,6 +11,7 @@ struct egr_plan {
   std::vector<egr_op> ops;
   std::vector<TcPrepared*> tc;  // per op, nullptr unless GEMM_TC
   Spaces sp;
+  void* scratch = nullptr;      // split-K partial tiles followed by the per-tile arrival counters (library-owned)
 };
 
 static int run_op(const egr_plan* p, int i, cudaStream_t st) {
@@ -65,8 +66,32 @@ extern "C" int egr_plan_create(const egr_op* h_ops, int n_ops, void* d_workspace
       if (rc) { egr_plan_destroy(p); return rc; }
     }
   }
+  // split-K scratch: ops run in stream order, so one buffer sized for the largest op serves them all
+  size_t part = 0; int ctr = 0;
+  for (TcPrepared* t : p->tc)
+    if (t) { part = tc_partial_bytes(t) > part ? tc_partial_bytes(t) : part; ctr = tc_num_counters(t) > ctr ? tc_num_counters(t) : ctr; }
+  if (part > 0) {
+    part = (part + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&p->scratch, part + (size_t)ctr * sizeof(unsigned int));
+    if (e != cudaSuccess) {
+      int rc = fail(EGR_ERR_CUDA, "egr_plan_create: cudaMalloc of %zu B split-K scratch failed: %s", part, cudaGetErrorString(e));
+      egr_plan_destroy(p);
+      return rc;
+    }
+    unsigned int* counters = reinterpret_cast<unsigned int*>(static_cast<char*>(p->scratch) + part);
+    cudaMemset(counters, 0, (size_t)ctr * sizeof(unsigned int));
+    for (TcPrepared* t : p->tc)
+      if (t && tc_partial_bytes(t) > 0) tc_bind_scratch(t, static_cast<float*>(p->scratch), counters);
+  }
   *out = p;
   return EGR_OK;
+}
+
+// debug hook (not in the public header): tile configuration the library chose for op `op_index`
+extern "C" int egr_debug_tc_config(const egr_plan* plan, int op_index, int* out8) {
+  if (!plan || op_index < 0 || op_index >= (int)plan->ops.size() || !plan->tc[op_index]) return -1;
+  tc_describe(plan->tc[op_index], out8);
+  return 0;
 }
 
 extern "C" int egr_plan_run(egr_plan* plan, int first, int last, void* stream) {
@@ -110,5 +135,6 @@ extern "C" void egr_plan_destroy(egr_plan* plan) {
   if (!plan) return;
   for (TcPrepared* t : plan->tc)
     if (t) tc_free(t);
+  if (plan->scratch) cudaFree(plan->scratch);
   delete plan;
 }

@@ -47,6 +47,62 @@ def test_conv2d_tc(cin, cout, H, W, B, k, cuda_dev):
     assert rel_err(mp.read(y), ref) < TC_TOL
 
 
+@pytest.mark.parametrize("cin,cout,H,W,B,k", [
+    (640, 640, 8, 4, 1, 3),      # UNet bottom: 32 pixels, K = 5760 -> split-K, last-arriver reduction
+    (640, 640, 8, 4, 3, 1),      # same tile shared by 3 batch items (bb = 4)
+    (384, 384, 16, 8, 2, 3),     # one 128-row tile per item, 2 items
+    (1280, 640, 8, 4, 1, 3),     # concat-width K
+    (256, 2048, 32, 16, 1, 1),   # wide N (GEGLU projection), 4 m-tiles
+    (128, 128, 64, 32, 1, 3),    # 16 m-tiles, 18 k-steps
+])
+def test_conv2d_tc_splitk(cin, cout, H, W, B, k, cuda_dev):
+    Wt = {"c.weight": _w((cout, cin, k, k), 1), "c.bias": _x((cout,), 2) * 0.1}
+    x = _x((B, cin, H, W), 3)
+    res = _x((B, cout, H, W), 4)
+    mp = MiniPlan(Wt)
+    xi, ri = mp.input(x), mp.input(res)
+    y = mp.be.conv2d(xi, "c", cin, cout, k, add=ri)
+    y16 = mp.be.conv2d(xi, "c", cin, cout, k, out="f16", act="silu")
+    mp.run_gpu()
+    ref = F.conv2d(x, Wt["c.weight"], Wt["c.bias"], padding=k // 2)
+    assert rel_err(mp.read(y), ref + res) < TC_TOL
+    assert rel_err(mp.read(y16), F.silu(ref)) < TC_TOL
+    # second launch of the same plan ops reuses the arrival counters: must give the same answer
+    mp2 = MiniPlan(Wt)
+    y2 = mp2.be.conv2d(mp2.input(x), "c", cin, cout, k)
+    y3 = mp2.be.conv2d(mp2.input(x), "c", cin, cout, k)
+    mp2.run_gpu()
+    assert torch.equal(mp2.read(y2), mp2.read(y3))  # deterministic reduction order
+
+
+@pytest.mark.parametrize("cin,cout,H,W,B,k", [
+    (32, 64, 256, 128, 2, 3),    # 512 tiles of 128 pixels > 148 SMs: persistent loop, TMEM double buffering
+    (64, 48, 200, 130, 1, 3),    # ragged W (tile tail), N = 48
+    (16, 256, 128, 256, 1, 1),   # BLOCK_N 256 (single sub-tile), 256 tiles
+])
+def test_conv2d_tc_persistent(cin, cout, H, W, B, k, cuda_dev):
+    Wt = {"c.weight": _w((cout, cin, k, k), 1), "c.bias": _x((cout,), 2) * 0.1}
+    x = _x((B, cin, H, W), 3)
+    res = _x((B, cout, H, W), 4)
+    mp = MiniPlan(Wt)
+    y = mp.be.conv2d(mp.input(x), "c", cin, cout, k, add=mp.input(res))
+    mp.run_gpu()
+    ref = F.conv2d(x, Wt["c.weight"], Wt["c.bias"], padding=k // 2) + res
+    assert rel_err(mp.read(y), ref) < TC_TOL
+
+
+@pytest.mark.parametrize("cin,cout,k,d,T,B", [(64, 64, 3, 1, 40000, 2), (96, 96, 11, 5, 50000, 1), (48, 48, 7, 3, 70001, 1)])
+def test_conv1d_tc_persistent(cin, cout, k, d, T, B, cuda_dev):
+    Wt = {"c.weight": _w((cout, cin, k), 1), "c.bias": _x((cout,), 2) * 0.1}
+    x = _x((B, cin, 1, T), 3)
+    res = _x((B, cout, 1, T), 4)
+    mp = MiniPlan(Wt)
+    y = mp.be.conv1d(mp.input(x), "c", cin, cout, k, dilation=d, add=mp.input(res))
+    mp.run_gpu()
+    ref = F.conv1d(x[:, :, 0], Wt["c.weight"], Wt["c.bias"], padding=d * (k // 2), dilation=d) + res[:, :, 0]
+    assert rel_err(mp.read(y)[:, :, 0], ref) < TC_TOL
+
+
 @pytest.mark.parametrize("cin,cout,pad", [(64, 64, "ldm_down"), (128, 128, "same"), (32, 32, "same")])
 def test_conv2d_stride2_tc(cin, cout, pad, cuda_dev):
     Wt = {"c.weight": _w((cout, cin, 3, 3), 1), "c.bias": _x((cout,), 2) * 0.1}
