@@ -7,9 +7,9 @@
 // through a rank-5 TMA tensor map, so every tap is just a shifted box load and zero padding is TMA's
 // out-of-bounds fill — no im2col buffer ever exists in HBM.
 //
-// PERSISTENT, warp-specialised CTA (one per SM, 224 threads) looping over work items (m-tile, n-tile, k-split):
+// PERSISTENT, warp-specialised CTA (one per SM, 256 threads) looping over work items (m-tile, n-tile, k-split):
 //   warp 0 / 6  TMA producers of the A / B rings (cp.async.bulk.tensor, SWIZZLE_128B, expect_tx)  [UTMALDG]
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (M=128, N=BLOCK_N, K=16 f16)   [UTCHMMA]
+//   warp 1 / 7  tcgen05.mma issuers (M=128, K=16 f16), each owning half of the CTA tile; warp 1 allocates TMEM [UTCHMMA]
 //   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> shared-memory transpose -> bias/act/residual ->
 //               row-contiguous (coalesced) vector stores                                         [LDTM]
 // The accumulator is double-buffered in TMEM (2 x MT x BLOCK_N f32 columns of the 512), so the epilogue of
@@ -46,7 +46,7 @@ struct TcKernelArgs {
   GemmArgs g;
   Taps taps;
   short tapw[EGR_MAX_TAPS];  // tap offset along dimW (halo mode)
-  int mt, halo, kchunks, n_outer, n_inner, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin;
+  int mt, halo, n_iss, kchunks, n_outer, n_inner, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin;
   int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
   int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (<= 256)
   int vec_ok;
@@ -269,7 +269,7 @@ __device__ __forceinline__ void finish1(const GemmArgs& g, float acc, long long 
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(224, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB,
                                                           const __grid_constant__ TcKernelArgs ka) {
   extern __shared__ uint8_t smem_raw[];
@@ -298,9 +298,11 @@ __global__ void __launch_bounds__(224, 1) gemm_tc_kernel(const __grid_constant__
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < ka.SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], 1); }
-    for (int s = 0; s < ka.SB; ++s) { mbar_init(&fullB[s], 1); mbar_init(&emptyB[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+    // halo mode: A and B rings advance at different rates and have their own barriers; otherwise the A stage rides
+    // on the B barriers (both producers arrive on fullB, one wait and one commit per k-step for the issuers)
+    for (int s = 0; s < ka.SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], (uint32_t)ka.n_iss); }
+    for (int s = 0; s < ka.SB; ++s) { mbar_init(&fullB[s], ka.halo ? 1u : 2u); mbar_init(&emptyB[s], (uint32_t)ka.n_iss); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], (uint32_t)ka.n_iss); mbar_init(&acc_empty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -318,7 +320,8 @@ __global__ void __launch_bounds__(224, 1) gemm_tc_kernel(const __grid_constant__
     // ============================================================ A producer (whole warp, one elected lane issues)
     if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     __syncwarp();
-    const uint32_t ringA_u = smem_u32(ringA), fullA_u = smem_u32(fullA), emptyA_u = smem_u32(emptyA);
+    const uint32_t ringA_u = smem_u32(ringA);
+    const uint32_t fullA_u = smem_u32(ka.halo ? fullA : fullB), emptyA_u = smem_u32(ka.halo ? emptyA : emptyB);
     int sa = 0;
     uint32_t pa = 0;  // ring phase
     int tcount = 0;
@@ -399,11 +402,22 @@ __global__ void __launch_bounds__(224, 1) gemm_tc_kernel(const __grid_constant__
         if (++kc == ka.kchunks && !ka.halo) { kc = 0; ++tap; }
       }
     }
-  } else if (warp == 1) {
-    // ============================================================ MMA issuer (whole warp, one elected lane issues)
-    {
+  } else if (warp == 1 || warp == 7) {
+    // ============================================================ MMA issuers (whole warp, one elected lane issues)
+    // A UTCHMMA costs ~55 issue cycles whatever its N, and every k-step adds a barrier wait and a commit on top, so
+    // one issuing thread cannot keep the tensor pipe busy at N <= 128.  With two issuers each owns half of the CTA
+    // tile (a sub-tile when MT = 2, a BLOCK_N/2 column half when MT = 1): disjoint TMEM accumulators, so no ordering
+    // between them is needed; stages are released when both have committed (empty barriers count n_iss arrivals).
+    const int u = warp == 1 ? 0 : 1;
+    if (u < ka.n_iss) {
+      const bool split_n = (ka.n_iss == 2 && ka.mt == 1);
+      const int NI = split_n ? (BN >> 1) : BN;  // N of one instruction
+      const int m_lo = (ka.n_iss == 2 && ka.mt == 2) ? u : 0;
+      const int m_hi = (ka.n_iss == 2 && ka.mt == 2) ? u + 1 : ka.mt;
+      const uint32_t b_off = split_n ? (uint32_t)(u * NI * 128) : 0u;  // rows of the B stage owned by this issuer
+      const uint32_t c_off = split_n ? (uint32_t)(u * NI) : 0u;          // accumulator columns owned by this issuer
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(NI >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
       const uint32_t ringA_u = smem_u32(ringA), ringB_u = smem_u32(ringB);
       const uint32_t fullA_u = smem_u32(fullA), emptyA_u = smem_u32(emptyA), fullB_u = smem_u32(fullB), emptyB_u = smem_u32(emptyB);
       const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
@@ -414,24 +428,24 @@ __global__ void __launch_bounds__(224, 1) gemm_tc_kernel(const __grid_constant__
         WorkItem wi;
         decode_work(ka, w, wi);
         const int buf = it & 1;
-        const uint32_t acc = tmem_base + (uint32_t)(buf * ka.acc_cols);
+        const uint32_t acc = tmem_base + (uint32_t)(buf * ka.acc_cols) + c_off;
         mbar_wait(accE_u + 8 * buf, (((uint32_t)(it >> 1)) & 1u) ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
         uint32_t first = 0;  // 0 until the first MMA of this item has been issued (accumulate flag)
         for (int io = wi.o_begin; io < wi.o_end; ++io) {
-          mbar_wait(fullA_u + 8 * sa, pa);
+          if (ka.halo) mbar_wait(fullA_u + 8 * sa, pa);  // otherwise A rides on the B barriers (same stage index)
           const uint32_t aBase = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
           for (int ii = 0; ii < ka.n_inner; ++ii) {
             mbar_wait(fullB_u + 8 * sb, pb);
             tc_fence_after();
-            const uint64_t bdesc = make_smem_desc(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes);
+            const uint64_t bdesc = make_smem_desc(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes + b_off);
             const uint32_t shift = ka.halo ? (uint32_t)((ka.tapw[ii] - ka.tmin) * 128) : 0u;
             const bool lastB = (ii == ka.n_inner - 1);
             if (elect_one()) {
-              if (tr && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
+              if (tr && u == 0 && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
-                if (m < wi.mt_eff) {
+                if (m >= m_lo && m < m_hi && m < wi.mt_eff) {
                   const uint64_t adesc = make_smem_desc(aBase + shift + (uint32_t)m * A_BOX_BYTES);
 #pragma unroll
                   for (int k = 0; k < KBLK / 16; ++k) {
@@ -442,9 +456,9 @@ __global__ void __launch_bounds__(224, 1) gemm_tc_kernel(const __grid_constant__
               }
               tc_commit(emptyB_u + 8 * sb);
               if (lastB) {
-                tc_commit(emptyA_u + 8 * sa);
+                if (ka.halo) tc_commit(emptyA_u + 8 * sa);
                 if (io == wi.o_end - 1) tc_commit(accF_u + 8 * buf);
-                if (tr && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
+                if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
               }
             }
             __syncwarp();
@@ -795,6 +809,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   g.block_n = bn;
 
   ka.mt = mt; ka.halo = halo ? 1 : 0; ka.kchunks = kchunks; ka.tmin = tmin;
+  ka.n_iss = (env_int("EGR_TC_ONE_ISSUER", 0) == 0 && (mt == 2 || bn % 32 == 0)) ? 2 : 1;
   ka.n_outer = n_outer; ka.n_inner = n_inner;
   ka.tiles1 = tiles1;
   ka.tiles_w = halo ? ceil_div(g.Wo, TILE_M * mt) : tiles_w128;
@@ -883,7 +898,7 @@ int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
     return fail(EGR_ERR_STATE, "%s: split-K scratch not bound", p->name);
   TcKernelArgs ka = p->ka;
   ka.trace = g_trace_dev;
-  gemm_tc_kernel<<<p->grid, 224, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
+  gemm_tc_kernel<<<p->grid, 256, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
   EGR_CHECK_LAUNCH(p->name);
   return EGR_OK;
 }
