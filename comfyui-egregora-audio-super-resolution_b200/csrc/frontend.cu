@@ -5,6 +5,7 @@
 // memory, transformed by an in-smem Stockham FFT (real input packed as an n_fft/2 complex transform + split),
 // reduced to magnitudes and projected on the (sparse, triangular) mel filters without leaving the SM, so the
 // only HBM traffic is 4*hop bytes in (frames overlap in L2) and 4*n_mels bytes out per frame.
+#include <cstdlib>
 #include "ops.cuh"
 
 using namespace egr;
@@ -117,12 +118,16 @@ int egr::launch_stft_mel(const Spaces& s, const egr_op& op, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // Low-pass: cutoff bin = (#bins whose cumulative energy < percentile*total) - 1, then scipy-style
 // sosfiltfilt (odd extension of 3*(2*nsec+1) samples, sosfilt_zi initial conditions, forward + backward) in
-// f64.  The IIR recurrence is parallelised over time: the whole cascade is one linear system, so each of the
-// 256 threads runs a chunk from zero state, a 256-step serial scan stitches chunk boundary states with the
-// chunk transition matrix, and a second sweep re-runs every chunk from its true initial state.
+// f64.  The IIR recurrence is parallelised over time: the whole cascade is one linear system with 2*nsec
+// states, so each of the 1024 threads of a CTA (one CTA per batch item) runs its chunk from zero state, a
+// two-level scan (32 lanes x 32 warps, with M and M^32) turns the chunk end states into true chunk start states,
+// and a second sweep re-runs every chunk from there.  Between the passes the signal lives in a chunk-transposed
+// f64 scratch ([step within chunk][chunk]), so every per-step access of the 1024 threads is one contiguous 8 KB
+// row; the natural-order input / output is transposed through 32x32 shared-memory tiles.
 // ------------------------------------------------------------------------------------------------
-#define LP_THREADS 256
+#define LP_NT 1024
 #define LP_MAXSEC 4
+#define LP_NS (2 * LP_MAXSEC)
 
 struct SosState { double z[LP_MAXSEC][2]; };
 
@@ -139,94 +144,219 @@ __device__ __forceinline__ double sos_step(const double (*sos)[6], int nsec, Sos
   return x;
 }
 
-// one direction of filtfilt over the (virtually) extended signal of length Lx; `get(n)` supplies input n.
-template <class In, class Out>
-__device__ void lp_sweep(const double (*sos)[6], const double (*zi)[2], int nsec, int Lx, In get, Out put,
-                         double (*Mx)[2 * LP_MAXSEC], double (*ends)[2 * LP_MAXSEC]) {
+struct LpShared {
+  double sos[LP_MAXSEC][6];
+  double zi[LP_MAXSEC][2];
+  double M1[LP_NS][LP_NS];    // state transition of one chunk
+  double M32[LP_NS][LP_NS];   // ... of 32 chunks
+  double tmp[LP_NS][LP_NS];
+  double ends[LP_NT + 1][LP_NS];
+  double wtot[33][LP_NS];
+  float tile[32][32][33];
+  int bin, dbg;
+};
+
+// r = M * v (+ add)
+__device__ __forceinline__ void lp_matvec(const double (*M)[LP_NS], const double* v, const double* add, double* r, int ns2) {
+  for (int i = 0; i < ns2; ++i) {
+    double a = add ? add[i] : 0.0;
+    for (int c = 0; c < ns2; ++c) a = fma(M[i][c], v[c], a);
+    r[i] = a;
+  }
+}
+
+// One direction of filtfilt over the transposed scratch `buf` (in place).  REV: thread r walks positions
+// Lx-1-(r*Lc+j), i.e. the time-reversed signal, reading what the forward sweep wrote.
+template <bool REV>
+__device__ void lp_sweep(LpShared& sh, int nsec, int Lx, int Lc, double* __restrict__ buf) {
   const int tid = threadIdx.x, ns2 = 2 * nsec;
-  const int Lc = (Lx + LP_THREADS - 1) / LP_THREADS;
-  // transition matrix of a full chunk: column k = response of the state to unit state k, zero input
+  const long long c0 = clock64();
+  // chunk transition matrix: column k = response of the state to unit state k under zero input
   if (tid < ns2) {
     SosState s;
     for (int i = 0; i < LP_MAXSEC; ++i) s.z[i][0] = s.z[i][1] = 0.0;
     s.z[tid >> 1][tid & 1] = 1.0;
-    for (int n = 0; n < Lc; ++n) sos_step(sos, nsec, s, 0.0);
-    for (int r = 0; r < ns2; ++r) Mx[r][tid] = s.z[r >> 1][r & 1];
+    for (int n = 0; n < Lc; ++n) sos_step(sh.sos, nsec, s, 0.0);
+    for (int r = 0; r < ns2; ++r) sh.M1[r][tid] = s.z[r >> 1][r & 1];
   }
-  const int lo = tid * Lc, hi = min(Lx, lo + Lc);
+  // this thread's positions: m = tid*Lc + j (sweep order), n = REV ? Lx-1-m : m (storage order)
+  const int m_lo = tid * Lc, m_hi = min(Lx, m_lo + Lc);
+  int q0, l0;  // transposed coordinates of the first position: n = q*Lc + l
+  if (!REV) { q0 = tid; l0 = 0; }
+  else { const int n0 = Lx - 1 - m_lo; q0 = n0 >= 0 ? n0 / Lc : 0; l0 = n0 >= 0 ? n0 - q0 * Lc : 0; }
+  auto run = [&](SosState& s, bool store) {
+    int q = q0, l = l0;
+    for (int m = m_lo; m < m_hi; ++m) {
+      double* p = buf + (size_t)l * LP_NT + q;
+      const double y = sos_step(sh.sos, nsec, s, *p);
+      if (store) *p = y;
+      if (!REV) ++l;
+      else if (--l < 0) { l = Lc - 1; --q; }
+    }
+  };
   {
     SosState s;
     for (int i = 0; i < LP_MAXSEC; ++i) s.z[i][0] = s.z[i][1] = 0.0;
-    for (int n = lo; n < hi; ++n) sos_step(sos, nsec, s, get(n));
-    for (int r = 0; r < ns2; ++r) ends[tid + 1][r] = s.z[r >> 1][r & 1];  // zero-state end of chunk tid
+    run(s, false);
+    for (int r = 0; r < ns2; ++r) sh.ends[tid][r] = s.z[r >> 1][r & 1];  // zero-state end of chunk tid
   }
   __syncthreads();
-  if (tid == 0) {  // serial scan: start[i+1] = M*start[i] + end0[i]; `ends[i]` becomes the true start state of chunk i
-    const double x0 = get(0);
-    double cur[2 * LP_MAXSEC];
-    for (int r = 0; r < ns2; ++r) cur[r] = zi[r >> 1][r & 1] * x0;
-    for (int i = 0; i < LP_THREADS; ++i) {
-      double nxt[2 * LP_MAXSEC];
-      for (int r = 0; r < ns2; ++r) {
-        double a = ends[i + 1][r];
-        for (int c = 0; c < ns2; ++c) a = fma(Mx[r][c], cur[c], a);
-        nxt[r] = a;
-      }
-      for (int r = 0; r < ns2; ++r) { ends[i][r] = cur[r]; cur[r] = nxt[r]; }
+  const long long c1 = clock64();
+  // M32 = M1^32 by five squarings (64 threads, one element each)
+  for (int it = 0; it < 5; ++it) {
+    const double (*src)[LP_NS] = it == 0 ? sh.M1 : sh.M32;
+    if (tid < ns2 * ns2) {
+      const int r = tid / ns2, c = tid % ns2;
+      double a = 0.0;
+      for (int k = 0; k < ns2; ++k) a = fma(src[r][k], src[k][c], a);
+      sh.tmp[r][c] = a;
+    }
+    __syncthreads();
+    if (tid < ns2 * ns2) sh.M32[tid / ns2][tid % ns2] = sh.tmp[tid / ns2][tid % ns2];
+    __syncthreads();
+  }
+  // Scans: one warp per sequence, lane r < ns2 owns state component r (row r of the matrix in registers, the
+  // vector exchanged by shuffles), so a step is ns2 dependent DFMAs instead of a serial ns2 x ns2 loop.
+  const int lane = tid & 31, wid = tid >> 5;
+  const int rr = lane < ns2 ? lane : 0;
+  double m1row[LP_NS], m32row[LP_NS];
+#pragma unroll
+  for (int c = 0; c < LP_NS; ++c) { m1row[c] = c < ns2 ? sh.M1[rr][c] : 0.0; m32row[c] = c < ns2 ? sh.M32[rr][c] : 0.0; }
+  auto matvec_row = [&](const double (&row)[LP_NS], double v, double add) {
+    double a = add;
+#pragma unroll
+    for (int c = 0; c < LP_NS; ++c) a = fma(row[c], __shfl_sync(0xffffffffu, v, c), a);
+    return a;
+  };
+  // level 1: every warp scans its 32 chunks from zero: ends[k] <- local prefix (state at the START of chunk k if
+  // the warp had started from zero), wtot[w+1] <- state after the warp's last chunk
+  {
+    double cur = 0.0;
+    for (int i = 0; i < 32; ++i) {
+      const int k = wid * 32 + i;
+      const double e = sh.ends[k][rr];
+      const double nxt = matvec_row(m1row, cur, e);
+      if (lane < ns2) sh.ends[k][lane] = cur;
+      cur = nxt;
+    }
+    if (lane < ns2) sh.wtot[wid + 1][lane] = cur;
+  }
+  __syncthreads();
+  // level 2: warp 0 scans the 32 warp totals with M^32; wtot[w] <- true state at the start of warp w
+  if (wid == 0) {
+    const double x0 = buf[REV ? ((size_t)((Lx - 1) % Lc) * LP_NT + (Lx - 1) / Lc) : 0];
+    double cur = sh.zi[rr >> 1][rr & 1] * x0;
+    for (int w = 0; w < 32; ++w) {
+      const double e = sh.wtot[w + 1][rr];
+      const double nxt = matvec_row(m32row, cur, e);
+      if (lane < ns2) sh.wtot[w][lane] = cur;
+      cur = nxt;
     }
   }
   __syncthreads();
+  // level 3: true start of chunk k = M1^i * start(warp) + local prefix
+  {
+    double v = sh.wtot[wid][rr];
+    for (int i = 0; i < 32; ++i) {
+      const int k = wid * 32 + i;
+      if (lane < ns2) sh.ends[k][lane] += v;
+      v = matvec_row(m1row, v, 0.0);
+    }
+  }
+  __syncthreads();
+  const long long c2 = clock64();
   {
     SosState s;
     for (int i = 0; i < LP_MAXSEC; ++i) s.z[i][0] = s.z[i][1] = 0.0;
-    for (int r = 0; r < ns2; ++r) s.z[r >> 1][r & 1] = ends[tid][r];
-    for (int n = lo; n < hi; ++n) put(n, sos_step(sos, nsec, s, get(n)));
+    for (int r = 0; r < ns2; ++r) s.z[r >> 1][r & 1] = sh.ends[tid][r];
+    run(s, true);
   }
   __syncthreads();
+  if (sh.dbg && tid == 0 && blockIdx.x == 0) printf("sweep: pass1 %lld scan %lld pass2 %lld\n", c1 - c0, c2 - c1, clock64() - c2);
 }
 
-__global__ void __launch_bounds__(LP_THREADS) lowpass_kernel(const float* __restrict__ wav, int T, const double* __restrict__ energy,
-                                                              int n_freq, double percentile, const double* __restrict__ sos_tab,
-                                                              const double* __restrict__ zi_tab, int nsec, double* __restrict__ scratch,
-                                                              float* __restrict__ out, int* __restrict__ cutoff_out) {
-  __shared__ double sos[LP_MAXSEC][6];
-  __shared__ double zi[LP_MAXSEC][2];
-  __shared__ double Mx[2 * LP_MAXSEC][2 * LP_MAXSEC];
-  __shared__ double ends[LP_THREADS + 1][2 * LP_MAXSEC];
-  __shared__ int s_bin;
-  const int b = blockIdx.x;
-  if (threadIdx.x == 0) {
+__global__ void __launch_bounds__(LP_NT) lowpass_kernel(const float* __restrict__ wav, int T, const double* __restrict__ energy,
+                                                         int n_freq, double percentile, const double* __restrict__ sos_tab,
+                                                         const double* __restrict__ zi_tab, int nsec, double* __restrict__ scratch,
+                                                         float* __restrict__ out, int* __restrict__ cutoff_out, int debug) {
+  extern __shared__ __align__(16) unsigned char lp_raw[];
+  long long tk[6];
+  tk[0] = clock64();
+  LpShared& sh = *reinterpret_cast<LpShared*>(lp_raw);
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
     const double* e = energy + (long long)b * n_freq;
     double total = 0.0;
     for (int k = 0; k < n_freq; ++k) total += e[k];
     const double thr = total * percentile;
     double cum = 0.0; int cnt = 0;
     for (int k = 0; k < n_freq; ++k) { cum += e[k]; if (cum < thr) ++cnt; }
-    s_bin = max(cnt - 1, 0);
-    if (cutoff_out) cutoff_out[b] = s_bin;
+    sh.bin = max(cnt - 1, 0);
+    if (cutoff_out) cutoff_out[b] = sh.bin;
+    sh.dbg = debug;
   }
   __syncthreads();
-  const int bin = s_bin;
-  if (threadIdx.x < nsec * 6) sos[threadIdx.x / 6][threadIdx.x % 6] = sos_tab[((long long)bin * nsec) * 6 + threadIdx.x];
-  if (threadIdx.x < nsec * 2) zi[threadIdx.x / 2][threadIdx.x % 2] = zi_tab[((long long)bin * nsec) * 2 + threadIdx.x];
-  __syncthreads();
+  const int bin = sh.bin;
+  if (tid < nsec * 6) sh.sos[tid / 6][tid % 6] = sos_tab[((long long)bin * nsec) * 6 + tid];
+  if (tid < nsec * 2) sh.zi[tid / 2][tid % 2] = zi_tab[((long long)bin * nsec) * 2 + tid];
   const int edge = 3 * (2 * nsec + 1);
   const int Lx = T + 2 * edge;
+  const int Lc = (Lx + LP_NT - 1) / LP_NT;
   const float* x = wav + (long long)b * T;
-  double* y1 = scratch + (long long)b * Lx;
-  auto ext = [&](int n) -> double {  // odd extension
-    const int i = n - edge;
-    if (i < 0) return 2.0 * (double)x[0] - (double)x[-i];
-    if (i >= T) return 2.0 * (double)x[T - 1] - (double)x[2 * (T - 1) - i];
-    return (double)x[i];
-  };
-  lp_sweep(sos, zi, nsec, Lx, ext, [&](int n, double v) { y1[n] = v; }, Mx, ends);
+  double* buf = scratch + (size_t)b * ((size_t)Lc * LP_NT);
+  const double xl = 2.0 * (double)x[0], xr = 2.0 * (double)x[T - 1];
+  // transpose in: tile = 32 chunks x 32 steps; rows of a chunk are read contiguously, written chunk-contiguous
+  const int ltiles = (Lc + 31) / 32;
+  for (int tile = warp; tile < 32 * ltiles; tile += 32) {
+    const int qt = tile / ltiles, lt = tile - qt * ltiles;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const int n = (qt * 32 + r) * Lc + lt * 32 + lane;
+      float v = 0.f;
+      if (lt * 32 + lane < Lc && n < Lx) {
+        int i = n - edge;
+        if (i < 0) i = -i;
+        else if (i >= T) i = 2 * (T - 1) - i;
+        v = x[i];
+      }
+      sh.tile[warp][r][lane] = v;
+    }
+    __syncwarp();
+    for (int l = 0; l < 32; ++l) {
+      const int ll = lt * 32 + l, q = qt * 32 + lane;
+      if (ll < Lc) {
+        const int n = q * Lc + ll, i = n - edge;
+        const double v = (double)sh.tile[warp][lane][l];
+        buf[(size_t)ll * LP_NT + q] = i < 0 ? xl - v : (i >= T ? xr - v : v);  // odd extension at both ends
+      }
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  tk[1] = clock64();
+  lp_sweep<false>(sh, nsec, Lx, Lc, buf);
+  tk[2] = clock64();
+  lp_sweep<true>(sh, nsec, Lx, Lc, buf);
+  tk[3] = clock64();
+  // transpose out
   float* o = out + (long long)b * T;
-  lp_sweep(sos, zi, nsec, Lx, [&](int n) -> double { return y1[Lx - 1 - n]; },
-           [&](int n, double v) {
-             const int t = (Lx - 1 - n) - edge;
-             if (t >= 0 && t < T) o[t] = (float)v;
-           }, Mx, ends);
+  for (int tile = warp; tile < 32 * ltiles; tile += 32) {
+    const int qt = tile / ltiles, lt = tile - qt * ltiles;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) {
+      const int ll = lt * 32 + l, q = qt * 32 + lane;
+      sh.tile[warp][lane][l] = ll < Lc ? (float)buf[(size_t)ll * LP_NT + q] : 0.f;
+    }
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {
+      const int n = (qt * 32 + r) * Lc + lt * 32 + lane, t = n - edge;
+      if (lt * 32 + lane < Lc && t >= 0 && t < T) o[t] = sh.tile[warp][r][lane];
+    }
+    __syncwarp();
+  }
+  if (debug && tid == 0 && b == 0)
+    printf("lowpass cycles: transpose-in %lld fwd %lld bwd %lld transpose-out %lld\n", tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2],
+           clock64() - tk[3]);
 }
 
 int egr::launch_lowpass(const Spaces& s, const egr_op& op, cudaStream_t st) {
@@ -241,7 +371,14 @@ int egr::launch_lowpass(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (!wav || !energy || !sos_tab || !zi_tab || !scratch || !out || B <= 0 || T <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
   if (nsec < 1 || nsec > LP_MAXSEC) return fail(EGR_ERR_UNSUPPORTED, "%s: 1..%d second-order sections supported", op.name, LP_MAXSEC);
   if (T <= 3 * (2 * nsec + 1)) return fail(EGR_ERR_ARG, "%s: signal shorter than the filtfilt edge", op.name);
-  lowpass_kernel<<<B, LP_THREADS, 0, st>>>(wav, T, energy, n_freq, op.f[EGR_F_A], sos_tab, zi_tab, nsec, scratch, out, cutoff);
+  // scratch must hold B * ceil(Lx/1024)*1024 doubles (flashsr_plan.py sizes it as B*(Lx+1024)*8 bytes)
+  static bool attr_done = false;
+  if (!attr_done) {
+    EGR_CUDA(cudaFuncSetAttribute(lowpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpShared)));
+    attr_done = true;
+  }
+  lowpass_kernel<<<B, LP_NT, sizeof(LpShared), st>>>(wav, T, energy, n_freq, op.f[EGR_F_A], sos_tab, zi_tab, nsec, scratch, out, cutoff,
+                                                          getenv("EGR_LP_DEBUG") ? 1 : 0);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }

@@ -42,12 +42,29 @@ static constexpr int STAGE_LD = 36;  // floats per row of the epilogue staging t
 static constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_LD * 4;
 static constexpr int MAX_SPLITS = 16;
 
+// division by a launch-time constant as multiply-high + shift (the scalar loops and the per-row index math run
+// on single threads: a 32-bit hardware-less division costs ~100+ cycles there)
+struct FastDiv {
+  unsigned int mul, shr, d;
+};
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = (unsigned int)(d < 1 ? 1 : d);
+  if (f.d == 1) { f.mul = 0; f.shr = 0; return f; }
+  unsigned int l = 0;
+  while ((1ull << l) < f.d) ++l;  // ceil(log2 d)
+  f.shr = l;
+  f.mul = (unsigned int)(((1ull << 32) * ((1ull << l) - f.d)) / f.d + 1);
+  return f;
+}
+
 struct TcKernelArgs {
   GemmArgs g;
   Taps taps;
   short tapw[EGR_MAX_TAPS];  // tap offset along dimW (halo mode)
   int mt, halo, n_iss, kchunks, n_outer, n_inner, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin;
   int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
+  FastDiv d_splits, d_tiles_n, d_tiles_w, d_tiles_h, d_kchunks, d_bw, d_bh, d_c4n;
   int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (<= 256)
   int vec_ok;
   float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
@@ -162,6 +179,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return d;
 }
 
+// n / d for 0 <= n < 2^31 (Granlund-Montgomery round-up variant: q = (mulhi(n, mul) + n) >> shr, 33-bit safe form)
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  if (f.d == 1) return n;
+  const unsigned int t = __umulhi((unsigned int)n, f.mul);
+  return (int)((t + (((unsigned int)n - t) >> 1)) >> (f.shr - 1));
+}
+
 // ------------------------------------------------------------------------------------------------ work decoding
 struct WorkItem {
   int tm, tn, ks;
@@ -172,10 +196,10 @@ struct WorkItem {
 
 __device__ __forceinline__ void decode_work(const TcKernelArgs& ka, int w, WorkItem& wi) {
   const GemmArgs& g = ka.g;
-  wi.ks = w % ka.splits;
-  int t = w / ka.splits;
-  wi.tn = t % ka.tiles_n;
-  wi.tm = t / ka.tiles_n;
+  int t = fdiv(w, ka.d_splits);
+  wi.ks = w - t * ka.splits;
+  wi.tm = fdiv(t, ka.d_tiles_n);
+  wi.tn = t - wi.tm * ka.tiles_n;
   wi.o_begin = wi.ks * ka.outer_per_split;
   wi.o_end = min(ka.n_outer, wi.o_begin + ka.outer_per_split);
   wi.mt_eff = 0;
@@ -187,15 +211,18 @@ __device__ __forceinline__ void decode_work(const TcKernelArgs& ka, int w, WorkI
     int q;
     if (ka.halo) {  // CTA tile = mt*128 consecutive positions along W inside one (h, b) row
       q = wi.tm;
-      wi.w0[m] = (q % ka.tiles_w) * (TILE_M * ka.mt) + TILE_M * m; q /= ka.tiles_w;
+      const int q1 = fdiv(q, ka.d_tiles_w);
+      wi.w0[m] = (q - q1 * ka.tiles_w) * (TILE_M * ka.mt) + TILE_M * m; q = q1;
       valid = wi.w0[m] < g.Wo;
     } else {
       q = wi.tm * ka.mt + m;
       valid = q < ka.tiles1;
-      wi.w0[m] = (q % ka.tiles_w) * g.bw; q /= ka.tiles_w;
+      const int q1 = fdiv(q, ka.d_tiles_w);
+      wi.w0[m] = (q - q1 * ka.tiles_w) * g.bw; q = q1;
     }
-    wi.h0[m] = (q % ka.tiles_h) * g.bh; q /= ka.tiles_h;
-    wi.b0[m] = q * g.bb;
+    const int q2 = fdiv(q, ka.d_tiles_h);
+    wi.h0[m] = (q - q2 * ka.tiles_h) * g.bh;
+    wi.b0[m] = q2 * g.bb;
     if (valid) wi.mt_eff = m + 1;
   }
 }
@@ -213,8 +240,9 @@ __device__ __forceinline__ RowInfo row_info(const TcKernelArgs& ka, const WorkIt
   int w, h, b;
   if (ka.halo) { w = wi.w0[m] + row; h = wi.h0[m]; b = wi.b0[m]; }
   else {
-    const int wl = row % g.bw, t = row / g.bw;
-    w = wi.w0[m] + wl; h = wi.h0[m] + t % g.bh; b = wi.b0[m] + t / g.bh;
+    const int t = fdiv(row, ka.d_bw), wl = row - t * g.bw;
+    const int t2 = fdiv(t, ka.d_bh);
+    w = wi.w0[m] + wl; h = wi.h0[m] + (t - t2 * g.bh); b = wi.b0[m] + t2;
   }
   RowInfo r;
   r.ok = (w < g.Wo) && (h < g.Ho) && (b < g.Bo);
@@ -337,7 +365,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         for (int d = 0; d < 5; ++d)
           cb[m][d] = (g.dimW == d ? wi.w0[m] : 0) + (g.dimH == d ? wi.h0[m] : 0) + (g.dimB == d ? wi.b0[m] : 0);
       int tap = 0, kc = wi.o_begin;
-      if (!ka.halo) { tap = wi.o_begin / ka.kchunks; kc = wi.o_begin - tap * ka.kchunks; }
+      if (!ka.halo) { tap = fdiv(wi.o_begin, ka.d_kchunks); kc = wi.o_begin - tap * ka.kchunks; }
       for (int io = wi.o_begin; io < wi.o_end; ++io) {
         mbar_wait(emptyA_u + 8 * sa, pa ^ 1u);
         const uint32_t dstA = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
@@ -387,7 +415,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       decode_work(ka, w, wi);
       const int n0 = wi.tn * BN;
       int tap = 0, kc = wi.o_begin;
-      if (!ka.halo) { tap = wi.o_begin / ka.kchunks; kc = wi.o_begin - tap * ka.kchunks; }
+      if (!ka.halo) { tap = fdiv(wi.o_begin, ka.d_kchunks); kc = wi.o_begin - tap * ka.kchunks; }
       for (int io = wi.o_begin; io < wi.o_end; ++io) {
         for (int ii = 0; ii < ka.n_inner; ++ii) {
           mbar_wait(emptyB_u + 8 * sb, pb ^ 1u);
@@ -635,7 +663,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           const int c4n = BN >> 2;
           const int total = wi.mt_eff * TILE_M * c4n;
           for (int e = (int)threadIdx.x - 64; e < total; e += 128) {
-            const int row = e / c4n, c = (e - row * c4n) * 4;
+            const int row = fdiv(e, ka.d_c4n), c = (e - row * c4n) * 4;
             const int m = row >> 7;
             const RowInfo ri = row_info(ka, wi, m, row & 127);
             const int n = n0 + c;
@@ -819,6 +847,9 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   ka.splits = splits; ka.outer_per_split = ops;
   ka.n_work = ka.tiles_m * ka.tiles_n * splits;
   ka.acc_cols = mt * bn;
+  ka.d_splits = make_fastdiv(splits); ka.d_tiles_n = make_fastdiv(ka.tiles_n); ka.d_tiles_w = make_fastdiv(ka.tiles_w);
+  ka.d_tiles_h = make_fastdiv(tiles_h); ka.d_kchunks = make_fastdiv(kchunks); ka.d_bw = make_fastdiv(g.bw);
+  ka.d_bh = make_fastdiv(g.bh); ka.d_c4n = make_fastdiv(bn / 4);
   if (halo) {
     ka.boxA_bytes = HALO_BOX_ROWS * KBLK * 2;
     ka.nboxA = ceil_div(TILE_M * mt + (tmax - tmin), HALO_BOX_ROWS);

@@ -146,7 +146,10 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(View a, GemmArgs g, Taps
   }
 }
 
-// SIMT tap-GEMM for N <= 4: one warp per pixel, lanes stride the channel dimension (coalesced), shuffle reduce.
+// SIMT tap-GEMM for N <= 4 (the 1-channel output convs): one warp per pixel, lanes stride the channel dimension.
+// The bounds test and the address of a tap are computed once per (pixel, tap); with VEC the lanes read 4 channels
+// per load (uint2 of f16 or float4) and the weights as float4, so a 128-channel tap is one load instruction.
+template <bool VEC>
 __global__ void __launch_bounds__(256) gemm_simt_smalln_kernel(View a, GemmArgs g, Taps taps) {
   const int lane = threadIdx.x & 31;
   const long long p = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -160,16 +163,74 @@ __global__ void __launch_bounds__(256) gemm_simt_smalln_kernel(View a, GemmArgs 
 #pragma unroll
     for (int d = 0; d < 5; ++d) c[d] = taps.t[tap][d];
     c[g.dimW] += w; c[g.dimH] += h; c[g.dimB] += b;
+    bool inb = true;
+    long long off = 0;
+#pragma unroll
+    for (int d = 1; d < 5; ++d) {
+      inb = inb && c[d] >= 0 && c[d] < a.dim[d];
+      off += c[d] * a.stride[d];
+    }
+    if (!inb) continue;  // warp-uniform: the whole pixel row of this tap is padding
     const long long c0 = c[0];
-    for (int k = lane; k < g.K; k += 32) {
-      c[0] = c0 + k;
-      const float av = load_view(a, c);
-      for (int n = 0; n < g.N; ++n) acc[n] = fmaf(av, W[(long long)tap * g.wstride_z + (long long)n * g.wstride_n + k], acc[n]);
+    const float* wt = W + (long long)tap * g.wstride_z;
+    if (VEC) {
+      for (int k = lane * 4; k < g.K; k += 128) {
+        const long long ch = c0 + k;  // c0 is a multiple of 4 and dim[0] too (checked on the host)
+        if (ch < 0 || ch >= a.dim[0]) continue;
+        float av[4];
+        if (a.elem) {
+          const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(a.p) + off + ch));
+          const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+          const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+          av[0] = f0.x; av[1] = f0.y; av[2] = f1.x; av[3] = f1.y;
+        } else {
+          const float4 raw = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.p) + off + ch));
+          av[0] = raw.x; av[1] = raw.y; av[2] = raw.z; av[3] = raw.w;
+        }
+        for (int n = 0; n < g.N; ++n) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wt + (long long)n * g.wstride_n + k));
+          acc[n] = fmaf(av[0], wv.x, acc[n]); acc[n] = fmaf(av[1], wv.y, acc[n]);
+          acc[n] = fmaf(av[2], wv.z, acc[n]); acc[n] = fmaf(av[3], wv.w, acc[n]);
+        }
+      }
+    } else {
+      for (int k = lane; k < g.K; k += 32) {
+        const long long ch = c0 + k;
+        if (ch < 0 || ch >= a.dim[0]) continue;
+        const float av = a.elem ? __half2float(reinterpret_cast<const __half*>(a.p)[off + ch]) : reinterpret_cast<const float*>(a.p)[off + ch];
+        for (int n = 0; n < g.N; ++n) acc[n] = fmaf(av, wt[(long long)n * g.wstride_n + k], acc[n]);
+      }
     }
   }
   for (int n = 0; n < g.N; ++n) {
     const float v = warp_sum(acc[n]);
     if (lane == 0) epilogue_store(g, b, (long long)h * g.Wo + w, n, v);
+  }
+}
+
+// GEMV for a handful of rows (time-embedding MLP and the per-block embedding projections: M = 1): one warp per
+// output feature, lanes stride K with float4 loads of the f32 weight row.  A must be f32 with unit channel stride.
+__global__ void __launch_bounds__(256) gemm_simt_gemv_kernel(View a, GemmArgs g, int npix) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= g.N) return;
+  const float* wrow = reinterpret_cast<const float*>(g.W) + (long long)n * g.wstride_n;
+  for (int p = 0; p < npix; ++p) {
+    const int w = p % g.Wo, h = (p / g.Wo) % g.Ho, b = p / (g.Wo * g.Ho);
+    const float* x = reinterpret_cast<const float*>(a.p) + (long long)w * a.stride[g.dimW] + (long long)h * a.stride[g.dimH] +
+                     (long long)b * a.stride[g.dimB];
+    float acc = 0.f;
+    if ((g.K & 3) == 0) {
+      for (int k = lane * 4; k < g.K; k += 128) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + k));
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + k));
+        acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc); acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+      }
+    } else {
+      for (int k = lane; k < g.K; k += 32) acc = fmaf(x[k], wrow[k], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) epilogue_store(g, b, (long long)h * g.Wo + w, n, acc);
   }
 }
 
@@ -179,8 +240,19 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (rc) return rc;
   if (g.wz_batch) return fail(EGR_ERR_UNSUPPORTED, "%s: batch-indexed B operand needs the tensor-core path", op.name);
   const long long npix = (long long)g.Wo * g.Ho * g.Bo;
-  if (g.N <= 4) {
-    gemm_simt_smalln_kernel<<<(unsigned)((npix + 7) / 8), 256, 0, st>>>(a, g, taps);
+  auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+  bool zero_taps = true;
+  for (int t = 0; t < g.ntaps; ++t)
+    for (int d = 0; d < 5; ++d) zero_taps = zero_taps && taps.t[t][d] == 0;
+  if (npix <= 8 && g.ntaps == 1 && zero_taps && a.elem == 0 && a.stride[0] == 1 && g.K <= a.dim[0] && al16(a.p) && al16(g.W) &&
+      (g.wstride_n & 3) == 0 && (a.stride[g.dimW] & 3) == 0 && (a.stride[g.dimH] & 3) == 0 && (a.stride[g.dimB] & 3) == 0) {
+    gemm_simt_gemv_kernel<<<(unsigned)((g.N + 7) / 8), 256, 0, st>>>(a, g, (int)npix);
+  } else if (g.N <= 4) {
+    bool vec = (g.K & 3) == 0 && (a.dim[0] & 3) == 0 && al16(a.p) && al16(g.W) && (g.wstride_n & 3) == 0 && (g.wstride_z & 3) == 0;
+    for (int d = 1; d < 5; ++d) vec = vec && (a.stride[d] & 3) == 0;
+    for (int t = 0; t < g.ntaps; ++t) vec = vec && (taps.t[t][0] & 3) == 0;
+    if (vec) gemm_simt_smalln_kernel<true><<<(unsigned)((npix + 7) / 8), 256, 0, st>>>(a, g, taps);
+    else gemm_simt_smalln_kernel<false><<<(unsigned)((npix + 7) / 8), 256, 0, st>>>(a, g, taps);
   } else {
     dim3 grid((unsigned)((npix + 31) / 32), (unsigned)((g.N + 31) / 32));
     gemm_simt_kernel<<<grid, 256, 0, st>>>(a, g, taps);
