@@ -98,6 +98,7 @@ def load() -> C.CDLL:
         "egr_last_error": (C.c_char_p, []),
         "egr_init": (C.c_int, [i32]),
         "egr_sm_count": (C.c_int, []),
+        "egr_launch_count": (C.c_int64, []),
         "egr_sizeof": (C.c_int, [i32]),
         "egr_chunk_gather": (C.c_int, [f32p, i32, i64, vp, vp, i32, i32, f32p, vp]),
         "egr_wola_stitch": (C.c_int, [f32p, i32, vp, vp, i32, i32, i64, i32, f32p, f32p, vp]),

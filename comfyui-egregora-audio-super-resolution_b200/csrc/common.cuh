@@ -19,6 +19,8 @@ namespace egr {
 // thread-local last-error text, exposed through egr_last_error()
 char* err_buf();
 int fail(int code, const char* fmt, ...);
+// kernels launched by this library in this process (every EGR_CHECK_LAUNCH site counts one)
+unsigned long long& launch_count();
 
 #define EGR_CUDA(call)                                                                          \
   do {                                                                                          \
@@ -30,6 +32,7 @@ int fail(int code, const char* fmt, ...);
 
 #define EGR_CHECK_LAUNCH(what)                                                                  \
   do {                                                                                          \
+    ++egr::launch_count();                                                                      \
     cudaError_t e__ = cudaGetLastError();                                                       \
     if (e__ != cudaSuccess)                                                                     \
       return egr::fail(EGR_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e__)); \

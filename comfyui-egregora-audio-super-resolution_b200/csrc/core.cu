@@ -16,6 +16,11 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+unsigned long long& launch_count() {
+  static unsigned long long n = 0;
+  return n;
+}
+
 DeviceInfo& devinfo() {
   static DeviceInfo d;
   return d;
@@ -58,6 +63,7 @@ extern "C" int egr_init(int device) {
 }
 
 extern "C" int egr_sm_count(void) { return devinfo().sm_count; }
+extern "C" int64_t egr_launch_count(void) { return (int64_t)launch_count(); }
 
 // ------------------------------------------------------------------------------------------------
 // absmax: grid-stride float4 loads, warp-shuffle + one atomicMax (as uint bits; values are >= 0).

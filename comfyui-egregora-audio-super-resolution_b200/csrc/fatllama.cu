@@ -342,6 +342,7 @@ extern "C" int egr_fatllama_run(const float* d_in, float* d_out, int C, int64_t 
       fl_row_kernel<<<gr, p->row_threads, smr, st>>>(d, threshold, work);
       if (it + 1 < iters) fl_col_kernel<FL_MID><<<gc, p->col_threads, smc, st>>>(d, d_in, n, upscale, threshold, work, d_out, peaks);
     }
+    launch_count() += (unsigned long long)(2 * iters - 2);  // the loop's launches beyond the one counted below
     EGR_CHECK_LAUNCH("fl_row_kernel / fl_col_kernel<mid>");
     fl_col_kernel<FL_LAST><<<gc, p->col_threads, smc, st>>>(d, d_in, n, upscale, threshold, work, d_out, peaks);
     EGR_CHECK_LAUNCH("fl_col_kernel<last>");

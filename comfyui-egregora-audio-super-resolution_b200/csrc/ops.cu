@@ -3,6 +3,7 @@
 // element-wise glue, anti-aliased SnakeBeta, time embedding.  All are HBM-bound streaming kernels:
 // coalesced float4 / half2 accesses with channels innermost, warp-shuffle reductions, f64 accumulators
 // where cancellation matters (GroupNorm moments).
+#include <cstdlib>
 #include "ops.cuh"
 
 namespace egr {
@@ -377,6 +378,76 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* 
   }
 }
 
+// Small feature maps (the UNet, the VAE mid block): ONE kernel, one CTA per (group, batch item).  The group's
+// P x cpg elements (L2-resident: the producing GEMM has just written them) are read twice — f32 partials per
+// thread combined in f64 in a fixed order (deterministic, independent of the batch size), then normalise (+SiLU)
+// and store.  Replaces the stats + finalize + apply launches whose grids of 1..32 CTAs were pure latency.
+#define GN_FUSED_THREADS 512
+__global__ void __launch_bounds__(GN_FUSED_THREADS) gn_fused_kernel(CatArgs a, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, float eps, int silu,
+                                                                    float* __restrict__ out32, __half* __restrict__ out16) {
+  __shared__ double red[2][GN_FUSED_THREADS / 32];
+  __shared__ float s_mean, s_rstd;
+  const int C = a.C0 + a.C1, cpg = C / a.G, q4 = cpg >> 2;
+  const int gi = blockIdx.x, b = blockIdx.y;
+  const int c_lo = gi * cpg;
+  const int units = (int)a.P * q4;  // float4 units of this group (P <= 4096)
+  auto src = [&](long long p, int c) -> const float* {
+    return c < a.C0 ? a.x0 + ((long long)b * a.P + p) * a.C0 + c : a.x1 + ((long long)b * a.P + p) * a.C1 + (c - a.C0);
+  };
+  float s = 0.f, ss = 0.f;
+  for (int u = threadIdx.x; u < units; u += GN_FUSED_THREADS) {
+    const int p = u / q4;
+    const int c = c_lo + (u - p * q4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src(p, c)));
+    s += (v.x + v.y) + (v.z + v.w);
+    ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+  }
+  double ds = warp_sum((double)s), dss = warp_sum((double)ss);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ds; red[1][threadIdx.x >> 5] = dss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0, tt = 0.0;
+    for (int w = 0; w < GN_FUSED_THREADS / 32; ++w) { t += red[0][w]; tt += red[1][w]; }
+    const double cnt = (double)cpg * (double)a.P;
+    const double mean = t / cnt;
+    double var = tt / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean = (float)mean;
+    s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float mean = s_mean, rstd = s_rstd;
+  for (int u = threadIdx.x; u < units; u += GN_FUSED_THREADS) {
+    const int p = u / q4;
+    const int c = c_lo + (u - p * q4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src(p, c)));
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float r[4] = {fmaf(v.x, rstd * g4.x, b4.x - mean * (rstd * g4.x)), fmaf(v.y, rstd * g4.y, b4.y - mean * (rstd * g4.y)),
+                  fmaf(v.z, rstd * g4.z, b4.z - mean * (rstd * g4.z)), fmaf(v.w, rstd * g4.w, b4.w - mean * (rstd * g4.w))};
+    if (silu) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] = egr_silu(r[k]);
+    }
+    const long long o = ((long long)b * a.P + p) * C + c;
+    if (out32) *reinterpret_cast<float4*>(out32 + o) = make_float4(r[0], r[1], r[2], r[3]);
+    if (out16) {
+      __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<unsigned*>(&h0);
+      pk.y = *reinterpret_cast<unsigned*>(&h1);
+      *reinterpret_cast<uint2*>(out16 + o) = pk;
+    }
+  }
+}
+
+// single-kernel path: small maps whose groups are whole float4 columns (a function of the op's geometry only)
+static bool gn_use_fused(const CatArgs& a) {
+  const int C = a.C0 + a.C1, cpg = C / a.G;
+  return a.P <= 4096 && (cpg & 3) == 0 && getenv("EGR_GN_NO_FUSED") == nullptr;
+}
+
 static int cat_args(const Spaces& s, const egr_op& op, CatArgs* a) {
   a->x0 = (const float*)resolve(s, op.x0.addr);
   a->x1 = (const float*)resolve(s, op.x1.addr);
@@ -406,6 +477,7 @@ int egr::launch_gn_stats(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (rc) return rc;
   double* stats = (double*)resolve(s, op.ptr[EGR_P_STATS]);
   if (!stats) return fail(EGR_ERR_ARG, "%s: null stats", op.name);
+  if (gn_use_fused(a)) return EGR_OK;  // the apply op computes the moments itself
   int ns; int slab = slab_for(a.P, &ns);
   if (op.i[EGR_I_AUX1] != ns) return fail(EGR_ERR_ARG, "%s: plan was built for %lld slabs, kernel wants %d", op.name, (long long)op.i[EGR_I_AUX1], ns);
   const int C = a.C0 + a.C1, G2 = 2 * a.G;
@@ -430,6 +502,11 @@ int egr::launch_gn_apply(const Spaces& s, const egr_op& op, cudaStream_t st) {
   float* o32 = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
   __half* o16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
   if (!stats || !gamma || !beta || (!o32 && !o16)) return fail(EGR_ERR_ARG, "%s: null pointer", op.name);
+  if (gn_use_fused(a)) {
+    gn_fused_kernel<<<dim3(a.G, a.B), GN_FUSED_THREADS, 0, st>>>(a, gamma, beta, (float)op.f[EGR_F_EPS], (int)op.i[EGR_I_MODE], o32, o16);
+    EGR_CHECK_LAUNCH(op.name);
+    return EGR_OK;
+  }
   int ns; int slab = slab_for(a.P, &ns);
   const int C = a.C0 + a.C1;
   gn_apply_kernel<<<dim3(ns, a.B), 256, 2 * C * sizeof(float), st>>>(a, stats, gamma, beta, (float)op.f[EGR_F_EPS],
@@ -748,29 +825,37 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
 #pragma unroll
   for (int r = 0; r < 5; ++r) xw[r + 1] = xat(t0 + r);  // slots 1..5 hold x[t0 .. t0+4]
   const int t_end = min(T, t0 + SNAKE_TT);
-#pragma unroll 4
-  for (int t = t0; t < t_end; ++t) {
+  for (int tb = t0; tb < t_end; tb += 8) {
+    // the 8 new input samples of this group are independent of the recurrence: issue their loads together
+    float xn[8];
 #pragma unroll
-    for (int j = 0; j < 10; ++j) sw[j] = sw[j + 2];
+    for (int i = 0; i < 8; ++i) xn[i] = xat(tb + i + 5);
 #pragma unroll
-    for (int r = 0; r < 5; ++r) xw[r] = xw[r + 1];
-    xw[5] = xat(t + 5);
-    // s[2t+5] (odd phase of m = t+2) and s[2t+6] (even phase of m = t+3) both read x[t .. t+5]
-    float uo = 0.f, ue = 0.f;
+    for (int i = 0; i < 8; ++i) {
+      const int t = tb + i;
+      if (t >= t_end) break;
 #pragma unroll
-    for (int r = 0; r < 6; ++r) {
-      uo = fmaf(xw[r], f[10 - 2 * r], uo);
-      ue = fmaf(xw[r], f[11 - 2 * r], ue);
+      for (int j = 0; j < 10; ++j) sw[j] = sw[j + 2];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) xw[r] = xw[r + 1];
+      xw[5] = xn[i];
+      // s[2t+5] (odd phase of m = t+2) and s[2t+6] (even phase of m = t+3) both read x[t .. t+5]
+      float uo = 0.f, ue = 0.f;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        uo = fmaf(xw[r], f[10 - 2 * r], uo);
+        ue = fmaf(xw[r], f[11 - 2 * r], ue);
+      }
+      const float so = snake_eval(2.0f * uo, alpha, inv_beta), se = snake_eval(2.0f * ue, alpha, inv_beta);
+      sw[10] = (2 * t + 5 <= n_last) ? so : sw[9];
+      sw[11] = (2 * t + 6 <= n_last) ? se : sw[10];
+      float y = 0.f;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
+      const long long o = ((long long)b * T + t) * C + c;
+      if (o32) o32[o] = y;
+      if (o16) o16[o] = __float2half_rn(y);
     }
-    const float so = snake_eval(2.0f * uo, alpha, inv_beta), se = snake_eval(2.0f * ue, alpha, inv_beta);
-    sw[10] = (2 * t + 5 <= n_last) ? so : sw[9];
-    sw[11] = (2 * t + 6 <= n_last) ? se : sw[10];
-    float y = 0.f;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
-    const long long o = ((long long)b * T + t) * C + c;
-    if (o32) o32[o] = y;
-    if (o16) o16[o] = __float2half_rn(y);
   }
 }
 

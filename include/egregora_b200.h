@@ -37,6 +37,8 @@ const char* egr_last_error(void);
  * Fails (no CPU fallback) when no sm_100 device is present. */
 int         egr_init(int device);
 int         egr_sm_count(void);
+/* kernels this library has launched in this process so far (bench.py reports the delta over its timed region) */
+int64_t     egr_launch_count(void);
 /* size of the C structs below, for the ctypes mirror's self-check: 0=egr_tensor, 1=egr_op */
 int         egr_sizeof(int which);
 
