@@ -66,7 +66,7 @@ struct TcKernelArgs {
   int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
   FastDiv d_splits, d_tiles_n, d_tiles_w, d_tiles_h, d_kchunks, d_bw, d_bh, d_c4n;
   int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (<= 256)
-  int vec_ok;
+  int vec_ok, need_crop;
   float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
   unsigned int* counters;  // one per output tile, zero between launches
   unsigned long long* trace;  // debug: clock64() stamps of CTA 0 when non-null
@@ -151,6 +151,20 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld16x256_x2(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -318,12 +332,16 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   uint32_t* last_flag = tmem_slot + 1;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef EGR_TC_TRACE  // debug build only (make TRACE=1): clock stamps of CTA 0; the optimiser drops all of it otherwise
   unsigned long long* tr = (ka.trace && blockIdx.x == 0) ? ka.trace : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = clock64();
   if (ka.trace && threadIdx.x == 0 && blockIdx.x < 148) {  // per-CTA wall-clock start (ns)
     unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     ka.trace[1100 + 2 * blockIdx.x] = gt;
   }
+#else
+  unsigned long long* const tr = nullptr;
+#endif
 
   if (threadIdx.x == 0) {
     // halo mode: A and B rings advance at different rates and have their own barriers; otherwise the A stage rides
@@ -510,14 +528,22 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       decode_work(ka, w, wi);
       const int buf = it & 1;
       const int n0 = wi.tn * BN;
+      int ecount = 0;
       if (g.resid && ka.splits == 1 && !g.transposed) {
-        // the mainloop of this item is still running: pull the residual tile into L2 meanwhile, so that the loads of
-        // the store pass below pay an L2 hit instead of a DRAM round trip per 32x32 block
-        for (int m = 0; m < wi.mt_eff; ++m) {
-          const RowInfo rp = row_info(ka, wi, m, lg * 32 + lane);
-          if (rp.ok) {
-            const float* q = g.resid + rp.base + n0;
-            for (int c = 0; c < BN; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+        // Pull the residual tile of the NEXT item into L2 now (the first item also fetches its own): when the
+        // epilogue is the critical path the accumulator is already waiting, so a prefetch for the current item
+        // would be issued right before its loads; one item ahead gives it a whole epilogue of lead time.
+        for (int pass = (it == 0 ? 0 : 1); pass < 2; ++pass) {
+          const int wn = w + pass * (int)gridDim.x;
+          if (wn >= ka.n_work) break;
+          WorkItem wp;
+          decode_work(ka, wn, wp);
+          for (int m = 0; m < wp.mt_eff; ++m) {
+            const RowInfo rp = row_info(ka, wp, m, lg * 32 + lane);
+            if (rp.ok) {
+              const float* q = g.resid + rp.base + wp.tn * BN;
+              for (int c = 0; c < BN; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
+            }
           }
         }
       }
@@ -527,16 +553,22 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       const int tile_id = wi.tm * ka.tiles_n + wi.tn;
       const size_t pstride = (size_t)ka.mt * TILE_M * BN;
       float* part = ka.splits > 1 ? ka.partial + ((size_t)tile_id * ka.splits + wi.ks) * pstride : nullptr;
+      // NOTE: r[] must only ever be indexed by compile-time constants (fully unrolled loops): one dynamic index sends
+      // the whole array to local memory and every epilogue block then pays ~60 extra local loads/stores.
       for (int m = 0; m < wi.mt_eff; ++m) {
         const RowInfo ri = row_info(ka, wi, m, lg * 32 + lane);  // this thread's own row
         const uint32_t any_ok = __ballot_sync(0xffffffffu, ri.ok);
+        const long long base_l0 = __shfl_sync(0xffffffffu, ri.base, 0);
+        const int roff = (int)(ri.base - base_l0);      // row offset inside the tile (host checked: fits 32 bits)
+        const int foff = (int)(ri.flat0 - __shfl_sync(0xffffffffu, ri.flat0, 0));
+        const long long flat_l0 = __shfl_sync(0xffffffffu, ri.flat0, 0);
         for (int cb = 0; cb < BN; cb += 32) {
           uint32_t r[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ka.acc_cols + m * BN + cb);
           const int ncols = min(32, BN - cb);  // BN is a multiple of 16
           if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
           tc_wait_ld();
-          if (m == wi.mt_eff - 1 && cb + 32 >= BN) {  // last TMEM read of this buffer: hand it back to the MMA warp
+          if (m == wi.mt_eff - 1 && cb + 32 >= BN) {  // last TMEM read of this buffer: hand it back to the MMA warps
             tc_fence_before();
             if (lane == 0) mbar_arrive(accE_u + 8 * buf);
           }
@@ -546,15 +578,13 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             // out[b][n][pix]: consecutive rows are consecutive addresses -> already coalesced per column
             if (ri.ok) {
               const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
-              for (int j = 0; j < ncols; ++j) {
-                const int n = nb + j;
-                if (n >= g.N) break;
-                finish1(g, __uint_as_float(r[j]), ri.base + (long long)n * g.out_n_stride, n, rb);
-              }
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncols && nb + j < g.N) finish1(g, __uint_as_float(r[j]), ri.base + (long long)(nb + j) * g.out_n_stride, nb + j, rb);
             }
             continue;
           }
-          // transpose through shared memory: thread = row  ->  lane = column group
+          // transpose through shared memory: thread = row  ->  8 lanes per row, 4 rows per instruction
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             if (j < ncols)
@@ -573,70 +603,66 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
               }
             }
           } else if (ka.vec_ok) {
-            // 4 rows x 8 float4 per pass; all residual / row-bias loads of the 8 passes are issued before the first
-            // store so one memory latency covers the whole 32x32 block (stores may alias the residual for ptxas)
+            // 4 rows x 128 contiguous bytes per instruction; one 32-bit shuffle per pass; every residual load of the
+            // block is issued before the first store (the stores may alias the residual as far as ptxas knows)
             const int n = nb + c4;
             const bool col_ok = c4 < ncols && n < g.N;
             float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (col_ok && g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-            long long idx[8];
+            int off[8];
             float4 rv[8];
-            int bbs[8];
-            uint32_t okm = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i + rsub;
-              const long long base = __shfl_sync(0xffffffffu, ri.base, rr);
-              const long long fl = __shfl_sync(0xffffffffu, ri.flat0, rr) + n;
-              const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
-              const bool ok = col_ok && ((any_ok >> rr) & 1u) && fl >= g.out_lo && fl < g.out_hi;
-              idx[i] = base + n;
-              bbs[i] = bb;
-              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok) {
-                okm |= 1u << i;
-                if (g.resid) rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + idx[i]));
-                if (g.rowbias) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bb * g.rowbias_stride + n));
-                  // the row bias is added before the activation, the residual after it: keep them apart
-                  if (!g.act) { rv[i].x += b4.x; rv[i].y += b4.y; rv[i].z += b4.z; rv[i].w += b4.w; }
-                }
+              off[i] = __shfl_sync(0xffffffffu, roff, rr);
+              bool ok = col_ok && ((any_ok >> rr) & 1u);
+              if (ka.need_crop) {
+                const long long fl = flat_l0 + __shfl_sync(0xffffffffu, foff, rr) + n;
+                ok = ok && fl >= g.out_lo && fl < g.out_hi;
               }
+              if (!ok) off[i] = -1;
+              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (ok && g.resid) rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              if (!((okm >> i) & 1u)) continue;
               const int rr = 4 * i + rsub;
+              int bb = 0;
+              if (g.rowbias) bb = __shfl_sync(0xffffffffu, ri.b, rr);  // warp-uniform branch, executed by all lanes
+              if (off[i] < 0) continue;
               const float4 a = *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4);
-              float v[4] = {fmaf(a.x, g.alpha, bias4.x), fmaf(a.y, g.alpha, bias4.y), fmaf(a.z, g.alpha, bias4.z), fmaf(a.w, g.alpha, bias4.w)};
-              if (g.act) {
-                if (g.rowbias) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bbs[i] * g.rowbias_stride + n));
-                  v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = egr_apply_act(v[u], g.act);
+              float x[4] = {fmaf(a.x, g.alpha, bias4.x), fmaf(a.y, g.alpha, bias4.y), fmaf(a.z, g.alpha, bias4.z), fmaf(a.w, g.alpha, bias4.w)};
+              if (g.rowbias) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bb * g.rowbias_stride + n));
+                x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
               }
-              v[0] += rv[i].x; v[1] += rv[i].y; v[2] += rv[i].z; v[3] += rv[i].w;
-              if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx[i]) = make_float4(v[0], v[1], v[2], v[3]);
+              if (g.act) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = egr_apply_act(x[u], g.act);
+              }
+              x[0] += rv[i].x; x[1] += rv[i].y; x[2] += rv[i].z; x[3] += rv[i].w;
+              const long long idx = base_l0 + off[i] + n;
+              if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(x[0], x[1], x[2], x[3]);
               if (g.out16) {
-                __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+                __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
                 uint2 pk;
                 pk.x = *reinterpret_cast<unsigned*>(&h0);
                 pk.y = *reinterpret_cast<unsigned*>(&h1);
-                *reinterpret_cast<uint2*>(g.out16 + idx[i]) = pk;
+                *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
               }
             }
           } else {
+            // scalar path (odd alignments): lane = column, one row per pass
+#pragma unroll 4
             for (int rr = 0; rr < 32; ++rr) {
-              const long long base = __shfl_sync(0xffffffffu, ri.base, rr);
-              const long long fl0 = __shfl_sync(0xffffffffu, ri.flat0, rr);
+              const int o = __shfl_sync(0xffffffffu, roff, rr);
+              const int fo = __shfl_sync(0xffffffffu, foff, rr);
               const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
               const int n = nb + lane;
-              const long long fl = fl0 + n;
+              const long long fl = flat_l0 + fo + n;
               if (((any_ok >> rr) & 1u) && lane < ncols && n < g.N && fl >= g.out_lo && fl < g.out_hi) {
                 const float* rb = g.rowbias ? g.rowbias + (long long)bb * g.rowbias_stride : nullptr;
-                finish1(g, stg[rr * STAGE_LD + lane], base + n, n, rb);
+                finish1(g, stg[rr * STAGE_LD + lane], base_l0 + o + n, n, rb);
               }
             }
           }
@@ -706,10 +732,12 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+#ifdef EGR_TC_TRACE
   if (ka.trace && threadIdx.x == 64 && blockIdx.x < 148) {  // per-CTA wall-clock end (ns), after the barrier released
     unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     ka.trace[1100 + 2 * blockIdx.x + 1] = gt;
   }
+#endif
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -897,6 +925,14 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
              (g.out_offset % 4 == 0) && (g.out_lo % 4 == 0) && (g.out_hi % 4 == 0) && (g.rowbias_stride % 4 == 0);
   auto al = [](const void* q, int a) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % a == 0; };
   vec = vec && al(g.out32, 16) && al(g.out16, 8) && al(g.resid, 16) && al(g.bias, 16) && al(g.rowbias, 16);
+  {
+    // row offsets inside a tile are exchanged as 32-bit values
+    const long long span = (long long)(g.Bo + g.bb) * (g.out_batch_stride > 0 ? g.out_batch_stride : 1) +
+                           ((long long)g.Ho * g.Wo + TILE_M) * (g.out_pix_stride > 0 ? g.out_pix_stride : 1) +
+                           (long long)g.N * (g.out_n_stride > 0 ? g.out_n_stride : 1);
+    if (span >= (1ll << 31)) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: output of %lld elements exceeds the 32-bit tile offsets", op.name, span));
+    ka.need_crop = (g.out_lo > 0 || g.out_hi < (long long)g.Ho * g.Wo * g.out_pix_stride + g.out_offset + g.N) ? 1 : 0;
+  }
   ka.vec_ok = vec ? 1 : 0;
   *out = p;
   return EGR_OK;
