@@ -66,7 +66,7 @@ struct TcKernelArgs {
   int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
   FastDiv d_splits, d_tiles_n, d_tiles_w, d_tiles_h, d_kchunks, d_bw, d_bh, d_c4n;
   int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (<= 256)
-  int vec_ok, need_crop;
+  int vec_ok, need_crop, epi_plain;
   float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
   unsigned int* counters;  // one per output tile, zero between launches
   unsigned long long* trace;  // debug: clock64() stamps of CTA 0 when non-null
@@ -529,24 +529,6 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
       const int buf = it & 1;
       const int n0 = wi.tn * BN;
       int ecount = 0;
-      if (g.resid && ka.splits == 1 && !g.transposed) {
-        // Pull the residual tile of the NEXT item into L2 now (the first item also fetches its own): when the
-        // epilogue is the critical path the accumulator is already waiting, so a prefetch for the current item
-        // would be issued right before its loads; one item ahead gives it a whole epilogue of lead time.
-        for (int pass = (it == 0 ? 0 : 1); pass < 2; ++pass) {
-          const int wn = w + pass * (int)gridDim.x;
-          if (wn >= ka.n_work) break;
-          WorkItem wp;
-          decode_work(ka, wn, wp);
-          for (int m = 0; m < wp.mt_eff; ++m) {
-            const RowInfo rp = row_info(ka, wp, m, lg * 32 + lane);
-            if (rp.ok) {
-              const float* q = g.resid + rp.base + wp.tn * BN;
-              for (int c = 0; c < BN; c += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + c));
-            }
-          }
-        }
-      }
       mbar_wait(accF_u + 8 * buf, ((uint32_t)(it >> 1)) & 1u);
       tc_fence_after();
       if (tr && threadIdx.x == 64 && it < 6) tr[2 + 2 * it] = clock64();
@@ -562,12 +544,51 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         const int roff = (int)(ri.base - base_l0);      // row offset inside the tile (host checked: fits 32 bits)
         const int foff = (int)(ri.flat0 - __shfl_sync(0xffffffffu, ri.flat0, 0));
         const long long flat_l0 = __shfl_sync(0xffffffffu, ri.flat0, 0);
+        const bool vecpath = ka.vec_ok && !part && !g.transposed;
+        // vector path: the 8 (row, 4-column) cells this lane stores per block; row offsets do not depend on the block
+        int off[8], foffs[8], bbs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = 4 * i + rsub;
+          off[i] = __shfl_sync(0xffffffffu, roff, rr);
+          foffs[i] = __shfl_sync(0xffffffffu, foff, rr);
+          bbs[i] = __shfl_sync(0xffffffffu, ri.b, rr);
+          if (!((any_ok >> rr) & 1u)) off[i] = -1;
+        }
+        // residual + bias of a block are fetched one block ahead (software pipeline over cb)
+        float4 rv[8], bias4;
+        const bool has_resid = g.resid != nullptr, has_bias = g.bias != nullptr;
+        auto fetch = [&](int cb_, float4 (&rv_)[8], float4& bias_) {
+          const int n = n0 + cb_ + c4;
+          const bool col_ok = cb_ + c4 < BN && n < g.N;
+          bias_ = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok && has_bias) bias_ = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) rv_[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!has_resid) return;
+          if (!ka.need_crop) {  // predicated loads, no per-cell branches
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (col_ok && off[i] >= 0) rv_[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
+          } else {              // cropped cells (transposed-conv margins) may lie outside the residual tensor
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const long long fl = flat_l0 + foffs[i] + n;
+              if (col_ok && off[i] >= 0 && fl >= g.out_lo && fl < g.out_hi)
+                rv_[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
+            }
+          }
+        };
+        if (vecpath && any_ok) fetch(0, rv, bias4);
         for (int cb = 0; cb < BN; cb += 32) {
           uint32_t r[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ka.acc_cols + m * BN + cb);
           const int ncols = min(32, BN - cb);  // BN is a multiple of 16
+          const bool trc = tr && threadIdx.x == 64 && it == 1 && ecount < 16;
+          if (trc) tr[800 + 5 * ecount] = clock64();
           if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
           tc_wait_ld();
+          if (trc) tr[801 + 5 * ecount] = clock64();
           if (m == wi.mt_eff - 1 && cb + 32 >= BN) {  // last TMEM read of this buffer: hand it back to the MMA warps
             tc_fence_before();
             if (lane == 0) mbar_arrive(accE_u + 8 * buf);
@@ -584,6 +605,9 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             }
             continue;
           }
+          float4 rv_next[8], bias_next;
+          if (vecpath && cb + 32 < BN) fetch(cb + 32, rv_next, bias_next);
+          if (trc) tr[802 + 5 * ecount] = clock64();
           // transpose through shared memory: thread = row  ->  8 lanes per row, 4 rows per instruction
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
@@ -591,49 +615,49 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
               *reinterpret_cast<float4*>(stg + lane * STAGE_LD + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                                                  __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           __syncwarp();
+          if (trc) tr[803 + 5 * ecount] = clock64();
           if (part) {
             // raw partial sums, row-major [mt*128][BN]
             if (c4 < ncols) {
 #pragma unroll
-              for (int r0 = 0; r0 < 32; r0 += 4) {
-                const int rr = r0 + rsub;
-                if ((any_ok >> rr) & 1u)
+              for (int i = 0; i < 8; ++i) {
+                const int rr = 4 * i + rsub;
+                if (off[i] >= 0)
                   __stcg(reinterpret_cast<float4*>(part + ((size_t)(m * TILE_M + lg * 32 + rr)) * BN + cb + c4),
                          *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4));
               }
             }
-          } else if (ka.vec_ok) {
-            // 4 rows x 128 contiguous bytes per instruction; one 32-bit shuffle per pass; every residual load of the
-            // block is issued before the first store (the stores may alias the residual as far as ptxas knows)
+          } else if (vecpath) {
+            // 4 rows x 128 contiguous bytes per store instruction
             const int n = nb + c4;
             const bool col_ok = c4 < ncols && n < g.N;
-            float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (col_ok && g.bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-            int off[8];
-            float4 rv[8];
+            if (ka.epi_plain) {
+              // plain f32 output (+bias, +residual): branch-free passes, only the store is predicated, so the eight
+              // passes interleave (the general variant below serialises on its per-pass uniform branches)
+              float4 a[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * STAGE_LD + c4);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 o;
+                o.x = fmaf(a[i].x, g.alpha, bias4.x) + rv[i].x; o.y = fmaf(a[i].y, g.alpha, bias4.y) + rv[i].y;
+                o.z = fmaf(a[i].z, g.alpha, bias4.z) + rv[i].z; o.w = fmaf(a[i].w, g.alpha, bias4.w) + rv[i].w;
+                if (col_ok && off[i] >= 0) *reinterpret_cast<float4*>(g.out32 + base_l0 + off[i] + n) = o;
+              }
+            } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i + rsub;
-              off[i] = __shfl_sync(0xffffffffu, roff, rr);
-              bool ok = col_ok && ((any_ok >> rr) & 1u);
+              bool ok = col_ok && off[i] >= 0;
               if (ka.need_crop) {
-                const long long fl = flat_l0 + __shfl_sync(0xffffffffu, foff, rr) + n;
+                const long long fl = flat_l0 + foffs[i] + n;
                 ok = ok && fl >= g.out_lo && fl < g.out_hi;
               }
-              if (!ok) off[i] = -1;
-              rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok && g.resid) rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 4 * i + rsub;
-              int bb = 0;
-              if (g.rowbias) bb = __shfl_sync(0xffffffffu, ri.b, rr);  // warp-uniform branch, executed by all lanes
-              if (off[i] < 0) continue;
+              if (!ok) continue;
               const float4 a = *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4);
               float x[4] = {fmaf(a.x, g.alpha, bias4.x), fmaf(a.y, g.alpha, bias4.y), fmaf(a.z, g.alpha, bias4.z), fmaf(a.w, g.alpha, bias4.w)};
               if (g.rowbias) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bb * g.rowbias_stride + n));
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bbs[i] * g.rowbias_stride + n));
                 x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
               }
               if (g.act) {
@@ -651,6 +675,12 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
                 *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
               }
             }
+            }
+            if (cb + 32 < BN) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) rv[i] = rv_next[i];
+              bias4 = bias_next;
+            }
           } else {
             // scalar path (odd alignments): lane = column, one row per pass
 #pragma unroll 4
@@ -667,6 +697,8 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
             }
           }
           __syncwarp();
+          if (trc) tr[804 + 5 * ecount] = clock64();
+          ++ecount;
         }
       }
       if (part) {
@@ -931,9 +963,11 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
                            ((long long)g.Ho * g.Wo + TILE_M) * (g.out_pix_stride > 0 ? g.out_pix_stride : 1) +
                            (long long)g.N * (g.out_n_stride > 0 ? g.out_n_stride : 1);
     if (span >= (1ll << 31)) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: output of %lld elements exceeds the 32-bit tile offsets", op.name, span));
+    ka.epi_plain = 0;
     ka.need_crop = (g.out_lo > 0 || g.out_hi < (long long)g.Ho * g.Wo * g.out_pix_stride + g.out_offset + g.N) ? 1 : 0;
   }
   ka.vec_ok = vec ? 1 : 0;
+  ka.epi_plain = (vec && g.out32 && !g.out16 && g.act == EGR_ACT_NONE && !g.rowbias && !ka.need_crop) ? 1 : 0;
   *out = p;
   return EGR_OK;
 }
