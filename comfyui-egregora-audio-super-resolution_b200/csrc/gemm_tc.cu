@@ -343,6 +343,10 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   unsigned long long* const tr = nullptr;
 #endif
 
+  if (threadIdx.x == 64) {  // descriptor fetches overlap the barrier / TMEM set-up instead of delaying the first TMA
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
   if (threadIdx.x == 0) {
     // halo mode: A and B rings advance at different rates and have their own barriers; otherwise the A stage rides
     // on the B barriers (both producers arrive on fullB, one wait and one commit per k-step for the issuers)
@@ -364,8 +368,6 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
 
   if (warp == 0) {
     // ============================================================ A producer (whole warp, one elected lane issues)
-    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-    __syncwarp();
     const uint32_t ringA_u = smem_u32(ringA);
     const uint32_t fullA_u = smem_u32(ka.halo ? fullA : fullB), emptyA_u = smem_u32(ka.halo ? emptyA : emptyB);
     int sa = 0;
@@ -423,8 +425,6 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     }
   } else if (warp == 6) {
     // ============================================================ B producer (weights / batch-indexed operand)
-    if (lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-    __syncwarp();
     const uint32_t ringB_u = smem_u32(ringB), fullB_u = smem_u32(fullB), emptyB_u = smem_u32(emptyB);
     int sb = 0;
     uint32_t pb = 0;

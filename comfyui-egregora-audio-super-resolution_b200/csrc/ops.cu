@@ -209,6 +209,72 @@ __global__ void __launch_bounds__(256) gemm_simt_smalln_kernel(View a, GemmArgs 
   }
 }
 
+// N <= 4 convolutions with K a multiple of 8 (vae.decoder.conv_out 128->1, vocoder.conv_post 48->1): 8 lanes per
+// pixel, each lane owns 8-channel slices (one 16-byte f16 load or two float4 per slice), the packed weights
+// [taps][N][K] sit in shared memory, partial sums meet through three xor-shuffles.
+__global__ void __launch_bounds__(256) conv_smalln8_kernel(View a, GemmArgs g, Taps taps) {
+  extern __shared__ float wsm[];
+  const int WN = g.ntaps * g.N * g.K;
+  const float* W = reinterpret_cast<const float*>(g.W);
+  for (int i = threadIdx.x; i < WN; i += blockDim.x) {
+    const int k = i % g.K, tn = i / g.K, n = tn % g.N, tap = tn / g.N;
+    wsm[i] = W[(long long)tap * g.wstride_z + (long long)n * g.wstride_n + k];
+  }
+  __syncthreads();
+  const int sub = threadIdx.x & 7;
+  const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const long long npix = (long long)g.Wo * g.Ho * g.Bo;
+  const bool live = p < npix;
+  const long long pp = live ? p : 0;
+  const int w = (int)(pp % g.Wo), h = (int)((pp / g.Wo) % g.Ho), b = (int)(pp / ((long long)g.Wo * g.Ho));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tap = 0; tap < g.ntaps; ++tap) {
+    bool inb = live;
+    long long off = 0;
+#pragma unroll
+    for (int d = 1; d < 5; ++d) {
+      const long long c = taps.t[tap][d] + (d == g.dimW ? w : 0) + (d == g.dimH ? h : 0) + (d == g.dimB ? b : 0);
+      inb = inb && c >= 0 && c < a.dim[d];
+      off += c * a.stride[d];
+    }
+    if (!inb) continue;
+    const int c0 = taps.t[tap][0];
+    const float* wt = wsm + (size_t)tap * g.N * g.K;
+    for (int k = sub * 8; k < g.K; k += 64) {
+      const long long ch = c0 + k;
+      if (ch < 0 || ch + 8 > a.dim[0]) continue;  // slices are 8-aligned (checked on the host)
+      float x[8];
+      if (a.elem) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.p) + off + ch));
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
+        const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&raw.w));
+        x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y; x[4] = f2.x; x[5] = f2.y; x[6] = f3.x; x[7] = f3.y;
+      } else {
+        const float4 r0 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.p) + off + ch));
+        const float4 r1 = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.p) + off + ch + 4));
+        x[0] = r0.x; x[1] = r0.y; x[2] = r0.z; x[3] = r0.w; x[4] = r1.x; x[5] = r1.y; x[6] = r1.z; x[7] = r1.w;
+      }
+      for (int n = 0; n < g.N; ++n) {
+        const float4 w0 = *reinterpret_cast<const float4*>(wt + (size_t)n * g.K + k);
+        const float4 w1 = *reinterpret_cast<const float4*>(wt + (size_t)n * g.K + k + 4);
+        float s = acc[n];
+        s = fmaf(x[0], w0.x, s); s = fmaf(x[1], w0.y, s); s = fmaf(x[2], w0.z, s); s = fmaf(x[3], w0.w, s);
+        s = fmaf(x[4], w1.x, s); s = fmaf(x[5], w1.y, s); s = fmaf(x[6], w1.z, s); s = fmaf(x[7], w1.w, s);
+        acc[n] = s;
+      }
+    }
+  }
+  for (int n = 0; n < g.N; ++n) {
+    float v = acc[n];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    if (sub == 0 && live) epilogue_store(g, b, (long long)h * g.Wo + w, n, v);
+  }
+}
+
 // GEMV for a handful of rows (time-embedding MLP and the per-block embedding projections: M = 1): one warp per
 // output feature, lanes stride K with float4 loads of the f32 weight row.  A must be f32 with unit channel stride.
 __global__ void __launch_bounds__(256) gemm_simt_gemv_kernel(View a, GemmArgs g, int npix) {
@@ -248,6 +314,15 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (npix <= 8 && g.ntaps == 1 && zero_taps && a.elem == 0 && a.stride[0] == 1 && g.K <= a.dim[0] && al16(a.p) && al16(g.W) &&
       (g.wstride_n & 3) == 0 && (a.stride[g.dimW] & 3) == 0 && (a.stride[g.dimH] & 3) == 0 && (a.stride[g.dimB] & 3) == 0) {
     gemm_simt_gemv_kernel<<<(unsigned)((g.N + 7) / 8), 256, 0, st>>>(a, g, (int)npix);
+  } else if (g.N <= 4 && (g.K & 7) == 0 && (a.dim[0] & 7) == 0 && a.stride[0] == 1 && al16(a.p) &&
+             (size_t)g.ntaps * g.N * g.K * sizeof(float) <= 48 * 1024 && [&] {
+               bool ok = true;
+               for (int d = 1; d < 5; ++d) ok = ok && (a.stride[d] & 7) == 0;
+               for (int t = 0; t < g.ntaps; ++t) ok = ok && (taps.t[t][0] & 7) == 0;
+               return ok;
+             }()) {
+    const long long threads = npix * 8;
+    conv_smalln8_kernel<<<(unsigned)((threads + 255) / 256), 256, (size_t)g.ntaps * g.N * g.K * sizeof(float), st>>>(a, g, taps);
   } else if (g.N <= 4) {
     bool vec = (g.K & 3) == 0 && (a.dim[0] & 3) == 0 && al16(a.p) && al16(g.W) && (g.wstride_n & 3) == 0 && (g.wstride_z & 3) == 0;
     for (int d = 1; d < 5; ++d) vec = vec && (a.stride[d] & 3) == 0;
@@ -633,6 +708,128 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __half* __restric
   }
 }
 
+// Same contract, head_dim 16 / 32 and S <= 512: K and V of one (b, head) are staged as f16 with a 16-byte aligned,
+// conflict-free row stride; one warp owns a query row at a time and its LANES SPLIT THE KEYS in both phases: a lane
+// holds the scaled query in registers, reads whole K / V rows with 16-byte loads (32 FMAs per 4 loads instead of one
+// FMA per 2-byte load), keeps its scores in registers (no probability buffer), and the per-lane partial outputs are
+// combined by a reduce-scatter of 31 shuffles.
+template <int HD>
+__global__ void __launch_bounds__(256) attn_rows_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
+                                                        const __half* __restrict__ v, __half* __restrict__ out, int S,
+                                                        int heads, float scale) {
+  extern __shared__ unsigned char smraw[];
+  constexpr int KST = HD + 8;  // halves per staged row
+  __half* Ks = reinterpret_cast<__half*>(smraw);
+  __half* Vs = Ks + (size_t)S * KST;
+  const int C = heads * HD;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const long long base = (long long)b * S * C + (long long)h * HD;
+  for (int i = threadIdx.x; i < S * (HD / 8); i += blockDim.x) {
+    const int j = i / (HD / 8), c8 = (i % (HD / 8)) * 8;
+    *reinterpret_cast<uint4*>(Ks + j * KST + c8) = __ldg(reinterpret_cast<const uint4*>(k + base + (long long)j * C + c8));
+    *reinterpret_cast<uint4*>(Vs + j * KST + c8) = __ldg(reinterpret_cast<const uint4*>(v + base + (long long)j * C + c8));
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_block = (S + gridDim.x - 1) / gridDim.x;
+  const int r_lo = blockIdx.x * rows_per_block, r_hi = min(S, r_lo + rows_per_block);
+  const int njj = (S + 31) >> 5;  // keys per lane (<= 16)
+  auto row8 = [](const __half* p, float* x) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
+    const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&raw.w));
+    x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y; x[4] = f2.x; x[5] = f2.y; x[6] = f3.x; x[7] = f3.y;
+  };
+  for (int r = r_lo + warp; r < r_hi; r += 8) {
+    float qv[HD];
+#pragma unroll
+    for (int c8 = 0; c8 < HD; c8 += 8) {
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(q + base + (long long)r * C + c8));
+      const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float2 f = __half22float2(hp[u]);
+        qv[c8 + 2 * u] = f.x * scale; qv[c8 + 2 * u + 1] = f.y * scale;
+      }
+    }
+    float sc[16];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      sc[jj] = -INFINITY;
+      const int j = jj * 32 + lane;
+      if (jj < njj && j < S) {
+        float dot = 0.f;
+#pragma unroll
+        for (int c8 = 0; c8 < HD; c8 += 8) {
+          float x[8];
+          row8(Ks + j * KST + c8, x);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) dot = fmaf(qv[c8 + u], x[u], dot);
+        }
+        sc[jj] = dot;
+        mx = fmaxf(mx, dot);
+      }
+    }
+    mx = warp_max(mx);
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) {
+      const int j = jj * 32 + lane;
+      if (jj < njj && j < S) {
+        const float p = __expf(sc[jj] - mx);
+        sum += p;
+#pragma unroll
+        for (int c8 = 0; c8 < HD; c8 += 8) {
+          float x[8];
+          row8(Vs + j * KST + c8, x);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) o[c8 + u] = fmaf(p, x[u], o[c8 + u]);
+        }
+      }
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    // reduce-scatter: after the step with mask m a lane keeps the half of its values selected by (lane & m)
+    if (HD == 32) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float mine = (lane & 16) ? o[16 + i] : o[i], send = (lane & 16) ? o[i] : o[16 + i];
+        o[i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+    } else {  // HD == 16: fold the two half-warps first, every lane keeps all 16 values
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float mine = (lane & 8) ? o[8 + i] : o[i], send = (lane & 8) ? o[i] : o[8 + i];
+      o[i] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float mine = (lane & 4) ? o[4 + i] : o[i], send = (lane & 4) ? o[i] : o[4 + i];
+      o[i] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float mine = (lane & 2) ? o[2 + i] : o[i], send = (lane & 2) ? o[i] : o[2 + i];
+      o[i] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    {
+      const float mine = (lane & 1) ? o[1] : o[0], send = (lane & 1) ? o[0] : o[1];
+      o[0] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+    // lane now holds output dim d = bits of lane: for HD 32 d = lane; for HD 16 d = lane & 15 (both half-warps equal)
+    const int d = HD == 32 ? lane : (lane & 15);
+    if (HD == 32 || lane < 16) out[base + (long long)r * C + d] = __float2half_rn(o[0] * inv);
+  }
+}
+
 int egr::launch_attn_small(const Spaces& s, const egr_op& op, cudaStream_t st) {
   const __half* q = (const __half*)resolve(s, op.x0.addr);
   const __half* k = (const __half*)resolve(s, op.x1.addr);
@@ -640,6 +837,23 @@ int egr::launch_attn_small(const Spaces& s, const egr_op& op, cudaStream_t st) {
   __half* o = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
   const int S = (int)op.i[EGR_I_SEQ], heads = (int)op.i[EGR_I_HEADS], hd = (int)op.i[EGR_I_HEADDIM], B = (int)op.i[EGR_I_BATCH];
   if (!q || !k || !v || !o || S <= 0 || heads <= 0 || hd <= 0 || B <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
+  const int C_ = heads * hd;
+  auto al16 = [](const void* p_) { return reinterpret_cast<uintptr_t>(p_) % 16 == 0; };
+  if ((hd == 32 || hd == 16) && S <= 512 && C_ % 8 == 0 && al16(q) && al16(k) && al16(v) && getenv("EGR_ATTN_OLD") == nullptr) {
+    const size_t sm = (size_t)2 * S * (hd + 8) * sizeof(__half);
+    static bool attr2 = false;
+    if (!attr2) {
+      EGR_CUDA(cudaFuncSetAttribute(attn_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EGR_CUDA(cudaFuncSetAttribute(attn_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr2 = true;
+    }
+    // 16 query rows per block (2 per warp): K/V re-staged per block from L2, many blocks for the short sequences
+    const int qblocks = (S + 15) / 16;
+    if (hd == 32) attn_rows_kernel<32><<<dim3(qblocks, heads, B), 256, sm, st>>>(q, k, v, o, S, heads, (float)op.f[EGR_F_ALPHA]);
+    else attn_rows_kernel<16><<<dim3(qblocks, heads, B), 256, sm, st>>>(q, k, v, o, S, heads, (float)op.f[EGR_F_ALPHA]);
+    EGR_CHECK_LAUNCH(op.name);
+    return EGR_OK;
+  }
   size_t smem = (size_t)2 * S * (hd + 2) * sizeof(__half) + (size_t)8 * S * sizeof(float) + 8 * hd * sizeof(float);
   if (smem > 200 * 1024) return fail(EGR_ERR_UNSUPPORTED, "%s: S=%d hd=%d needs %zu B smem; use the GEMM attention path", op.name, S, hd, smem);
   static bool attr_done = false;
