@@ -7,7 +7,7 @@
 // through a rank-5 TMA tensor map, so every tap is just a shifted box load and zero padding is TMA's
 // out-of-bounds fill — no im2col buffer ever exists in HBM.
 //
-// PERSISTENT, warp-specialised CTA (one per SM, 256 threads) looping over work items (m-tile, n-tile, k-split):
+// PERSISTENT, warp-specialised CTA (one per SM, 384 threads) looping over work items (m-tile, n-tile, k-split):
 //   warp 0 / 6  TMA producers of the A / B rings (cp.async.bulk.tensor, SWIZZLE_128B, expect_tx)  [UTMALDG]
 //   warp 1 / 7  tcgen05.mma issuers (M=128, K=16 f16), each owning half of the CTA tile; warp 1 allocates TMEM [UTCHMMA]
 //   warps 2..5  epilogue: tcgen05.ld 32x32b -> registers -> shared-memory transpose -> bias/act/residual ->
@@ -176,7 +176,7 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
 // descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
@@ -311,7 +311,7 @@ __device__ __forceinline__ void finish1(const GemmArgs& g, float acc, long long 
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
-__global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB,
                                                           const __grid_constant__ TcKernelArgs ka) {
   extern __shared__ uint8_t smem_raw[];
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
   uint8_t* ringA = smem;
   uint8_t* ringB = ringA + (size_t)ka.SA * ka.a_stage_bytes;
   float* stage_all = reinterpret_cast<float*>(ringB + (size_t)ka.SB * ka.b_stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_all) + 4 * STAGE_BYTES_PER_WARP);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_all) + 8 * STAGE_BYTES_PER_WARP);
   uint64_t* fullA = bars;
   uint64_t* emptyA = fullA + ka.SA;
   uint64_t* fullB = emptyA + ka.SA;
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
     // on the B barriers (both producers arrive on fullB, one wait and one commit per k-step for the issuers)
     for (int s = 0; s < ka.SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], (uint32_t)ka.n_iss); }
     for (int s = 0; s < ka.SB; ++s) { mbar_init(&fullB[s], ka.halo ? 1u : 2u); mbar_init(&emptyB[s], (uint32_t)ka.n_iss); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], (uint32_t)ka.n_iss); mbar_init(&acc_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], (uint32_t)ka.n_iss); mbar_init(&acc_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -516,196 +516,204 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
         }
       }
     }
-  } else {
-    // ============================================================ epilogue warps 2..5 (TMEM lanes 32*(warp%4) ..)
+  } else if ((warp >= 2 && warp <= 5) || warp >= 8) {
+    // ============================================================ epilogue: warps 2..5 (set 0) and 8..11 (set 1)
+    // A warp may only read TMEM lanes 32*(warp%4)..+31, so each lane group has one warp per set; the two warps
+    // take alternate 32-column blocks of the tile.  The store pass is ALU-latency bound inside a single warp
+    // (address math, predicates, FMAs on a dependent chain): a second warp per scheduler hides that latency.
     const int lg = warp & 3;
-    float* stg = stage_all + (size_t)(warp - 2) * (32 * STAGE_LD);
+    const int eset = warp >= 8 ? 1 : 0;
+    const int ew = eset * 4 + (eset ? warp - 8 : warp - 2);   // 0..7
+    const int et = ew * 32 + lane;                             // epilogue thread id 0..255
+    float* stg = stage_all + (size_t)ew * (32 * STAGE_LD);
     const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // vector pass: 4 rows x 8 float4 per instruction
+    const int nblk = (BN + 31) >> 5;
+    const bool has_resid = g.resid != nullptr, has_bias = g.bias != nullptr;
     int it = 0;
     for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
       WorkItem wi;
       decode_work(ka, w, wi);
       const int buf = it & 1;
       const int n0 = wi.tn * BN;
-      int ecount = 0;
       mbar_wait(accF_u + 8 * buf, ((uint32_t)(it >> 1)) & 1u);
       tc_fence_after();
       if (tr && threadIdx.x == 64 && it < 6) tr[2 + 2 * it] = clock64();
       const int tile_id = wi.tm * ka.tiles_n + wi.tn;
       const size_t pstride = (size_t)ka.mt * TILE_M * BN;
       float* part = ka.splits > 1 ? ka.partial + ((size_t)tile_id * ka.splits + wi.ks) * pstride : nullptr;
-      // NOTE: r[] must only ever be indexed by compile-time constants (fully unrolled loops): one dynamic index sends
-      // the whole array to local memory and every epilogue block then pays ~60 extra local loads/stores.
-      for (int m = 0; m < wi.mt_eff; ++m) {
-        const RowInfo ri = row_info(ka, wi, m, lg * 32 + lane);  // this thread's own row
-        const uint32_t any_ok = __ballot_sync(0xffffffffu, ri.ok);
-        const long long base_l0 = __shfl_sync(0xffffffffu, ri.base, 0);
-        const int roff = (int)(ri.base - base_l0);      // row offset inside the tile (host checked: fits 32 bits)
-        const int foff = (int)(ri.flat0 - __shfl_sync(0xffffffffu, ri.flat0, 0));
-        const long long flat_l0 = __shfl_sync(0xffffffffu, ri.flat0, 0);
-        const bool vecpath = ka.vec_ok && !part && !g.transposed;
-        // vector path: the 8 (row, 4-column) cells this lane stores per block; row offsets do not depend on the block
-        int off[8], foffs[8], bbs[8];
+      const bool vecpath = ka.vec_ok && !part && !g.transposed;
+      const int ntot = wi.mt_eff * nblk;
+      const int last_bi = ntot - 1 - ((ntot - 1 - eset) & 1);  // last block of this set (< eset when it has none)
+      if (last_bi < eset) {  // nothing to read for this warp: hand the buffer back right away
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(accE_u + 8 * buf);
+      }
+      // NOTE: r[] and the other per-block arrays must only be indexed by compile-time constants (fully unrolled
+      // loops): one dynamic index sends the whole array to local memory.
+      int m_prev = -1;
+      RowInfo ri;
+      uint32_t any_ok = 0;
+      long long base_l0 = 0, flat_l0 = 0;
+      int roff = 0, foff = 0;
+      int off[8];
+      for (int bi = eset; bi < ntot; bi += 2) {
+        const int m = bi >= nblk ? 1 : 0;
+        const int cb = (bi - m * nblk) * 32;
+        if (m != m_prev) {
+          m_prev = m;
+          ri = row_info(ka, wi, m, lg * 32 + lane);  // this thread's own row
+          any_ok = __ballot_sync(0xffffffffu, ri.ok);
+          base_l0 = __shfl_sync(0xffffffffu, ri.base, 0);
+          flat_l0 = __shfl_sync(0xffffffffu, ri.flat0, 0);
+          roff = (int)(ri.base - base_l0);   // row offsets inside the tile (host checked: fit 32 bits)
+          foff = (int)(ri.flat0 - flat_l0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + rsub;
-          off[i] = __shfl_sync(0xffffffffu, roff, rr);
-          foffs[i] = __shfl_sync(0xffffffffu, foff, rr);
-          bbs[i] = __shfl_sync(0xffffffffu, ri.b, rr);
-          if (!((any_ok >> rr) & 1u)) off[i] = -1;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + rsub;
+            off[i] = __shfl_sync(0xffffffffu, roff, rr);
+            if (!((any_ok >> rr) & 1u)) off[i] = -1;
+          }
         }
-        // residual + bias of a block are fetched one block ahead (software pipeline over cb)
-        float4 rv[8], bias4;
-        const bool has_resid = g.resid != nullptr, has_bias = g.bias != nullptr;
-        auto fetch = [&](int cb_, float4 (&rv_)[8], float4& bias_) {
-          const int n = n0 + cb_ + c4;
-          const bool col_ok = cb_ + c4 < BN && n < g.N;
-          bias_ = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (col_ok && has_bias) bias_ = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ka.acc_cols + m * BN + cb);
+        const int ncols = min(32, BN - cb);  // BN is a multiple of 16
+        if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
+        const int nb = n0 + cb;
+        const int n = nb + c4;
+        const bool col_ok = c4 < ncols && n < g.N;
+        // bias / residual loads of the vector path are issued under the TMEM load
+        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 rv[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) rv_[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!has_resid) return;
-          if (!ka.need_crop) {  // predicated loads, no per-cell branches
+        for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vecpath && any_ok) {
+          if (col_ok && has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+          if (has_resid) {
+            if (!ka.need_crop) {  // predicated loads, no per-cell branches
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (col_ok && off[i] >= 0) rv_[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
-          } else {              // cropped cells (transposed-conv margins) may lie outside the residual tensor
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const long long fl = flat_l0 + foffs[i] + n;
-              if (col_ok && off[i] >= 0 && fl >= g.out_lo && fl < g.out_hi)
-                rv_[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
-            }
-          }
-        };
-        if (vecpath && any_ok) fetch(0, rv, bias4);
-        for (int cb = 0; cb < BN; cb += 32) {
-          uint32_t r[32];
-          const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ka.acc_cols + m * BN + cb);
-          const int ncols = min(32, BN - cb);  // BN is a multiple of 16
-          const bool trc = tr && threadIdx.x == 64 && it == 1 && ecount < 16;
-          if (trc) tr[800 + 5 * ecount] = clock64();
-          if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
-          tc_wait_ld();
-          if (trc) tr[801 + 5 * ecount] = clock64();
-          if (m == wi.mt_eff - 1 && cb + 32 >= BN) {  // last TMEM read of this buffer: hand it back to the MMA warps
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(accE_u + 8 * buf);
-          }
-          if (!any_ok) continue;
-          const int nb = n0 + cb;
-          if (g.transposed && !part) {
-            // out[b][n][pix]: consecutive rows are consecutive addresses -> already coalesced per column
-            if (ri.ok) {
-              const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncols && nb + j < g.N) finish1(g, __uint_as_float(r[j]), ri.base + (long long)(nb + j) * g.out_n_stride, nb + j, rb);
-            }
-            continue;
-          }
-          float4 rv_next[8], bias_next;
-          if (vecpath && cb + 32 < BN) fetch(cb + 32, rv_next, bias_next);
-          if (trc) tr[802 + 5 * ecount] = clock64();
-          // transpose through shared memory: thread = row  ->  8 lanes per row, 4 rows per instruction
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (j < ncols)
-              *reinterpret_cast<float4*>(stg + lane * STAGE_LD + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          __syncwarp();
-          if (trc) tr[803 + 5 * ecount] = clock64();
-          if (part) {
-            // raw partial sums, row-major [mt*128][BN]
-            if (c4 < ncols) {
+              for (int i = 0; i < 8; ++i)
+                if (col_ok && off[i] >= 0) rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
+            } else {              // cropped cells (transposed-conv margins) may lie outside the residual tensor
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const int rr = 4 * i + rsub;
-                if (off[i] >= 0)
-                  __stcg(reinterpret_cast<float4*>(part + ((size_t)(m * TILE_M + lg * 32 + rr)) * BN + cb + c4),
-                         *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4));
+                const long long fl = flat_l0 + __shfl_sync(0xffffffffu, foff, 4 * i + rsub) + n;
+                if (col_ok && off[i] >= 0 && fl >= g.out_lo && fl < g.out_hi)
+                  rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
               }
             }
-          } else if (vecpath) {
-            // 4 rows x 128 contiguous bytes per store instruction
-            const int n = nb + c4;
-            const bool col_ok = c4 < ncols && n < g.N;
-            if (ka.epi_plain) {
-              // plain f32 output (+bias, +residual): branch-free passes, only the store is predicated, so the eight
-              // passes interleave (the general variant below serialises on its per-pass uniform branches)
-              float4 a[8];
+          }
+        }
+        tc_wait_ld();
+        if (bi == last_bi) {  // last TMEM read of this buffer by this warp: hand it back to the MMA warps
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(accE_u + 8 * buf);
+        }
+        if (!any_ok) continue;
+        if (g.transposed && !part) {
+          // out[b][n][pix]: consecutive rows are consecutive addresses -> already coalesced per column
+          if (ri.ok) {
+            const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const float4*>(stg + (4 * i + rsub) * STAGE_LD + c4);
+            for (int j = 0; j < 32; ++j)
+              if (j < ncols && nb + j < g.N) finish1(g, __uint_as_float(r[j]), ri.base + (long long)(nb + j) * g.out_n_stride, nb + j, rb);
+          }
+          continue;
+        }
+        // transpose through shared memory: thread = row  ->  8 lanes per row, 4 rows per instruction
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float4 o;
-                o.x = fmaf(a[i].x, g.alpha, bias4.x) + rv[i].x; o.y = fmaf(a[i].y, g.alpha, bias4.y) + rv[i].y;
-                o.z = fmaf(a[i].z, g.alpha, bias4.z) + rv[i].z; o.w = fmaf(a[i].w, g.alpha, bias4.w) + rv[i].w;
-                if (col_ok && off[i] >= 0) *reinterpret_cast<float4*>(g.out32 + base_l0 + off[i] + n) = o;
-              }
-            } else {
+        for (int j = 0; j < 32; j += 4)
+          if (j < ncols)
+            *reinterpret_cast<float4*>(stg + lane * STAGE_LD + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+        __syncwarp();
+        if (part) {
+          // raw partial sums, row-major [mt*128][BN]
+          if (c4 < ncols) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = 4 * i + rsub;
-              bool ok = col_ok && off[i] >= 0;
-              if (ka.need_crop) {
-                const long long fl = flat_l0 + foffs[i] + n;
-                ok = ok && fl >= g.out_lo && fl < g.out_hi;
-              }
-              if (!ok) continue;
-              const float4 a = *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4);
-              float x[4] = {fmaf(a.x, g.alpha, bias4.x), fmaf(a.y, g.alpha, bias4.y), fmaf(a.z, g.alpha, bias4.z), fmaf(a.w, g.alpha, bias4.w)};
-              if (g.rowbias) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bbs[i] * g.rowbias_stride + n));
-                x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
-              }
-              if (g.act) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) x[u] = egr_apply_act(x[u], g.act);
-              }
-              x[0] += rv[i].x; x[1] += rv[i].y; x[2] += rv[i].z; x[3] += rv[i].w;
-              const long long idx = base_l0 + off[i] + n;
-              if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(x[0], x[1], x[2], x[3]);
-              if (g.out16) {
-                __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
-                uint2 pk;
-                pk.x = *reinterpret_cast<unsigned*>(&h0);
-                pk.y = *reinterpret_cast<unsigned*>(&h1);
-                *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
-              }
+              if (off[i] >= 0)
+                __stcg(reinterpret_cast<float4*>(part + ((size_t)(m * TILE_M + lg * 32 + rr)) * BN + cb + c4),
+                       *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4));
             }
-            }
-            if (cb + 32 < BN) {
+          }
+        } else if (vecpath) {
+          // 4 rows x 128 contiguous bytes per store instruction
+          if (ka.epi_plain) {
+            // plain f32 output (+bias, +residual): branch-free passes, only the store is predicated, so the passes
+            // interleave (the general variant below serialises on its per-pass uniform branches)
 #pragma unroll
-              for (int i = 0; i < 8; ++i) rv[i] = rv_next[i];
-              bias4 = bias_next;
+            for (int half = 0; half < 2; ++half) {
+              float4 a[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(stg + (4 * (4 * half + i) + rsub) * STAGE_LD + c4);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int k = 4 * half + i;
+                float4 o;
+                o.x = fmaf(a[i].x, g.alpha, bias4.x) + rv[k].x; o.y = fmaf(a[i].y, g.alpha, bias4.y) + rv[k].y;
+                o.z = fmaf(a[i].z, g.alpha, bias4.z) + rv[k].z; o.w = fmaf(a[i].w, g.alpha, bias4.w) + rv[k].w;
+                if (col_ok && off[k] >= 0) *reinterpret_cast<float4*>(g.out32 + base_l0 + off[k] + n) = o;
+              }
             }
           } else {
-            // scalar path (odd alignments): lane = column, one row per pass
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-              const int o = __shfl_sync(0xffffffffu, roff, rr);
-              const int fo = __shfl_sync(0xffffffffu, foff, rr);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = 4 * i + rsub;
+              const int fo = __shfl_sync(0xffffffffu, foff, rr);   // convergent: before any per-lane skip
               const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
-              const int n = nb + lane;
-              const long long fl = flat_l0 + fo + n;
-              if (((any_ok >> rr) & 1u) && lane < ncols && n < g.N && fl >= g.out_lo && fl < g.out_hi) {
-                const float* rb = g.rowbias ? g.rowbias + (long long)bb * g.rowbias_stride : nullptr;
-                finish1(g, stg[rr * STAGE_LD + lane], base_l0 + o + n, n, rb);
+              bool ok = col_ok && off[i] >= 0;
+              if (ka.need_crop) {
+                const long long fl = flat_l0 + fo + n;
+                ok = ok && fl >= g.out_lo && fl < g.out_hi;
+              }
+              if (ok) {
+                const float4 a = *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4);
+                float x[4] = {fmaf(a.x, g.alpha, bias4.x), fmaf(a.y, g.alpha, bias4.y), fmaf(a.z, g.alpha, bias4.z), fmaf(a.w, g.alpha, bias4.w)};
+                if (g.rowbias) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bb * g.rowbias_stride + n));
+                  x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
+                }
+                if (g.act) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) x[u] = egr_apply_act(x[u], g.act);
+                }
+                x[0] += rv[i].x; x[1] += rv[i].y; x[2] += rv[i].z; x[3] += rv[i].w;
+                const long long idx = base_l0 + off[i] + n;
+                if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(x[0], x[1], x[2], x[3]);
+                if (g.out16) {
+                  __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<unsigned*>(&h0);
+                  pk.y = *reinterpret_cast<unsigned*>(&h1);
+                  *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
+                }
               }
             }
           }
-          __syncwarp();
-          if (trc) tr[804 + 5 * ecount] = clock64();
-          ++ecount;
+        } else {
+          // scalar path (odd alignments): lane = column, one row per pass
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int o = __shfl_sync(0xffffffffu, roff, rr);
+            const int fo = __shfl_sync(0xffffffffu, foff, rr);
+            const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
+            const int nn = nb + lane;
+            const long long fl = flat_l0 + fo + nn;
+            if (((any_ok >> rr) & 1u) && lane < ncols && nn < g.N && fl >= g.out_lo && fl < g.out_hi) {
+              const float* rb = g.rowbias ? g.rowbias + (long long)bb * g.rowbias_stride : nullptr;
+              finish1(g, stg[rr * STAGE_LD + lane], base_l0 + o + nn, nn, rb);
+            }
+          }
         }
+        __syncwarp();
       }
       if (part) {
         // split-K: the last CTA to finish this output tile reduces all partials in split order
         __threadfence();
         epi_bar_sync();
-        if (threadIdx.x == 64) {
+        if (et == 0) {
           const unsigned int old = atomicAdd(ka.counters + tile_id, 1u);
           const unsigned int last = (old == (unsigned int)(ka.splits - 1)) ? 1u : 0u;
           if (last) ka.counters[tile_id] = 0u;  // ready for the next launch
@@ -720,7 +728,7 @@ __global__ void __launch_bounds__(256, 1) gemm_tc_kernel(const __grid_constant__
           const float* pt = ka.partial + (size_t)tile_id * ka.splits * pstride;
           const int c4n = BN >> 2;
           const int total = wi.mt_eff * TILE_M * c4n;
-          for (int e = (int)threadIdx.x - 64; e < total; e += 128) {
+          for (int e = et; e < total; e += 256) {
             const int row = fdiv(e, ka.d_c4n), c = (e - row * c4n) * 4;
             const int m = row >> 7;
             const RowInfo ri = row_info(ka, wi, m, row & 127);
@@ -935,7 +943,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   if (rc) return bail(rc);
 
   // ---- ring depths: ~195 KB of the 227 KB for the two rings (the rest: epilogue staging, barriers, alignment slack)
-  const int budget = 195 * 1024;
+  const int budget = 184 * 1024;
   int SB, SA;
   if (halo) {
     SB = (96 * 1024) / ka.b_stage_bytes; if (SB > 8) SB = 8; if (SB < 2) SB = 2;
@@ -947,7 +955,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     SB = SA;
   }
   ka.SA = SA; ka.SB = SB;
-  p->smem_bytes = SA * ka.a_stage_bytes + SB * ka.b_stage_bytes + 4 * STAGE_BYTES_PER_WARP + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
+  p->smem_bytes = SA * ka.a_stage_bytes + SB * ka.b_stage_bytes + 8 * STAGE_BYTES_PER_WARP + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
   if (p->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: %d B of shared memory needed", op.name, p->smem_bytes));
   p->grid = ka.n_work < sms ? ka.n_work : sms;
   p->partial_bytes = splits > 1 ? (size_t)ka.tiles_m * ka.tiles_n * splits * mt * TILE_M * bn * sizeof(float) : 0;
@@ -999,7 +1007,7 @@ int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
     return fail(EGR_ERR_STATE, "%s: split-K scratch not bound", p->name);
   TcKernelArgs ka = p->ka;
   ka.trace = g_trace_dev;
-  gemm_tc_kernel<<<p->grid, 256, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
+  gemm_tc_kernel<<<p->grid, 384, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
   EGR_CHECK_LAUNCH(p->name);
   return EGR_OK;
 }

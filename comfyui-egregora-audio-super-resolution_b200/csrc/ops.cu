@@ -275,6 +275,49 @@ __global__ void __launch_bounds__(256) conv_smalln8_kernel(View a, GemmArgs g, T
   }
 }
 
+// Convolutions with a tiny reduction (1-channel inputs: vae.encoder.conv_in, vocoder.wave_pre; K <= 4): a thread
+// owns 4 consecutive output channels of one pixel, gathers its <= 64 input values once and reads the packed
+// weights [taps*K][N] from shared memory as float4 (consecutive threads -> consecutive channels: coalesced stores).
+__global__ void __launch_bounds__(256) conv_smallk_kernel(View a, GemmArgs g, Taps taps) {
+  extern __shared__ float wsm[];  // [ntaps][K][N]
+  const int R = g.ntaps * g.K;
+  const float* W = reinterpret_cast<const float*>(g.W);
+  for (int i = threadIdx.x; i < R * g.N; i += blockDim.x) {
+    const int n = i % g.N, r = i / g.N, tap = r / g.K, k = r % g.K;
+    wsm[i] = W[(long long)tap * g.wstride_z + (long long)n * g.wstride_n + k];
+  }
+  __syncthreads();
+  const int n4 = g.N >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long npix = (long long)g.Wo * g.Ho * g.Bo;
+  if (idx >= npix * n4) return;
+  const long long p = idx / n4;
+  const int n = (int)(idx - p * n4) * 4;
+  const int w = (int)(p % g.Wo), h = (int)((p / g.Wo) % g.Ho), b = (int)(p / ((long long)g.Wo * g.Ho));
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tap = 0; tap < g.ntaps; ++tap) {
+    bool inb = true;
+    long long off = 0;
+#pragma unroll
+    for (int d = 1; d < 5; ++d) {
+      const long long c = taps.t[tap][d] + (d == g.dimW ? w : 0) + (d == g.dimH ? h : 0) + (d == g.dimB ? b : 0);
+      inb = inb && c >= 0 && c < a.dim[d];
+      off += c * a.stride[d];
+    }
+    if (!inb) continue;
+    for (int k = 0; k < g.K; ++k) {
+      const long long ch = taps.t[tap][0] + k;
+      if (ch < 0 || ch >= a.dim[0]) continue;
+      const float x = a.elem ? __half2float(reinterpret_cast<const __half*>(a.p)[off + ch]) : reinterpret_cast<const float*>(a.p)[off + ch];
+      const float4 wv = *reinterpret_cast<const float4*>(wsm + (size_t)(tap * g.K + k) * g.N + n);
+      acc[0] = fmaf(x, wv.x, acc[0]); acc[1] = fmaf(x, wv.y, acc[1]); acc[2] = fmaf(x, wv.z, acc[2]); acc[3] = fmaf(x, wv.w, acc[3]);
+    }
+  }
+  const long long pix = (long long)h * g.Wo + w;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) epilogue_store(g, b, pix, n + u, acc[u]);
+}
+
 // GEMV for a handful of rows (time-embedding MLP and the per-block embedding projections: M = 1): one warp per
 // output feature, lanes stride K with float4 loads of the f32 weight row.  A must be f32 with unit channel stride.
 __global__ void __launch_bounds__(256) gemm_simt_gemv_kernel(View a, GemmArgs g, int npix) {
@@ -314,6 +357,9 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (npix <= 8 && g.ntaps == 1 && zero_taps && a.elem == 0 && a.stride[0] == 1 && g.K <= a.dim[0] && al16(a.p) && al16(g.W) &&
       (g.wstride_n & 3) == 0 && (a.stride[g.dimW] & 3) == 0 && (a.stride[g.dimH] & 3) == 0 && (a.stride[g.dimB] & 3) == 0) {
     gemm_simt_gemv_kernel<<<(unsigned)((g.N + 7) / 8), 256, 0, st>>>(a, g, (int)npix);
+  } else if (g.K <= 4 && (g.N & 3) == 0 && (size_t)g.ntaps * g.K * g.N * sizeof(float) <= 48 * 1024) {
+    const long long threads = npix * (g.N >> 2);
+    conv_smallk_kernel<<<(unsigned)((threads + 255) / 256), 256, (size_t)g.ntaps * g.K * g.N * sizeof(float), st>>>(a, g, taps);
   } else if (g.N <= 4 && (g.K & 7) == 0 && (a.dim[0] & 7) == 0 && a.stride[0] == 1 && al16(a.p) &&
              (size_t)g.ntaps * g.N * g.K * sizeof(float) <= 48 * 1024 && [&] {
                bool ok = true;
@@ -391,17 +437,24 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(CatArgs a, double* __rest
   }
 }
 
-// stats[b][g][2] = sum over slabs (fixed order: 8 strided lanes, then lane order)
+// stats[b][g][2] = sum over slabs in a fixed order (16 strided rows x 4 interleaved accumulators, then row order):
+// 64 slab loads per thread would be one long L2-latency chain, so four independent chains run at once
 __global__ void gn_finalize_kernel(const double* __restrict__ partials, double* __restrict__ stats, int G2, int nslabs) {
-  extern __shared__ double shf64[];  // [8][G2]
+  extern __shared__ double shf64[];  // [16][G2]
   const int b = blockIdx.x, i = threadIdx.x, y = threadIdx.y;
-  double acc = 0.0;
-  for (int sl = y; sl < nslabs; sl += 8) acc += partials[((long long)b * nslabs + sl) * G2 + i];
-  shf64[y * G2 + i] = acc;
+  const double* p = partials + (long long)b * nslabs * G2 + i;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int sl = y;
+  for (; sl + 48 < nslabs; sl += 64) {
+    a0 += p[(long long)sl * G2]; a1 += p[(long long)(sl + 16) * G2];
+    a2 += p[(long long)(sl + 32) * G2]; a3 += p[(long long)(sl + 48) * G2];
+  }
+  for (; sl < nslabs; sl += 16) a0 += p[(long long)sl * G2];
+  shf64[y * G2 + i] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (y == 0) {
     double t = 0.0;
-    for (int k = 0; k < 8; ++k) t += shf64[k * G2 + i];
+    for (int k = 0; k < 16; ++k) t += shf64[k * G2 + i];
     stats[(long long)b * G2 + i] = t;
   }
 }
@@ -559,10 +612,10 @@ int egr::launch_gn_stats(const Spaces& s, const egr_op& op, cudaStream_t st) {
   double* partials = stats + (long long)a.B * G2;
   const size_t smem = (size_t)C * 2 * sizeof(double);
   if (smem > 48 * 1024) return fail(EGR_ERR_UNSUPPORTED, "%s: C=%d too wide for the GroupNorm reduction", op.name, C);
-  if (G2 > 128) return fail(EGR_ERR_UNSUPPORTED, "%s: at most 64 groups", op.name);
+  if (G2 > 64) return fail(EGR_ERR_UNSUPPORTED, "%s: at most 32 groups", op.name);
   gn_stats_kernel<<<dim3(ns, a.B), 256, smem, st>>>(a, partials, slab, ns);
   EGR_CHECK_LAUNCH(op.name);
-  gn_finalize_kernel<<<a.B, dim3(G2, 8), (size_t)8 * G2 * sizeof(double), st>>>(partials, stats, G2, ns);
+  gn_finalize_kernel<<<a.B, dim3(G2, 16), (size_t)16 * G2 * sizeof(double), st>>>(partials, stats, G2, ns);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }
