@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
     const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // vector pass: 4 rows x 8 float4 per instruction
     const int nblk = (BN + 31) >> 5;
-    const bool has_resid = g.resid != nullptr, has_bias = g.bias != nullptr;
+    const bool has_resid = g.resid != nullptr, has_bias = g.bias != nullptr, has_out16 = g.out16 != nullptr;
     int it = 0;
     for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
       WorkItem wi;
@@ -654,7 +654,16 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
                 float4 o;
                 o.x = fmaf(a[i].x, g.alpha, bias4.x) + rv[k].x; o.y = fmaf(a[i].y, g.alpha, bias4.y) + rv[k].y;
                 o.z = fmaf(a[i].z, g.alpha, bias4.z) + rv[k].z; o.w = fmaf(a[i].w, g.alpha, bias4.w) + rv[k].w;
-                if (col_ok && off[k] >= 0) *reinterpret_cast<float4*>(g.out32 + base_l0 + off[k] + n) = o;
+                if (col_ok && off[k] >= 0) {
+                  *reinterpret_cast<float4*>(g.out32 + base_l0 + off[k] + n) = o;
+                  if (has_out16) {  // f16 copy for a following tensor-core layer (uniform flag)
+                    __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<unsigned*>(&h0);
+                    pk.y = *reinterpret_cast<unsigned*>(&h1);
+                    *reinterpret_cast<uint2*>(g.out16 + base_l0 + off[k] + n) = pk;
+                  }
+                }
               }
             }
           } else {
@@ -975,7 +984,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     ka.need_crop = (g.out_lo > 0 || g.out_hi < (long long)g.Ho * g.Wo * g.out_pix_stride + g.out_offset + g.N) ? 1 : 0;
   }
   ka.vec_ok = vec ? 1 : 0;
-  ka.epi_plain = (vec && g.out32 && !g.out16 && g.act == EGR_ACT_NONE && !g.rowbias && !ka.need_crop) ? 1 : 0;
+  ka.epi_plain = (vec && g.out32 && g.act == EGR_ACT_NONE && !g.rowbias && !ka.need_crop) ? 1 : 0;
   *out = p;
   return EGR_OK;
 }

@@ -275,47 +275,59 @@ __global__ void __launch_bounds__(256) conv_smalln8_kernel(View a, GemmArgs g, T
   }
 }
 
-// Convolutions with a tiny reduction (1-channel inputs: vae.encoder.conv_in, vocoder.wave_pre; K <= 4): a thread
-// owns 4 consecutive output channels of one pixel, gathers its <= 64 input values once and reads the packed
-// weights [taps*K][N] from shared memory as float4 (consecutive threads -> consecutive channels: coalesced stores).
+// Convolutions with a tiny reduction (1-channel inputs: vae.encoder.conv_in, vocoder.wave_pre; taps*K <= 64): a CTA
+// owns 64 pixels.  Phase 1 gathers the 64 x R input patch into shared memory (the tap bounds / address math runs
+// once per patch value, not once per output); phase 2: 4 threads per pixel sweep the output channels as float4
+// against the packed weights [R][N] in shared memory (4 threads x 16 B = 64 contiguous bytes per store).
+#define SMK_PIX 64
 __global__ void __launch_bounds__(256) conv_smallk_kernel(View a, GemmArgs g, Taps taps) {
-  extern __shared__ float wsm[];  // [ntaps][K][N]
+  extern __shared__ float wsm[];  // [R][N] weights, then [SMK_PIX][R] patch
   const int R = g.ntaps * g.K;
+  float* xs = wsm + (size_t)R * g.N;
   const float* W = reinterpret_cast<const float*>(g.W);
   for (int i = threadIdx.x; i < R * g.N; i += blockDim.x) {
     const int n = i % g.N, r = i / g.N, tap = r / g.K, k = r % g.K;
     wsm[i] = W[(long long)tap * g.wstride_z + (long long)n * g.wstride_n + k];
   }
-  __syncthreads();
-  const int n4 = g.N >> 2;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long npix = (long long)g.Wo * g.Ho * g.Bo;
-  if (idx >= npix * n4) return;
-  const long long p = idx / n4;
-  const int n = (int)(idx - p * n4) * 4;
-  const int w = (int)(p % g.Wo), h = (int)((p / g.Wo) % g.Ho), b = (int)(p / ((long long)g.Wo * g.Ho));
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int tap = 0; tap < g.ntaps; ++tap) {
-    bool inb = true;
-    long long off = 0;
+  const long long p0 = (long long)blockIdx.x * SMK_PIX;
+  for (int i = threadIdx.x; i < SMK_PIX * R; i += blockDim.x) {
+    const int pl = i / R, r = i - pl * R, tap = r / g.K, k = r - tap * g.K;
+    const long long p = p0 + pl;
+    float x = 0.f;
+    if (p < npix) {
+      const int w = (int)(p % g.Wo), h = (int)((p / g.Wo) % g.Ho), b = (int)(p / ((long long)g.Wo * g.Ho));
+      bool inb = true;
+      long long off = 0;
 #pragma unroll
-    for (int d = 1; d < 5; ++d) {
-      const long long c = taps.t[tap][d] + (d == g.dimW ? w : 0) + (d == g.dimH ? h : 0) + (d == g.dimB ? b : 0);
-      inb = inb && c >= 0 && c < a.dim[d];
-      off += c * a.stride[d];
-    }
-    if (!inb) continue;
-    for (int k = 0; k < g.K; ++k) {
+      for (int d = 1; d < 5; ++d) {
+        const long long c = taps.t[tap][d] + (d == g.dimW ? w : 0) + (d == g.dimH ? h : 0) + (d == g.dimB ? b : 0);
+        inb = inb && c >= 0 && c < a.dim[d];
+        off += c * a.stride[d];
+      }
       const long long ch = taps.t[tap][0] + k;
-      if (ch < 0 || ch >= a.dim[0]) continue;
-      const float x = a.elem ? __half2float(reinterpret_cast<const __half*>(a.p)[off + ch]) : reinterpret_cast<const float*>(a.p)[off + ch];
-      const float4 wv = *reinterpret_cast<const float4*>(wsm + (size_t)(tap * g.K + k) * g.N + n);
+      if (inb && ch >= 0 && ch < a.dim[0])
+        x = a.elem ? __half2float(reinterpret_cast<const __half*>(a.p)[off + ch]) : reinterpret_cast<const float*>(a.p)[off + ch];
+    }
+    xs[i] = x;
+  }
+  __syncthreads();
+  const int pl = threadIdx.x >> 2, q = threadIdx.x & 3;
+  const long long p = p0 + pl;
+  if (p >= npix) return;
+  const int w = (int)(p % g.Wo), h = (int)((p / g.Wo) % g.Ho), b = (int)(p / ((long long)g.Wo * g.Ho));
+  const long long pix = (long long)h * g.Wo + w;
+  const float* xp = xs + (size_t)pl * R;
+  for (int n = q * 4; n < g.N; n += 16) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < R; ++r) {
+      const float x = xp[r];
+      const float4 wv = *reinterpret_cast<const float4*>(wsm + (size_t)r * g.N + n);
       acc[0] = fmaf(x, wv.x, acc[0]); acc[1] = fmaf(x, wv.y, acc[1]); acc[2] = fmaf(x, wv.z, acc[2]); acc[3] = fmaf(x, wv.w, acc[3]);
     }
-  }
-  const long long pix = (long long)h * g.Wo + w;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) epilogue_store(g, b, pix, n + u, acc[u]);
+    for (int u = 0; u < 4; ++u) epilogue_store(g, b, pix, n + u, acc[u]);
+  }
 }
 
 // GEMV for a handful of rows (time-embedding MLP and the per-block embedding projections: M = 1): one warp per
@@ -357,9 +369,8 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (npix <= 8 && g.ntaps == 1 && zero_taps && a.elem == 0 && a.stride[0] == 1 && g.K <= a.dim[0] && al16(a.p) && al16(g.W) &&
       (g.wstride_n & 3) == 0 && (a.stride[g.dimW] & 3) == 0 && (a.stride[g.dimH] & 3) == 0 && (a.stride[g.dimB] & 3) == 0) {
     gemm_simt_gemv_kernel<<<(unsigned)((g.N + 7) / 8), 256, 0, st>>>(a, g, (int)npix);
-  } else if (g.K <= 4 && (g.N & 3) == 0 && (size_t)g.ntaps * g.K * g.N * sizeof(float) <= 48 * 1024) {
-    const long long threads = npix * (g.N >> 2);
-    conv_smallk_kernel<<<(unsigned)((threads + 255) / 256), 256, (size_t)g.ntaps * g.K * g.N * sizeof(float), st>>>(a, g, taps);
+  } else if (g.K <= 4 && g.ntaps * g.K <= 64 && (g.N & 3) == 0 && (size_t)g.ntaps * g.K * (g.N + SMK_PIX) * sizeof(float) <= 48 * 1024) {
+    conv_smallk_kernel<<<(unsigned)((npix + SMK_PIX - 1) / SMK_PIX), 256, (size_t)g.ntaps * g.K * (g.N + SMK_PIX) * sizeof(float), st>>>(a, g, taps);
   } else if (g.N <= 4 && (g.K & 7) == 0 && (a.dim[0] & 7) == 0 && a.stride[0] == 1 && al16(a.p) &&
              (size_t)g.ntaps * g.N * g.K * sizeof(float) <= 48 * 1024 && [&] {
                bool ok = true;
@@ -1054,7 +1065,7 @@ __device__ __forceinline__ float snake_eval(float u, float alpha, float inv_beta
 // consecutive lanes read consecutive channels (coalesced).  Both the 6-sample input window and the 12-sample
 // activated window slide in registers: per output 1 load, 12 FMAs (two up-sampling phases), 2 snake evaluations,
 // 12 FMAs (down-sampling), 1 store.
-__global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__ x, int T, int C, int nruns,
+__global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__ x, int T, int C, int nruns, int tt,
                                                         const float* __restrict__ log_alpha,
                                                         const float* __restrict__ log_beta,
                                                         const float* __restrict__ filt, float* __restrict__ o32,
@@ -1062,7 +1073,7 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)nruns * C) return;
   const int c = (int)(idx % C);
-  const int t0 = (int)(idx / C) * SNAKE_TT;
+  const int t0 = (int)(idx / C) * tt;
   const int b = blockIdx.y;
   const float alpha = __expf(log_alpha[c]);
   const float inv_beta = 1.0f / (__expf(log_beta[c]) + 1e-9f);
@@ -1091,7 +1102,7 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
   float xw[6];
 #pragma unroll
   for (int r = 0; r < 5; ++r) xw[r + 1] = xat(t0 + r);  // slots 1..5 hold x[t0 .. t0+4]
-  const int t_end = min(T, t0 + SNAKE_TT);
+  const int t_end = min(T, t0 + tt);
   for (int tb = t0; tb < t_end; tb += 8) {
     // the 8 new input samples of this group are independent of the recurrence: issue their loads together
     float xn[8];
@@ -1136,9 +1147,28 @@ int egr::launch_snake_aa(const Spaces& s, const egr_op& op, cudaStream_t st) {
   const int B = (int)op.i[EGR_I_BATCH], T = (int)op.i[EGR_I_ROWS], C = (int)op.i[EGR_I_COLS];
   if (!x || !la || !lb || !filt || (!o32 && !o16) || B <= 0 || T <= 0 || C <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
   if (op.i[EGR_I_AUX0] != 12) return fail(EGR_ERR_UNSUPPORTED, "%s: only the 12-tap anti-alias filter is built", op.name);
-  const int nruns = (T + SNAKE_TT - 1) / SNAKE_TT;
+  // Outputs per thread: every run pays ~10 warm-up evaluations of the activation, and a grid slightly larger than
+  // what the GPU holds at once costs a whole extra wave — pick the run length (multiple of 8) that minimises
+  // waves x (run + warm-up) for this tensor.
+  static int resident = 0;
+  if (!resident) {
+    int per_sm = 0;
+    EGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snake_aa_kernel, 128, 0));
+    resident = (per_sm > 0 ? per_sm : 8) * (devinfo().sm_count ? devinfo().sm_count : 148);
+  }
+  int tt = SNAKE_TT;
+  {
+    double best = 1e30;
+    for (int cand = 16; cand <= 128; cand += 8) {
+      const long long blocks = (((long long)((T + cand - 1) / cand) * C + 127) / 128) * B;
+      const long long waves = (blocks + resident - 1) / resident;
+      const double cost = (double)waves * (cand + 10);
+      if (cost < best) { best = cost; tt = cand; }
+    }
+  }
+  const int nruns = (T + tt - 1) / tt;
   dim3 grid((unsigned)(((long long)nruns * C + 127) / 128), B);
-  snake_aa_kernel<<<grid, 128, 0, st>>>(x, T, C, nruns, la, lb, filt, o32, o16);
+  snake_aa_kernel<<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }

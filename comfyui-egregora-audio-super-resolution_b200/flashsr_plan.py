@@ -47,6 +47,7 @@ class PT:
         self.coff = int(coff)                   # channel offset inside the row
         self.parts = parts                      # (PT, PT) for a virtual concat
         self.f16_transposed = f16_transposed    # f16 stored as [B][C][H*W]
+        self.producer = None                    # RawOp that writes .f32 and can also emit an f16 copy at the same indices
 
     @property
     def P(self):
@@ -64,6 +65,7 @@ class RawOp:
         self.taps = []
         self.reads: List[Buf] = []
         self.writes: List[Buf] = []
+        self.index = -1
 
 
 class WeightBlob:
@@ -157,6 +159,7 @@ class PlanBackend:
 
     def emit(self, op: RawOp) -> RawOp:
         idx = len(self.ops)
+        op.index = idx
         for b in op.reads + op.writes:
             if b.first is None:
                 b.first = idx
@@ -219,6 +222,16 @@ class PlanBackend:
     def _materialize16(self, x: PT, tag="cast") -> PT:
         """Return a PT whose .f16 holds x (concats and f32-only tensors go through one CAST16 pass)."""
         if x.f16 is not None and x.parts is None and not x.f16_transposed and x.ld == x.C:
+            return x
+        prod = x.producer
+        if (x.f16 is None and x.parts is None and x.ld == x.C and x.coff == 0 and prod is not None and prod.index >= 0
+                and "OUT16" not in prod.ptr):
+            # the op that produced the f32 tensor writes the f16 copy in its own epilogue: no separate cast pass
+            buf = self.buf(x.B * x.P * x.C * 2, tag + ".f16", persistent=self.debug)
+            buf.first = buf.last = prod.index
+            prod.ptr["OUT16"] = ("ws", buf, 0)
+            prod.writes.append(buf)
+            x.f16 = buf
             return x
         parts = x.parts if x.parts else (x, None)
         a, b = parts
@@ -286,7 +299,10 @@ class PlanBackend:
             self.tc_flops += fl
         self.layer_table.append({"name": name, "kind": "simt" if simt else "tc", "M": Bo * Ho * Wo, "N": N, "K": Kdim * ntaps,
                                  "taps": ntaps, "flops": fl, "block_n": bn})
-        return self.emit(op)
+        self.emit(op)
+        if out32 and not out16 and not transposed:
+            out_pt.producer = op   # f16 copy on demand (same indices as the f32 store)
+        return op
 
     @staticmethod
     def _use_tc(cin, cout):
@@ -468,6 +484,8 @@ class PlanBackend:
             op.x1 = (y.f32, 0, 1, 0, [y.C], [1]); op.reads.append(y.f32)
         self._ws(op, "OUT32", o.f32, write=True)
         self.emit(op)
+        if mode in (K["EGR_ELT_AXPBY"], K["EGR_ELT_SCALE_SHIFT"]):
+            o.producer = op
         return o
 
     def axpby(self, x: PT, y: PT, a, b):
