@@ -604,7 +604,7 @@ static int cat_args(const Spaces& s, const egr_op& op, CatArgs* a) {
 static int slab_for(long long P, int* nslabs) {
   // ~1184 slabs for the largest maps (8 per SM at batch 1); a function of P only, so results do not depend on B
   long long slab = (P + 1183) / 1184;
-  if (slab < 64) slab = 64;
+  if (slab < 16) slab = 16;
   if (slab > P) slab = P;
   *nslabs = (int)((P + slab - 1) / slab);
   return (int)slab;
@@ -1097,17 +1097,45 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
     return snake_eval(2.0f * u, alpha, inv_beta);
   };
   float sw[12];
-#pragma unroll
-  for (int j = 0; j < 10; ++j) sw[j + 2] = s_at(2 * t0 - 5 + j);  // slots 2..11 hold s[2t0-5 .. 2t0+4]
   float xw[6];
+  if (t0 >= 5 && 2 * t0 + 4 <= n_last && t0 + 4 < T) {
+    // interior run: the ten warm-up samples s[2t0-5 .. 2t0+4] only need x[t0-5 .. t0+4] — ten independent loads
+    // issued together instead of sixty dependent-latency ones
+    float xr[10];
 #pragma unroll
-  for (int r = 0; r < 5; ++r) xw[r + 1] = xat(t0 + r);  // slots 1..5 hold x[t0 .. t0+4]
+    for (int i = 0; i < 10; ++i) xr[i] = __ldg(xb + (long long)(t0 - 5 + i) * C);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      // n = 2 t0 - 5 + j ; odd n (j even): m = t0 - 3 + j/2, taps x[m-2 .. m+3] ; even n (j odd): m = t0 - 2 + (j-1)/2, x[m-3 .. m+2]
+      float u = 0.f;
+      if ((j & 1) == 0) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) u = fmaf(xr[(j >> 1) + r], f[10 - 2 * r], u);
+      } else {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) u = fmaf(xr[((j - 1) >> 1) + r], f[11 - 2 * r], u);
+      }
+      sw[j + 2] = snake_eval(2.0f * u, alpha, inv_beta);
+    }
+#pragma unroll
+    for (int r = 0; r < 5; ++r) xw[r + 1] = xr[5 + r];  // slots 1..5 hold x[t0 .. t0+4]
+  } else {
+#pragma unroll
+    for (int j = 0; j < 10; ++j) sw[j + 2] = s_at(2 * t0 - 5 + j);  // slots 2..11 hold s[2t0-5 .. 2t0+4]
+#pragma unroll
+    for (int r = 0; r < 5; ++r) xw[r + 1] = xat(t0 + r);
+  }
   const int t_end = min(T, t0 + tt);
-  for (int tb = t0; tb < t_end; tb += 8) {
-    // the 8 new input samples of this group are independent of the recurrence: issue their loads together
-    float xn[8];
+  // the new input samples of a group are independent of the recurrence: their loads are issued one group ahead
+  float xn[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xn[i] = xat(tb + i + 5);
+  for (int i = 0; i < 8; ++i) xn[i] = xat(t0 + i + 5);
+  for (int tb = t0; tb < t_end; tb += 8) {
+    float xnext[8];
+    if (tb + 8 < t_end) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xnext[i] = xat(tb + 8 + i + 5);
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int t = tb + i;
@@ -1134,6 +1162,8 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
       if (o32) o32[o] = y;
       if (o16) o16[o] = __float2half_rn(y);
     }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xn[i] = xnext[i];
   }
 }
 

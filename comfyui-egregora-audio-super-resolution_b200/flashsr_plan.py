@@ -112,7 +112,7 @@ def tile_geometry(Wo: int, Ho: int, Bo: int) -> Tuple[int, int, int]:
 def gn_slabs(P: int) -> Tuple[int, int]:
     """(slab, n_slabs) of the GroupNorm reduction — must match slab_for() in csrc/ops.cu; a function of the pixel
     count only, so results are bit-identical for any batch size."""
-    slab = min(max((P + 1183) // 1184, 64), P)
+    slab = min(max((P + 1183) // 1184, 16), P)
     return slab, (P + slab - 1) // slab
 
 
