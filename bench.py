@@ -117,6 +117,19 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(kernel: str):
+    """Per-launch DRAM bytes of `kernel` from the committed ncu pass of one c2 step (tools/gpu_ncu2.sh writes
+    profiles/*_traffic_c2_b1.json: dram__bytes_read.sum + dram__bytes_write.sum over every launch)."""
+    cands = sorted((ROOT / "profiles").glob("*_traffic_c2_b1.json"))
+    if not cands:
+        return None
+    d = json.loads(cands[-1].read_text()).get(kernel)
+    if not d or not d.get("launches"):
+        return None
+    return {"bytes_per_launch": (d["dram_read_bytes"] + d["dram_write_bytes"]) / d["launches"], "source": cands[-1].name,
+            "tensor_pipe_pct": d.get("tensor_pipe_pct_time_weighted")}
+
+
 def peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -345,7 +358,9 @@ def run_b200(args):
         achieved = be.tc_flops / t_tc / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 tap-GEMM, f16 operands, f32 TMEM accumulate)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long pass)", "traffic": None,
+                "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long pass)",
+                "traffic": (ncu_traffic("gemm_tc_kernel") or {}).get("bytes_per_launch"),
+                "traffic_note": ncu_traffic("gemm_tc_kernel"),
                 "launches_per_pass": n_tc, "flops_per_pass": be.tc_flops, "avg_launch_us": 1e6 * t_tc / max(n_tc, 1),
                 "gemm_share_of_plan": t_tc / t_plan, "plan_ms": 1e3 * t_plan}
         # ---- batched throughput (c3's per-GPU share: 33 chunk-channels, 4 steps), extra information

@@ -2,6 +2,7 @@
 // blob.  Creation validates every op and encodes the TMA tensor maps of the tensor-core GEMMs once; run just
 // enqueues kernels on the caller's stream (no allocation, no synchronisation), so a whole forward pass can be
 // captured into a CUDA graph by the host.
+#include <cstdlib>
 #include <vector>
 #include "ops.cuh"
 
@@ -12,6 +13,11 @@ struct egr_plan {
   std::vector<TcPrepared*> tc;  // per op, nullptr unless GEMM_TC
   Spaces sp;
   void* scratch = nullptr;      // split-K partial tiles followed by the per-tile arrival counters (library-owned)
+  // whole-plan CUDA graph: the op list is static (fixed addresses, shapes, launch geometry), so after one eager pass
+  // the ~900 launches are captured once and replayed with a single cudaGraphLaunch
+  cudaGraphExec_t graph_exec = nullptr;
+  int full_runs = 0;
+  unsigned long long launches_per_run = 0;
 };
 
 static int run_op(const egr_plan* p, int i, cudaStream_t st) {
@@ -99,10 +105,45 @@ extern "C" int egr_plan_run(egr_plan* plan, int first, int last, void* stream) {
   const int n = (int)plan->ops.size();
   if (first < 0) first = 0;
   if (last < 0 || last > n) last = n;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool full = (first == 0 && last == n);
+  static const bool use_graph = getenv("EGR_NO_GRAPH") == nullptr;
+  if (full && use_graph && plan->graph_exec) {
+    EGR_CUDA(cudaGraphLaunch(plan->graph_exec, st));
+    launch_count() += plan->launches_per_run;
+    return EGR_OK;
+  }
+  if (full && use_graph && plan->full_runs >= 1 && !plan->graph_exec) {
+    // second full pass: every lazy one-time setting (function attributes, occupancy queries) has been made
+    const unsigned long long before = launch_count();
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      int rc = EGR_OK;
+      for (int i = first; i < last && rc == EGR_OK; ++i) rc = run_op(plan, i, st);
+      cudaError_t e = cudaStreamEndCapture(st, &graph);
+      if (rc == EGR_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&plan->graph_exec, graph, 0) == cudaSuccess) {
+        plan->launches_per_run = launch_count() - before;
+        cudaGraphDestroy(graph);
+        launch_count() = before;
+        EGR_CUDA(cudaGraphLaunch(plan->graph_exec, st));
+        launch_count() += plan->launches_per_run;
+        ++plan->full_runs;
+        return EGR_OK;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      plan->graph_exec = nullptr;
+      launch_count() = before;
+      cudaGetLastError();
+      if (rc) return rc;
+      // capture failed: fall through to the eager path (and do not try again)
+      plan->full_runs = -1000000;
+    }
+  }
   for (int i = first; i < last; ++i) {
-    int rc = run_op(plan, i, (cudaStream_t)stream);
+    int rc = run_op(plan, i, st);
     if (rc) return rc;
   }
+  if (full) ++plan->full_runs;
   return EGR_OK;
 }
 
@@ -135,6 +176,7 @@ extern "C" void egr_plan_destroy(egr_plan* plan) {
   if (!plan) return;
   for (TcPrepared* t : plan->tc)
     if (t) tc_free(t);
+  if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
   if (plan->scratch) cudaFree(plan->scratch);
   delete plan;
 }
