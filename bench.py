@@ -335,24 +335,25 @@ def run_b200(args):
     if rank == 0:
         pk = peaks()
         lib = engine.lib
-        st = torch.cuda.current_stream(dev).cuda_stream
+        es = engine.stream  # the engine's launching stream: CUDA events are recorded on it
+        st = es.cuda_stream
         # ---- roofline of the dominant kernel: every GEMM_TC launch of one pass, timed alone on its stream
         n_tc = lib.egr_plan_count_code(handle, K["EGR_OP_GEMM_TC"])
         for _ in range(3):
             _abi.check(lib.egr_plan_run_code(handle, K["EGR_OP_GEMM_TC"], st))
         torch.cuda.synchronize(dev)
         reps = 5
-        e0.record()
+        e0.record(es)
         for _ in range(reps):
             _abi.check(lib.egr_plan_run_code(handle, K["EGR_OP_GEMM_TC"], st))
-        e1.record()
+        e1.record(es)
         torch.cuda.synchronize(dev)
         t_tc = e0.elapsed_time(e1) / 1e3 / reps
         # whole plan alone (no host plumbing) for the share of the step
-        e0.record()
+        e0.record(es)
         for _ in range(reps):
             _abi.check(lib.egr_plan_run(handle, 0, -1, st))
-        e1.record()
+        e1.record(es)
         torch.cuda.synchronize(dev)
         t_plan = e0.elapsed_time(e1) / 1e3 / reps
         achieved = be.tc_flops / t_tc / 1e12

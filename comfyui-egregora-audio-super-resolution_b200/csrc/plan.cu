@@ -137,6 +137,9 @@ extern "C" int egr_plan_run(egr_plan* plan, int first, int last, void* stream) {
       if (rc) return rc;
       // capture failed: fall through to the eager path (and do not try again)
       plan->full_runs = -1000000;
+    } else {
+      cudaGetLastError();  // e.g. the legacy default stream cannot be captured: stay eager on this plan
+      plan->full_runs = -1000000;
     }
   }
   for (int i = first; i < last; ++i) {

@@ -36,6 +36,9 @@ class FlashSREngine:
         self.blob.frozen = True
         raw = self.blob.tobytes()
         self.d_weights = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        # plan runs go to a private stream: the legacy default stream cannot be captured into the plan's CUDA graph;
+        # ordering against the caller's stream is kept with events (wait_stream), never with a host sync
+        self.stream = torch.cuda.Stream(device=device)
         self.ws: Optional[torch.Tensor] = None
         self.plans: Dict[Tuple[int, int, bool], Tuple[PlanBackend, int]] = {}
         self.launches_last = 0
@@ -101,19 +104,25 @@ class FlashSREngine:
             noise = self.make_noise(N, seed)
         noise = noise.to(self.device, torch.float32).permute(0, 2, 3, 1).contiguous()  # NHWC
         out = torch.empty_like(x)
-        st = torch.cuda.current_stream(self.device).cuda_stream
+        caller = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(caller)
         self.launches_last = 0
-        i = 0
-        while i < N:
-            b = min(self.max_batch, N - i)
-            be, h = self.plan(b, steps, lowpass)
-            wav_in, nz_in = be.inputs["wav"], be.inputs["noise"]
-            self.view(wav_in.f32, torch.float32, (b, x.shape[1])).copy_(x[i:i + b])
-            self.view(nz_in.f32, torch.float32, tuple(noise[i:i + b].shape)).copy_(noise[i:i + b])
-            _abi.check(self.lib.egr_plan_run(h, 0, -1, st), "egr_plan_run")
-            self.launches_last += len(be.ops)
-            out[i:i + b].copy_(self.view(be.output.f32, torch.float32, (b, x.shape[1])))
-            i += b
+        with torch.cuda.stream(self.stream):
+            st = self.stream.cuda_stream
+            i = 0
+            while i < N:
+                b = min(self.max_batch, N - i)
+                be, h = self.plan(b, steps, lowpass)
+                wav_in, nz_in = be.inputs["wav"], be.inputs["noise"]
+                self.view(wav_in.f32, torch.float32, (b, x.shape[1])).copy_(x[i:i + b])
+                self.view(nz_in.f32, torch.float32, tuple(noise[i:i + b].shape)).copy_(noise[i:i + b])
+                _abi.check(self.lib.egr_plan_run(h, 0, -1, st), "egr_plan_run")
+                self.launches_last += len(be.ops)
+                out[i:i + b].copy_(self.view(be.output.f32, torch.float32, (b, x.shape[1])))
+                i += b
+        caller.wait_stream(self.stream)
+        for t in (x, noise, out):
+            t.record_stream(self.stream)
         return out
 
     def close(self):

@@ -33,7 +33,8 @@ start = 0
 for i in range(1, len(names) + 1):
     if i == len(names) or labels[i] != labels[start]:
         bounds.append((labels[start], start, i)); start = i
-st = torch.cuda.current_stream(dev).cuda_stream
+es = eng.stream
+st = es.cuda_stream
 lib = eng.lib
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 tot = {}
@@ -41,13 +42,13 @@ for lab, a, b in bounds:
     for _ in range(2): _abi.check(lib.egr_plan_run(h, a, b, st))
     torch.cuda.synchronize()
     reps = 10
-    e0.record()
+    e0.record(es)
     for _ in range(reps): _abi.check(lib.egr_plan_run(h, a, b, st))
-    e1.record(); torch.cuda.synchronize()
+    e1.record(es); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     tot[lab] = tot.get(lab, [0, 0.0]); tot[lab][0] += b - a; tot[lab][1] += ms
 for k, v in tot.items(): print(f"{k:14s} ops={v[0]:4d} ms={v[1]:7.3f}")
-e0.record()
+e0.record(es)
 for _ in range(10): _abi.check(lib.egr_plan_run(h, 0, -1, st))
-e1.record(); torch.cuda.synchronize()
+e1.record(es); torch.cuda.synchronize()
 print("whole plan ms", e0.elapsed_time(e1) / 10, "ops", len(names))
