@@ -5,6 +5,7 @@
 #include <functional>
 #include <map>
 #include <mutex>
+#include <cstdlib>
 #include "fft_plan.cuh"
 
 using namespace egr;
@@ -56,6 +57,10 @@ static bool plan_radices(int L, Radices* out) {
 static void split(int64_t M, int* R1, int* R2) {
   *R1 = 0; *R2 = 0;
   if (M <= kMaxLen) { *R1 = 1; *R2 = (int)M; return; }
+  if (const char* e = getenv("EGR_FFT_R1")) {  // tuning override: column length (must divide M, both factors <= kMaxLen)
+    const int64_t a = atoll(e);
+    if (a >= 2 && M % a == 0 && a <= kMaxLen && M / a <= kMaxLen) { *R1 = (int)a; *R2 = (int)(M / a); return; }
+  }
   for (int64_t d = (int64_t)std::floor(std::sqrt((double)M)) + 1; d >= 2; --d) {
     if (M % d) continue;
     int64_t a = d, b = M / d;
@@ -163,7 +168,7 @@ const Fft2Plan* egr::fft2_get_plan(int64_t M) {
     return nullptr;
   }
   // column tile width: keep the tile under ~96 KB so two CTAs share an SM
-  p->cw = 8;
+  p->cw = getenv("EGR_FFT_CW") ? atoi(getenv("EGR_FFT_CW")) : 8;
   while (p->cw > 2 && (size_t)R1 * p->cw * sizeof(float2) > 96 * 1024) p->cw >>= 1;
   if (R1 == 1) p->cw = 256;
   g_plans[key] = p;
