@@ -23,8 +23,8 @@
 // Split-K: layers with few output tiles (the UNet at 8x4 .. 64x32 latent pixels) would leave most SMs idle while a
 // handful of CTAs stream megabytes of weights; their reduction range is cut into `splits` work items, each CTA
 // writes its raw f32 partial tile to a library-owned workspace and the LAST one to arrive (one atomic counter per
-// output tile) sums the partials in split order — deterministic — and applies the epilogue.  `splits` depends only
-// on the per-item geometry, never on the batch size, so results are identical alone or inside a batch.
+// output tile) sums the partials in split order — deterministic for a given launch geometry — and applies the
+// epilogue.  Splitting is used only when the launch as a whole cannot fill the SMs (small batches).
 //
 // The single-thread producer / issuer loops are kept free of integer divisions and of dynamically indexed local
 // arrays: a clock trace of the previous version showed ~1400 cycles per k-step spent in exactly that scalar code.
@@ -291,6 +291,12 @@ __device__ __forceinline__ void finish4(const GemmArgs& g, float4 acc, long long
     const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid + idx));
     v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
   }
+  if (g.resid2) {
+    const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid2 + idx));
+    v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] *= g.post;
   if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
   if (g.out16) {
     __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
@@ -306,6 +312,8 @@ __device__ __forceinline__ void finish1(const GemmArgs& g, float acc, long long 
   if (rb) v += rb[n];
   v = egr_apply_act(v, g.act);
   if (g.resid) v += g.resid[idx];
+  if (g.resid2) v += g.resid2[idx];
+  v *= g.post;
   if (g.out32) g.out32[idx] = v;
   if (g.out16) g.out16[idx] = __float2half_rn(v);
 }
@@ -530,6 +538,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // vector pass: 4 rows x 8 float4 per instruction
     const int nblk = (BN + 31) >> 5;
     const bool has_resid = g.resid != nullptr, has_bias = g.bias != nullptr, has_out16 = g.out16 != nullptr;
+    const bool has_resid2 = g.resid2 != nullptr;
     int it = 0;
     for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
       WorkItem wi;
@@ -594,12 +603,25 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (col_ok && off[i] >= 0) rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
+              if (has_resid2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (col_ok && off[i] >= 0) {
+                    const float4 r2 = __ldg(reinterpret_cast<const float4*>(g.resid2 + base_l0 + off[i] + n));
+                    rv[i].x += r2.x; rv[i].y += r2.y; rv[i].z += r2.z; rv[i].w += r2.w;
+                  }
+              }
             } else {              // cropped cells (transposed-conv margins) may lie outside the residual tensor
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const long long fl = flat_l0 + __shfl_sync(0xffffffffu, foff, 4 * i + rsub) + n;
-                if (col_ok && off[i] >= 0 && fl >= g.out_lo && fl < g.out_hi)
+                if (col_ok && off[i] >= 0 && fl >= g.out_lo && fl < g.out_hi) {
                   rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
+                  if (has_resid2) {
+                    const float4 r2 = __ldg(reinterpret_cast<const float4*>(g.resid2 + base_l0 + off[i] + n));
+                    rv[i].x += r2.x; rv[i].y += r2.y; rv[i].z += r2.z; rv[i].w += r2.w;
+                  }
+                }
               }
             }
           }
@@ -652,8 +674,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
               for (int i = 0; i < 4; ++i) {
                 const int k = 4 * half + i;
                 float4 o;
-                o.x = fmaf(a[i].x, g.alpha, bias4.x) + rv[k].x; o.y = fmaf(a[i].y, g.alpha, bias4.y) + rv[k].y;
-                o.z = fmaf(a[i].z, g.alpha, bias4.z) + rv[k].z; o.w = fmaf(a[i].w, g.alpha, bias4.w) + rv[k].w;
+                o.x = (fmaf(a[i].x, g.alpha, bias4.x) + rv[k].x) * g.post; o.y = (fmaf(a[i].y, g.alpha, bias4.y) + rv[k].y) * g.post;
+                o.z = (fmaf(a[i].z, g.alpha, bias4.z) + rv[k].z) * g.post; o.w = (fmaf(a[i].w, g.alpha, bias4.w) + rv[k].w) * g.post;
                 if (col_ok && off[k] >= 0) {
                   *reinterpret_cast<float4*>(g.out32 + base_l0 + off[k] + n) = o;
                   if (has_out16) {  // f16 copy for a following tensor-core layer (uniform flag)
@@ -688,7 +710,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
                   for (int u = 0; u < 4; ++u) x[u] = egr_apply_act(x[u], g.act);
                 }
-                x[0] += rv[i].x; x[1] += rv[i].y; x[2] += rv[i].z; x[3] += rv[i].w;
+                x[0] = (x[0] + rv[i].x) * g.post; x[1] = (x[1] + rv[i].y) * g.post;
+                x[2] = (x[2] + rv[i].z) * g.post; x[3] = (x[3] + rv[i].w) * g.post;
                 const long long idx = base_l0 + off[i] + n;
                 if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(x[0], x[1], x[2], x[3]);
                 if (g.out16) {
@@ -869,9 +892,10 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   const int n_outer = halo ? kchunks : g.ntaps * kchunks;
   const int n_inner = halo ? g.ntaps : 1;
 
-  // ---- split-K: a function of the per-item geometry only (batch-invariant results)
-  const long long pix_item = (long long)g.Wo * g.Ho;
-  const int units = ceil_div(pix_item, TILE_M) * ceil_div(g.N, 128);  // 128x128 output blocks of one batch item
+  // ---- split-K: only when the whole launch (all batch items) has too few 128x128 output blocks to fill the GPU.
+  // The reduction order is fixed for a given launch geometry (deterministic); a different batch size may pick a
+  // different split count, i.e. a different f32 summation order (differences at the 1e-6 relative level).
+  const int units = tiles1 * ceil_div(g.N, 128);
   int splits = 1;
   if (!g.wz_batch && env_int("EGR_TC_NO_SPLITK", 0) == 0) {
     splits = sms / (units > 0 ? units : 1);
@@ -973,7 +997,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   bool vec = !g.transposed && (g.N % 4 == 0) && (g.out_pix_stride % 4 == 0) && (g.out_batch_stride % 4 == 0) &&
              (g.out_offset % 4 == 0) && (g.out_lo % 4 == 0) && (g.out_hi % 4 == 0) && (g.rowbias_stride % 4 == 0);
   auto al = [](const void* q, int a) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % a == 0; };
-  vec = vec && al(g.out32, 16) && al(g.out16, 8) && al(g.resid, 16) && al(g.bias, 16) && al(g.rowbias, 16);
+  vec = vec && al(g.out32, 16) && al(g.out16, 8) && al(g.resid, 16) && al(g.resid2, 16) && al(g.bias, 16) && al(g.rowbias, 16);
   {
     // row offsets inside a tile are exchanged as 32-bit values
     const long long span = (long long)(g.Bo + g.bb) * (g.out_batch_stride > 0 ? g.out_batch_stride : 1) +

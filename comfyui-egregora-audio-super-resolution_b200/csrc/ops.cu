@@ -24,6 +24,8 @@ int gemm_args_from_op(const Spaces& s, const egr_op& op, GemmArgs* g, Taps* taps
   g->rowbias = (const float*)resolve(s, op.ptr[EGR_P_ROWBIAS]);
   g->rowbias_stride = op.i[EGR_I_ROWBIAS_STRIDE];
   g->resid = (const float*)resolve(s, op.ptr[EGR_P_RESID]);
+  g->resid2 = (const float*)resolve(s, op.ptr[EGR_P_RESID2]);
+  g->post = op.f[EGR_F_POST] != 0.0 ? (float)op.f[EGR_F_POST] : 1.0f;
   g->out32 = (float*)resolve(s, op.ptr[EGR_P_OUT32]);
   g->out16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
   g->out_pix_stride = op.i[EGR_I_OUT_PIX_STRIDE]; g->out_batch_stride = op.i[EGR_I_OUT_BATCH_STRIDE];
@@ -62,6 +64,8 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& g, int b, long lo
     idx = (long long)b * g.out_batch_stride + flat;
   }
   if (g.resid) v += g.resid[idx];
+  if (g.resid2) v += g.resid2[idx];
+  v *= g.post;
   if (g.out32) g.out32[idx] = v;
   if (g.out16) g.out16[idx] = __float2half_rn(v);
 }

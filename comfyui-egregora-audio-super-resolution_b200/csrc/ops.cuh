@@ -38,6 +38,8 @@ struct GemmArgs {
   const float* rowbias;
   long long rowbias_stride;
   const float* resid;
+  const float* resid2;  // second residual (vocoder: running sum of the parallel residual blocks)
+  float post;           // scale applied after the residual adds
   float* out32;
   __half* out16;
   long long out_pix_stride, out_batch_stride, out_offset, out_lo, out_hi, out_n_stride;

@@ -274,6 +274,10 @@ def init_weights(spec: dict, seed: int = 0) -> Dict[str, torch.Tensor]:
     return out
 
 
+def name_prefix(i: int, nk: int, j: int) -> str:
+    return f"vocoder.resblocks.{i * nk + j}"
+
+
 # ------------------------------------------------------------------------------------------------ the graph
 class FlashSRGraph:
     def __init__(self, spec: dict):
@@ -436,15 +440,23 @@ class FlashSRGraph:
             cin = chans[i]
             xs = None
             for j, rk in enumerate(vc["resblock_kernel_sizes"]):
-                name = f"vocoder.resblocks.{i * nk + j}"
+                name = f"{name_prefix(i, nk, j)}"
                 y = x
+                nd = len(vc["resblock_dilations"])
                 for di, d in enumerate(vc["resblock_dilations"]):
                     yt = be.snake_aa(y, f"{name}.activations.{2 * di}", cin)
                     yt = be.conv1d(yt, f"{name}.convs1.{di}", cin, cin, rk, dilation=d)
                     yt = be.snake_aa(yt, f"{name}.activations.{2 * di + 1}", cin)
-                    y = be.conv1d(yt, f"{name}.convs2.{di}", cin, cin, rk, add=y)
-                xs = y if xs is None else be.add(xs, y)
-            x = be.scale(xs, 1.0 / nk)
+                    if di == nd - 1 and xs is not None:
+                        # last conv of a parallel block: its epilogue also accumulates the running sum of the blocks
+                        # (and the 1/nk average on the last one) — x_next = (Y_0 + .. + Y_{nk-1}) / nk with no
+                        # separate add / scale passes over the feature map
+                        y = be.conv1d(yt, f"{name}.convs2.{di}", cin, cin, rk, add=y, add2=xs,
+                                      post=(1.0 / nk) if j == nk - 1 else 1.0)
+                    else:
+                        y = be.conv1d(yt, f"{name}.convs2.{di}", cin, cin, rk, add=y)
+                xs = y
+            x = xs if nk > 1 else be.scale(xs, 1.0 / nk)
         x = be.snake_aa(x, "vocoder.activation_post", cin)
         return be.conv1d(x, "vocoder.conv_post", cin, 1, 7, act="tanh")
 

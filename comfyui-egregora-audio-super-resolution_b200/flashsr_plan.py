@@ -253,7 +253,7 @@ class PlanBackend:
               out_pt: PT, out16: bool, out32: bool, bias_off=None, rowbias: Optional[PT] = None, resid: Optional[PT] = None,
               act=None, alpha=1.0, out_pix_stride=None, out_batch_stride=None, out_offset=0, out_lo=0, out_hi=BIG,
               transposed=False, out_n_stride=0, wstride_n=None, wstride_z=None, wz_batch=False, w_buf: Optional[Buf] = None,
-              a_elem=1):
+              a_elem=1, resid2: Optional[PT] = None, post=1.0):
         op = RawOp(K["EGR_OP_GEMM_SIMT"] if simt else K["EGR_OP_GEMM_TC"], name)
         buf, off, dims, strides = a_view
         op.x0 = (buf, off, len(dims), a_elem, dims, strides)
@@ -276,7 +276,7 @@ class PlanBackend:
                 "TRANSPOSED": 1 if transposed else 0, "OUT_N_STRIDE": out_n_stride,
                 "ACT": {None: K["EGR_ACT_NONE"], "silu": K["EGR_ACT_SILU"], "tanh": K["EGR_ACT_TANH"]}[act],
                 "KBLOCK": 64}
-        op.f = {"ALPHA": alpha}
+        op.f = {"ALPHA": alpha, "POST": post}
         op.taps = taps
         if w_buf is not None:
             self._ws(op, "W", w_buf, w_off)
@@ -289,6 +289,9 @@ class PlanBackend:
         if resid is not None:
             assert resid.f32 is not None and resid.parts is None and resid.ld == resid.C
             self._ws(op, "RESID", resid.f32)
+        if resid2 is not None:
+            assert resid is not None and resid2.f32 is not None and resid2.parts is None and resid2.ld == resid2.C
+            self._ws(op, "RESID2", resid2.f32)
         if out32:
             self._ws(op, "OUT32", out_pt.f32, write=True)
         if out16:
@@ -508,7 +511,7 @@ class PlanBackend:
         return o
 
     # ------------------------------------------------------------------ 1-D ops ([B,1,T,C])
-    def conv1d(self, x: PT, name, cin, cout, k, dilation=1, add=None, act=None):
+    def conv1d(self, x: PT, name, cin, cout, k, dilation=1, add=None, act=None, add2=None, post=1.0):
         assert x.C == cin and x.H == 1, name
         tc = self._use_tc(cin, cout)
         if tc:
@@ -522,7 +525,8 @@ class PlanBackend:
         w_off, _, _ = self.w_taps(name, "conv1d", f16=tc)
         o = self.new(B, 1, T, cout, f32=True, tag=name)
         self._gemm(name, x, (abuf, 0, dims, strides), taps, cin, cout, w_off, simt=not tc, dimW=1, dimH=2, dimB=3, Wo=T, Ho=1,
-                   Bo=B, out_pt=o, out16=False, out32=True, bias_off=self.w_bias(name), resid=add, act=act, a_elem=elem)
+                   Bo=B, out_pt=o, out16=False, out32=True, bias_off=self.w_bias(name), resid=add, act=act, a_elem=elem,
+                   resid2=add2, post=post)
         return o
 
     def conv1d_strided(self, x: PT, name, cin, cout, k, stride):

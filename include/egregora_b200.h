@@ -92,7 +92,7 @@ typedef struct egr_op {
 } egr_op;
 
 /* op codes */
-#define EGR_OP_GEMM_TC      1   /* tcgen05 tap-GEMM: out[pix,n] = act(alpha*sum_t sum_k A[pix+tap_t,k]*B[t,n,k] + bias ...) */
+#define EGR_OP_GEMM_TC      1   /* tcgen05 tap-GEMM: out[pix,n] = post*(act(alpha*sum_t sum_k A[pix+tap_t,k]*B[t,n,k] + bias + rowbias) + resid + resid2) */
 #define EGR_OP_GEMM_SIMT    2   /* same contract, fp32 CUDA-core path (tiny K/N layers, and the in-library cross-check) */
 #define EGR_OP_GN_STATS     3   /* GroupNorm partial sums (f64) over a virtual channel-concat of x0|x1 */
 #define EGR_OP_GN_APPLY     4   /* GroupNorm normalise (+SiLU) -> f16 and/or f32 */
@@ -118,6 +118,7 @@ typedef struct egr_op {
 #define EGR_P_GAMMA    7
 #define EGR_P_BETA     8
 #define EGR_P_AUX      9
+#define EGR_P_RESID2   9   /* GEMM ops: second residual, addressed like RESID (the slot is AUX for the other ops) */
 
 /* i[] slots (GEMM family) */
 #define EGR_I_DIMW      0  /* which x0 dim the tile's w extent walks */
@@ -166,6 +167,7 @@ typedef struct egr_op {
 #define EGR_F_ALPHA    0
 #define EGR_F_EPS      1
 #define EGR_F_A        2
+#define EGR_F_POST     2   /* GEMM ops: out = POST * (act(...) + resid + resid2); 0 means 1 */
 #define EGR_F_B        3
 #define EGR_F_C        4
 #define EGR_F_D        5

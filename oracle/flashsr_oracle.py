@@ -131,10 +131,14 @@ class TorchBackend:
         return torch.cat([torch.cos(args), torch.sin(args)])[None].to(self.dt)
 
     # ------------------------------------------------------------------ 1-D
-    def conv1d(self, x, name, cin, cout, k, dilation=1, add=None, act=None):
+    def conv1d(self, x, name, cin, cout, k, dilation=1, add=None, act=None, add2=None, post=1.0):
         y = F.conv1d(x, self.W[name + ".weight"], self.W[name + ".bias"], padding=dilation * (k // 2), dilation=dilation)
         if add is not None:
             y = y + add
+        if add2 is not None:   # running sum of the parallel residual blocks (BigVGAN: xs += resblock(x); x = xs / nk)
+            y = y + add2
+        if post != 1.0:
+            y = y * post
         if act == "tanh":
             y = torch.tanh(y)
         return self._rec(name, y)

@@ -107,6 +107,12 @@ class Interp:
         res = self.p(op, "RESID", torch.float32)
         if res is not None:
             v = v + res[idx]
+        res2 = self.p(op, "RESID2", torch.float32) if op.code in (self.K["EGR_OP_GEMM_TC"], self.K["EGR_OP_GEMM_SIMT"]) else None
+        if res2 is not None:
+            v = v + res2[idx]
+        post = self.f(op, "POST")
+        if post != 0.0:
+            v = v * post
         o32, o16 = self.p(op, "OUT32", torch.float32), self.p(op, "OUT16", torch.float16)
         if o32 is not None:
             o32[idx] = v

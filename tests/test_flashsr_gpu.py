@@ -76,10 +76,18 @@ def test_tiny_e2e(tiny, cuda_dev, B, steps, lowpass):
     assert not torch.isnan(y).any()
     rms = float((y - yo).pow(2).mean().sqrt())
     assert rms < RMS_TOL, rms
-    # batch items are independent model evaluations: same result alone or inside a batch
+    # Batch items are independent model evaluations.  The split-K factor of the small layers follows the launch size,
+    # so alone vs inside a batch the f32 summation order differs; the ~1e-7 differences flip f16 operand roundings
+    # downstream and end up at the same level as the f16 noise itself: both results sit within RMS_TOL of the fp32
+    # oracle, hence within 2*RMS_TOL of each other (measured ~7e-4 on the random-weight tiny model).
     if B > 1:
         y0 = eng.infer(wav[:1].to(cuda_dev), lowpass=lowpass, steps=steps, noise=noise[:1]).cpu()
-        assert float((y0 - y[:1]).abs().max()) < 1e-5
+        yo0, _ = O.run_flashsr(spec, W, wav[:1], noise[:1], steps=steps, lowpass=lowpass)
+        assert float((y0 - yo0).pow(2).mean().sqrt()) < RMS_TOL
+        assert float((y0 - y[:1]).pow(2).mean().sqrt()) < 2 * RMS_TOL, float((y0 - y[:1]).abs().max())
+        # and a given launch geometry is deterministic
+        y0b = eng.infer(wav[:1].to(cuda_dev), lowpass=lowpass, steps=steps, noise=noise[:1]).cpu()
+        assert torch.equal(y0, y0b)
 
 
 def test_full_spec_single_chunk_properties(cuda_dev):
@@ -93,5 +101,7 @@ def test_full_spec_single_chunk_properties(cuda_dev):
     y1 = eng.infer(wav[:1].to(cuda_dev), lowpass=True, steps=1, noise=noise[:1])
     y2 = eng.infer(wav.to(cuda_dev), lowpass=True, steps=1, noise=noise)
     assert y1.shape == (1, 245760) and torch.isfinite(y2).all()
-    assert float((y1 - y2[:1]).abs().max()) < 1e-5
+    assert float((y1 - y2[:1]).pow(2).mean().sqrt()) < 2e-3, float((y1 - y2[:1]).abs().max())  # see test_tiny_e2e
+    y1b = eng.infer(wav[:1].to(cuda_dev), lowpass=True, steps=1, noise=noise[:1])
+    assert torch.equal(y1, y1b)  # deterministic for a given launch geometry
     assert 0.005 < float(y2.pow(2).mean().sqrt()) < 0.9
