@@ -1130,7 +1130,47 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
     for (int r = 0; r < 5; ++r) xw[r + 1] = xat(t0 + r);
   }
   const int t_end = min(T, t0 + tt);
-  // the new input samples of a group are independent of the recurrence: their loads are issued one group ahead
+  if (t0 >= 5 && t0 + tt + 13 <= T && (tt & 7) == 0) {
+    // Interior run (all but the first / last runs of a signal): every index is in range, so the clamps, the end-of-
+    // signal selects and the per-output bounds test disappear and addresses advance by pointer increments — the
+    // clamped form spends more instructions on integer index math than on the filter itself.
+    const float* px = xb + (long long)(t0 + 5) * C;   // next input sample to enter the window
+    float* p32 = o32 ? o32 + ((long long)b * T + t0) * C + c : nullptr;
+    __half* p16 = o16 ? o16 + ((long long)b * T + t0) * C + c : nullptr;
+    float xn[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { xn[i] = __ldg(px); px += C; }
+    for (int tb = t0; tb < t_end; tb += 8) {
+      float xnext[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { xnext[i] = __ldg(px); px += C; }  // one group ahead (in range by the run test)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < 10; ++j) sw[j] = sw[j + 2];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) xw[r] = xw[r + 1];
+        xw[5] = xn[i];
+        float uo = 0.f, ue = 0.f;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          uo = fmaf(xw[r], f[10 - 2 * r], uo);
+          ue = fmaf(xw[r], f[11 - 2 * r], ue);
+        }
+        sw[10] = snake_eval(2.0f * uo, alpha, inv_beta);
+        sw[11] = snake_eval(2.0f * ue, alpha, inv_beta);
+        float y = 0.f;
+#pragma unroll
+        for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
+        if (p32) { *p32 = y; p32 += C; }
+        if (p16) { *p16 = __float2half_rn(y); p16 += C; }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xn[i] = xnext[i];
+    }
+    return;
+  }
+  // boundary runs: clamped indices (replicate padding of the input and of the activated signal)
   float xn[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) xn[i] = xat(t0 + i + 5);
