@@ -70,6 +70,10 @@ __global__ void __launch_bounds__(256) fl_col_kernel(FlDev d, const float* __res
   const float* x = d_in + (long long)ch * n;
   float2* wk = work + (long long)ch * d.M;
   const int tile = R1 * cw;
+  // stage twiddles of the length-R1 transform in shared memory: every butterfly reads R-1 of them, and as global
+  // (L1) loads they were the dominant long-scoreboard stall of this kernel
+  float2* tws = sm + tile;
+  for (int i = threadIdx.x; i < R1; i += blockDim.x) tws[i] = d.tw1[i];
   float pk = 0.f;
   if (MODE == FL_FIRST) {
     for (int i = threadIdx.x; i < tile; i += blockDim.x) {
@@ -94,9 +98,9 @@ __global__ void __launch_bounds__(256) fl_col_kernel(FlDev d, const float* __res
   }
   __syncthreads();
   const Tile g{R1, cw, cw, 1};
-  if (MODE != FL_FIRST) fft_inverse<true>(sm, g, d.rd1, d.tw1);  // -> s in natural time order
+  if (MODE != FL_FIRST) fft_inverse<true>(sm, g, d.rd1, tws);  // -> s in natural time order
   if (MODE != FL_LAST) {
-    fft_forward<true>(sm, g, d.rd1, d.tw1);
+    fft_forward<true>(sm, g, d.rd1, tws);
     for (int i = threadIdx.x; i < tile; i += blockDim.x) {
       const int r = i / cw, c = i - r * cw;
       if (c0 + c < R2) wk[(long long)r * R2 + c0 + c] = sm[i];
@@ -151,13 +155,15 @@ __global__ void __launch_bounds__(256) fl_row_kernel(FlDev d, float thr, float2*
   float2* rowB = wk + (long long)pb * R2;
   float2* sA = sm;
   float2* sB = sm + R2;
+  float2* tws = sm + 2 * R2;  // stage twiddles of the length-R2 transform (see fl_col_kernel)
+  for (int i = threadIdx.x; i < R2; i += blockDim.x) tws[i] = d.tw2[i];
   for (int i = threadIdx.x; i < R2; i += blockDim.x) {
     sA[i] = k1a ? cmulf(rowA[i], tw_split(d.twM_hi, d.twM_lo, (long long)i * k1a)) : rowA[i];
     if (two) sB[i] = cmulf(rowB[i], tw_split(d.twM_hi, d.twM_lo, (long long)i * k1b));
   }
   __syncthreads();
   const Tile g{R2, two ? 2 : 1, 1, R2};
-  fft_forward<false>(sm, g, d.rd2, d.tw2);
+  fft_forward<false>(sm, g, d.rd2, tws);
   if (two) {
     for (int p2 = threadIdx.x; p2 < R2; p2 += blockDim.x) {
       const int k2 = d.perm2[p2];
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(256) fl_row_kernel(FlDev d, float thr, float2*
     }
   }
   __syncthreads();
-  fft_inverse<false>(sm, g, d.rd2, d.tw2);
+  fft_inverse<false>(sm, g, d.rd2, tws);
   const float sc = (float)(1.0 / (double)d.M);
   for (int i = threadIdx.x; i < R2; i += blockDim.x) {
     float2 v = k1a ? cmulc(sA[i], tw_split(d.twM_hi, d.twM_lo, (long long)i * k1a)) : sA[i];
@@ -328,7 +334,7 @@ extern "C" int egr_fatllama_run(const float* d_in, float* d_out, int C, int64_t 
     if (upscale == 1 && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 7))
       return fail(EGR_ERR_ARG, "egr_fatllama_run: buffers must be 8-byte aligned");
     const FlDev d = fl_dev(p);
-    const size_t smc = (size_t)p->R1 * p->cw * sizeof(float2), smr = 2 * (size_t)p->R2 * sizeof(float2);
+    const size_t smc = ((size_t)p->R1 * p->cw + p->R1) * sizeof(float2), smr = 3 * (size_t)p->R2 * sizeof(float2);
     if (smc > 48 * 1024) {
       EGR_CUDA(cudaFuncSetAttribute(fl_col_kernel<FL_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
       EGR_CUDA(cudaFuncSetAttribute(fl_col_kernel<FL_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));

@@ -245,7 +245,7 @@ struct Tile {
 
 template <int R, bool INV, bool COLFAST>
 __device__ __forceinline__ void fft_stage(float2* __restrict__ data, const Tile g, const int Lb,
-                                          const float2* __restrict__ tw /* exp(-2 pi i t / L), t < L */) {
+                                          const float2* __restrict__ tw /* exp(-2 pi i t / L), t < L; global or shared */) {
   const int Ls = Lb / R;
   const int nb = g.L / R;
   const int tstep = g.L / Lb;
@@ -264,12 +264,12 @@ __device__ __forceinline__ void fft_stage(float2* __restrict__ data, const Tile 
       Dft<R, false>::run(v);
       if (Ls > 1) {
 #pragma unroll
-        for (int q = 1; q < R; ++q) v[q] = cmulf(v[q], __ldg(tw + j * q * tstep));
+        for (int q = 1; q < R; ++q) v[q] = cmulf(v[q], tw[j * q * tstep]);
       }
     } else {
       if (Ls > 1) {
 #pragma unroll
-        for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], __ldg(tw + j * q * tstep));
+        for (int q = 1; q < R; ++q) v[q] = cmulc(v[q], tw[j * q * tstep]);
       }
       Dft<R, true>::run(v);
     }

@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
 
   if (warp == 0) {
     // ============================================================ A producer (whole warp, one elected lane issues)
+    if (tr && lane == 0) tr[5] = clock64();
     const uint32_t ringA_u = smem_u32(ringA);
     const uint32_t fullA_u = smem_u32(ka.halo ? fullA : fullB), emptyA_u = smem_u32(ka.halo ? emptyA : emptyB);
     int sa = 0;
@@ -394,8 +395,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
           cb[m][d] = (g.dimW == d ? wi.w0[m] : 0) + (g.dimH == d ? wi.h0[m] : 0) + (g.dimB == d ? wi.b0[m] : 0);
       int tap = 0, kc = wi.o_begin;
       if (!ka.halo) { tap = fdiv(wi.o_begin, ka.d_kchunks); kc = wi.o_begin - tap * ka.kchunks; }
+      if (tr && lane == 0 && tcount == 0) tr[6] = clock64();
       for (int io = wi.o_begin; io < wi.o_end; ++io) {
         mbar_wait(emptyA_u + 8 * sa, pa ^ 1u);
+        if (tr && lane == 0 && tcount == 0) tr[7] = clock64();
         const uint32_t dstA = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
         if (elect_one()) {
           if (tr && tcount < 250) tr[16 + 2 * tcount] = clock64();

@@ -35,6 +35,7 @@ def main():
             print(f"   CTAs {len(st)}: start spread {max(st) - g0} ns, first end {min(en) - g0} ns, last end {max(en) - g0} ns; per-CTA duration min/max {min(e - s_ for s_, e in zip(st, en))}/{max(e - s_ for s_, e in zip(st, en))} ns")
         ep = [tuple(t[800 + 5 * i + j] - t[800 + 5 * i] for j in range(1, 5)) for i in range(16) if t[800 + 5 * i]]
         print("   epilogue blocks of item 1 (+tmem ld, +next loads issued, +smem staged, +computed/stored):", ep[:10])
+        print("   producer warp: role entry", rel(t[5]), "decoded", rel(t[6]), "first wait passed", rel(t[7]))
         prod = [(rel(t[16 + 2 * i]), rel(t[17 + 2 * i])) for i in range(250) if t[16 + 2 * i]]
         mma = [(rel(t[528 + 2 * i]), rel(t[529 + 2 * i])) for i in range(250) if t[528 + 2 * i]]
         print("   producer (slot free, issued):", prod[:12], "...", prod[-3:])
