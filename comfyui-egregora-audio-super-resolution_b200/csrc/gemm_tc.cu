@@ -266,7 +266,7 @@ __device__ __forceinline__ RowInfo row_info(const TcKernelArgs& ka, const WorkIt
     r.flat0 = 0;
     r.base = (long long)b * g.out_batch_stride + pix + g.out_offset;
   } else {
-    r.flat0 = pix * g.out_pix_stride + g.out_offset;
+    r.flat0 = (long long)h * g.out_h_stride + (long long)w * g.out_pix_stride + g.out_offset;
     r.base = (long long)b * g.out_batch_stride + r.flat0;
   }
   return r;
@@ -997,18 +997,18 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   p->partial_bytes = splits > 1 ? (size_t)ka.tiles_m * ka.tiles_n * splits * mt * TILE_M * bn * sizeof(float) : 0;
   p->n_counters = splits > 1 ? ka.tiles_m * ka.tiles_n : 0;
   // vector epilogue needs 16-byte aligned groups of 4 columns
-  bool vec = !g.transposed && (g.N % 4 == 0) && (g.out_pix_stride % 4 == 0) && (g.out_batch_stride % 4 == 0) &&
+  bool vec = !g.transposed && (g.N % 4 == 0) && (g.out_pix_stride % 4 == 0) && (g.out_h_stride % 4 == 0) && (g.out_batch_stride % 4 == 0) &&
              (g.out_offset % 4 == 0) && (g.out_lo % 4 == 0) && (g.out_hi % 4 == 0) && (g.rowbias_stride % 4 == 0);
   auto al = [](const void* q, int a) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % a == 0; };
   vec = vec && al(g.out32, 16) && al(g.out16, 8) && al(g.resid, 16) && al(g.resid2, 16) && al(g.bias, 16) && al(g.rowbias, 16);
   {
     // row offsets inside a tile are exchanged as 32-bit values
     const long long span = (long long)(g.Bo + g.bb) * (g.out_batch_stride > 0 ? g.out_batch_stride : 1) +
-                           ((long long)g.Ho * g.Wo + TILE_M) * (g.out_pix_stride > 0 ? g.out_pix_stride : 1) +
+                           (long long)(g.Ho + TILE_M) * g.out_h_stride + (long long)(g.Wo + TILE_M) * (g.out_pix_stride > 0 ? g.out_pix_stride : 1) +
                            (long long)g.N * (g.out_n_stride > 0 ? g.out_n_stride : 1);
     if (span >= (1ll << 31)) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: output of %lld elements exceeds the 32-bit tile offsets", op.name, span));
     ka.epi_plain = 0;
-    ka.need_crop = (g.out_lo > 0 || g.out_hi < (long long)g.Ho * g.Wo * g.out_pix_stride + g.out_offset + g.N) ? 1 : 0;
+    ka.need_crop = (g.out_lo > 0 || g.out_hi < (long long)(g.Ho - 1) * g.out_h_stride + (long long)g.Wo * g.out_pix_stride + g.out_offset + g.N) ? 1 : 0;
   }
   ka.vec_ok = vec ? 1 : 0;
   ka.epi_plain = (vec && g.out32 && g.act == EGR_ACT_NONE && !g.rowbias && !ka.need_crop) ? 1 : 0;

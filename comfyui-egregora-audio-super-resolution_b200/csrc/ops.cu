@@ -31,6 +31,7 @@ int gemm_args_from_op(const Spaces& s, const egr_op& op, GemmArgs* g, Taps* taps
   g->out_pix_stride = op.i[EGR_I_OUT_PIX_STRIDE]; g->out_batch_stride = op.i[EGR_I_OUT_BATCH_STRIDE];
   g->out_offset = op.i[EGR_I_OUT_OFFSET]; g->out_lo = op.i[EGR_I_OUT_LO]; g->out_hi = op.i[EGR_I_OUT_HI];
   g->out_n_stride = op.i[EGR_I_OUT_N_STRIDE];
+  g->out_h_stride = (op.code == EGR_OP_GEMM_TC && op.i[EGR_I_OUT_H_STRIDE] > 0) ? op.i[EGR_I_OUT_H_STRIDE] : (long long)g->Wo * g->out_pix_stride;
   g->transposed = (int)op.i[EGR_I_TRANSPOSED]; g->act = (int)op.i[EGR_I_ACT];
   g->alpha = (float)op.f[EGR_F_ALPHA];
   if (g->ntaps < 1 || g->ntaps > EGR_MAX_TAPS) return fail(EGR_ERR_ARG, "%s: ntaps=%d out of range", op.name, g->ntaps);

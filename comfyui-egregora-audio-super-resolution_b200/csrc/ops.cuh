@@ -43,6 +43,7 @@ struct GemmArgs {
   float* out32;
   __half* out16;
   long long out_pix_stride, out_batch_stride, out_offset, out_lo, out_hi, out_n_stride;
+  long long out_h_stride;  // stride of one step along H (tensor-core path; Wo*out_pix_stride when dense)
   int transposed, act;
   float alpha;
 };

@@ -212,6 +212,10 @@ class _ParamBackend:
         self.P.conv1d(name, cin, cout, k)
         return None
 
+    def upsample_conv2d(self, x, name, cin, cout, **kw):
+        self.P.conv2d(name, cin, cout, 3)
+        return None
+
     def conv1d_strided(self, x, name, cin, cout, k, stride, **kw):
         self.P.conv1d(name, cin, cout, k)
         return None
@@ -338,7 +342,7 @@ class FlashSRGraph:
                 h = self._vae_res(be, h, f"vae.decoder.up.{i}.block.{j}", cin, cout)
                 cin = cout
             if i != 0:
-                h = be.conv2d(be.upsample2x(h), f"vae.decoder.up.{i}.upsample.conv", cin, cin, 3)
+                h = be.upsample_conv2d(h, f"vae.decoder.up.{i}.upsample.conv", cin, cin)
         h = be.groupnorm(h, "vae.decoder.norm_out", cin, v["groups"], v["eps"], silu=True)
         return be.conv2d(h, "vae.decoder.conv_out", cin, v["in_channels"], 3)
 
@@ -412,7 +416,7 @@ class FlashSRGraph:
                     h = self._unet_attn(be, h, f"unet.output_blocks.{idx}.{sub}", ch)
                     sub += 1
                 if level and i == nrb:
-                    h = be.conv2d(be.upsample2x(h), f"unet.output_blocks.{idx}.{sub}.conv", ch, ch, 3)
+                    h = be.upsample_conv2d(h, f"unet.output_blocks.{idx}.{sub}.conv", ch, ch)
                     ds //= 2
                 idx += 1
         h = be.groupnorm(h, "unet.out.0", ch, u["groups"], u["eps"], silu=True)

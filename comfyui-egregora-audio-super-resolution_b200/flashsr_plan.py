@@ -253,7 +253,7 @@ class PlanBackend:
               out_pt: PT, out16: bool, out32: bool, bias_off=None, rowbias: Optional[PT] = None, resid: Optional[PT] = None,
               act=None, alpha=1.0, out_pix_stride=None, out_batch_stride=None, out_offset=0, out_lo=0, out_hi=BIG,
               transposed=False, out_n_stride=0, wstride_n=None, wstride_z=None, wz_batch=False, w_buf: Optional[Buf] = None,
-              a_elem=1, resid2: Optional[PT] = None, post=1.0):
+              a_elem=1, resid2: Optional[PT] = None, post=1.0, out_h_stride=0, flops_scale=1.0):
         op = RawOp(K["EGR_OP_GEMM_SIMT"] if simt else K["EGR_OP_GEMM_TC"], name)
         buf, off, dims, strides = a_view
         op.x0 = (buf, off, len(dims), a_elem, dims, strides)
@@ -276,6 +276,9 @@ class PlanBackend:
                 "TRANSPOSED": 1 if transposed else 0, "OUT_N_STRIDE": out_n_stride,
                 "ACT": {None: K["EGR_ACT_NONE"], "silu": K["EGR_ACT_SILU"], "tanh": K["EGR_ACT_TANH"]}[act],
                 "KBLOCK": 64}
+        if out_h_stride:
+            assert not simt
+            op.i["OUT_H_STRIDE"] = out_h_stride
         op.f = {"ALPHA": alpha, "POST": post}
         op.taps = taps
         if w_buf is not None:
@@ -355,6 +358,33 @@ class PlanBackend:
         self._gemm(name, x, (abuf, 0, dims, strides), taps, cin, cout, w_off, simt=not tc, dimW=dimW, dimH=dimH, dimB=dimB,
                    Wo=Wo, Ho=Ho, Bo=B, out_pt=o, out16=want16, out32=not want16, bias_off=self.w_bias(name),
                    rowbias=rowbias, resid=add, act=act, a_elem=elem, **kw)
+        return o
+
+    def upsample_conv2d(self, x: PT, name, cin, cout):
+        """conv3x3(nearest_upsample2x(x)) without the 4x larger intermediate: output pixel (2y+a, 2x+b) only sees a
+        2x2 window of the low-resolution map, so each of the four output phases is a 4-tap GEMM over x whose weights
+        are sums of the 3x3 taps that land on the same source pixel (2.25x fewer FLOPs, no up-sampled copy in HBM)."""
+        assert x.C == cin and self._use_tc(cin, cout)
+        xa = self._materialize16(x, name + ".in16")
+        B, H, W = x.B, x.H, x.W
+        o = self.new(B, 2 * H, 2 * W, cout, f32=True, tag=name)
+        w = self.Wt[name + ".weight"].float()           # [cout, cin, 3, 3]
+        groups = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}   # phase -> [(source offset, kernel rows/cols)]
+        dims, strides = [cin, W, H, B], [1, cin, W * cin, H * W * cin]
+        for a in (0, 1):
+            for b in (0, 1):
+                taps, mats = [], []
+                for dy, kys in groups[a]:
+                    for dx, kxs in groups[b]:
+                        taps.append([0, dx, dy, 0, 0])
+                        mats.append(sum(w[:, :, ky, kx] for ky in kys for kx in kxs))   # [cout, cin]
+                pk = torch.stack(mats, 0).contiguous()
+                w_off = self.blob.put(f"f16:{name}.weight:up{a}{b}", pk.numpy().astype(np.float16))
+                self._gemm(f"{name}.p{a}{b}", x, (xa.f16, 0, dims, strides), taps, cin, cout, w_off, simt=False, dimW=1, dimH=2,
+                           dimB=3, Wo=W, Ho=H, Bo=B, out_pt=o, out16=False, out32=True, bias_off=self.w_bias(name),
+                           out_pix_stride=2 * cout, out_h_stride=4 * W * cout, out_batch_stride=4 * H * W * cout,
+                           out_offset=(a * 2 * W + b) * cout, out_lo=0, out_hi=4 * H * W * cout)
+        o.producer = None   # four writers: an f16 copy would need all of them
         return o
 
     def linear(self, x: PT, name, cin, cout, bias=True, small=False, act=None, out=None, add=None):

@@ -159,6 +159,7 @@ typedef struct egr_op {
 #define EGR_I_SEQ      34
 #define EGR_I_BATCH    35
 #define EGR_I_AUX0     36
+#define EGR_I_OUT_H_STRIDE 36 /* GEMM_TC ops: output stride of one step along H (0 = WO*OUT_PIX_STRIDE, the dense default) */
 #define EGR_I_AUX1     37
 #define EGR_I_AUX2     38
 #define EGR_I_AUX3     39

@@ -131,6 +131,10 @@ class TorchBackend:
         return torch.cat([torch.cos(args), torch.sin(args)])[None].to(self.dt)
 
     # ------------------------------------------------------------------ 1-D
+    def upsample_conv2d(self, x, name, cin, cout):
+        """ldm Upsample: nearest 2x then conv3x3 (the CUDA plan evaluates the same thing as four 2x2-tap phases)."""
+        return self.conv2d(self.upsample2x(x), name, cin, cout, 3)
+
     def conv1d(self, x, name, cin, cout, k, dilation=1, add=None, act=None, add2=None, post=1.0):
         y = F.conv1d(x, self.W[name + ".weight"], self.W[name + ".bias"], padding=dilation * (k // 2), dilation=dilation)
         if add is not None:

@@ -100,7 +100,8 @@ class Interp:
             idx = bI * i("OUT_BATCH_STRIDE") + nI * i("OUT_N_STRIDE") + pix + i("OUT_OFFSET")
             keep = torch.ones_like(idx, dtype=torch.bool)
         else:
-            flat = pix * i("OUT_PIX_STRIDE") + i("OUT_OFFSET") + nI
+            hs = i("OUT_H_STRIDE") if op.code == self.K["EGR_OP_GEMM_TC"] else 0
+            flat = (hI * hs + wI * i("OUT_PIX_STRIDE") if hs else pix * i("OUT_PIX_STRIDE")) + i("OUT_OFFSET") + nI
             keep = (flat >= i("OUT_LO")) & (flat < i("OUT_HI"))
             idx = bI * i("OUT_BATCH_STRIDE") + flat
         idx, v = idx[keep], v[keep]

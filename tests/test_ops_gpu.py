@@ -103,6 +103,18 @@ def test_conv1d_tc_persistent(cin, cout, k, d, T, B, cuda_dev):
     assert rel_err(mp.read(y)[:, :, 0], ref) < TC_TOL
 
 
+@pytest.mark.parametrize("cin,cout,H,W,B", [(64, 64, 8, 16, 2), (128, 128, 32, 64, 1), (32, 48, 5, 12, 3)])
+def test_upsample_conv2d_tc(cin, cout, H, W, B, cuda_dev):
+    """nearest-2x + conv3x3 evaluated as four 2x2-tap phase GEMMs with pre-summed weights and strided output."""
+    Wt = {"c.weight": _w((cout, cin, 3, 3), 1), "c.bias": _x((cout,), 2) * 0.1}
+    x = _x((B, cin, H, W), 3)
+    mp = MiniPlan(Wt)
+    y = mp.be.upsample_conv2d(mp.input(x), "c", cin, cout)
+    mp.run_gpu()
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), Wt["c.weight"], Wt["c.bias"], padding=1)
+    assert rel_err(mp.read(y), ref) < TC_TOL
+
+
 @pytest.mark.parametrize("cin,cout,pad", [(64, 64, "ldm_down"), (128, 128, "same"), (32, 32, "same")])
 def test_conv2d_stride2_tc(cin, cout, pad, cuda_dev):
     Wt = {"c.weight": _w((cout, cin, 3, 3), 1), "c.bias": _x((cout,), 2) * 0.1}
