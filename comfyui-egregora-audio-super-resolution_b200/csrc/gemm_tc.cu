@@ -677,8 +677,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
               for (int i = 0; i < 4; ++i) {
                 const int k = 4 * half + i;
                 float4 o;
-                o.x = (fmaf(a[i].x, g.alpha, bias4.x) + rv[k].x) * g.post; o.y = (fmaf(a[i].y, g.alpha, bias4.y) + rv[k].y) * g.post;
-                o.z = (fmaf(a[i].z, g.alpha, bias4.z) + rv[k].z) * g.post; o.w = (fmaf(a[i].w, g.alpha, bias4.w) + rv[k].w) * g.post;
+                o.x = fmaf(a[i].x, g.alpha, bias4.x) + rv[k].x; o.y = fmaf(a[i].y, g.alpha, bias4.y) + rv[k].y;
+                o.z = fmaf(a[i].z, g.alpha, bias4.z) + rv[k].z; o.w = fmaf(a[i].w, g.alpha, bias4.w) + rv[k].w;
                 if (col_ok && off[k] >= 0) {
                   *reinterpret_cast<float4*>(g.out32 + base_l0 + off[k] + n) = o;
                   if (has_out16) {  // f16 copy for a following tensor-core layer (uniform flag)
@@ -1011,7 +1011,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     ka.need_crop = (g.out_lo > 0 || g.out_hi < (long long)(g.Ho - 1) * g.out_h_stride + (long long)g.Wo * g.out_pix_stride + g.out_offset + g.N) ? 1 : 0;
   }
   ka.vec_ok = vec ? 1 : 0;
-  ka.epi_plain = (vec && g.out32 && g.act == EGR_ACT_NONE && !g.rowbias && !ka.need_crop) ? 1 : 0;
+  ka.epi_plain = (vec && g.out32 && g.post == 1.0f && g.act == EGR_ACT_NONE && !g.rowbias && !ka.need_crop) ? 1 : 0;
   *out = p;
   return EGR_OK;
 }

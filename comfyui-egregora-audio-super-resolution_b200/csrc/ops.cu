@@ -990,6 +990,24 @@ __global__ void __launch_bounds__(256) elt_axpby_kernel(const float* __restrict_
   }
 }
 
+// out = a*((x + y) + z): one pass instead of two adds, a scale and a cast (n is a multiple of 4, 16-byte aligned)
+__global__ void __launch_bounds__(256) elt_sum3_kernel(const float4* __restrict__ x, const float4* __restrict__ y,
+                                                        const float4* __restrict__ z, float a, long long n4,
+                                                        float4* __restrict__ o32, uint2* __restrict__ o16) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 p = __ldg(x + i), q = __ldg(y + i), r = __ldg(z + i);
+    const float4 v = make_float4(((p.x + q.x) + r.x) * a, ((p.y + q.y) + r.y) * a, ((p.z + q.z) + r.z) * a, ((p.w + q.w) + r.w) * a);
+    if (o32) o32[i] = v;
+    if (o16) {
+      __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<unsigned*>(&h0);
+      pk.y = *reinterpret_cast<unsigned*>(&h1);
+      o16[i] = pk;
+    }
+  }
+}
+
 // nearest 2x upsample of [B,H,W,C] f32 -> [B,2H,2W,C] f16 (and/or f32)
 __global__ void __launch_bounds__(256) elt_up2x_kernel(const float* __restrict__ x, int B, int H, int W, int C,
                                                         float* __restrict__ o32, __half* __restrict__ o16) {
@@ -1031,6 +1049,17 @@ int egr::launch_eltwise(const Spaces& s, const egr_op& op, cudaStream_t st) {
       elt_axpby_kernel<<<grid1d(op.i[EGR_I_ROWS]), 256, 0, st>>>(x0, nullptr, (float)op.f[EGR_F_A], (float)op.f[EGR_F_B],
                                                                  op.i[EGR_I_ROWS], o32, o16);
       break;
+    case EGR_ELT_SUM3: {
+      const float* x2 = (const float*)resolve(s, op.ptr[EGR_P_AUX]);
+      const long long n = op.i[EGR_I_ROWS];
+      auto al = [](const void* q) { return q == nullptr || reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+      if (!x1 || !x2 || (n & 3) || !al(x0) || !al(x1) || !al(x2) || !al(o32) || !al(o16))
+        return fail(EGR_ERR_ARG, "%s: SUM3 needs three 16-byte aligned inputs and a multiple of 4 elements", op.name);
+      elt_sum3_kernel<<<grid1d(n / 4), 256, 0, st>>>(reinterpret_cast<const float4*>(x0), reinterpret_cast<const float4*>(x1),
+                                                    reinterpret_cast<const float4*>(x2), (float)op.f[EGR_F_A], n / 4,
+                                                    reinterpret_cast<float4*>(o32), reinterpret_cast<uint2*>(o16));
+      break;
+    }
     case EGR_ELT_UPSAMPLE2X: {
       const int B = (int)op.i[EGR_I_BATCH], H = (int)op.i[EGR_I_AUX0], W = (int)op.i[EGR_I_AUX1], C = (int)op.i[EGR_I_C0];
       elt_up2x_kernel<<<grid1d((long long)B * 4 * H * W * C), 256, 0, st>>>(x0, B, H, W, C, o32, o16);

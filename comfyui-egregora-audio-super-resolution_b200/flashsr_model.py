@@ -442,25 +442,17 @@ class FlashSRGraph:
         for i, (r, k) in enumerate(zip(rates, ksz)):
             x = be.convT1d(x, f"vocoder.ups.{i}.0", cin, chans[i], k, r, add=feats.get(i))
             cin = chans[i]
-            xs = None
+            ys = []
             for j, rk in enumerate(vc["resblock_kernel_sizes"]):
                 name = f"{name_prefix(i, nk, j)}"
                 y = x
-                nd = len(vc["resblock_dilations"])
                 for di, d in enumerate(vc["resblock_dilations"]):
                     yt = be.snake_aa(y, f"{name}.activations.{2 * di}", cin)
                     yt = be.conv1d(yt, f"{name}.convs1.{di}", cin, cin, rk, dilation=d)
                     yt = be.snake_aa(yt, f"{name}.activations.{2 * di + 1}", cin)
-                    if di == nd - 1 and xs is not None:
-                        # last conv of a parallel block: its epilogue also accumulates the running sum of the blocks
-                        # (and the 1/nk average on the last one) — x_next = (Y_0 + .. + Y_{nk-1}) / nk with no
-                        # separate add / scale passes over the feature map
-                        y = be.conv1d(yt, f"{name}.convs2.{di}", cin, cin, rk, add=y, add2=xs,
-                                      post=(1.0 / nk) if j == nk - 1 else 1.0)
-                    else:
-                        y = be.conv1d(yt, f"{name}.convs2.{di}", cin, cin, rk, add=y)
-                xs = y
-            x = xs if nk > 1 else be.scale(xs, 1.0 / nk)
+                    y = be.conv1d(yt, f"{name}.convs2.{di}", cin, cin, rk, add=y)
+                ys.append(y)
+            x = be.mean_blocks(ys)   # BigVGAN: xs = sum of the parallel blocks, x = xs / num_kernels
         x = be.snake_aa(x, "vocoder.activation_post", cin)
         return be.conv1d(x, "vocoder.conv_post", cin, 1, 7, act="tanh")
 

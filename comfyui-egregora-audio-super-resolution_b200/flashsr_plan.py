@@ -528,6 +528,27 @@ class PlanBackend:
     def add(self, a: PT, b: PT):
         return self._elt("add", K["EGR_ELT_AXPBY"], a, b, 1.0, 1.0, a.B * a.P * a.C)
 
+    def mean_blocks(self, ys):
+        """(y0 + y1 + ...) / n of the vocoder's parallel residual blocks; three blocks are one fused pass."""
+        n = len(ys)
+        if n == 3 and all(y.f32 is not None and y.parts is None and y.ld == y.C for y in ys) and (ys[0].B * ys[0].P * ys[0].C) % 4 == 0:
+            x = ys[0]
+            o = self.new(x.B, x.H, x.W, x.C, f32=True, tag="mean3")
+            op = RawOp(K["EGR_OP_ELTWISE"], "mean3")
+            op.i = {"MODE": K["EGR_ELT_SUM3"], "ROWS": x.B * x.P * x.C}
+            op.f = {"A": 1.0 / n}
+            op.x0 = (ys[0].f32, 0, 1, 0, [x.C], [1]); op.reads.append(ys[0].f32)
+            op.x1 = (ys[1].f32, 0, 1, 0, [x.C], [1]); op.reads.append(ys[1].f32)
+            self._ws(op, "AUX", ys[2].f32)
+            self._ws(op, "OUT32", o.f32, write=True)
+            self.emit(op)
+            o.producer = op
+            return o
+        xs = ys[0]
+        for y in ys[1:]:
+            xs = self.add(xs, y)
+        return self.scale(xs, 1.0 / n)
+
     def scale(self, a: PT, s):
         return self._elt("scale", K["EGR_ELT_SCALE_SHIFT"], a, None, s, 0.0, a.B * a.P * a.C)
 

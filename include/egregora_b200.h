@@ -183,6 +183,7 @@ typedef struct egr_op {
 #define EGR_ELT_UPSAMPLE2X  3  /* nearest 2x in H and W of x0 [C,W,H,B] -> out16 (and/or out32) */
 #define EGR_ELT_COPY32      4  /* out32 = concat(x0,x1) as f32 */
 #define EGR_ELT_SCALE_SHIFT 5  /* out32 = A*x0 + B */
+#define EGR_ELT_SUM3        6  /* out = A*((x0 + x1) + x2), x2 in ptr[EGR_P_AUX]; f32 and/or f16 out (mean of the vocoder's parallel blocks) */
 
 typedef struct egr_plan egr_plan;
 

@@ -184,6 +184,12 @@ class TorchBackend:
     def scale(self, a, s):
         return a * s
 
+    def mean_blocks(self, ys):
+        xs = ys[0]
+        for y in ys[1:]:
+            xs = xs + y
+        return xs * (1.0 / len(ys))
+
     # ------------------------------------------------------------------ front end
     def stft_mag(self, wav):
         m = self.s["mel"]

@@ -200,6 +200,10 @@ class Interp:
         elif mode == K["EGR_ELT_SCALE_SHIFT"]:
             n = self.i(op, "ROWS")
             y = self.f(op, "A") * self.flat(op.x0.addr, torch.float32, n) + self.f(op, "B")
+        elif mode == K["EGR_ELT_SUM3"]:
+            n = self.i(op, "ROWS")
+            y = self.f(op, "A") * ((self.flat(op.x0.addr, torch.float32, n) + self.flat(op.x1.addr, torch.float32, n))
+                                   + self.p(op, "AUX", torch.float32, n))
         elif mode == K["EGR_ELT_UPSAMPLE2X"]:
             B, H, W, Cc = self.i(op, "BATCH"), self.i(op, "AUX0"), self.i(op, "AUX1"), self.i(op, "C0")
             x = self.flat(op.x0.addr, torch.float32, B * H * W * Cc).view(B, H, W, Cc)
