@@ -497,20 +497,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* 
   }
   __syncthreads();
   const long long p_lo = (long long)blockIdx.x * slab, p_hi = min(p_lo + slab, a.P);
-  const long long total = (p_hi - p_lo) * C4;
-  for (long long i = threadIdx.x; i < total; i += blockDim.x) {
-    const long long p = p_lo + i / C4;
-    const int c = (int)(i % C4) << 2;
-    const float* src = c < a.C0 ? a.x0 + ((long long)b * a.P + p) * a.C0 + c
-                                : a.x1 + ((long long)b * a.P + p) * a.C1 + (c - a.C0);
+  const int total = (int)(p_hi - p_lo) * C4;  // float4 units of this slab (slab <= a few thousand pixels)
+  const long long row0 = (long long)b * a.P + p_lo;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int pl = i / C4;
+    const int c = (i - pl * C4) << 2;
+    const long long p = row0 + pl;
+    const float* src = c < a.C0 ? a.x0 + p * a.C0 + c : a.x1 + p * a.C1 + (c - a.C0);
     const float4 v = __ldg(reinterpret_cast<const float4*>(src));
-    float r[4] = {fmaf(v.x, scale[c], shift[c]), fmaf(v.y, scale[c + 1], shift[c + 1]),
-                  fmaf(v.z, scale[c + 2], shift[c + 2]), fmaf(v.w, scale[c + 3], shift[c + 3])};
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+    float r[4] = {fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)};
     if (silu) {
 #pragma unroll
       for (int u = 0; u < 4; ++u) r[u] = egr_silu(r[u]);
     }
-    const long long o = ((long long)b * a.P + p) * C + c;
+    const long long o = p * C + c;
     if (out32) *reinterpret_cast<float4*>(out32 + o) = make_float4(r[0], r[1], r[2], r[3]);
     if (out16) {
       __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
@@ -1099,6 +1100,7 @@ __device__ __forceinline__ float snake_eval(float u, float alpha, float inv_beta
 // consecutive lanes read consecutive channels (coalesced).  Both the 6-sample input window and the 12-sample
 // activated window slide in registers: per output 1 load, 12 FMAs (two up-sampling phases), 2 snake evaluations,
 // 12 FMAs (down-sampling), 1 store.
+template <bool O32, bool O16>   // which outputs exist: compile-time, so the per-sample stores carry no branches
 __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__ x, int T, int C, int nruns, int tt,
                                                         const float* __restrict__ log_alpha,
                                                         const float* __restrict__ log_beta,
@@ -1165,8 +1167,8 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
     // signal selects and the per-output bounds test disappear and addresses advance by pointer increments — the
     // clamped form spends more instructions on integer index math than on the filter itself.
     const float* px = xb + (long long)(t0 + 5) * C;   // next input sample to enter the window
-    float* p32 = o32 ? o32 + ((long long)b * T + t0) * C + c : nullptr;
-    __half* p16 = o16 ? o16 + ((long long)b * T + t0) * C + c : nullptr;
+    float* p32 = O32 ? o32 + ((long long)b * T + t0) * C + c : nullptr;
+    __half* p16 = O16 ? o16 + ((long long)b * T + t0) * C + c : nullptr;
     float xn[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { xn[i] = __ldg(px); px += C; }
@@ -1192,8 +1194,8 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
         float y = 0.f;
 #pragma unroll
         for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
-        if (p32) { *p32 = y; p32 += C; }
-        if (p16) { *p16 = __float2half_rn(y); p16 += C; }
+        if (O32) { *p32 = y; p32 += C; }
+        if (O16) { *p16 = __float2half_rn(y); p16 += C; }
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) xn[i] = xnext[i];
@@ -1233,8 +1235,8 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
 #pragma unroll
       for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
       const long long o = ((long long)b * T + t) * C + c;
-      if (o32) o32[o] = y;
-      if (o16) o16[o] = __float2half_rn(y);
+      if (O32) o32[o] = y;
+      if (O16) o16[o] = __float2half_rn(y);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) xn[i] = xnext[i];
@@ -1257,7 +1259,7 @@ int egr::launch_snake_aa(const Spaces& s, const egr_op& op, cudaStream_t st) {
   static int resident = 0;
   if (!resident) {
     int per_sm = 0;
-    EGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snake_aa_kernel, 128, 0));
+    EGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snake_aa_kernel<false, true>, 128, 0));
     resident = (per_sm > 0 ? per_sm : 8) * (devinfo().sm_count ? devinfo().sm_count : 148);
   }
   int tt = SNAKE_TT;
@@ -1272,7 +1274,9 @@ int egr::launch_snake_aa(const Spaces& s, const egr_op& op, cudaStream_t st) {
   }
   const int nruns = (T + tt - 1) / tt;
   dim3 grid((unsigned)(((long long)nruns * C + 127) / 128), B);
-  snake_aa_kernel<<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
+  if (o32 && o16) snake_aa_kernel<true, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
+  else if (o16) snake_aa_kernel<false, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
+  else snake_aa_kernel<true, false><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }
