@@ -29,18 +29,24 @@ int fft2_inverse_from_positions(const Fft2Plan* p, float2* d_pos, float2* d_out,
 }
 
 struct FlDev {
-  int R1, R2, cw;
+  int R1, R2, cw, cw_shift;
+  float inv_m;  // 1/M, rounded once from double on the host
   long long M;
   Radices rd1, rd2;
-  const float2 *tw1, *tw2, *twM_lo, *twM_hi, *twN_lo, *twN_hi;
-  const int *perm1, *pos1, *perm2, *pos2;
+  const float2 *tw1, *tw2, *twM_lo, *twM_hi, *twN_lo, *twN_hi, *twH;
+  const int *perm1, *pos1, *perm2, *pos2, *pairT, *pairZ;
+  const float2* twHp;
 };
 
 static FlDev fl_dev(const Fft2Plan* p) {
   FlDev d;
   d.R1 = p->R1; d.R2 = p->R2; d.cw = p->cw; d.M = p->M; d.rd1 = p->rd1; d.rd2 = p->rd2;
-  d.tw1 = p->tw1; d.tw2 = p->tw2; d.twM_lo = p->twM_lo; d.twM_hi = p->twM_hi; d.twN_lo = p->twN_lo; d.twN_hi = p->twN_hi;
+  d.tw1 = p->tw1; d.tw2 = p->tw2; d.twM_lo = p->twM_lo; d.twM_hi = p->twM_hi; d.twN_lo = p->twN_lo; d.twN_hi = p->twN_hi; d.twH = p->twH;
   d.perm1 = p->perm1; d.pos1 = p->pos1; d.perm2 = p->perm2; d.pos2 = p->pos2;
+  d.pairT = p->pairT; d.pairZ = p->pairZ; d.twHp = p->twHp;
+  d.cw_shift = 0;
+  while ((1 << d.cw_shift) < d.cw) ++d.cw_shift;
+  d.inv_m = (float)(1.0 / (double)p->M);
   return d;
 }
 
@@ -53,48 +59,71 @@ __device__ __forceinline__ void block_atomic_max(float v, unsigned int* slot) {
   if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(slot, __float_as_uint(v));
 }
 
+// Global -> shared staging with U independent loads in flight per thread.  (ncu source view, profiles/r1_n: written as
+// a plain `for (i...) sm[i] = g[i]` loop the compiler keeps ONE load in flight, and 34 % / 43 % of the row / column
+// kernel's samples sat on the store that waits for it.)
+template <int U, typename T, class LD, class ST>
+__device__ __forceinline__ void staged(const int n, LD ld, ST st) {
+  for (int base = threadIdx.x; base < n; base += U * blockDim.x) {
+    T v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < n) v[u] = ld(i);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * blockDim.x;
+      if (i < n) st(i, v[u]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ column kernel
 #define FL_FIRST 0
 #define FL_MID 1
 #define FL_LAST 2
 
 // d_in [C][n] f32 (integer-scaled samples), work [C][M] float2 in position order, d_out [C][N] f32, peaks [C][2] uint
-template <int MODE>
-__global__ void __launch_bounds__(256) fl_col_kernel(FlDev d, const float* __restrict__ d_in, long long n, int U, float thr,
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(MINB == 4 ? 256 : 320, MINB) fl_col_kernel(FlDev d, const float* __restrict__ d_in, long long n, int U, float thr,
                                                      float2* __restrict__ work, float* __restrict__ d_out,
                                                      unsigned int* __restrict__ peaks) {
   extern __shared__ float2 sm[];
-  const int cw = d.cw, R1 = d.R1, R2 = d.R2;
+  const int cw = d.cw, R1 = d.R1, R2 = d.R2, cs = d.cw_shift;
   const int c0 = blockIdx.x * cw, ch = blockIdx.y;
   const long long N = 2 * d.M;
   const float* x = d_in + (long long)ch * n;
   float2* wk = work + (long long)ch * d.M;
   const int tile = R1 * cw;
-  // stage twiddles of the length-R1 transform in shared memory: every butterfly reads R-1 of them, and as global
-  // (L1) loads they were the dominant long-scoreboard stall of this kernel
+  // stage twiddles of the length-R1 transform in shared memory: every butterfly reads R-1 of them
   float2* tws = sm + tile;
-  for (int i = threadIdx.x; i < R1; i += blockDim.x) tws[i] = d.tw1[i];
+  staged<8, float2>(R1, [&](int i) { return __ldg(d.tw1 + i); }, [&](int i, float2 v) { tws[i] = v; });
   float pk = 0.f;
+  auto expanded = [&](long long m) {  // the pair (2m, 2m+1) of the sample-repeated input
+    if (U == 1) return __ldg(reinterpret_cast<const float2*>(x + 2 * m));
+    return make_float2(__ldg(x + (2 * m) / U), __ldg(x + (2 * m + 1) / U));
+  };
   if (MODE == FL_FIRST) {
-    for (int i = threadIdx.x; i < tile; i += blockDim.x) {
-      const int r = i / cw, c = i - r * cw;
-      float2 v = make_float2(0.f, 0.f);
-      if (c0 + c < R2) {
-        const long long m = (long long)r * R2 + c0 + c;
-        if (U == 1) v = *reinterpret_cast<const float2*>(x + 2 * m);
-        else v = make_float2(x[(2 * m) / U], x[(2 * m + 1) / U]);
-        pk = fmaxf(pk, fmaxf(fabsf(v.x), fabsf(v.y)));
-        v.x = fabsf(v.x) > thr ? v.x : 0.f;
-        v.y = fabsf(v.y) > thr ? v.y : 0.f;
-      }
-      sm[i] = v;
-    }
+    staged<8, float2>(tile,
+        [&](int i) {
+          const int r = i >> cs, c = i & (cw - 1);
+          return (c0 + c < R2) ? expanded((long long)r * R2 + c0 + c) : make_float2(0.f, 0.f);
+        },
+        [&](int i, float2 v) {
+          pk = fmaxf(pk, fmaxf(fabsf(v.x), fabsf(v.y)));
+          v.x = fabsf(v.x) > thr ? v.x : 0.f;
+          v.y = fabsf(v.y) > thr ? v.y : 0.f;
+          sm[i] = v;
+        });
     block_atomic_max(pk, peaks + 2 * ch);
   } else {
-    for (int i = threadIdx.x; i < tile; i += blockDim.x) {
-      const int r = i / cw, c = i - r * cw;
-      sm[i] = (c0 + c < R2) ? wk[(long long)r * R2 + c0 + c] : make_float2(0.f, 0.f);
-    }
+    staged<8, float2>(tile,
+        [&](int i) {
+          const int r = i >> cs, c = i & (cw - 1);
+          return (c0 + c < R2) ? wk[(long long)r * R2 + c0 + c] : make_float2(0.f, 0.f);
+        },
+        [&](int i, float2 v) { sm[i] = v; });
   }
   __syncthreads();
   const Tile g{R1, cw, cw, 1};
@@ -102,24 +131,26 @@ __global__ void __launch_bounds__(256) fl_col_kernel(FlDev d, const float* __res
   if (MODE != FL_LAST) {
     fft_forward<true>(sm, g, d.rd1, tws);
     for (int i = threadIdx.x; i < tile; i += blockDim.x) {
-      const int r = i / cw, c = i - r * cw;
+      const int r = i >> cs, c = i & (cw - 1);
       if (c0 + c < R2) wk[(long long)r * R2 + c0 + c] = sm[i];
     }
   } else {
     float* y = d_out + (long long)ch * N;
-    for (int i = threadIdx.x; i < tile; i += blockDim.x) {
-      const int r = i / cw, c = i - r * cw;
-      if (c0 + c < R2) {
-        const long long m = (long long)r * R2 + c0 + c;
-        float2 e;
-        if (U == 1) e = *reinterpret_cast<const float2*>(x + 2 * m);
-        else e = make_float2(x[(2 * m) / U], x[(2 * m + 1) / U]);
-        const float2 s = sm[i];
-        const float2 o = make_float2(__fadd_rn(e.x, s.x), __fadd_rn(e.y, s.y));
-        *reinterpret_cast<float2*>(y + 2 * m) = o;
-        pk = fmaxf(pk, fmaxf(fabsf(o.x), fabsf(o.y)));
-      }
-    }
+    staged<8, float2>(tile,
+        [&](int i) {
+          const int r = i >> cs, c = i & (cw - 1);
+          return (c0 + c < R2) ? expanded((long long)r * R2 + c0 + c) : make_float2(0.f, 0.f);
+        },
+        [&](int i, float2 e) {
+          const int r = i >> cs, c = i & (cw - 1);
+          if (c0 + c < R2) {
+            const long long m = (long long)r * R2 + c0 + c;
+            const float2 sv = sm[i];
+            const float2 o = make_float2(__fadd_rn(e.x, sv.x), __fadd_rn(e.y, sv.y));
+            *reinterpret_cast<float2*>(y + 2 * m) = o;
+            pk = fmaxf(pk, fmaxf(fabsf(o.x), fabsf(o.y)));
+          }
+        });
     block_atomic_max(pk, peaks + 2 * ch + 1);
   }
 }
@@ -144,7 +175,8 @@ __device__ __forceinline__ void gate_pair(float2& za, float2& zb, const float2 w
   zb = make_float2(E2.x + O2.y, -E2.y + O2.x);  // conj(E') + i conj(O')
 }
 
-__global__ void __launch_bounds__(256) fl_row_kernel(FlDev d, float thr, float2* __restrict__ work) {
+template <int MINB>
+__global__ void __launch_bounds__(MINB == 4 ? 256 : 320, MINB) fl_row_kernel(FlDev d, float thr, float2* __restrict__ work) {
   extern __shared__ float2 sm[];
   const int R1 = d.R1, R2 = d.R2;
   const int k1a = blockIdx.x, k1b = (R1 - k1a) % R1;
@@ -156,58 +188,118 @@ __global__ void __launch_bounds__(256) fl_row_kernel(FlDev d, float thr, float2*
   float2* sA = sm;
   float2* sB = sm + R2;
   float2* tws = sm + 2 * R2;  // stage twiddles of the length-R2 transform (see fl_col_kernel)
-  for (int i = threadIdx.x; i < R2; i += blockDim.x) tws[i] = d.tw2[i];
-  for (int i = threadIdx.x; i < R2; i += blockDim.x) {
-    sA[i] = k1a ? cmulf(rowA[i], tw_split(d.twM_hi, d.twM_lo, (long long)i * k1a)) : rowA[i];
-    if (two) sB[i] = cmulf(rowB[i], tw_split(d.twM_hi, d.twM_lo, (long long)i * k1b));
+  // Row twiddles w_M^(i*k1), i < R2, as a two-level product built once per CTA: i = 64 a + b,
+  // w^(i k1) = HI[a] * LO[b].  (Looking every element up in the global hi/lo tables cost ~6.5 L1 sectors per
+  // element — 26x the data volume of the row itself — and made the kernel long-scoreboard bound.)
+  const int NA = (R2 + 63) >> 6;
+  float2* hiA = sm + 3 * R2;       // [NA]
+  float2* loA = hiA + NA;          // [64]
+  float2* hiB = loA + 64;          // [NA]
+  float2* loB = hiB + NA;          // [64]
+  struct Pair { float2 a, b; };
+  constexpr int UB = 4;
+  const int T = blockDim.x;
+  auto load_pair = [&](int i) {
+    Pair v;
+    v.a = rowA[i];
+    v.b = two ? rowB[i] : make_float2(0.f, 0.f);
+    return v;
+  };
+  auto store_pair = [&](int i, const Pair& v) {
+    sA[i] = k1a ? cmulf(v.a, cmulf(hiA[i >> 6], loA[i & 63])) : v.a;
+    if (two) sB[i] = cmulf(v.b, cmulf(hiB[i >> 6], loB[i & 63]));
+  };
+  // first batch of row loads goes out before anything else; the twiddle staging below overlaps their latency
+  Pair first[UB];
+#pragma unroll
+  for (int u = 0; u < UB; ++u) {
+    const int i = threadIdx.x + u * T;
+    if (i < R2) first[u] = load_pair(i);
+  }
+  staged<8, float2>(R2, [&](int i) { return __ldg(d.tw2 + i); }, [&](int i, float2 v) { tws[i] = v; });
+  for (int i = threadIdx.x; i < 2 * (NA + 64); i += T) {
+    const int row = i >= NA + 64, e = row ? i - (NA + 64) : i;
+    const long long k1 = row ? k1b : k1a;
+    const long long idx = (e < NA ? (long long)(e << 6) : (long long)(e - NA)) * k1;
+    hiA[i] = tw_split(d.twM_hi, d.twM_lo, idx);  // hiA/loA/hiB/loB are contiguous
+  }
+  const float2 wN0 = tw_split(d.twN_hi, d.twN_lo, k1a);  // w_N^k1a; w_N^(k1a + R1 k2) = wN0 * twH[k2]
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < UB; ++u) {
+    const int i = threadIdx.x + u * T;
+    if (i < R2) store_pair(i, first[u]);
+  }
+  for (int base = threadIdx.x + UB * T; base < R2; base += UB * T) {
+    Pair v[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u)
+      if (base + u * T < R2) v[u] = load_pair(base + u * T);
+#pragma unroll
+    for (int u = 0; u < UB; ++u)
+      if (base + u * T < R2) store_pair(base + u * T, v[u]);
   }
   __syncthreads();
   const Tile g{R2, two ? 2 : 1, 1, R2};
   fft_forward<false>(sm, g, d.rd2, tws);
+  // gate: every table is indexed by the POSITION p2 (coalesced, no dependent gathers):
+  //   perm2[p2] = k2,  pairT[p2] = pos2[R2-1-k2],  pairZ[p2] = pos2[(R2-k2) % R2],  twHp[p2] = w_N^(R1 k2)
+  struct GateIn { int k2, q2; float2 w; };
   if (two) {
-    for (int p2 = threadIdx.x; p2 < R2; p2 += blockDim.x) {
-      const int k2 = d.perm2[p2];
-      const int q2 = d.pos2[R2 - 1 - k2];
-      const long long k = k1a + (long long)R1 * k2;
-      float2 za = sA[p2], zb = sB[q2];
-      gate_pair(za, zb, tw_split(d.twN_hi, d.twN_lo, k), thr);
-      sA[p2] = za;
-      sB[q2] = zb;
-    }
+    staged<4, GateIn>(R2,
+        [&](int p2) {
+          GateIn in;
+          in.k2 = 0;
+          in.q2 = __ldg(d.pairT + p2);
+          in.w = __ldg(d.twHp + p2);
+          return in;
+        },
+        [&](int p2, const GateIn& in) {
+          float2 za = sA[p2], zb = sB[in.q2];
+          gate_pair(za, zb, cmulf(wN0, in.w), thr);
+          sA[p2] = za;
+          sB[in.q2] = zb;
+        });
   } else {
-    for (int p2 = threadIdx.x; p2 < R2; p2 += blockDim.x) {
-      const int k2 = d.perm2[p2];
-      const long long k = k1a + (long long)R1 * k2;
-      const long long kb = (d.M - k) % d.M;
-      if (k > kb) continue;
-      float2 za = sA[p2];
-      if (k == 0) {  // X[0] = re + im, X[M] = re - im, both real
-        const float x0 = za.x + za.y, xm = za.x - za.y;
-        const bool g0 = fabsf(x0) > thr, gm = fabsf(xm) > thr;
-        if (!(g0 && gm)) {
-          const float P = g0 ? x0 : 0.f, Q = gm ? xm : 0.f;
-          sA[p2] = make_float2(0.5f * (P + Q), 0.5f * (P - Q));
-        }
-      } else if (k == kb) {  // k = M/2: X = conj(Z)
-        if (!(sqrtf(fmaf(za.x, za.x, za.y * za.y)) > thr)) sA[p2] = make_float2(0.f, 0.f);
-      } else {
-        const int k2b = k1a == 0 ? (R2 - k2) % R2 : R2 - 1 - k2;
-        const int q2 = d.pos2[k2b];
-        float2 zb = sA[q2];
-        gate_pair(za, zb, tw_split(d.twN_hi, d.twN_lo, k), thr);
-        sA[p2] = za;
-        sA[q2] = zb;
-      }
-    }
+    const int* pair = k1a == 0 ? d.pairZ : d.pairT;
+    staged<4, GateIn>(R2,
+        [&](int p2) {
+          GateIn in;
+          in.k2 = __ldg(d.perm2 + p2);
+          in.q2 = __ldg(pair + p2);
+          in.w = __ldg(d.twHp + p2);
+          return in;
+        },
+        [&](int p2, const GateIn& in) {
+          const long long k = k1a + (long long)R1 * in.k2;
+          const long long kb = (d.M - k) % d.M;
+          if (k > kb) return;
+          float2 za = sA[p2];
+          if (k == 0) {  // X[0] = re + im, X[M] = re - im, both real
+            const float x0 = za.x + za.y, xm = za.x - za.y;
+            const bool g0 = fabsf(x0) > thr, gm = fabsf(xm) > thr;
+            if (!(g0 && gm)) {
+              const float P = g0 ? x0 : 0.f, Q = gm ? xm : 0.f;
+              sA[p2] = make_float2(0.5f * (P + Q), 0.5f * (P - Q));
+            }
+          } else if (k == kb) {  // k = M/2: X = conj(Z)
+            if (!(sqrtf(fmaf(za.x, za.x, za.y * za.y)) > thr)) sA[p2] = make_float2(0.f, 0.f);
+          } else {
+            float2 zb = sA[in.q2];
+            gate_pair(za, zb, cmulf(wN0, in.w), thr);
+            sA[p2] = za;
+            sA[in.q2] = zb;
+          }
+        });
   }
   __syncthreads();
   fft_inverse<false>(sm, g, d.rd2, tws);
-  const float sc = (float)(1.0 / (double)d.M);
-  for (int i = threadIdx.x; i < R2; i += blockDim.x) {
-    float2 v = k1a ? cmulc(sA[i], tw_split(d.twM_hi, d.twM_lo, (long long)i * k1a)) : sA[i];
+  const float sc = d.inv_m;
+  for (int i = threadIdx.x; i < R2; i += T) {
+    float2 v = k1a ? cmulc(sA[i], cmulf(hiA[i >> 6], loA[i & 63])) : sA[i];
     rowA[i] = make_float2(v.x * sc, v.y * sc);
     if (two) {
-      v = cmulc(sB[i], tw_split(d.twM_hi, d.twM_lo, (long long)i * k1b));
+      v = cmulc(sB[i], cmulf(hiB[i >> 6], loB[i & 63]));
       rowB[i] = make_float2(v.x * sc, v.y * sc);
     }
   }
@@ -290,6 +382,31 @@ static unsigned grid1(long long n) {
 
 static bool fast_path(long long N) { return N >= 2 && (N % 2 == 0) && fft2_plannable(N / 2); }
 
+template <int MINB>
+static int fl_fast_loop(const Fft2Plan* p, const FlDev& d, const float* d_in, long long n, int upscale, int iters,
+                        float threshold, float2* work, float* d_out, unsigned int* peaks, int C, size_t smc, size_t smr,
+                        cudaStream_t st) {
+  if (smc > 48 * 1024) {
+    EGR_CUDA(cudaFuncSetAttribute(fl_col_kernel<FL_FIRST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+    EGR_CUDA(cudaFuncSetAttribute(fl_col_kernel<FL_MID, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+    EGR_CUDA(cudaFuncSetAttribute(fl_col_kernel<FL_LAST, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+  }
+  if (smr > 48 * 1024) EGR_CUDA(cudaFuncSetAttribute(fl_row_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
+  const dim3 gc(ceil_div(p->R2, p->cw), C), gr(p->R1 / 2 + 1, C);
+  fl_col_kernel<FL_FIRST, MINB><<<gc, p->col_threads, smc, st>>>(d, d_in, n, upscale, threshold, work, d_out, peaks);
+  EGR_CHECK_LAUNCH("fl_col_kernel<first>");
+  for (int it = 0; it < iters; ++it) {
+    fl_row_kernel<MINB><<<gr, p->row_threads, smr, st>>>(d, threshold, work);
+    if (it + 1 < iters)
+      fl_col_kernel<FL_MID, MINB><<<gc, p->col_threads, smc, st>>>(d, d_in, n, upscale, threshold, work, d_out, peaks);
+  }
+  launch_count() += (unsigned long long)(2 * iters - 2);  // the loop's launches beyond the one counted below
+  EGR_CHECK_LAUNCH("fl_row_kernel / fl_col_kernel<mid>");
+  fl_col_kernel<FL_LAST, MINB><<<gc, p->col_threads, smc, st>>>(d, d_in, n, upscale, threshold, work, d_out, peaks);
+  EGR_CHECK_LAUNCH("fl_col_kernel<last>");
+  return EGR_OK;
+}
+
 struct GenPlanCache {
   long long N = 0;
   int batch = 0;
@@ -334,24 +451,14 @@ extern "C" int egr_fatllama_run(const float* d_in, float* d_out, int C, int64_t 
     if (upscale == 1 && ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 7))
       return fail(EGR_ERR_ARG, "egr_fatllama_run: buffers must be 8-byte aligned");
     const FlDev d = fl_dev(p);
-    const size_t smc = ((size_t)p->R1 * p->cw + p->R1) * sizeof(float2), smr = 3 * (size_t)p->R2 * sizeof(float2);
-    if (smc > 48 * 1024) {
-      EGR_CUDA(cudaFuncSetAttribute(fl_col_kernel<FL_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
-      EGR_CUDA(cudaFuncSetAttribute(fl_col_kernel<FL_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
-      EGR_CUDA(cudaFuncSetAttribute(fl_col_kernel<FL_LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smc));
+    const size_t smc = ((size_t)p->R1 * p->cw + p->R1) * sizeof(float2), smr = (3 * (size_t)p->R2 + 2 * (((size_t)p->R2 + 63) / 64 + 64)) * sizeof(float2);
+    int rc = 0;
+    switch (p->min_blocks) {
+      case 3: rc = fl_fast_loop<3>(p, d, d_in, n, upscale, iters, threshold, work, d_out, peaks, C, smc, smr, st); break;
+      case 4: rc = fl_fast_loop<4>(p, d, d_in, n, upscale, iters, threshold, work, d_out, peaks, C, smc, smr, st); break;
+      default: rc = fl_fast_loop<2>(p, d, d_in, n, upscale, iters, threshold, work, d_out, peaks, C, smc, smr, st); break;
     }
-    if (smr > 48 * 1024) EGR_CUDA(cudaFuncSetAttribute(fl_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smr));
-    const dim3 gc(ceil_div(p->R2, p->cw), C), gr(p->R1 / 2 + 1, C);
-    fl_col_kernel<FL_FIRST><<<gc, p->col_threads, smc, st>>>(d, d_in, n, upscale, threshold, work, d_out, peaks);
-    EGR_CHECK_LAUNCH("fl_col_kernel<first>");
-    for (int it = 0; it < iters; ++it) {
-      fl_row_kernel<<<gr, p->row_threads, smr, st>>>(d, threshold, work);
-      if (it + 1 < iters) fl_col_kernel<FL_MID><<<gc, p->col_threads, smc, st>>>(d, d_in, n, upscale, threshold, work, d_out, peaks);
-    }
-    launch_count() += (unsigned long long)(2 * iters - 2);  // the loop's launches beyond the one counted below
-    EGR_CHECK_LAUNCH("fl_row_kernel / fl_col_kernel<mid>");
-    fl_col_kernel<FL_LAST><<<gc, p->col_threads, smc, st>>>(d, d_in, n, upscale, threshold, work, d_out, peaks);
-    EGR_CHECK_LAUNCH("fl_col_kernel<last>");
+    if (rc) return rc;
   } else {
     if (g_gen.N != N || g_gen.batch != C) {
       if (g_gen.plan) { cudaStreamSynchronize(st); egr_fft_plan_destroy(g_gen.plan); g_gen.plan = nullptr; }

@@ -22,6 +22,14 @@ static bool smooth(int64_t n) {
   return n == 1;
 }
 
+static int max_radix() {  // tuning override: cap on the in-register radix (default 16)
+  if (const char* e = getenv("EGR_FFT_MAXR")) {
+    const int r = atoi(e);
+    if (r >= 7 && r <= 16) return r;
+  }
+  return 16;
+}
+
 // fewest stages with radices in [2,16]; larger radices first
 static bool plan_radices(int L, Radices* out) {
   std::vector<int> best;
@@ -32,7 +40,7 @@ static bool plan_radices(int L, Radices* out) {
     auto it = memo.find(l);
     if (it != memo.end()) return it->second;
     int b = 1 << 20;
-    for (int r = 16; r >= 2; --r)
+    for (int r = max_radix(); r >= 2; --r)
       if (l % r == 0) {
         int c = cost(l / r);
         if (c + 1 < b) b = c + 1;
@@ -45,7 +53,7 @@ static bool plan_radices(int L, Radices* out) {
   out->n = 0;
   while (l > 1) {
     int pick = 0;
-    for (int r = 16; r >= 2; --r)
+    for (int r = max_radix(); r >= 2; --r)
       if (l % r == 0 && cost(l / r) + 1 == cost(l)) { pick = r; break; }
     if (!pick || out->n >= EGR_FFT_MAX_STAGES) return false;
     out->r[out->n++] = pick;
@@ -129,13 +137,13 @@ const Fft2Plan* egr::fft2_get_plan(int64_t M) {
   }
   const int R1 = p->R1, R2 = p->R2;
   const int64_t nhi = (M >> 10) + 2;
-  std::vector<float2> tw1(R1), tw2(R2), mlo(1024), mhi(nhi), nlo(1024), nhi_(nhi);
+  std::vector<float2> tw1(R1), tw2(R2), mlo(1024), mhi(nhi), nlo(1024), nhi_(nhi), twh(R2);
   auto unit = [](double num, double den) {
     const double a = -2.0 * M_PI * (num / den);
     return make_float2((float)std::cos(a), (float)std::sin(a));
   };
   for (int t = 0; t < R1; ++t) tw1[t] = unit(t, R1);
-  for (int t = 0; t < R2; ++t) tw2[t] = unit(t, R2);
+  for (int t = 0; t < R2; ++t) { tw2[t] = unit(t, R2); twh[t] = unit(t, 2.0 * (double)R2); }
   for (int l = 0; l < 1024; ++l) { mlo[l] = unit(l, (double)M); nlo[l] = unit(l, 2.0 * (double)M); }
   for (int64_t h = 0; h < nhi; ++h) { mhi[h] = unit((double)(h << 10), (double)M); nhi_[h] = unit((double)(h << 10), 2.0 * (double)M); }
   std::vector<int> perm1, perm2, pos1(R1), pos2(R2);
@@ -143,7 +151,15 @@ const Fft2Plan* egr::fft2_get_plan(int64_t M) {
   digit_perm(R2, p->rd2, 0, perm2);
   for (int i = 0; i < R1; ++i) pos1[perm1[i]] = i;
   for (int i = 0; i < R2; ++i) pos2[perm2[i]] = i;
-  size_t bytes = 256 * 12 + sizeof(float2) * (R1 + R2 + 2048 + 2 * nhi) + sizeof(int) * 2 * (R1 + R2);
+  std::vector<int> pairT(R2), pairZ(R2);
+  std::vector<float2> twhp(R2);
+  for (int i = 0; i < R2; ++i) {
+    const int k2 = perm2[i];
+    pairT[i] = pos2[R2 - 1 - k2];
+    pairZ[i] = pos2[(R2 - k2) % R2];
+    twhp[i] = twh[k2];
+  }
+  size_t bytes = 256 * 16 + sizeof(float2) * (R1 + 3 * R2 + 2048 + 2 * nhi) + sizeof(int) * 2 * (R1 + 2 * R2);
   if (cudaMalloc(&p->d_block, bytes) != cudaSuccess) {
     delete p;
     fail(EGR_ERR_CUDA, "fft: cudaMalloc of %zu table bytes failed", bytes);
@@ -155,22 +171,37 @@ const Fft2Plan* egr::fft2_get_plan(int64_t M) {
   p->perm2 = carve<int>(q, R2); p->pos2 = carve<int>(q, R2);
   p->twM_lo = carve<float2>(q, 1024); p->twM_hi = carve<float2>(q, nhi);
   p->twN_lo = carve<float2>(q, 1024); p->twN_hi = carve<float2>(q, nhi);
+  p->twH = carve<float2>(q, R2); p->twHp = carve<float2>(q, R2);
+  p->pairT = carve<int>(q, R2); p->pairZ = carve<int>(q, R2);
   auto up = [](void* d, const void* h, size_t n) { return cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) == cudaSuccess; };
   bool ok = up(p->tw1, tw1.data(), sizeof(float2) * R1) && up(p->tw2, tw2.data(), sizeof(float2) * R2) &&
             up(p->perm1, perm1.data(), sizeof(int) * R1) && up(p->pos1, pos1.data(), sizeof(int) * R1) &&
             up(p->perm2, perm2.data(), sizeof(int) * R2) && up(p->pos2, pos2.data(), sizeof(int) * R2) &&
             up(p->twM_lo, mlo.data(), sizeof(float2) * 1024) && up(p->twM_hi, mhi.data(), sizeof(float2) * nhi) &&
-            up(p->twN_lo, nlo.data(), sizeof(float2) * 1024) && up(p->twN_hi, nhi_.data(), sizeof(float2) * nhi);
+            up(p->twN_lo, nlo.data(), sizeof(float2) * 1024) && up(p->twN_hi, nhi_.data(), sizeof(float2) * nhi) &&
+            up(p->twH, twh.data(), sizeof(float2) * R2) && up(p->twHp, twhp.data(), sizeof(float2) * R2) &&
+            up(p->pairT, pairT.data(), sizeof(int) * R2) && up(p->pairZ, pairZ.data(), sizeof(int) * R2);
   if (!ok) {
     cudaFree(p->d_block);
     delete p;
     fail(EGR_ERR_CUDA, "fft: table upload failed");
     return nullptr;
   }
-  // column tile width: keep the tile under ~96 KB so two CTAs share an SM
-  p->cw = getenv("EGR_FFT_CW") ? atoi(getenv("EGR_FFT_CW")) : 8;
-  while (p->cw > 2 && (size_t)R1 * p->cw * sizeof(float2) > 96 * 1024) p->cw >>= 1;
+  // column tile width: keep tile + staged twiddles under ~56 KB so FOUR CTAs share an SM (measured on c4: 2 CTAs/SM
+  // at cw=4 330 us/iteration, 4 CTAs/SM at cw=2 281 us; the loop is latency-bound between its block-wide barriers)
+  if (getenv("EGR_FFT_CW")) {
+    p->cw = 1;
+    while (p->cw * 2 <= atoi(getenv("EGR_FFT_CW")) && p->cw < 256) p->cw <<= 1;  // power of two (kernels use shifts)
+    while (p->cw > 2 && (size_t)R1 * p->cw * sizeof(float2) > 96 * 1024) p->cw >>= 1;
+  } else {
+    p->cw = 8;
+    while (p->cw > 2 && (size_t)R1 * (p->cw + 1) * sizeof(float2) > 56 * 1024) p->cw >>= 1;
+  }
   if (R1 == 1) p->cw = 256;
+  if (const char* e = getenv("EGR_FL_MINB")) { const int t = atoi(e); if (t >= 2 && t <= 4) p->min_blocks = t; }
+  const int tmax = p->min_blocks == 4 ? 256 : 320;
+  if (const char* e = getenv("EGR_FL_ROW_T")) { const int t = atoi(e); if (t >= 64 && t <= tmax && t % 32 == 0) p->row_threads = t; }
+  if (const char* e = getenv("EGR_FL_COL_T")) { const int t = atoi(e); if (t >= 64 && t <= tmax && t % 32 == 0) p->col_threads = t; }
   g_plans[key] = p;
   return p;
 }

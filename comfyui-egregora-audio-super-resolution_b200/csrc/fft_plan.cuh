@@ -26,8 +26,12 @@ struct Fft2Plan {
   int *perm2 = nullptr, *pos2 = nullptr;
   float2 *twM_lo = nullptr, *twM_hi = nullptr; // exp(-2 pi i l / M), l < 1024 ; exp(-2 pi i 1024 h / M)
   float2 *twN_lo = nullptr, *twN_hi = nullptr; // same for N = 2M (real-transform split)
+  float2 *twHp = nullptr;                      // twH in position order: twHp[p2] = twH[perm2[p2]]
+  int *pairT = nullptr, *pairZ = nullptr;      // pairT[p2] = pos2[R2-1-perm2[p2]], pairZ[p2] = pos2[(R2-perm2[p2]) % R2]
+  float2 *twH = nullptr;                       // exp(-2 pi i k2 / (2 R2)) = w_N^(R1 k2), k2 < R2
   int cw = 4;                                  // columns per column-pass CTA
   int col_threads = 256, row_threads = 256;
+  int min_blocks = 4;                          // __launch_bounds__ min CTAs/SM variant of the fused Fat-Llama kernels
 };
 
 // true when M is {2,3,5,7,11,13}-smooth and splits into R1*R2 with both factors <= 8192

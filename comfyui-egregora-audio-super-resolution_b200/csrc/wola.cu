@@ -143,3 +143,111 @@ extern "C" int egr_wola_stitch(const float* d_chunks, int l_pred, const int64_t*
   EGR_CHECK_LAUNCH("wola_stitch_kernel");
   return EGR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Polyphase rational resampler either side of path A.
+// Replaces the scipy branch of _resample_hq (egregora_audio_super_resolution.py:181-191):
+// scipy.signal.resample_poly(x, up, down) on float32 data = upfirdn with a float32 Kaiser FIR.
+// Output sample y (index into the un-trimmed upfirdn result) has phase t = (y*down) % up and newest
+// input xi = (y*down) / up; it is  sum_{j=0}^{hpp-1} x[xi-hpp+1+j] * hflip[t][j]  accumulated in float32
+// from a zero start in ascending j with separately rounded multiply and add — the order of scipy's
+// upfirdn inner loop, so the result is bit-identical (zeros stand for samples outside [0, n_in)).
+// hflip is scipy's transposed+flipped polyphase bank (host side: _resample_design in the node module).
+//
+// Persistent CTAs: the coefficient bank ([hpp][up] in smem, j-major so lanes with different phases hit
+// different banks) is staged once per CTA, then the CTA walks output tiles; every tile stages its input
+// window with coalesced loads.  HBM roofline: 4*n_in read + 4*n_out written per channel.
+// ------------------------------------------------------------------------------------------------
+template <bool BANK_SMEM>
+__global__ void __launch_bounds__(256) resample_poly_kernel(const float* __restrict__ x, int64_t n_in, int up,
+                                                             int down, const float* __restrict__ hflip, int hpp,
+                                                             int64_t y_first, int64_t n_out,
+                                                             float* __restrict__ y, int blk, int x_tile,
+                                                             int64_t n_tiles) {
+  extern __shared__ float rs_smem[];
+  float* xs = rs_smem;                 // [x_tile]
+  float* hs = rs_smem + x_tile;        // [hpp][up] when BANK_SMEM
+  const int c = blockIdx.y;
+  const float* xc = x + (int64_t)c * n_in;
+  float* yc = y + (int64_t)c * n_out;
+  if (BANK_SMEM) {
+    for (int i = threadIdx.x; i < up * hpp; i += blockDim.x) {
+      const int t = i / hpp, j = i - t * hpp;
+      hs[j * up + t] = __ldg(hflip + i);
+    }
+  }
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t o0 = tile * blk;                       // first output of this tile (trimmed index)
+    const int64_t p0 = (y_first + o0) * (int64_t)down;   // position on the up-sampled grid
+    const int64_t xi0 = p0 / up;
+    const int t0 = (int)(p0 - xi0 * up);
+    const int64_t xlo = xi0 - hpp + 1;                   // global input index of xs[0]
+    const int nb = (int)min((int64_t)blk, n_out - o0);
+    const int need = (int)(((int64_t)t0 + (int64_t)(nb - 1) * down) / up) + hpp;
+    __syncthreads();                                     // previous tile's readers are done (and hs is staged)
+    for (int i = threadIdx.x; i < need; i += blockDim.x) {
+      const int64_t g = xlo + i;
+      xs[i] = (g >= 0 && g < n_in) ? __ldg(xc + g) : 0.f;
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < nb; o += blockDim.x) {
+      const int q = t0 + o * down;
+      const int xr = q / up;
+      const int t = q - xr * up;
+      float acc = 0.f;
+      if (BANK_SMEM) {
+        for (int j = 0; j < hpp; ++j) acc = __fadd_rn(acc, __fmul_rn(xs[xr + j], hs[j * up + t]));
+      } else {
+        const float* hr = hflip + (int64_t)t * hpp;
+        for (int j = 0; j < hpp; ++j) acc = __fadd_rn(acc, __fmul_rn(xs[xr + j], __ldg(hr + j)));
+      }
+      yc[o0 + o] = acc;
+    }
+  }
+}
+
+extern "C" int egr_resample_poly(const float* d_x, int C, int64_t n_in, int up, int down, const float* d_hflip,
+                                 int hpp, int64_t y_first, int64_t n_out, float* d_y, void* stream) {
+  if (n_out == 0 || C == 0) return EGR_OK;
+  if (!d_x || !d_hflip || !d_y || C < 0 || C > 65535 || n_in <= 0 || up < 1 || down < 1 || hpp < 1 ||
+      y_first < 0 || n_out < 0)
+    return fail(EGR_ERR_ARG, "egr_resample_poly: bad arguments");
+  if ((int64_t)up * hpp > (1 << 24) || down > (1 << 16) || up > (1 << 16))
+    return fail(EGR_ERR_ARG, "egr_resample_poly: up/down/filter too large");
+  // every produced sample must exist in the un-trimmed upfirdn output: ((n_in-1)*up + hpp*up - 1)/down + 1
+  const int64_t full = (((n_in - 1) * (int64_t)up + (int64_t)hpp * up) - 1) / down + 1;
+  if (y_first + n_out > full) return fail(EGR_ERR_ARG, "egr_resample_poly: output range beyond the filtered signal");
+  const size_t bank_bytes = (size_t)up * hpp * sizeof(float);
+  const bool bank_smem = bank_bytes <= 96 * 1024;
+  // outputs per tile: the staged input window (blk*down/up + hpp + 2 floats) stays under 64 KB
+  int64_t blk = 4096;
+  const int64_t cap = (int64_t)(16384 - hpp - 2) * up / down;
+  if (cap < 32) return fail(EGR_ERR_ARG, "egr_resample_poly: decimation factor too large");
+  if (blk > cap) blk = cap;
+  blk = (blk / 32) * 32;
+  const int x_tile = (int)((blk * down) / up) + hpp + 2;
+  const int64_t n_tiles = (n_out + blk - 1) / blk;
+  const size_t smem = sizeof(float) * (size_t)x_tile + (bank_smem ? bank_bytes : 0);
+  int sms = 148;
+  {
+    int dev = 0;
+    EGR_CUDA(cudaGetDevice(&dev));
+    EGR_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int64_t gx = (2 * (int64_t)sms + C - 1) / C;
+  if (gx > n_tiles) gx = n_tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid((unsigned)gx, (unsigned)C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bank_smem) {
+    EGR_CUDA(cudaFuncSetAttribute(resample_poly_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    resample_poly_kernel<true><<<grid, 256, smem, st>>>(d_x, n_in, up, down, d_hflip, hpp, y_first, n_out, d_y,
+                                                         (int)blk, x_tile, n_tiles);
+  } else {
+    EGR_CUDA(cudaFuncSetAttribute(resample_poly_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    resample_poly_kernel<false><<<grid, 256, smem, st>>>(d_x, n_in, up, down, d_hflip, hpp, y_first, n_out, d_y,
+                                                          (int)blk, x_tile, n_tiles);
+  }
+  EGR_CHECK_LAUNCH("resample_poly_kernel");
+  return EGR_OK;
+}

@@ -9,6 +9,7 @@ RuntimeError messages.  What differs is where the work happens:
   numpy slice + pad per span (:411-416)       one egr_chunk_gather launch for all spans, on device
   sequential model call per span (:417)       all chunk-channels batched through the CUDA plan
   numpy Hann WOLA (:227-251)                  egr_wola_stitch (bit-identical, one HBM pass)
+  scipy resample_poly on the host (:181-191)  egr_resample_poly (bit-identical, on device)
   model rebuilt on every run() (:393)         process-level engine cache
 
 With torch.distributed initialised (world_size > 1) the span list is sharded contiguously across ranks
@@ -17,6 +18,7 @@ Host code here is plumbing only; all arithmetic is in libegregora_b200.so.  No C
 """
 from __future__ import annotations
 
+import functools
 import os
 from typing import Any, Dict, List, Optional, Tuple
 
@@ -70,20 +72,61 @@ def _from_audio_dict(AUDIO: Any) -> Tuple[torch.Tensor, int]:
     raise RuntimeError("No valid AUDIO provided.")
 
 
-# --------------------------------------------------------------------------------- resample (host)
-def _resample_hq(x_cs: torch.Tensor, src_sr: int, dst_sr: int) -> torch.Tensor:
-    """Sample-rate conversion either side of the hot path (ref :159-207, scipy polyphase branch).
-    SURVEY.md §8(f) rank 2 — a "next" row: still host-side scipy here, to be replaced by the polyphase
-    CUDA kernel; it is not exercised by any BASELINE config (all are 48 kHz in, 48 kHz out)."""
-    if src_sr == dst_sr:
-        return x_cs.float()
+# ------------------------------------------------------------------------------- resample (device)
+@functools.lru_cache(maxsize=64)
+def _resample_design(up: int, down: int, n_in: int):
+    """Filter bank and trimming of scipy.signal.resample_poly(x, up, down) for float32 x (the reference's
+    branch, ref :181-191): Kaiser(5.0) windowed-sinc low-pass of 20*max(up,down)+1 taps designed in float64,
+    cast to float32, scaled by `up`, zero-padded so the kept samples are centred, then split into `up`
+    flipped phases.  Returns (up, down, hflip [up,hpp] f32, n_pre_remove, n_out) with up/down reduced.
+    Host side only designs the (tiny) filter; the filtering itself is egr_resample_poly."""
     from math import gcd
-    from scipy.signal import resample_poly  # the reference's branch when soxr is absent
-    g = gcd(src_sr, dst_sr)
-    x = x_cs.detach().cpu().float().numpy()
-    chans = [resample_poly(x[c], up=dst_sr // g, down=src_sr // g).astype(np.float32) for c in range(x.shape[0])]
-    n = min(len(c) for c in chans)
-    return torch.from_numpy(np.stack([c[:n] for c in chans], axis=0))
+    g = gcd(up, down)
+    up, down = up // g, down // g
+    max_rate = max(up, down)
+    f_c = 1.0 / max_rate
+    half_len = 10 * max_rate
+    ntaps = 2 * half_len + 1
+    m = np.arange(ntaps, dtype=np.float64) - 0.5 * (ntaps - 1)
+    h = f_c * np.sinc(f_c * m) * np.kaiser(ntaps, 5.0)
+    h = (h / h.sum()).astype(np.float32)
+    h *= np.float32(up)
+    n_out = -(-(n_in * up) // down)
+    n_pre_pad = down - half_len % down
+    n_pre_remove = (half_len + n_pre_pad) // down
+    n_post_pad = 0
+    while ((n_in - 1) * up + ntaps + n_pre_pad + n_post_pad - 1) // down + 1 < n_out + n_pre_remove:
+        n_post_pad += 1
+    n_h = n_pre_pad + ntaps + n_post_pad
+    hpp = -(-n_h // up)
+    padded = np.zeros(hpp * up, np.float32)
+    padded[n_pre_pad:n_pre_pad + ntaps] = h
+    hflip = np.ascontiguousarray(padded.reshape(hpp, up).T[:, ::-1])
+    return up, down, hflip, n_pre_remove, n_out
+
+
+_BANK_CACHE: Dict[Tuple[int, int, int, str], torch.Tensor] = {}  # (up, down, hash of the bank, device)
+
+
+def _resample_hq(x_cs: torch.Tensor, src_sr: int, dst_sr: int) -> torch.Tensor:
+    """Sample-rate conversion either side of the hot path (ref :159-207; soxr is not a dependency of this
+    package, so the scipy polyphase branch :181-191 is the one reproduced — bit for bit, on the device).
+    [C,S] host or device tensor -> [C,S'] DEVICE f32 tensor."""
+    device = _require_cuda()
+    x = x_cs.detach().to(device=device, dtype=torch.float32).contiguous()
+    if src_sr == dst_sr or x.shape[1] == 0:
+        return x
+    C, n_in = x.shape
+    up, down, hflip, n_pre_remove, n_out = _resample_design(int(dst_sr), int(src_sr), n_in)
+    key = (up, down, hash(hflip.tobytes()), str(device))  # the padding (hence the bank) can depend on n_in
+    bank = _BANK_CACHE.get(key)
+    if bank is None:
+        bank = _BANK_CACHE[key] = torch.from_numpy(hflip).to(device)
+    y = torch.empty((C, n_out), dtype=torch.float32, device=device)
+    lib = _abi.init(device.index or 0)
+    _abi.check(lib.egr_resample_poly(x.data_ptr(), C, n_in, up, down, bank.data_ptr(), hflip.shape[1],
+                                     n_pre_remove, n_out, y.data_ptr(), _stream_ptr()), "egr_resample_poly")
+    return y
 
 
 # --------------------------------------------------------------------------------- spans and WOLA
@@ -233,10 +276,10 @@ class EgregoraAudioSuperResolution:
         in_cs, in_sr = _from_audio_dict(audio)
         device = _require_cuda()
         engine = get_engine(device)
-        if in_sr != REQ_SR:
-            in_cs = _resample_hq(in_cs, in_sr, REQ_SR)
-            in_sr = REQ_SR
         x_dev = in_cs.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        if in_sr != REQ_SR:
+            x_dev = _resample_hq(x_dev, in_sr, REQ_SR)
+            in_sr = REQ_SR
         steps, seed, lp = int(self.NUM_STEPS), int(self.SEED), bool(lowpass_input)
         out_48k = upscale_48k(x_dev, lambda chunks: engine.infer(chunks, lowpass=lp, steps=steps, seed=seed))
         tgt_sr = int(output_sr)

@@ -58,6 +58,16 @@ int egr_wola_stitch(const float* d_chunks, int l_pred, const int64_t* d_starts, 
                     int n_spans, int C, int64_t total, int win, const float* d_window,
                     float* d_out, void* stream);
 
+/* Replaces the scipy branch of _resample_hq (egregora_audio_super_resolution.py:181-191):
+ * scipy.signal.resample_poly(x, up, down) on float32 data, default Kaiser(5.0) FIR, zero padding.
+ * d_x [C,n_in] f32 -> d_y [C,n_out] f32.  d_hflip [up,hpp] f32 is the transposed, flipped polyphase bank
+ * of the padded filter (scipy's _pad_h), y_first the number of leading upfirdn outputs that resample_poly
+ * trims (n_pre_remove) and n_out = ceil(n_in*up/down); the node module's _resample_design computes all
+ * three.  Every output is accumulated in float32 in scipy's tap order with separately rounded multiply
+ * and add: bit-identical to the reference's result. */
+int egr_resample_poly(const float* d_x, int C, int64_t n_in, int up, int down, const float* d_hflip,
+                      int hpp, int64_t y_first, int64_t n_out, float* d_y, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* path A model: a plan is a straight-line list of ops over one workspace + one weight blob     */
 /* ------------------------------------------------------------------------------------------ */

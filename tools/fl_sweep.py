@@ -1,9 +1,15 @@
 import subprocess, sys, os
-cfgs = [("", ""), ("1000", "8"), ("600", "16"), ("504", "16"), ("504", "32"), ("1960", "4"), ("980", "8"), ("2025", "4")]
-for r1, cw in cfgs:
+"""Sweep of the path-B tuning overrides (env vars read at plan creation): EGR_FFT_R1 / EGR_FFT_CW (split and column
+tile), EGR_FFT_MAXR (radix cap), EGR_FL_ROW_T / EGR_FL_COL_T (threads per CTA), EGR_FL_MINB (__launch_bounds__ variant).
+    python tools/fl_sweep.py [quick]"""
+cfgs = [
+    {},
+    {"EGR_FL_MINB": "3"},
+    {"EGR_FL_MINB": "2", "EGR_FFT_CW": "4"},
+]
+for cfg in cfgs:
     env = dict(os.environ)
-    if r1: env["EGR_FFT_R1"] = r1
-    if cw: env["EGR_FFT_CW"] = cw
+    env.update(cfg)
     code = '''
 import sys, time, torch
 sys.path.insert(0, ".")
@@ -20,4 +26,4 @@ e0.record(); _abi.check(lib.egr_fatllama_run(x.data_ptr(), y.data_ptr(), C, S, 1
 print("us/iter", e0.elapsed_time(e1) * 1e3 / iters, "checksum", float(y.double().abs().sum()))
 '''
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
-    print(f"R1={r1 or 'auto'} cw={cw or 'auto'}:", out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr.strip()[-300:], flush=True)
+    print(f"{cfg}:", out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr.strip()[-300:], flush=True)
