@@ -10,3 +10,4 @@ run ops_tc_rest tests/test_ops_gpu.py -k "stride2 or transposed or conv1d or con
 run flashsr_tiny tests/test_flashsr_gpu.py -k "tiny"
 run fft tests/test_fft_gpu.py
 run fatllama tests/test_fatllama_gpu.py
+run resample tests/test_resample.py
