@@ -6,6 +6,7 @@
 // reduced to magnitudes and projected on the (sparse, triangular) mel filters without leaving the SM, so the
 // only HBM traffic is 4*hop bytes in (frames overlap in L2) and 4*n_mels bytes out per frame.
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include "ops.cuh"
 
 using namespace egr;
@@ -119,15 +120,22 @@ int egr::launch_stft_mel(const Spaces& s, const egr_op& op, cudaStream_t st) {
 // Low-pass: cutoff bin = (#bins whose cumulative energy < percentile*total) - 1, then scipy-style
 // sosfiltfilt (odd extension of 3*(2*nsec+1) samples, sosfilt_zi initial conditions, forward + backward) in
 // f64.  The IIR recurrence is parallelised over time: the whole cascade is one linear system with 2*nsec
-// states, so each of the 1024 threads of a CTA (one CTA per batch item) runs its chunk from zero state, a
-// two-level scan (32 lanes x 32 warps, with M and M^32) turns the chunk end states into true chunk start states,
-// and a second sweep re-runs every chunk from there.  Between the passes the signal lives in a chunk-transposed
-// f64 scratch ([step within chunk][chunk]), so every per-step access of the 1024 threads is one contiguous 8 KB
-// row; the natural-order input / output is transposed through 32x32 shared-memory tiles.
+// states, so every thread runs its chunk from zero state, a hierarchical scan turns the chunk end states into
+// true chunk start states, and a second sweep re-runs every chunk from there.
+// One thread-block CLUSTER of 8 CTAs x 1024 threads per batch item (the sweeps are FP64-issue bound, and one SM
+// has 1/8 of the FP64 lanes a cluster has): 8192 chunks; scan levels = 32 lanes-worth of chunks per warp (M),
+// 32 warps per CTA (M^32), 8 CTAs per cluster (M^1024, CTA totals exchanged through distributed shared memory).
+// Between the passes the signal lives in a chunk-transposed f64 scratch ([step within chunk][chunk]), so every
+// per-step access of a CTA's 1024 threads is one contiguous 8 KB row; the natural-order input / output is
+// transposed through 32x32 shared-memory tiles.
 // ------------------------------------------------------------------------------------------------
 #define LP_NT 1024
+#define LP_NC 8
+#define LP_NQ (LP_NT * LP_NC)
 #define LP_MAXSEC 4
 #define LP_NS (2 * LP_MAXSEC)
+
+namespace cg = cooperative_groups;
 
 struct SosState { double z[LP_MAXSEC][2]; };
 
@@ -148,29 +156,42 @@ struct LpShared {
   double sos[LP_MAXSEC][6];
   double zi[LP_MAXSEC][2];
   double M1[LP_NS][LP_NS];    // state transition of one chunk
-  double M32[LP_NS][LP_NS];   // ... of 32 chunks
+  double M32[LP_NS][LP_NS];   // ... of 32 chunks (one warp)
+  double M1k[LP_NS][LP_NS];   // ... of 1024 chunks (one CTA)
   double tmp[LP_NS][LP_NS];
   double ends[LP_NT + 1][LP_NS];
   double wtot[33][LP_NS];
+  double mytot[LP_NS];        // zero-start end state of this CTA's 1024 chunks (read by the other CTAs of the cluster)
   float tile[32][32][33];
   int bin, dbg;
 };
 
-// r = M * v (+ add)
-__device__ __forceinline__ void lp_matvec(const double (*M)[LP_NS], const double* v, const double* add, double* r, int ns2) {
-  for (int i = 0; i < ns2; ++i) {
-    double a = add ? add[i] : 0.0;
-    for (int c = 0; c < ns2; ++c) a = fma(M[i][c], v[c], a);
-    r[i] = a;
+// dst = src^(2^5) by five squarings (ns2*ns2 threads, one element each); ends with a __syncthreads()
+__device__ __forceinline__ void lp_pow32(LpShared& sh, const double (*src0)[LP_NS], double (*dst)[LP_NS], int ns2) {
+  const int tid = threadIdx.x;
+  for (int it = 0; it < 5; ++it) {
+    const double (*src)[LP_NS] = it == 0 ? src0 : dst;
+    if (tid < ns2 * ns2) {
+      const int r = tid / ns2, c = tid % ns2;
+      double a = 0.0;
+      for (int k = 0; k < ns2; ++k) a = fma(src[r][k], src[k][c], a);
+      sh.tmp[r][c] = a;
+    }
+    __syncthreads();
+    if (tid < ns2 * ns2) dst[tid / ns2][tid % ns2] = sh.tmp[tid / ns2][tid % ns2];
+    __syncthreads();
   }
 }
 
-// One direction of filtfilt over the transposed scratch `buf` (in place).  REV: thread r walks positions
-// Lx-1-(r*Lc+j), i.e. the time-reversed signal, reading what the forward sweep wrote.
+// One direction of filtfilt over the transposed scratch `buf` (in place).  Sweep chunk g = rank*1024 + tid covers sweep
+// positions m = g*Lc + j; REV: storage position n = Lx-1-m (the time-reversed signal, reading what the forward sweep
+// wrote — by other CTAs of the cluster, hence the cluster barrier at the end of every sweep).
 template <bool REV>
 __device__ void lp_sweep(LpShared& sh, int nsec, int Lx, int Lc, double* __restrict__ buf) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
   const int tid = threadIdx.x, ns2 = 2 * nsec;
-  const long long c0 = clock64();
+  const int gch = rank * LP_NT + tid;
   // chunk transition matrix: column k = response of the state to unit state k under zero input
   if (tid < ns2) {
     SosState s;
@@ -179,15 +200,14 @@ __device__ void lp_sweep(LpShared& sh, int nsec, int Lx, int Lc, double* __restr
     for (int n = 0; n < Lc; ++n) sos_step(sh.sos, nsec, s, 0.0);
     for (int r = 0; r < ns2; ++r) sh.M1[r][tid] = s.z[r >> 1][r & 1];
   }
-  // this thread's positions: m = tid*Lc + j (sweep order), n = REV ? Lx-1-m : m (storage order)
-  const int m_lo = tid * Lc, m_hi = min(Lx, m_lo + Lc);
+  const long long m_lo = (long long)gch * Lc, m_hi = min((long long)Lx, m_lo + Lc);
   int q0, l0;  // transposed coordinates of the first position: n = q*Lc + l
-  if (!REV) { q0 = tid; l0 = 0; }
-  else { const int n0 = Lx - 1 - m_lo; q0 = n0 >= 0 ? n0 / Lc : 0; l0 = n0 >= 0 ? n0 - q0 * Lc : 0; }
+  if (!REV) { q0 = gch; l0 = 0; }
+  else { const long long n0 = (long long)Lx - 1 - m_lo; q0 = n0 >= 0 ? (int)(n0 / Lc) : 0; l0 = n0 >= 0 ? (int)(n0 - (long long)q0 * Lc) : 0; }
   auto run = [&](SosState& s, bool store) {
     int q = q0, l = l0;
-    for (int m = m_lo; m < m_hi; ++m) {
-      double* p = buf + (size_t)l * LP_NT + q;
+    for (long long m = m_lo; m < m_hi; ++m) {
+      double* p = buf + (size_t)l * LP_NQ + q;
       const double y = sos_step(sh.sos, nsec, s, *p);
       if (store) *p = y;
       if (!REV) ++l;
@@ -201,20 +221,8 @@ __device__ void lp_sweep(LpShared& sh, int nsec, int Lx, int Lc, double* __restr
     for (int r = 0; r < ns2; ++r) sh.ends[tid][r] = s.z[r >> 1][r & 1];  // zero-state end of chunk tid
   }
   __syncthreads();
-  const long long c1 = clock64();
-  // M32 = M1^32 by five squarings (64 threads, one element each)
-  for (int it = 0; it < 5; ++it) {
-    const double (*src)[LP_NS] = it == 0 ? sh.M1 : sh.M32;
-    if (tid < ns2 * ns2) {
-      const int r = tid / ns2, c = tid % ns2;
-      double a = 0.0;
-      for (int k = 0; k < ns2; ++k) a = fma(src[r][k], src[k][c], a);
-      sh.tmp[r][c] = a;
-    }
-    __syncthreads();
-    if (tid < ns2 * ns2) sh.M32[tid / ns2][tid % ns2] = sh.tmp[tid / ns2][tid % ns2];
-    __syncthreads();
-  }
+  lp_pow32(sh, sh.M1, sh.M32, ns2);
+  lp_pow32(sh, sh.M32, sh.M1k, ns2);
   // Scans: one warp per sequence, lane r < ns2 owns state component r (row r of the matrix in registers, the
   // vector exchanged by shuffles), so a step is ns2 dependent DFMAs instead of a serial ns2 x ns2 loop.
   const int lane = tid & 31, wid = tid >> 5;
@@ -242,19 +250,38 @@ __device__ void lp_sweep(LpShared& sh, int nsec, int Lx, int Lc, double* __restr
     if (lane < ns2) sh.wtot[wid + 1][lane] = cur;
   }
   __syncthreads();
-  // level 2: warp 0 scans the 32 warp totals with M^32; wtot[w] <- true state at the start of warp w
+  // level 2: warp 0 scans the 32 warp totals with M^32 from a zero CTA start; wtot[w] <- local prefix of warp w,
+  // mytot <- zero-start end state of the whole CTA
   if (wid == 0) {
-    const double x0 = buf[REV ? ((size_t)((Lx - 1) % Lc) * LP_NT + (Lx - 1) / Lc) : 0];
-    double cur = sh.zi[rr >> 1][rr & 1] * x0;
+    double cur = 0.0;
     for (int w = 0; w < 32; ++w) {
       const double e = sh.wtot[w + 1][rr];
       const double nxt = matvec_row(m32row, cur, e);
       if (lane < ns2) sh.wtot[w][lane] = cur;
       cur = nxt;
     }
+    if (lane < ns2) sh.mytot[lane] = cur;
+  }
+  cluster.sync();
+  // level 3: true start of this CTA = M^1024 applied over the CTAs before it (totals read through DSMEM), then the
+  // warp starts pick it up through powers of M^32
+  if (wid == 0) {
+    double m1krow[LP_NS];
+#pragma unroll
+    for (int c = 0; c < LP_NS; ++c) m1krow[c] = c < ns2 ? sh.M1k[rr][c] : 0.0;
+    const double x0 = buf[REV ? ((size_t)((Lx - 1) % Lc) * LP_NQ + (Lx - 1) / Lc) : 0];
+    double cur = sh.zi[rr >> 1][rr & 1] * x0;
+    for (int r = 0; r < rank; ++r) {
+      const double* remote = cluster.map_shared_rank(&sh.mytot[0], r);
+      cur = matvec_row(m1krow, cur, remote[rr]);
+    }
+    for (int w = 0; w < 32; ++w) {
+      if (lane < ns2) sh.wtot[w][lane] += cur;
+      cur = matvec_row(m32row, cur, 0.0);
+    }
   }
   __syncthreads();
-  // level 3: true start of chunk k = M1^i * start(warp) + local prefix
+  // level 4: true start of chunk k = M1^i * start(warp) + local prefix
   {
     double v = sh.wtot[wid][rr];
     for (int i = 0; i < 32; ++i) {
@@ -264,27 +291,26 @@ __device__ void lp_sweep(LpShared& sh, int nsec, int Lx, int Lc, double* __restr
     }
   }
   __syncthreads();
-  const long long c2 = clock64();
   {
     SosState s;
     for (int i = 0; i < LP_MAXSEC; ++i) s.z[i][0] = s.z[i][1] = 0.0;
     for (int r = 0; r < ns2; ++r) s.z[r >> 1][r & 1] = sh.ends[tid][r];
     run(s, true);
   }
-  __syncthreads();
-  if (sh.dbg && tid == 0 && blockIdx.x == 0) printf("sweep: pass1 %lld scan %lld pass2 %lld\n", c1 - c0, c2 - c1, clock64() - c2);
+  __threadfence();
+  cluster.sync();  // the scratch written here is read by other CTAs next; mytot may be overwritten after this point
 }
 
-__global__ void __launch_bounds__(LP_NT) lowpass_kernel(const float* __restrict__ wav, int T, const double* __restrict__ energy,
-                                                         int n_freq, double percentile, const double* __restrict__ sos_tab,
-                                                         const double* __restrict__ zi_tab, int nsec, double* __restrict__ scratch,
-                                                         float* __restrict__ out, int* __restrict__ cutoff_out, int debug) {
+__global__ void __cluster_dims__(LP_NC, 1, 1) __launch_bounds__(LP_NT)
+lowpass_kernel(const float* __restrict__ wav, int T, const double* __restrict__ energy, int n_freq, double percentile,
+               const double* __restrict__ sos_tab, const double* __restrict__ zi_tab, int nsec, double* __restrict__ scratch,
+               float* __restrict__ out, int* __restrict__ cutoff_out) {
   extern __shared__ __align__(16) unsigned char lp_raw[];
-  long long tk[6];
-  tk[0] = clock64();
   LpShared& sh = *reinterpret_cast<LpShared*>(lp_raw);
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int b = blockIdx.x / LP_NC, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {  // every CTA of the cluster derives the same cutoff (sequential f64 sums, as numpy's cumsum)
     const double* e = energy + (long long)b * n_freq;
     double total = 0.0;
     for (int k = 0; k < n_freq; ++k) total += e[k];
@@ -292,8 +318,7 @@ __global__ void __launch_bounds__(LP_NT) lowpass_kernel(const float* __restrict_
     double cum = 0.0; int cnt = 0;
     for (int k = 0; k < n_freq; ++k) { cum += e[k]; if (cum < thr) ++cnt; }
     sh.bin = max(cnt - 1, 0);
-    if (cutoff_out) cutoff_out[b] = sh.bin;
-    sh.dbg = debug;
+    if (cutoff_out && rank == 0) cutoff_out[b] = sh.bin;
   }
   __syncthreads();
   const int bin = sh.bin;
@@ -301,62 +326,59 @@ __global__ void __launch_bounds__(LP_NT) lowpass_kernel(const float* __restrict_
   if (tid < nsec * 2) sh.zi[tid / 2][tid % 2] = zi_tab[((long long)bin * nsec) * 2 + tid];
   const int edge = 3 * (2 * nsec + 1);
   const int Lx = T + 2 * edge;
-  const int Lc = (Lx + LP_NT - 1) / LP_NT;
+  const int Lc = (Lx + LP_NQ - 1) / LP_NQ;
   const float* x = wav + (long long)b * T;
-  double* buf = scratch + (size_t)b * ((size_t)Lc * LP_NT);
+  double* buf = scratch + (size_t)b * ((size_t)Lc * LP_NQ);
   const double xl = 2.0 * (double)x[0], xr = 2.0 * (double)x[T - 1];
-  // transpose in: tile = 32 chunks x 32 steps; rows of a chunk are read contiguously, written chunk-contiguous
+  // transpose in (this CTA's 1024 chunks): tile = 32 chunks x 32 steps; rows of a chunk are read contiguously,
+  // written chunk-contiguous
   const int ltiles = (Lc + 31) / 32;
+  const int qbase = rank * LP_NT;
   for (int tile = warp; tile < 32 * ltiles; tile += 32) {
     const int qt = tile / ltiles, lt = tile - qt * ltiles;
 #pragma unroll 8
     for (int r = 0; r < 32; ++r) {
-      const int n = (qt * 32 + r) * Lc + lt * 32 + lane;
+      const long long n = (long long)(qbase + qt * 32 + r) * Lc + lt * 32 + lane;
       float v = 0.f;
       if (lt * 32 + lane < Lc && n < Lx) {
-        int i = n - edge;
+        long long i = n - edge;
         if (i < 0) i = -i;
-        else if (i >= T) i = 2 * (T - 1) - i;
+        else if (i >= T) i = 2 * ((long long)T - 1) - i;
         v = x[i];
       }
       sh.tile[warp][r][lane] = v;
     }
     __syncwarp();
     for (int l = 0; l < 32; ++l) {
-      const int ll = lt * 32 + l, q = qt * 32 + lane;
+      const int ll = lt * 32 + l, q = qbase + qt * 32 + lane;
       if (ll < Lc) {
-        const int n = q * Lc + ll, i = n - edge;
+        const long long n = (long long)q * Lc + ll, i = n - edge;
         const double v = (double)sh.tile[warp][lane][l];
-        buf[(size_t)ll * LP_NT + q] = i < 0 ? xl - v : (i >= T ? xr - v : v);  // odd extension at both ends
+        buf[(size_t)ll * LP_NQ + q] = i < 0 ? xl - v : (i >= T ? xr - v : v);  // odd extension at both ends
       }
     }
     __syncwarp();
   }
-  __syncthreads();
-  tk[1] = clock64();
+  __threadfence();
+  cluster.sync();  // the reverse sweep's first sample (x0) and, later, whole chunks come from other CTAs' columns
   lp_sweep<false>(sh, nsec, Lx, Lc, buf);
-  tk[2] = clock64();
   lp_sweep<true>(sh, nsec, Lx, Lc, buf);
-  tk[3] = clock64();
   // transpose out
   float* o = out + (long long)b * T;
   for (int tile = warp; tile < 32 * ltiles; tile += 32) {
     const int qt = tile / ltiles, lt = tile - qt * ltiles;
 #pragma unroll 8
     for (int l = 0; l < 32; ++l) {
-      const int ll = lt * 32 + l, q = qt * 32 + lane;
-      sh.tile[warp][lane][l] = ll < Lc ? (float)buf[(size_t)ll * LP_NT + q] : 0.f;
+      const int ll = lt * 32 + l, q = qbase + qt * 32 + lane;
+      sh.tile[warp][lane][l] = ll < Lc ? (float)buf[(size_t)ll * LP_NQ + q] : 0.f;
     }
     __syncwarp();
     for (int r = 0; r < 32; ++r) {
-      const int n = (qt * 32 + r) * Lc + lt * 32 + lane, t = n - edge;
+      const long long n = (long long)(qbase + qt * 32 + r) * Lc + lt * 32 + lane, t = n - edge;
       if (lt * 32 + lane < Lc && t >= 0 && t < T) o[t] = sh.tile[warp][r][lane];
     }
     __syncwarp();
   }
-  if (debug && tid == 0 && b == 0)
-    printf("lowpass cycles: transpose-in %lld fwd %lld bwd %lld transpose-out %lld\n", tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2],
-           clock64() - tk[3]);
 }
 
 int egr::launch_lowpass(const Spaces& s, const egr_op& op, cudaStream_t st) {
@@ -371,14 +393,14 @@ int egr::launch_lowpass(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (!wav || !energy || !sos_tab || !zi_tab || !scratch || !out || B <= 0 || T <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
   if (nsec < 1 || nsec > LP_MAXSEC) return fail(EGR_ERR_UNSUPPORTED, "%s: 1..%d second-order sections supported", op.name, LP_MAXSEC);
   if (T <= 3 * (2 * nsec + 1)) return fail(EGR_ERR_ARG, "%s: signal shorter than the filtfilt edge", op.name);
-  // scratch must hold B * ceil(Lx/1024)*1024 doubles (flashsr_plan.py sizes it as B*(Lx+1024)*8 bytes)
+  // scratch must hold B * ceil(Lx/8192)*8192 doubles (flashsr_plan.py sizes it as B*(Lx+8192)*8 bytes)
   static bool attr_done = false;
   if (!attr_done) {
     EGR_CUDA(cudaFuncSetAttribute(lowpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LpShared)));
     attr_done = true;
   }
-  lowpass_kernel<<<B, LP_NT, sizeof(LpShared), st>>>(wav, T, energy, n_freq, op.f[EGR_F_A], sos_tab, zi_tab, nsec, scratch, out, cutoff,
-                                                          getenv("EGR_LP_DEBUG") ? 1 : 0);
+  lowpass_kernel<<<B * LP_NC, LP_NT, sizeof(LpShared), st>>>(wav, T, energy, n_freq, op.f[EGR_F_A], sos_tab, zi_tab, nsec, scratch, out,
+                                                              cutoff);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }

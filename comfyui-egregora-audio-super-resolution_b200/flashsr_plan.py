@@ -693,7 +693,7 @@ class PlanBackend:
         self.emit(z)
         self._stft(wav, 1, None, energy, "lp.stft_energy")
         edge = 3 * (2 * nsec + 1)
-        scratch = self.buf(B * (T + 2 * edge + 1024) * 8, "lp.scratch")  # chunk-transposed f64 signal, padded to 1024 chunks
+        scratch = self.buf(B * (T + 2 * edge + 8192) * 8, "lp.scratch")  # chunk-transposed f64 signal, padded to 8192 chunks
         cut = self.buf(B * 4, "lp.cutoff", persistent=True)
         self.cutoff_buf = cut
         o = self.new(B, 1, T, 1, f32=True, tag="lp.out")
