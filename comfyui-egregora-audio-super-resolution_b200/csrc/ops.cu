@@ -4,6 +4,7 @@
 // coalesced float4 / half2 accesses with channels innermost, warp-shuffle reductions, f64 accumulators
 // where cancellation matters (GroupNorm moments).
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include "ops.cuh"
 
 namespace egr {
@@ -528,23 +529,29 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* 
 // thread combined in f64 in a fixed order (deterministic, independent of the batch size), then normalise (+SiLU)
 // and store.  Replaces the stats + finalize + apply launches whose grids of 1..32 CTAs were pure latency.
 #define GN_FUSED_THREADS 512
+// `ncl` CTAs (one thread-block cluster) share a (group, item): each takes a contiguous range of pixels, the partial
+// moments are exchanged through distributed shared memory and combined in rank order by every CTA (same bits
+// everywhere, independent of the batch size).  ncl is a function of the op's geometry only (gn_cluster_size).
 __global__ void __launch_bounds__(GN_FUSED_THREADS) gn_fused_kernel(CatArgs a, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, float eps, int silu,
-                                                                    float* __restrict__ out32, __half* __restrict__ out16) {
+                                                                    float* __restrict__ out32, __half* __restrict__ out16,
+                                                                    int ncl) {
   __shared__ double red[2][GN_FUSED_THREADS / 32];
+  __shared__ double part[2];
   __shared__ float s_mean, s_rstd;
   const int C = a.C0 + a.C1, cpg = C / a.G, q4 = cpg >> 2;
-  const int gi = blockIdx.x, b = blockIdx.y;
+  const int gi = blockIdx.x / ncl, rank = blockIdx.x - gi * ncl, b = blockIdx.y;
   const int c_lo = gi * cpg;
-  const int units = (int)a.P * q4;  // float4 units of this group (P <= 4096)
+  const int p_lo = (int)((long long)a.P * rank / ncl), p_hi = (int)((long long)a.P * (rank + 1) / ncl);
+  const int units = (p_hi - p_lo) * q4;  // float4 units of this CTA's share of the group (P <= 4096)
   auto src = [&](long long p, int c) -> const float* {
     return c < a.C0 ? a.x0 + ((long long)b * a.P + p) * a.C0 + c : a.x1 + ((long long)b * a.P + p) * a.C1 + (c - a.C0);
   };
   float s = 0.f, ss = 0.f;
   for (int u = threadIdx.x; u < units; u += GN_FUSED_THREADS) {
-    const int p = u / q4;
-    const int c = c_lo + (u - p * q4) * 4;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(src(p, c)));
+    const int pl = u / q4;
+    const int c = c_lo + (u - pl * q4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src(p_lo + pl, c)));
     s += (v.x + v.y) + (v.z + v.w);
     ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
   }
@@ -554,6 +561,19 @@ __global__ void __launch_bounds__(GN_FUSED_THREADS) gn_fused_kernel(CatArgs a, c
   if (threadIdx.x == 0) {
     double t = 0.0, tt = 0.0;
     for (int w = 0; w < GN_FUSED_THREADS / 32; ++w) { t += red[0][w]; tt += red[1][w]; }
+    part[0] = t; part[1] = tt;
+  }
+  if (ncl > 1) cooperative_groups::this_cluster().sync();
+  if (threadIdx.x == 0) {
+    double t = part[0], tt = part[1];
+    if (ncl > 1) {
+      cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+      t = 0.0; tt = 0.0;
+      for (int r = 0; r < ncl; ++r) {
+        const double* rp = cluster.map_shared_rank(&part[0], r);
+        t += rp[0]; tt += rp[1];
+      }
+    }
     const double cnt = (double)cpg * (double)a.P;
     const double mean = t / cnt;
     double var = tt / cnt - mean * mean;
@@ -564,8 +584,9 @@ __global__ void __launch_bounds__(GN_FUSED_THREADS) gn_fused_kernel(CatArgs a, c
   __syncthreads();
   const float mean = s_mean, rstd = s_rstd;
   for (int u = threadIdx.x; u < units; u += GN_FUSED_THREADS) {
-    const int p = u / q4;
-    const int c = c_lo + (u - p * q4) * 4;
+    const int pl = u / q4;
+    const int c = c_lo + (u - pl * q4) * 4;
+    const int p = p_lo + pl;
     const float4 v = __ldg(reinterpret_cast<const float4*>(src(p, c)));
     const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
     const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
@@ -585,6 +606,16 @@ __global__ void __launch_bounds__(GN_FUSED_THREADS) gn_fused_kernel(CatArgs a, c
       *reinterpret_cast<uint2*>(out16 + o) = pk;
     }
   }
+  if (ncl > 1) cooperative_groups::this_cluster().sync();  // keep `part` alive until every CTA of the cluster has read it
+}
+
+// CTAs per (group, item): at least 8192 elements per CTA, at most 8 (portable cluster size)
+static int gn_cluster_size(const CatArgs& a) {
+  const long long elems = (long long)a.P * ((a.C0 + a.C1) / a.G);
+  int ncl = 1;
+  while (ncl < 8 && elems / (ncl * 2) >= 8192) ncl *= 2;
+  if (getenv("EGR_GN_NO_CLUSTER")) ncl = 1;
+  return ncl;
 }
 
 // single-kernel path: small maps whose groups are whole float4 columns (a function of the op's geometry only)
@@ -648,7 +679,17 @@ int egr::launch_gn_apply(const Spaces& s, const egr_op& op, cudaStream_t st) {
   __half* o16 = (__half*)resolve(s, op.ptr[EGR_P_OUT16]);
   if (!stats || !gamma || !beta || (!o32 && !o16)) return fail(EGR_ERR_ARG, "%s: null pointer", op.name);
   if (gn_use_fused(a)) {
-    gn_fused_kernel<<<dim3(a.G, a.B), GN_FUSED_THREADS, 0, st>>>(a, gamma, beta, (float)op.f[EGR_F_EPS], (int)op.i[EGR_I_MODE], o32, o16);
+    const int ncl = gn_cluster_size(a);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(a.G * ncl, a.B);
+    cfg.blockDim = dim3(GN_FUSED_THREADS);
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = ncl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    EGR_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel, a, gamma, beta, (float)op.f[EGR_F_EPS], (int)op.i[EGR_I_MODE], o32, o16, ncl));
     EGR_CHECK_LAUNCH(op.name);
     return EGR_OK;
   }
