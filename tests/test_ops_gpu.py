@@ -215,6 +215,25 @@ def test_groupnorm(C0, C1, G, silu, cuda_dev):
     assert rel_err(mp.read(y), ref) < 1e-3  # f16 output rounding
 
 
+@pytest.mark.parametrize("C,H,W,B", [(1024, 64, 32, 1), (512, 64, 32, 2), (256, 64, 32, 3), (1024, 24, 20, 2)])
+def test_groupnorm_cluster_sizes(C, H, W, B, cuda_dev):
+    """Small-map GroupNorm whose groups are split over a thread-block cluster (8 / 4 / 2 CTAs per group, and a pixel
+    count that does not divide by the cluster size); batch items must not influence each other (bit-equal alone)."""
+    Wt = {"n.weight": 1 + 0.1 * _x((C,), 1), "n.bias": 0.1 * _x((C,), 2)}
+    x = _x((B, C, H, W), 3) * 2 + 0.7
+    mp = MiniPlan(Wt)
+    y = mp.be.groupnorm(mp.input(x), "n", C, 32, 1e-6, silu=True)
+    mp.run_gpu()
+    got = mp.read(y)
+    ref = F.silu(F.group_norm(x, 32, Wt["n.weight"], Wt["n.bias"], 1e-6))
+    assert rel_err(got, ref) < 1e-3
+    if B > 1:
+        mp1 = MiniPlan(Wt)
+        y1 = mp1.be.groupnorm(mp1.input(x[:1]), "n", C, 32, 1e-6, silu=True)
+        mp1.run_gpu()
+        assert torch.equal(mp1.read(y1), got[:1])
+
+
 def test_layernorm_geglu_softmax_cast_upsample(cuda_dev):
     Cc = 96
     Wt = {"n.weight": 1 + 0.1 * _x((Cc,), 1), "n.bias": 0.1 * _x((Cc,), 2)}
