@@ -360,7 +360,7 @@ def run_b200(args):
         # per-launch governing roofline: a layer with few output pixels is bound by streaming its weights, not by the
         # tensor pipe.  ideal = sum over launches of max(FLOP / tensor peak, algorithmic bytes / HBM peak), with
         # algorithmic bytes = f16 activations read once + f16 weights once + f32 output (+ f32 residual) per launch.
-        ideal_s, n_hbm = 0.0, 0
+        ideal_s, n_hbm, alg_bytes_tc = 0.0, 0, 0.0
         for l in be.layer_table:
             if l["kind"] != "tc":
                 continue
@@ -368,6 +368,7 @@ def run_b200(args):
             byt = 2.0 * l["M"] * k1 + 2.0 * l["N"] * l["K"] + 8.0 * l["M"] * l["N"]
             t_t, t_h = l["flops"] / (pk["bf16_sustained"] * 1e12), byt / (pk["hbm"] * 1e9)
             ideal_s += max(t_t, t_h)
+            alg_bytes_tc += byt
             n_hbm += t_h > t_t
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 tap-GEMM, f16 operands, f32 TMEM accumulate)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
@@ -376,6 +377,7 @@ def run_b200(args):
                 "traffic_note": ncu_traffic("gemm_tc_kernel"),
                 "launches_per_pass": n_tc, "flops_per_pass": be.tc_flops, "avg_launch_us": 1e6 * t_tc / max(n_tc, 1),
                 "gemm_share_of_plan": t_tc / t_plan, "plan_ms": 1e3 * t_plan,
+                "algorithmic_bytes_per_launch": alg_bytes_tc / max(n_tc, 1),
                 "composite": {"ideal_ms": 1e3 * ideal_s, "frac": ideal_s / t_tc, "hbm_bound_launches": int(n_hbm),
                               "note": "sum over the GEMM launches of max(FLOP/tensor peak, algorithmic bytes/HBM peak) / measured"}}
         # ---- batched throughput (c3's per-GPU share: 33 chunk-channels, 4 steps), extra information
