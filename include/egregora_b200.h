@@ -243,6 +243,29 @@ int  egr_pcm16_to_float(const int16_t* d_in, float* d_out, int64_t n, float scal
 /* max |x| over n f32 values -> d_out[0] (f32). */
 int  egr_absmax(const float* d_in, int64_t n, float* d_out, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* next row: adaptive wet/dry mix of Egregora_DeepFilterNet_Denoise        */
+/* ------------------------------------------------------------------------------------------ */
+#define EGR_VAD_NONE 0            /* constant strength */
+#define EGR_VAD_RMS  1            /* adaptive_vad_source="rms"  (egregora_audio_enhance_extras.py:548-559) */
+#define EGR_MIX_OFF            0  /* adaptive_mode, :575-594 */
+#define EGR_MIX_MORE_ON_NOISE  1
+#define EGR_MIX_MORE_ON_SPEECH 2
+#define EGR_MIX_GATE_ON_NOISE  3
+#define EGR_CURVE_EQUAL_POWER 0   /* mix_curve, :596-605 */
+#define EGR_CURVE_LINEAR      1
+/* Replaces steps 5-6 of Egregora_DeepFilterNet_Denoise.execute (egregora_audio_enhance_extras.py:657-704) and the
+ * helpers they call (:548-605): 10 ms frame RMS -> / 95th percentile -> smoothing -> per-frame strength -> dry/wet
+ * gains -> y = clip(g_dry*dry + g_wet*wet) -> post gain -> peak limiter -> clamp.  d_dry / d_wet / d_out: [C,T] f32 at
+ * 48 kHz (d_wet = the DeepFilterNet output, produced elsewhere).  Arguments carry the node's own parameter values;
+ * all float32 arithmetic follows numpy's operation order (frame means by pairwise summation, exact order statistics
+ * for the percentile), so the per-frame gains equal the reference's up to the last bit of sinf / cosf. */
+size_t egr_dfn_mix_workspace_bytes(int C, int64_t T);
+int egr_dfn_mix(const float* d_dry, const float* d_wet, float* d_out, int C, int64_t T, int sample_rate,
+                double strength, int mix_curve, int vad_source, int adaptive_mode, double adaptive_amount,
+                double vad_threshold, int vad_smooth_ms, double post_gain_db, int limit_ceiling, double ceiling,
+                void* d_work, size_t work_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
