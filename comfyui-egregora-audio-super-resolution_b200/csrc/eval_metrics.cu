@@ -1,0 +1,164 @@
+// eval_metrics.cu — clip-scale evaluation reductions on the device: the null test of the
+// reference's Audio_Null_Test node (/root/reference egregora_null_test_suite.py:421-470: optional least-squares scale,
+// inversion, null = A + B, correlation, null RMS, overshoot statistics) and SI-SDR (egregora_audio_eval_pack.py:414-429).
+// The STFT-based LSD of the same nodes is not here: its log of rounding-level bins has no stable cross-implementation
+// tolerance.
+//
+// Two streaming passes with deterministic two-stage reductions (per-CTA partials in fixed order, no float atomics):
+//   eval_pass1  mono means (float32, as A.mean(axis=0)) and their float64 dot products: k = <a,b>/<b,b>,
+//               alpha = <s_hat,s>/<s,s> (float64 channel means, as _si_sdr), sums for the correlation means
+//   eval_pass2  null signal (float32, bit-identical: (B*k).astype(f32), negate, add), |null| > 1 count, null energy,
+//               centred correlation sums, SI-SDR target / noise energies
+// HBM roofline: pass 1 reads 8*C*N bytes, pass 2 reads 8*C*N and writes 4*C*N.
+#include <cmath>
+#include "common.cuh"
+
+using namespace egr;
+
+#define EV_THREADS 256
+#define EV_NP1 6
+#define EV_NP2 7
+
+struct EvScalars {   // written by the finalize kernels, read by pass 2
+  double k, alpha, mean_a, mean_b_raw;
+  float kf;
+  int pad;
+};
+
+template <int NV>
+__device__ __forceinline__ void ev_block_reduce(double (&v)[NV], double* __restrict__ out /*[NV] of this CTA*/) {
+  __shared__ double red[NV][EV_THREADS / 32];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const double w = warp_sum(v[i]);
+    if ((threadIdx.x & 31) == 0) red[i][threadIdx.x >> 5] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double t = 0.0;
+    for (int w = 0; w < EV_THREADS / 32; ++w) t += red[threadIdx.x][w];
+    out[threadIdx.x] = t;
+  }
+}
+
+__device__ __forceinline__ float ev_mean32(const float* __restrict__ x, long long ld, int C, long long t) {
+  float s = __ldg(x + t);
+  for (int c = 1; c < C; ++c) s = __fadd_rn(s, __ldg(x + (long long)c * ld + t));
+  return __fdiv_rn(s, (float)C);
+}
+__device__ __forceinline__ double ev_mean64(const float* __restrict__ x, long long ld, int C, long long t) {
+  double s = (double)__ldg(x + t);
+  for (int c = 1; c < C; ++c) s += (double)__ldg(x + (long long)c * ld + t);
+  return s / (double)C;
+}
+
+__global__ void __launch_bounds__(EV_THREADS) eval_pass1_kernel(const float* __restrict__ A, long long lda,
+                                                                 const float* __restrict__ B, long long ldb, int C,
+                                                                 long long N, double* __restrict__ partials) {
+  double v[EV_NP1] = {0, 0, 0, 0, 0, 0};  // <a,b>, <b,b>, <s_hat,s>, <s,s>, sum a, sum b
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+    const double a = (double)ev_mean32(A, lda, C, t), b = (double)ev_mean32(B, ldb, C, t);
+    const double s = ev_mean64(A, lda, C, t), sh = ev_mean64(B, ldb, C, t);
+    v[0] = fma(a, b, v[0]); v[1] = fma(b, b, v[1]);
+    v[2] = fma(sh, s, v[2]); v[3] = fma(s, s, v[3]);
+    v[4] += a; v[5] += b;
+  }
+  ev_block_reduce<EV_NP1>(v, partials + (long long)blockIdx.x * EV_NP1);
+}
+
+__global__ void eval_fin1_kernel(const double* __restrict__ partials, int nblk, long long N, int ls_scale,
+                                 EvScalars* __restrict__ sc) {
+  if (threadIdx.x != 0) return;
+  double r[EV_NP1] = {0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < nblk; ++b)
+    for (int i = 0; i < EV_NP1; ++i) r[i] += partials[(long long)b * EV_NP1 + i];
+  const double k = ls_scale ? r[0] / (r[1] + 1e-20) : 1.0;
+  sc->k = k;
+  sc->kf = (float)k;
+  sc->alpha = r[2] / (r[3] + 1e-20);
+  sc->mean_a = r[4] / (double)N;
+  sc->mean_b_raw = r[5] / (double)N;
+}
+
+__global__ void __launch_bounds__(EV_THREADS) eval_pass2_kernel(const float* __restrict__ A, long long lda,
+                                                                 const float* __restrict__ B, long long ldb, int C,
+                                                                 long long N, int invert_b, int ls_scale,
+                                                                 const EvScalars* __restrict__ sc, float* __restrict__ null_out,
+                                                                 double* __restrict__ partials) {
+  const float kf = sc->kf;
+  const double alpha = sc->alpha, mean_a = sc->mean_a;
+  // b_m = (-B).mean(axis=0) after scaling / inversion: sign * (scaled B) mean
+  const double sgn = invert_b ? 1.0 : -1.0;
+  const double mean_b = sgn * (ls_scale ? (double)kf : 1.0) * sc->mean_b_raw;
+  double v[EV_NP2] = {0, 0, 0, 0, 0, 0, 0};  // overs, null energy, cab, caa, cbb, noise, target
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x) {
+    float nsum = 0.f, bsum = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float a = __ldg(A + (long long)c * lda + t);
+      float b = __ldg(B + (long long)c * ldb + t);
+      if (ls_scale) b = __fmul_rn(b, kf);
+      if (invert_b) b = -b;
+      const float nl = __fadd_rn(a, b);
+      if (null_out) null_out[(long long)c * N + t] = nl;
+      if (fabsf(nl) > 1.0f) v[0] += 1.0;
+      nsum = c ? __fadd_rn(nsum, nl) : nl;
+      bsum = c ? __fadd_rn(bsum, -b) : -b;
+    }
+    const double nm = (double)__fdiv_rn(nsum, (float)C);
+    v[1] = fma(nm, nm, v[1]);
+    const double am = (double)ev_mean32(A, lda, C, t) - mean_a;
+    const double bm = (double)__fdiv_rn(bsum, (float)C) - mean_b;
+    v[2] = fma(am, bm, v[2]); v[3] = fma(am, am, v[3]); v[4] = fma(bm, bm, v[4]);
+    const double s = ev_mean64(A, lda, C, t), sh = ev_mean64(B, ldb, C, t);
+    const double st = alpha * s, e = sh - st;
+    v[5] = fma(e, e, v[5]); v[6] = fma(st, st, v[6]);
+  }
+  ev_block_reduce<EV_NP2>(v, partials + (long long)blockIdx.x * EV_NP2);
+}
+
+__global__ void eval_fin2_kernel(const double* __restrict__ partials, int nblk, int C, long long N,
+                                 const EvScalars* __restrict__ sc, double* __restrict__ metrics) {
+  if (threadIdx.x != 0) return;
+  double r[EV_NP2] = {0, 0, 0, 0, 0, 0, 0};
+  for (int b = 0; b < nblk; ++b)
+    for (int i = 0; i < EV_NP2; ++i) r[i] += partials[(long long)b * EV_NP2 + i];
+  metrics[EGR_EVAL_SI_SDR_DB] = 10.0 * log10((r[6] + 1e-20) / (r[5] + 1e-20));
+  metrics[EGR_EVAL_CORR] = r[2] / (sqrt(r[3]) * sqrt(r[4]) + 1e-20);
+  metrics[EGR_EVAL_NULL_RMS_DBFS] = 10.0 * log10(r[1] / (double)N + 1e-20);
+  metrics[EGR_EVAL_OVERSHOOT] = r[0];
+  metrics[EGR_EVAL_CLIPPED_PCT] = 100.0 * r[0] / ((double)C * (double)N);
+  metrics[EGR_EVAL_SCALE_K] = sc->k;
+}
+
+static int ev_blocks(long long N) {
+  long long b = (N + EV_THREADS - 1) / EV_THREADS;
+  const long long cap = (long long)(devinfo().sm_count ? devinfo().sm_count : 148) * 8;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+extern "C" size_t egr_eval_workspace_bytes(void) { return 256 + sizeof(double) * 148 * 8 * 2 * (EV_NP1 + EV_NP2); }
+
+extern "C" int egr_eval_null_test(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_t ld_proc, int C, int64_t N,
+                                  int invert_b, int least_squares_scale, float* d_null, double* d_metrics, void* d_work,
+                                  size_t work_bytes, void* stream) {
+  if (!devinfo().inited) return fail(EGR_ERR_STATE, "egr_eval_null_test: call egr_init first");
+  if (!d_ref || !d_proc || !d_metrics || !d_work || C < 1 || C > 64 || N < 1 || ld_ref < N || ld_proc < N)
+    return fail(EGR_ERR_ARG, "egr_eval_null_test: bad arguments");
+  if (reinterpret_cast<uintptr_t>(d_work) % 256) return fail(EGR_ERR_ARG, "egr_eval_null_test: workspace must be 256-byte aligned");
+  const int nblk = ev_blocks(N);
+  const size_t need = 256 + sizeof(double) * (size_t)nblk * (EV_NP1 + EV_NP2);
+  if (work_bytes < need || need > egr_eval_workspace_bytes()) return fail(EGR_ERR_ARG, "egr_eval_null_test: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  EvScalars* sc = reinterpret_cast<EvScalars*>(d_work);
+  double* p1 = reinterpret_cast<double*>(reinterpret_cast<char*>(d_work) + 256);
+  double* p2 = p1 + (size_t)nblk * EV_NP1;
+  eval_pass1_kernel<<<nblk, EV_THREADS, 0, st>>>(d_ref, ld_ref, d_proc, ld_proc, C, N, p1);
+  EGR_CHECK_LAUNCH("eval_pass1_kernel");
+  eval_fin1_kernel<<<1, 32, 0, st>>>(p1, nblk, N, least_squares_scale, sc);
+  EGR_CHECK_LAUNCH("eval_fin1_kernel");
+  eval_pass2_kernel<<<nblk, EV_THREADS, 0, st>>>(d_ref, ld_ref, d_proc, ld_proc, C, N, invert_b, least_squares_scale, sc, d_null, p2);
+  EGR_CHECK_LAUNCH("eval_pass2_kernel");
+  eval_fin2_kernel<<<1, 32, 0, st>>>(p2, nblk, C, N, sc, d_metrics);
+  EGR_CHECK_LAUNCH("eval_fin2_kernel");
+  return EGR_OK;
+}

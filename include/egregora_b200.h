@@ -266,6 +266,25 @@ int egr_dfn_mix(const float* d_dry, const float* d_wet, float* d_out, int C, int
                 double vad_threshold, int vad_smooth_ms, double post_gain_db, int limit_ceiling, double ceiling,
                 void* d_work, size_t work_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* next row: clip-scale evaluation reductions                              */
+/* ------------------------------------------------------------------------------------------ */
+#define EGR_EVAL_SI_SDR_DB      0  /* _si_sdr, egregora_audio_eval_pack.py:414-429 (float64, mono means)       */
+#define EGR_EVAL_CORR           1  /* corr_coef, egregora_null_test_suite.py:444-448                           */
+#define EGR_EVAL_NULL_RMS_DBFS  2  /* _rms_db(null.mean(axis=0)), :119-122, :449-450                           */
+#define EGR_EVAL_OVERSHOOT      3  /* count of |null| > 1, :463                                                */
+#define EGR_EVAL_CLIPPED_PCT    4  /* :465                                                                     */
+#define EGR_EVAL_SCALE_K        5  /* least-squares scale k, :431-436                                          */
+#define EGR_EVAL_NUM            8
+/* Replaces the arithmetic of Audio_Null_Test.execute (egregora_null_test_suite.py:421-467, without its LUFS / LSD /
+ * HF-band options) and _si_sdr: d_ref / d_proc [C,N] f32 with row strides ld_* (so the "trim both to the shorter"
+ * step needs no copy), d_null [C,N] f32 or NULL, d_metrics [EGR_EVAL_NUM] f64 ON THE DEVICE (read it after a stream
+ * sync).  The null signal is bit-identical to numpy's; the reductions are deterministic float64 sums. */
+size_t egr_eval_workspace_bytes(void);
+int egr_eval_null_test(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_t ld_proc, int C, int64_t N,
+                       int invert_b, int least_squares_scale, float* d_null, double* d_metrics, void* d_work,
+                       size_t work_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,3 +11,5 @@ run flashsr_tiny tests/test_flashsr_gpu.py -k "tiny"
 run fft tests/test_fft_gpu.py
 run fatllama tests/test_fatllama_gpu.py
 run resample tests/test_resample.py
+run dfn_mix tests/test_dfn_mix.py
+run eval tests/test_eval_metrics.py
