@@ -14,6 +14,7 @@
 // HBM roofline: rms reads 4T, mix reads 8T + writes 4T, limit reads + writes 8T bytes per channel = 24*T.
 #include <cmath>
 #include "common.cuh"
+#include "select.cuh"  // radix_select_nonneg / percentile95_f32_nonneg (shared with eval_metrics.cu)
 
 using namespace egr;
 
@@ -89,58 +90,6 @@ struct DfnGainArgs {
   float alpha, oma;
 };
 
-// k-th smallest (0-based) of v[0..n) for non-negative floats: three radix passes over the bit pattern
-__device__ unsigned dfn_select(const float* __restrict__ v, int n, int k, unsigned* hist /*[4096] smem*/, unsigned* bc /*[2] smem*/,
-                               unsigned* wsum /*[32] smem*/) {
-  unsigned prefix = 0, mask = 0;
-  const int shifts[3] = {20, 8, 0}, widths[3] = {12, 12, 8};
-  for (int pass = 0; pass < 3; ++pass) {
-    const int sh = shifts[pass], nb = 1 << widths[pass];
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const unsigned b = __float_as_uint(v[i]);
-      if ((b & mask) == prefix) atomicAdd(&hist[(b >> sh) & (nb - 1)], 1u);
-    }
-    __syncthreads();
-    // block-wide exclusive scan of the histogram (each thread owns `per` consecutive bins), then the one thread whose
-    // range contains rank k walks its own bins
-    {
-      const int per = nb >= 1024 ? nb / 1024 : 1;
-      const int first = threadIdx.x * per;
-      unsigned mine = 0;
-      if (first < nb)
-        for (int j = 0; j < per; ++j) mine += hist[first + j];
-      unsigned incl = mine;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((threadIdx.x & 31) >= o) incl += up;
-      }
-      if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
-      __syncthreads();
-      unsigned woff = 0;
-      for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wsum[w];
-      const unsigned excl = woff + incl - mine;
-      if (first < nb && (int)excl <= k && k < (int)(excl + mine)) {
-        int acc = (int)excl, bin = first;
-        for (; bin < first + per - 1; ++bin) {
-          if (acc + (int)hist[bin] > k) break;
-          acc += (int)hist[bin];
-        }
-        bc[0] = (unsigned)bin;
-        bc[1] = (unsigned)acc;
-      }
-    }
-    __syncthreads();
-    prefix |= bc[0] << sh;
-    mask |= (unsigned)(nb - 1) << sh;
-    k -= (int)bc[1];
-    __syncthreads();
-  }
-  return prefix;
-}
-
 __global__ void __launch_bounds__(1024) dfn_frame_gain_kernel(DfnGainArgs g, float* __restrict__ rms /* in: rms, scratch */,
                                                                float* __restrict__ g_dry, float* __restrict__ g_wet) {
   __shared__ unsigned hist[4096];
@@ -153,16 +102,8 @@ __global__ void __launch_bounds__(1024) dfn_frame_gain_kernel(DfnGainArgs g, flo
   float* gd = g_dry + (long long)ch * n;
   float* gw = g_wet + (long long)ch * n;
   if (g.vad) {
-    // np.percentile(rms, 95) on float32 data: q/100, the virtual index (n-1)*q and its fractional part are float32,
-    // then numpy's _lerp (incl. its t >= 0.5 form) between the two neighbouring order statistics
-    const float q32 = __fdiv_rn(95.0f, 100.0f);
-    const float pos = __fmul_rn((float)(n - 1), q32);
-    const int lo = min((int)floorf(pos), n - 1), hi = min(lo + 1, n - 1);
-    const float a = __uint_as_float(dfn_select(p, n, lo, hist, bc, wsum));
-    const float b = __uint_as_float(dfn_select(p, n, hi, hist, bc, wsum));
-    const float t = __fsub_rn(pos, (float)lo);
-    const float d = __fsub_rn(b, a);
-    float p95 = t >= 0.5f ? __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, t))) : __fadd_rn(a, __fmul_rn(d, t));
+    // np.percentile(rms, 95) on float32 data (exact order statistics + numpy's float32 lerp, select.cuh)
+    float p95 = percentile95_f32_nonneg(p, n, hist, bc, wsum);
     if (p95 == 0.f) p95 = (float)1e-6;
     for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = fminf(fmaxf(__fdiv_rn(p[i], p95), 0.f), 1.f);
     __syncthreads();

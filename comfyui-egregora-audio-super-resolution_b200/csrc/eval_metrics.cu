@@ -1,8 +1,8 @@
 // eval_metrics.cu — clip-scale evaluation reductions on the device: the null test of the
 // reference's Audio_Null_Test node (/root/reference egregora_null_test_suite.py:421-470: optional least-squares scale,
 // inversion, null = A + B, correlation, null RMS, overshoot statistics) and SI-SDR (egregora_audio_eval_pack.py:414-429).
-// The STFT-based LSD of the same nodes is not here: its log of rounding-level bins has no stable cross-implementation
-// tolerance.
+// and the STFT log-spectral distance of the same nodes (_stft_mag / _lsd, egregora_audio_eval_pack.py:389-411 =
+// egregora_null_test_suite.py:167-189).
 //
 // Two streaming passes with deterministic two-stage reductions (per-CTA partials in fixed order, no float atomics):
 //   eval_pass1  mono means (float32, as A.mean(axis=0)) and their float64 dot products: k = <a,b>/<b,b>,
@@ -10,8 +10,18 @@
 //   eval_pass2  null signal (float32, bit-identical: (B*k).astype(f32), negate, add), |null| > 1 count, null energy,
 //               centred correlation sums, SI-SDR target / noise energies
 // HBM roofline: pass 1 reads 8*C*N bytes, pass 2 reads 8*C*N and writes 4*C*N.
+//
+// LSD (egr_eval_lsd), three launches:
+//   eval_lsd_tables  np.hanning(n_fft) (float64 -> float32) and exp(-2 pi i k / n_fft), built on the device per call
+//   eval_lsd_frames  one CTA per STFT frame: mono means of both clips, window, two packed-real radix-2 Stockham FFTs
+//                    in shared memory (the front end's validated scheme, frontend.cu), 20*log10(|X| + 1e-12) in
+//                    float32, per[frame] = sqrt(mean_k (LA - LB)^2 + 1e-12)
+//   eval_lsd_final   one CTA: mean of per[] (fixed-order float64 sum) and np.percentile(per, 95) by exact radix
+//                    select + numpy's float32 lerp (select.cuh)
+//   Frames overlap 4x (hop = n_fft/4 by default) but stay in L2: HBM reads 8*C*N bytes, writes 4*frames.
 #include <cmath>
 #include "common.cuh"
+#include "select.cuh"
 
 using namespace egr;
 
@@ -160,5 +170,150 @@ extern "C" int egr_eval_null_test(const float* d_ref, int64_t ld_ref, const floa
   EGR_CHECK_LAUNCH("eval_pass2_kernel");
   eval_fin2_kernel<<<1, 32, 0, st>>>(p2, nblk, C, N, sc, d_metrics);
   EGR_CHECK_LAUNCH("eval_fin2_kernel");
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LSD
+#define LSD_THREADS 256
+
+__global__ void eval_lsd_tables_kernel(int n_fft, float* __restrict__ window, float2* __restrict__ tw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // np.hanning(M) = 0.5 + 0.5*cos(pi*n/(M-1)), n = 1-M, 3-M, ..., M-1 (float64), then .astype(float32)
+  if (i < n_fft) window[i] = (float)(0.5 + 0.5 * cospi((double)(1 - n_fft + 2 * i) / (double)(n_fft - 1)));
+  if (i <= n_fft / 2) {
+    double sn, cs;
+    sincospi(-2.0 * (double)i / (double)n_fft, &sn, &cs);
+    tw[i] = make_float2((float)cs, (float)sn);
+  }
+}
+
+__device__ __forceinline__ float2 lsd_cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+// One frame of _stft_mag: mono[start : start + n_fft] (zero padded past N) * window -> rfft -> emit(k, 20*log10(|X_k| + 1e-12))
+// for k = 0..n_fft/2.  Real input packed as an M = n_fft/2 point complex transform + Hermitian split.
+template <class EMIT>
+__device__ __forceinline__ void lsd_frame_logmag(const float* __restrict__ x, long long ld, int C, long long N, long long start,
+                                                 int n_fft, const float* __restrict__ window, const float2* __restrict__ tw,
+                                                 float2* bufA, float2* bufB, EMIT emit) {
+  const int M = n_fft >> 1;
+  for (int m = threadIdx.x; m < M; m += LSD_THREADS) {
+    float v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = 2 * m + u;
+      const long long t = start + j;
+      v[u] = t < N ? __fmul_rn(ev_mean32(x, ld, C, t), __ldg(window + j)) : 0.f;
+    }
+    bufA[m] = make_float2(v[0], v[1]);
+  }
+  __syncthreads();
+  float2* src = bufA;
+  float2* dst = bufB;
+  for (int Ns = 1; Ns < M; Ns <<= 1) {  // Stockham radix-2, autosort, ping-pong; exp(-2 pi i k/M) = tw[2k]
+    const int tstep = M / (2 * Ns);
+    for (int j = threadIdx.x; j < (M >> 1); j += LSD_THREADS) {
+      const int k = j & (Ns - 1);
+      const float2 w = __ldg(tw + 2 * k * tstep);
+      const float2 a = src[j];
+      const float2 bb = lsd_cmul(src[j + (M >> 1)], w);
+      const int j0 = ((j - k) << 1) + k;
+      dst[j0] = make_float2(a.x + bb.x, a.y + bb.y);
+      dst[j0 + Ns] = make_float2(a.x - bb.x, a.y - bb.y);
+    }
+    __syncthreads();
+    float2* t = src; src = dst; dst = t;
+  }
+  // X[k] = (Z[k] + conj(Z[M-k]))/2 - i*w_k*(Z[k] - conj(Z[M-k]))/2, w_k = exp(-2 pi i k/n_fft)
+  for (int k = threadIdx.x; k <= M; k += LSD_THREADS) {
+    const float2 zk = src[k == M ? 0 : k];
+    const float2 zm = src[k == 0 ? 0 : M - k];
+    const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
+    const float2 o = make_float2(0.5f * (zk.x - zm.x), 0.5f * (zk.y + zm.y));
+    const float2 wo = lsd_cmul(__ldg(tw + k), o);
+    const float re = e.x + wo.y, im = e.y - wo.x;
+    emit(k, __fmul_rn(20.0f, log10f(__fadd_rn(sqrtf(re * re + im * im), 1e-12f))));
+  }
+  __syncthreads();  // the buffers are reused by the next call
+}
+
+__global__ void __launch_bounds__(LSD_THREADS) eval_lsd_frames_kernel(const float* __restrict__ A, long long lda,
+                                                                       const float* __restrict__ B, long long ldb, int C,
+                                                                       long long N, int n_fft, int hop,
+                                                                       const float* __restrict__ window,
+                                                                       const float2* __restrict__ tw, float* __restrict__ per) {
+  extern __shared__ float2 lsd_sm[];
+  __shared__ double red[LSD_THREADS / 32];
+  const int M = n_fft >> 1;
+  float2* bufA = lsd_sm;
+  float2* bufB = lsd_sm + M;
+  float* LA = reinterpret_cast<float*>(lsd_sm + 2 * M);  // [M+1]
+  const long long start = (long long)blockIdx.x * hop;
+  lsd_frame_logmag(A, lda, C, N, start, n_fft, window, tw, bufA, bufB, [&](int k, float l) { LA[k] = l; });
+  double acc = 0.0;  // every thread meets the bins k it wrote itself (same k -> thread mapping in both calls)
+  lsd_frame_logmag(B, ldb, C, N, start, n_fft, window, tw, bufA, bufB, [&](int k, float l) {
+    const float d = __fsub_rn(LA[k], l);
+    acc += (double)__fmul_rn(d, d);
+  });
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < LSD_THREADS / 32; ++w) t += red[w];
+    per[blockIdx.x] = __fsqrt_rn(__fadd_rn((float)(t / (double)(M + 1)), 1e-12f));
+  }
+}
+
+__global__ void __launch_bounds__(1024) eval_lsd_final_kernel(const float* __restrict__ per, int frames, double* __restrict__ metrics) {
+  __shared__ unsigned hist[4096];
+  __shared__ unsigned bc[2];
+  __shared__ unsigned wsum[32];
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < frames; i += 1024) s += (double)per[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  const float p95 = percentile95_f32_nonneg(per, frames, hist, bc, wsum);
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 32; ++w) t += red[w];
+    metrics[EGR_LSD_MEAN_DB] = (double)(float)(t / (double)frames);  // np.mean of a float32 array is a float32
+    metrics[EGR_LSD_P95_DB] = (double)p95;
+    metrics[EGR_LSD_FRAMES] = (double)frames;
+  }
+}
+
+static long long lsd_frames(long long N, int n_fft, int hop) { return 1 + (N > n_fft ? (N - n_fft) / hop : 0); }
+
+extern "C" size_t egr_eval_lsd_workspace_bytes(int64_t N, int n_fft, int hop) {
+  if (N < 1 || n_fft < 2 || hop < 1) return 0;
+  const size_t raw = sizeof(float) * (size_t)n_fft + sizeof(float2) * (size_t)(n_fft / 2 + 1) + sizeof(float) * (size_t)lsd_frames(N, n_fft, hop);
+  return (raw + 255) / 256 * 256;
+}
+
+extern "C" int egr_eval_lsd(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_t ld_proc, int C, int64_t N, int n_fft,
+                            int hop, double* d_metrics, void* d_work, size_t work_bytes, void* stream) {
+  if (!devinfo().inited) return fail(EGR_ERR_STATE, "egr_eval_lsd: call egr_init first");
+  if (!d_ref || !d_proc || !d_metrics || !d_work || C < 1 || C > 64 || N < 1 || ld_ref < N || ld_proc < N || hop < 1)
+    return fail(EGR_ERR_ARG, "egr_eval_lsd: bad arguments");
+  if (n_fft < 64 || n_fft > 8192 || (n_fft & (n_fft - 1)))
+    return fail(EGR_ERR_UNSUPPORTED, "egr_eval_lsd: n_fft must be a power of two in [64, 8192] (got %d)", n_fft);
+  if (reinterpret_cast<uintptr_t>(d_work) % 256) return fail(EGR_ERR_ARG, "egr_eval_lsd: workspace must be 256-byte aligned");
+  const long long frames = lsd_frames(N, n_fft, hop);
+  if (frames > 0x7fffffffLL) return fail(EGR_ERR_UNSUPPORTED, "egr_eval_lsd: too many frames");
+  if (work_bytes < egr_eval_lsd_workspace_bytes(N, n_fft, hop)) return fail(EGR_ERR_ARG, "egr_eval_lsd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* window = reinterpret_cast<float*>(d_work);
+  float2* tw = reinterpret_cast<float2*>(window + n_fft);
+  float* per = reinterpret_cast<float*>(tw + n_fft / 2 + 1);
+  eval_lsd_tables_kernel<<<ceil_div(n_fft, 256), 256, 0, st>>>(n_fft, window, tw);
+  EGR_CHECK_LAUNCH("eval_lsd_tables_kernel");
+  const size_t smem = sizeof(float2) * (size_t)n_fft + sizeof(float) * (size_t)(n_fft / 2 + 1);
+  if (smem > 48 * 1024) EGR_CUDA(cudaFuncSetAttribute(eval_lsd_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  eval_lsd_frames_kernel<<<(unsigned)frames, LSD_THREADS, smem, st>>>(d_ref, ld_ref, d_proc, ld_proc, C, N, n_fft, hop, window, tw, per);
+  EGR_CHECK_LAUNCH("eval_lsd_frames_kernel");
+  eval_lsd_final_kernel<<<1, 1024, 0, st>>>(per, (int)frames, d_metrics);
+  EGR_CHECK_LAUNCH("eval_lsd_final_kernel");
   return EGR_OK;
 }

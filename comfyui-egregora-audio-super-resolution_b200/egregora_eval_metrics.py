@@ -2,9 +2,10 @@
 
 Mirrors the arithmetic of the reference's `Audio_Null_Test.execute` (/root/reference/egregora_null_test_suite.py
 :421-467 — trim to the shorter clip, optional least-squares scale, inversion, null = A + B, corr_coef, null_rms_dbfs,
-overshoot_count, clipped_pct, scale_k) and of `_si_sdr` (egregora_audio_eval_pack.py:414-429).  Not here: the LUFS,
-LSD and HF-band options of those nodes (K-weighting / STFT paths).  One C-ABI call, two streaming
-passes; no CPU fallback.
+overshoot_count, clipped_pct, scale_k), of `_si_sdr` (egregora_audio_eval_pack.py:414-429) and of `_stft_mag` +
+`_lsd` (egregora_audio_eval_pack.py:389-411; the same two functions again at egregora_null_test_suite.py:167-189).
+Not here: the LUFS and HF-band options of those nodes (K-weighting IIR path).  One C-ABI call per
+metric group; no CPU fallback.
 """
 from __future__ import annotations
 
@@ -54,3 +55,31 @@ def si_sdr(ref: torch.Tensor, est: torch.Tensor) -> float:
     if r.shape[0] != e.shape[0]:  # the reference averages each side's channels separately
         r, e = r.double().mean(0, keepdim=True).float(), e.double().mean(0, keepdim=True).float()
     return null_test(r, e, want_null=False)[1]["si_sdr_db"]
+
+
+def lsd(ref: torch.Tensor, proc: torch.Tensor, n_fft: int = 2048, hop: int = 512) -> Tuple[float, float]:
+    """Log-spectral distance (lsd_mean_db, lsd_p95_db) of `proc` against `ref`, as Metrics_LSD_SISDR.execute computes
+    it (egregora_audio_eval_pack.py:453-467): channel means, both trimmed to the shorter clip, `_stft_mag` frames
+    (symmetric Hann, no centring), `_lsd`.  ref, proc: [C,N] or [N] float32, host or device."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("CUDA GPU not detected. The B200-native metrics have no CPU fallback (sm_100a kernels only).")
+    r = ref if ref.dim() == 2 else ref[None, :]
+    e = proc if proc.dim() == 2 else proc[None, :]
+    if r.dim() != 2 or e.dim() != 2:
+        raise RuntimeError(f"ref/proc must be [C, N] or [N]; got {tuple(ref.shape)} and {tuple(proc.shape)}")
+    device = torch.device("cuda", torch.cuda.current_device())
+    lib = _abi.init(device.index or 0)
+    a = r.detach().to(device=device, dtype=torch.float32).contiguous()
+    b = e.detach().to(device=device, dtype=torch.float32).contiguous()
+    if a.shape[0] != b.shape[0]:  # the reference takes each side's channel mean separately (float32, :456-457)
+        a, b = a.mean(0, keepdim=True), b.mean(0, keepdim=True)
+    C, n = a.shape[0], min(a.shape[1], b.shape[1])
+    if n == 0:
+        raise RuntimeError("empty audio")
+    met = torch.zeros(_abi.K["EGR_LSD_NUM"], dtype=torch.float64, device=device)
+    wb = int(lib.egr_eval_lsd_workspace_bytes(n, int(n_fft), int(hop)))
+    work = torch.empty(max(wb, 256), dtype=torch.uint8, device=device)
+    _abi.check(lib.egr_eval_lsd(a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], C, n, int(n_fft), int(hop),
+                                met.data_ptr(), work.data_ptr(), wb, torch.cuda.current_stream().cuda_stream), "egr_eval_lsd")
+    m = met.cpu().tolist()
+    return float(m[_abi.K["EGR_LSD_MEAN_DB"]]), float(m[_abi.K["EGR_LSD_P95_DB"]])

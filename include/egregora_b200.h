@@ -276,14 +276,31 @@ int egr_dfn_mix(const float* d_dry, const float* d_wet, float* d_out, int C, int
 #define EGR_EVAL_CLIPPED_PCT    4  /* :465                                                                     */
 #define EGR_EVAL_SCALE_K        5  /* least-squares scale k, :431-436                                          */
 #define EGR_EVAL_NUM            8
-/* Replaces the arithmetic of Audio_Null_Test.execute (egregora_null_test_suite.py:421-467, without its LUFS / LSD /
- * HF-band options) and _si_sdr: d_ref / d_proc [C,N] f32 with row strides ld_* (so the "trim both to the shorter"
+/* Replaces the arithmetic of Audio_Null_Test.execute (egregora_null_test_suite.py:421-467, without its LUFS / HF-band options; the LSD
+ * option is egr_eval_lsd below) and _si_sdr: d_ref / d_proc [C,N] f32 with row strides ld_* (so the "trim both to the shorter"
  * step needs no copy), d_null [C,N] f32 or NULL, d_metrics [EGR_EVAL_NUM] f64 ON THE DEVICE (read it after a stream
  * sync).  The null signal is bit-identical to numpy's; the reductions are deterministic float64 sums. */
 size_t egr_eval_workspace_bytes(void);
 int egr_eval_null_test(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_t ld_proc, int C, int64_t N,
                        int invert_b, int least_squares_scale, float* d_null, double* d_metrics, void* d_work,
                        size_t work_bytes, void* stream);
+
+
+#define EGR_LSD_MEAN_DB  0  /* lsd_mean_db = mean over frames,           egregora_audio_eval_pack.py:405-411 */
+#define EGR_LSD_P95_DB   1  /* lsd_p95_db  = np.percentile(per, 95),     same                                */
+#define EGR_LSD_FRAMES   2  /* 1 + max(0, (N - n_fft) // hop),           :393                                */
+#define EGR_LSD_NUM      4
+/* Replaces _stft_mag + _lsd (egregora_audio_eval_pack.py:389-411, identical copies in egregora_null_test_suite.py
+ * :167-189; callers Metrics_LSD_SISDR.execute :462-467 and Audio_Null_Test.execute :456-461): mono means of d_ref /
+ * d_proc [C,N] f32, frames of n_fft samples every hop samples (no centring, a clip shorter than n_fft is one zero-padded
+ * frame), symmetric Hann (np.hanning), float32 real FFT, L = 20*log10(|X| + 1e-12), per-frame sqrt(mean_k dL^2 + 1e-12),
+ * then the mean and the 95th percentile over frames into d_metrics [EGR_LSD_NUM] f64 ON THE DEVICE.  n_fft must be a
+ * power of two in [64, 8192] (the nodes' default is 2048); other sizes return an error, nothing falls back.  Two float32
+ * FFTs agree to rounding, so bins that hold real signal agree to ~1e-5 dB; bins that hold only rounding noise are noise
+ * in the reference too (tests state the tolerance per case). */
+size_t egr_eval_lsd_workspace_bytes(int64_t N, int n_fft, int hop);
+int egr_eval_lsd(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_t ld_proc, int C, int64_t N, int n_fft,
+                 int hop, double* d_metrics, void* d_work, size_t work_bytes, void* stream);
 
 #ifdef __cplusplus
 }

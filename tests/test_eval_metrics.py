@@ -1,10 +1,16 @@
 """Evaluation reductions: Audio_Null_Test arithmetic (egregora_null_test_suite.py:421-467)
-and _si_sdr (egregora_audio_eval_pack.py:414-429).
+, _si_sdr (egregora_audio_eval_pack.py:414-429) and the LSD pair _stft_mag / _lsd (:389-411).
 
 CPU: the numpy restatement against the golden file produced by the reference functions (null signal bit-exact,
 metrics to 1e-12 relative — the float64 dot products go through the same BLAS here).  GPU: egr_eval_null_test through
 `egregora_eval_metrics`: null signal bit-exact, float64 metrics within 1e-9 relative of the reference's (different
 summation order), corr_coef within 3e-6 (the reference forms it in float32).
+
+LSD: the oracle and a numpy float32 emulation of the kernel's own FFT scheme (tests/lsd_cases.py) are checked here on
+the CPU against goldens made by the reference node; the GPU run of egr_eval_lsd is tests/test_zz_eval_lsd_gpu.py.
+Tolerance 1e-4 dB wherever every STFT bin holds signal.  Where bins hold nothing but FFT rounding noise (the
+`bandlimited_noise_floor` case: exact zeros above a quarter of the band) the reference's own value is set by ITS FFT's
+rounding noise — another correct float32 FFT lands several dB away — so that case is only bounded, not matched.
 """
 import hashlib
 import json
@@ -14,6 +20,7 @@ import pytest
 import torch
 
 from conftest import GOLDEN
+from lsd_cases import emulate_kernel_lsd, signals as lsd_signals
 from oracle import eval_oracle as O
 
 
@@ -86,3 +93,35 @@ def test_kernel_properties_at_clip_scale(cuda_dev, pkg):
     assert m1["si_sdr_db"] > 120.0
     with pytest.raises(RuntimeError):
         M.null_test(torch.zeros(1, 10), torch.zeros(2, 10))
+
+
+# ------------------------------------------------------------------------------------------------ LSD
+@pytest.fixture(scope="module")
+def lgold():
+    return json.loads((GOLDEN / "eval_lsd_golden.json").read_text())
+
+
+def test_lsd_oracle_matches_reference_golden(lgold):
+    for name, c in lgold.items():
+        A, B = lsd_signals(name, c)
+        mean, p95 = O.lsd(A, B, c["n_fft"], c["hop"])
+        tol = 1e-5 if c["band"] >= 1.0 else 0.5  # same numpy FFT -> same rounding noise, but do not rely on it
+        assert abs(mean - c["lsd_mean_db"]) <= tol and abs(p95 - c["lsd_p95_db"]) <= tol, (name, mean, p95)
+        a, b = A.mean(axis=0), B.mean(axis=0)
+        n = min(a.size, b.size)
+        per = O.lsd_per_frame(O.stft_mag(a[:n], c["n_fft"], c["hop"]), O.stft_mag(b[:n], c["n_fft"], c["hop"]))
+        assert per.size == c["frames"]
+        assert np.allclose(per[c["probe_idx"]], c["per_probe"], rtol=0, atol=tol)
+
+
+def test_lsd_kernel_arithmetic_emulated_matches_reference_golden(lgold):
+    """The kernel's FFT scheme restated in numpy float32 (thread loops vectorised) against the reference numbers."""
+    for name, c in lgold.items():
+        A, B = lsd_signals(name, c)
+        mean, p95, per = emulate_kernel_lsd(A, B, c["n_fft"], c["hop"])
+        assert per.size == c["frames"]
+        if c["band"] >= 1.0:
+            assert abs(mean - c["lsd_mean_db"]) <= 1e-4 and abs(p95 - c["lsd_p95_db"]) <= 1e-4, (name, mean, p95)
+            assert np.allclose(per[c["probe_idx"]], c["per_probe"], rtol=0, atol=1e-4)
+        else:  # noise-floor bins: both implementations are "right"; they only have to be in the same region
+            assert abs(mean - c["lsd_mean_db"]) <= 8.0, (name, mean, c["lsd_mean_db"])
