@@ -1,5 +1,6 @@
-"""Device time of egr_eval_null_test at clip scale (5 / 10 min stereo at 48 kHz), CUDA events on the launching stream,
-against the HBM roofline (algorithmic bytes = 20*C*N: pass 1 reads 8CN, pass 2 reads 8CN and writes 4CN).
+"""Device time of egr_eval_null_test and egr_eval_lsd at clip scale (5 / 10 min stereo at 48 kHz), CUDA events on the launching stream,
+against the HBM roofline (null test: algorithmic bytes = 20*C*N — pass 1 reads 8CN, pass 2 reads 8CN and writes 4CN;
+LSD: 8*C*N, both clips read once, the 4x frame overlap is served by L2).
     python tools/eval_probe.py"""
 import sys
 from pathlib import Path
@@ -32,3 +33,14 @@ for secs, C in [(300, 2), (600, 2)]:
     ms = e0.elapsed_time(e1) / reps
     gb = 20.0 * C * N / 1e9
     print(f"{secs}s x{C}: {ms:8.3f} ms  {gb / ms * 1e3:8.1f} GB/s algorithmic ({gb / ms * 1e3 / 6532.9:.2%} of HBM peak)")
+    for _ in range(3):
+        M.lsd(a, b)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        M.lsd(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gb = 8.0 * C * N / 1e9
+    print(f"{secs}s x{C} lsd: {ms:8.3f} ms  {gb / ms * 1e3:8.1f} GB/s algorithmic ({gb / ms * 1e3 / 6532.9:.2%} of HBM peak)")
