@@ -378,6 +378,8 @@ def run_b200(args):
                 "launches_per_pass": n_tc, "flops_per_pass": be.tc_flops, "avg_launch_us": 1e6 * t_tc / max(n_tc, 1),
                 "gemm_share_of_plan": t_tc / t_plan, "plan_ms": 1e3 * t_plan,
                 "algorithmic_bytes_per_launch": alg_bytes_tc / max(n_tc, 1),
+                "layer_table": "roofline/flashsr_layers.json (tools/make_layer_table.py: per-op M/N/K/FLOPs/bytes of this plan, "
+                               "cross-checked against forward hooks on the fp32 oracle)",
                 "composite": {"ideal_ms": 1e3 * ideal_s, "frac": ideal_s / t_tc, "hbm_bound_launches": int(n_hbm),
                               "note": "sum over the GEMM launches of max(FLOP/tensor peak, algorithmic bytes/HBM peak) / measured"}}
         # ---- batched throughput (c3's per-GPU share: 33 chunk-channels, 4 steps), extra information

@@ -299,7 +299,7 @@ class PlanBackend:
             self._ws(op, "OUT32", out_pt.f32, write=True)
         if out16:
             self._ws(op, "OUT16", out_pt.f16, write=True)
-        fl = 2.0 * Bo * Ho * Wo * N * Kdim * ntaps
+        fl = 2.0 * Bo * Ho * Wo * N * Kdim * ntaps * flops_scale   # algorithmic FLOPs (zero-padded taps excluded)
         self.flops += fl
         if not simt:
             self.tc_flops += fl
@@ -595,7 +595,8 @@ class PlanBackend:
         w_off, _, _ = self.w_taps(name, "conv1d_strided", f16=tc, stride=stride)
         o = self.new(B, 1, To, cout, f32=True, tag=name)
         self._gemm(name, x, (abuf, 0, dims, strides), taps, Kd, cout, w_off, simt=not tc, dimW=1, dimH=2, dimB=3, Wo=To, Ho=1,
-                   Bo=B, out_pt=o, out16=False, out32=True, bias_off=self.w_bias(name), a_elem=elem)
+                   Bo=B, out_pt=o, out16=False, out32=True, bias_off=self.w_bias(name), a_elem=elem,
+                   flops_scale=2.0 / 3.0)   # k = 2*stride real taps inside the 3*stride-wide padded window
         return o
 
     def convT1d(self, x: PT, name, cin, cout, k, stride, add=None):

@@ -69,3 +69,22 @@ def test_tile_geometry_and_block_n():
         bw, bh, bb = P.tile_geometry(w, h, b)
         assert bw * bh * bb == 128
     assert [P.pick_block_n(n) for n in (16, 48, 96, 128, 384, 640, 1024, 1920, 4608, 5120)] == [16, 48, 96, 128, 192, 160, 256, 240, 256, 256]
+
+
+def test_committed_layer_table_matches_the_plan():
+    """roofline/flashsr_layers.json (written by tools/make_layer_table.py) is the table bench.py's
+    roofline.achieved rests on: it must list exactly the GEMM ops of the c2 plan built now, and its FLOP count must
+    agree with the oracle's hook count once the two documented differences are restated (phase GEMMs of the
+    up-sampling convs, attention products)."""
+    import json
+    from conftest import ROOT
+    tab = json.loads((ROOT / "roofline" / "flashsr_layers.json").read_text())
+    spec = M.default_spec()
+    be = P.build_plan(spec, M.init_weights(spec, 0), P.WeightBlob(), 1, 1, True)
+    assert len(tab["layers"]) == len(be.layer_table) == tab["totals"]["gemm_ops"]
+    for row, l in zip(tab["layers"], be.layer_table):
+        assert (row["name"], row["kind"], row["M"], row["N"], row["K"], row["taps"]) == \
+               (l["name"], l["kind"], l["M"], l["N"], l["K"], l["taps"])
+        assert row["flops"] == l["flops"]
+    assert tab["totals"]["tc_flops"] == be.tc_flops
+    assert tab["reconciliation"]["relative_difference"] < 1e-4
