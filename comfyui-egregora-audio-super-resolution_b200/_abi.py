@@ -80,20 +80,10 @@ def lib_path() -> Path:
     return Path(os.environ.get("EGREGORA_B200_LIB", str(_PKG / _LIB_NAME)))
 
 
-def load() -> C.CDLL:
-    """Load the shared library (no device needed) and declare every prototype of the header."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    p = lib_path()
-    if not p.exists():
-        raise RuntimeError(
-            f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(nvcc, sm_100a). There is no CPU fallback."
-        )
-    lib = C.CDLL(str(p))
+def signatures() -> dict:
+    """name -> (restype, argtypes) of every entry point declared in include/egregora_b200.h."""
     vp, i32, i64, f32p = C.c_void_p, C.c_int, C.c_int64, C.c_void_p
-    sigs = {
+    return {
         "egr_abi_version": (C.c_int, []),
         "egr_last_error": (C.c_char_p, []),
         "egr_init": (C.c_int, [i32]),
@@ -127,6 +117,21 @@ def load() -> C.CDLL:
         "egr_pcm16_to_float": (C.c_int, [vp, f32p, i64, C.c_float, vp]),
         "egr_absmax": (C.c_int, [f32p, i64, f32p, vp]),
     }
+
+
+def load() -> C.CDLL:
+    """Load the shared library (no device needed) and declare every prototype of the header."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not p.exists():
+        raise RuntimeError(
+            f"{p} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). There is no CPU fallback."
+        )
+    lib = C.CDLL(str(p))
+    sigs = signatures()
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)  # AttributeError here == the library does not export a declared symbol
         fn.restype = res

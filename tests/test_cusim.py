@@ -1,0 +1,249 @@
+"""The SIMT kernels' REAL source run on the CPU under tests/cusim (a fiber-per-thread emulation of blocks, shared memory,
+__syncthreads, warp shuffles and atomics — test infrastructure, see tests/cusim/cuda_runtime.h), against the same goldens
+and oracles as the `-m gpu` tests.  Covers: egr_chunk_gather / egr_wola_stitch / egr_resample_poly (bit-exact),
+egr_pcm16_* / egr_absmax, egr_dfn_mix, egr_eval_null_test, egr_eval_lsd, egr_fft_exec and egr_fatllama_run.
+
+What this is for: (1) kernels written without GPU time (egr_eval_lsd) execute their actual code — indexing, barriers,
+radix select — before their first hardware run; (2) the emulator reproducing what the B200 already verified for the other
+kernels is the check on the emulator itself.  What it is not: the product never loads this library (there is no CPU
+fallback, tests/test_abi.py::test_no_gpu_fails_loudly), nothing here says anything about speed, and the tcgen05 / TMA /
+cluster kernels (tap-GEMM, GroupNorm, low-pass, snake, attention) are outside its reach — those stay GPU-only.
+"""
+import ctypes as C
+import hashlib
+import json
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, load_pkg
+from lsd_cases import signals as lsd_signals
+
+sys.path.insert(0, str(ROOT / "tests" / "cusim"))
+
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ is needed to build the emulator")
+
+
+def _dev(nbytes_or_array):
+    """256-byte aligned host buffer standing in for device memory; accepts a byte count or an array to copy."""
+    if isinstance(nbytes_or_array, (int, np.integer)):
+        raw = np.zeros(int(nbytes_or_array) + 256, np.uint8)
+        off = (-raw.ctypes.data) % 256
+        return raw[off:off + int(nbytes_or_array)]
+    a = np.ascontiguousarray(nbytes_or_array)
+    buf = _dev(max(a.nbytes, 1))
+    out = buf[:a.nbytes].view(a.dtype).reshape(a.shape)
+    out[...] = a
+    return out
+
+
+@pytest.fixture(scope="session")
+def sim():
+    import build as cusim_build
+    load_pkg()
+    from egregora_b200 import _abi
+    lib = C.CDLL(str(cusim_build.build()))
+    for name, (res, args) in _abi.signatures().items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+    assert lib.egr_init(0) == 0, lib.egr_last_error()
+
+    def ck(rc):
+        assert rc == 0, lib.egr_last_error().decode()
+    lib.ck = ck
+    lib.K = _abi.K
+    return lib
+
+
+# ------------------------------------------------------------------------------------------------ driver kernels
+def _wola(sim, preds, spans, total, win, window):
+    n, Cc, lp = preds.shape
+    p, w = _dev(preds), _dev(window)
+    st, ln = _dev(np.array([s for s, _ in spans], np.int64)), _dev(np.array([l for _, l in spans], np.int32))
+    out = _dev(np.zeros((Cc, total), np.float32))
+    sim.ck(sim.egr_wola_stitch(p.ctypes.data, lp, st.ctypes.data, ln.ctypes.data, n, Cc, total, win, w.ctypes.data, out.ctypes.data, None))
+    return out
+
+
+@pytest.mark.parametrize("case", list("abcdef"))
+def test_wola_reference_golden_cases_bit_exact(case, golden, sim):
+    total, w, hp, Cc, lpred = (int(v) for v in golden[f"wola_{case}_meta"])
+    spans = [(int(s), int(L)) for s, L in golden[f"wola_{case}_spans"]]
+    out = _wola(sim, golden[f"wola_{case}_preds"], spans, total, w, np.hanning(w).astype(np.float32))
+    assert np.array_equal(out, golden[f"wola_{case}_out"])
+
+
+@pytest.mark.parametrize("total,Cc", [(300000, 2), (245761, 1), (100, 1)])
+def test_gather_and_wola_real_window_bit_exact(total, Cc, sim):
+    from oracle import driver_oracle as O
+    x = (np.random.default_rng(total).standard_normal((Cc, total)) * 0.1).astype(np.float32)
+    win, hop = O.win_hop()
+    spans = O.iter_chunks(total, win, hop)
+    xd = _dev(x)
+    st, ln = _dev(np.array([s for s, _ in spans], np.int64)), _dev(np.array([l for _, l in spans], np.int32))
+    chunks = _dev(np.zeros((len(spans), Cc, win), np.float32))
+    sim.ck(sim.egr_chunk_gather(xd.ctypes.data, Cc, total, st.ctypes.data, ln.ctypes.data, len(spans), win, chunks.ctypes.data, None))
+    assert np.array_equal(chunks, O.gather_chunks(x, spans, win))
+    y = (chunks * np.float32(0.5)).astype(np.float32)
+    got = _wola(sim, y, spans, total, win, np.hanning(win).astype(np.float32))
+    want = O.wola_stitch([(y[k], s, L) for k, (s, L) in enumerate(spans)], total, win)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("src,dst,n", [(16000, 48000, 5000), (44100, 48000, 4410), (48000, 44100, 9999), (48000, 96000, 3001)])
+def test_resample_poly_bit_exact_vs_scipy(src, dst, n, sim, pkg):
+    from scipy.signal import resample_poly
+    from egregora_b200 import egregora_audio_super_resolution as N
+    x = (np.random.default_rng(n).standard_normal((2, n)) * 0.3).astype(np.float32)
+    up, down, hflip, n_pre_remove, n_out = N._resample_design(dst, src, n)
+    xd, bank, y = _dev(x), _dev(hflip), _dev(np.zeros((2, n_out), np.float32))
+    sim.ck(sim.egr_resample_poly(xd.ctypes.data, 2, n, up, down, bank.ctypes.data, hflip.shape[1], n_pre_remove, n_out, y.ctypes.data, None))
+    want = np.stack([resample_poly(x[c], up, down).astype(np.float32) for c in range(2)])
+    assert np.array_equal(y, want)
+
+
+def test_pcm16_and_absmax(sim):
+    from oracle import fat_llama_oracle as FO
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-1.2, 1.2, 20001), [1.0, -1.0, 0.5 / 32768, 1.5 / 32768, 2.5 / 32768, 0.99999]]).astype(np.float32)
+    xd, q, f, m = _dev(x), _dev(np.zeros(x.shape, np.int16)), _dev(np.zeros(x.shape, np.float32)), _dev(np.zeros(1, np.float32))
+    sim.ck(sim.egr_pcm16_quantize(xd.ctypes.data, q.ctypes.data, x.size, None))
+    assert np.array_equal(q, FO.pcm16_write(x))
+    sim.ck(sim.egr_pcm16_to_float(q.ctypes.data, f.ctypes.data, x.size, 1.0 / 32768.0, None))
+    assert np.array_equal(f, FO.pcm16_read(FO.pcm16_write(x)))
+    sim.ck(sim.egr_absmax(xd.ctypes.data, x.size, m.ctypes.data, None))
+    assert float(m[0]) == float(np.max(np.abs(x)))
+
+
+# ------------------------------------------------------------------------------------------------ dfn mix
+def test_dfn_mix_reference_golden(sim):
+    from test_dfn_mix import DEFAULTS, _check, _signals
+    G, cases = np.load(GOLDEN / "dfn_mix_golden.npz"), json.loads((GOLDEN / "dfn_mix_cases.json").read_text())
+    K = sim.K
+    modes = {"off": "EGR_MIX_OFF", "more_on_noise": "EGR_MIX_MORE_ON_NOISE", "more_on_speech": "EGR_MIX_MORE_ON_SPEECH",
+             "gate_on_noise": "EGR_MIX_GATE_ON_NOISE"}
+    for name, c in cases.items():
+        if c["T"] > 48000 * 30:
+            continue  # the emulator is ~1000x slower than the device: clip-scale cases stay GPU-only
+        dry, wet = _signals(name, c["C"], c["T"])
+        p = dict(DEFAULTS)
+        p.update(c["kwargs"])
+        d, w, out = _dev(dry), _dev(wet), _dev(np.zeros_like(dry))
+        wb = sim.egr_dfn_mix_workspace_bytes(c["C"], c["T"])
+        wk = _dev(wb)
+        vad = K["EGR_VAD_RMS"] if p.get("adaptive_vad_source", "rms") == "rms" else K["EGR_VAD_NONE"]
+        sim.ck(sim.egr_dfn_mix(d.ctypes.data, w.ctypes.data, out.ctypes.data, c["C"], c["T"], 48000, float(p["strength"]),
+                               K["EGR_CURVE_EQUAL_POWER"] if p["mix_curve"] == "equal_power" else K["EGR_CURVE_LINEAR"], vad,
+                               K[modes.get(p["adaptive_mode"], "EGR_MIX_OFF")], float(p["adaptive_amount"]), float(p["vad_threshold"]),
+                               int(p["vad_smooth_ms"]), float(p["post_gain_db"]), 1 if p["limit_ceiling"] else 0, float(p["ceiling"]),
+                               wk.ctypes.data, wb, None))
+        _check(G, name, out, exact=p["mix_curve"] != "equal_power")
+
+
+# ------------------------------------------------------------------------------------------------ eval metrics
+def test_eval_null_test_reference_golden(sim):
+    from test_eval_metrics import _check_null, _close, _signals
+    egold = json.loads((GOLDEN / "eval_golden.json").read_text())
+    K = sim.K
+    for name, c in egold.items():
+        if max(c["Na"], c["Nb"]) > 100000:
+            continue
+        A, B = _signals(name, c)
+        n = min(A.shape[1], B.shape[1])
+        a, b, null, met = _dev(A), _dev(B), _dev(np.zeros((c["C"], n), np.float32)), _dev(np.zeros(K["EGR_EVAL_NUM"], np.float64))
+        wb = sim.egr_eval_workspace_bytes()
+        wk = _dev(wb)
+        sim.ck(sim.egr_eval_null_test(a.ctypes.data, A.shape[1], b.ctypes.data, B.shape[1], c["C"], n, int(c["invert_b"]),
+                                      int(c["least_squares_scale"]), null.ctypes.data, met.ctypes.data, wk.ctypes.data, wb, None))
+        _check_null(c, null)
+        ref = c["metrics"]
+        assert int(met[K["EGR_EVAL_OVERSHOOT"]]) == ref["overshoot_count"]
+        assert _close(met[K["EGR_EVAL_SCALE_K"]], ref["scale_k"], 1e-9)
+        assert _close(met[K["EGR_EVAL_NULL_RMS_DBFS"]], ref["null_rms_dbfs"], 1e-9)
+        assert _close(met[K["EGR_EVAL_CORR"]], ref["corr_coef"], 0.0, 3e-6)
+        assert _close(met[K["EGR_EVAL_SI_SDR_DB"]], c["si_sdr_db"], 1e-9, 1e-9)
+
+
+def test_eval_lsd_reference_golden(sim):
+    """egr_eval_lsd's actual kernels (tables, per-frame STFT distance, radix-select percentile) against the reference
+    node's numbers: 1e-4 dB wherever every bin holds signal (see test_eval_metrics.py for the noise-floor case)."""
+    lgold = json.loads((GOLDEN / "eval_lsd_golden.json").read_text())
+    K = sim.K
+    for name, c in lgold.items():
+        A, B = lsd_signals(name, c)
+        n = min(A.shape[1], B.shape[1])
+        a, b, met = _dev(A), _dev(B), _dev(np.zeros(K["EGR_LSD_NUM"], np.float64))
+        wb = sim.egr_eval_lsd_workspace_bytes(n, c["n_fft"], c["hop"])
+        wk = _dev(wb)
+        sim.ck(sim.egr_eval_lsd(a.ctypes.data, A.shape[1], b.ctypes.data, B.shape[1], c["C"], n, c["n_fft"], c["hop"],
+                                met.ctypes.data, wk.ctypes.data, wb, None))
+        assert int(met[K["EGR_LSD_FRAMES"]]) == c["frames"]
+        if c["band"] >= 1.0:
+            assert abs(met[K["EGR_LSD_MEAN_DB"]] - c["lsd_mean_db"]) <= 1e-4, (name, met)
+            assert abs(met[K["EGR_LSD_P95_DB"]] - c["lsd_p95_db"]) <= 1e-4, (name, met)
+        else:
+            assert abs(met[K["EGR_LSD_MEAN_DB"]] - c["lsd_mean_db"]) <= 8.0
+    # identical clips: exactly sqrt(1e-12) per frame; unsupported n_fft is an error, not a fallback
+    x = _dev((np.random.default_rng(3).standard_normal((2, 20000)) * 0.1).astype(np.float32))
+    met = _dev(np.zeros(4, np.float64))
+    wb = sim.egr_eval_lsd_workspace_bytes(20000, 2048, 512)
+    wk = _dev(wb)
+    sim.ck(sim.egr_eval_lsd(x.ctypes.data, 20000, x.ctypes.data, 20000, 2, 20000, 2048, 512, met.ctypes.data, wk.ctypes.data, wb, None))
+    assert met[0] == float(np.sqrt(np.float32(1e-12))) and met[1] == met[0]
+    assert sim.egr_eval_lsd(x.ctypes.data, 20000, x.ctypes.data, 20000, 2, 20000, 640, 160, met.ctypes.data, wk.ctypes.data, wb, None) != 0
+
+
+# ------------------------------------------------------------------------------------------------ path B
+def _fft(sim, x, inverse=False, scale=True):
+    batch, n = x.shape
+    plan = C.c_void_p()
+    sim.ck(sim.egr_fft_plan_create(n, batch, C.byref(plan)))
+    try:
+        d = _dev(np.ascontiguousarray(x).view(np.float32).reshape(batch, 2 * n))
+        wb = sim.egr_fft_plan_workspace_bytes(plan)
+        w = _dev(max(wb, 16))
+        sim.ck(sim.egr_fft_exec(plan, d.ctypes.data, w.ctypes.data, int(inverse), int(scale), None))
+        return d.view(np.complex64).reshape(batch, n).copy()
+    finally:
+        sim.egr_fft_plan_destroy(plan)
+
+
+def _rel(a, b):
+    return float(np.sqrt(np.mean(np.abs(a - b) ** 2)) / (np.sqrt(np.mean(np.abs(b) ** 2)) + 1e-30))
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 7, 11, 13, 16, 60, 210, 1000, 2100, 4096, 8190, 30030])
+def test_fft_smooth_lengths(n, sim):
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))).astype(np.complex64)
+    assert _rel(_fft(sim, x), np.fft.fft(x.astype(np.complex128), axis=1)) < 3e-6
+    assert _rel(_fft(sim, x, inverse=True), np.fft.ifft(x.astype(np.complex128), axis=1)) < 1e-5
+
+
+@pytest.mark.parametrize("n", [17, 10007])
+def test_fft_bluestein_lengths(n, sim):
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((1, n)) + 1j * rng.standard_normal((1, n))).astype(np.complex64)
+    assert _rel(_fft(sim, x), np.fft.fft(x.astype(np.complex128), axis=1)) < 1e-5
+
+
+@pytest.mark.parametrize("Cc,S,U,iters,thr", [(1, 16000, 1, 5, 0.5), (2, 9000, 2, 3, 0.6), (1, 4410, 1, 4, 300.0), (1, 10007, 1, 3, 0.5), (2, 4801, 1, 2, 0.6)])
+def test_fatllama_loop_matches_oracle(Cc, S, U, iters, thr, sim):
+    """egr_fatllama_run (fast two-kernel path for plannable even lengths, general / Bluestein path otherwise) against
+    the float64 oracle, pre-quantisation, 1e-5 of full scale (north_star tolerance)."""
+    from oracle import fat_llama_oracle as O
+    from test_fatllama_gpu import _audio
+    x = _audio(Cc, S, seed=S)
+    samples = O.pcm16_write(x.T).astype(np.float32)            # [S,C] integer-scaled
+    want = O.upscale(samples, U, iters, thr, True, True, dtype=np.float64).T
+    d_in, d_out = _dev(np.ascontiguousarray(samples.T)), _dev(np.zeros((Cc, S * U), np.float32))
+    wb = sim.egr_fatllama_workspace_bytes(Cc, S, U)
+    wk = _dev(wb)
+    flags = sim.K["EGR_FL_NORMALIZE"] | sim.K["EGR_FL_AUTOSCALE"]
+    sim.ck(sim.egr_fatllama_run(d_in.ctypes.data, d_out.ctypes.data, Cc, S, U, iters, thr, flags, wk.ctypes.data, wb, None))
+    assert d_out.shape == want.shape
+    assert float(np.max(np.abs(d_out - want))) <= 1e-5
