@@ -19,6 +19,21 @@
 //   eval_lsd_final   one CTA: mean of per[] (fixed-order float64 sum) and np.percentile(per, 95) by exact radix
 //                    select + numpy's float32 lerp (select.cuh)
 //   Frames overlap 4x (hop = n_fft/4 by default) but stay in L2: HBM reads 8*C*N bytes, writes 4*frames.
+//
+// Integrated loudness (egr_eval_lufs; integrated_lufs + _k_weight, egregora_null_test_suite.py:125-164 =
+// egregora_audio_eval_pack.py:132-167), four launches:
+//   lufs_hp_kernel     the reference's one-pole high-pass, z = fl(fl(c1*x) + fl(k*z)), y = fl(x - z), is a float32
+//                      recurrence evaluated sample by sample in Python.  Bit-exact AND parallel: every chunk of 2048
+//                      samples starts from a GUESSED state (the recurrence run over the 2048 samples before it, from
+//                      zero — a contraction with k = 0.984 forgets its start long before that) and records guess and
+//                      end state
+//   lufs_fix_kernel    one thread per channel walks the chunk boundaries: where a guess is not bit-identical to the
+//                      true end state of the previous chunk, that chunk is recomputed serially from the true state
+//                      (rare; the count is reported)
+//   lufs_block_kernel  one CTA per 400 ms block (100 ms hop): HF tilt y[n] += fl(0.02*(y[n] - y[n-1])) and the channel
+//                      mean in float32 as numpy does them, mean square in float64
+//   lufs_final_kernel  ungated mean, -10 LU relative gate, gated mean (fixed-order float64 sums)
+//   HBM: read 4*C*N + write 4*C*N (filtered signal) + read 4*C*N x 4 (block overlap, L2).
 #include <cmath>
 #include "common.cuh"
 #include "select.cuh"
@@ -315,5 +330,166 @@ extern "C" int egr_eval_lsd(const float* d_ref, int64_t ld_ref, const float* d_p
   EGR_CHECK_LAUNCH("eval_lsd_frames_kernel");
   eval_lsd_final_kernel<<<1, 1024, 0, st>>>(per, (int)frames, d_metrics);
   EGR_CHECK_LAUNCH("eval_lsd_final_kernel");
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ LUFS
+#define LUFS_CHUNK 2048
+#define LUFS_THREADS 256
+
+struct LufsCoef { float c1, k; };  // float32 images of the reference's python floats (1 - k) and k
+
+__device__ __forceinline__ float lufs_step(const LufsCoef q, float x, float& z) {
+  z = __fadd_rn(__fmul_rn(q.c1, x), __fmul_rn(q.k, z));
+  return __fsub_rn(x, z);
+}
+
+// grid (ceil(nchunks / 128), C); thread = one chunk of one channel
+__global__ void __launch_bounds__(128) lufs_hp_kernel(const float* __restrict__ x, long long ld, long long N, int nchunks,
+                                                      LufsCoef q, float* __restrict__ y, float* __restrict__ guess,
+                                                      float* __restrict__ endst) {
+  const int ci = blockIdx.x * blockDim.x + threadIdx.x, ch = blockIdx.y;
+  if (ci >= nchunks) return;
+  const float* xc = x + (long long)ch * ld;
+  float* yc = y + (long long)ch * N;
+  const long long s0 = (long long)ci * LUFS_CHUNK;
+  float z = 0.f;
+  for (long long n = s0 > LUFS_CHUNK ? s0 - LUFS_CHUNK : 0; n < s0; ++n) lufs_step(q, __ldg(xc + n), z);  // warm-up (exact for chunks 0 and 1)
+  guess[(long long)ch * nchunks + ci] = z;
+  const long long s1 = s0 + LUFS_CHUNK < N ? s0 + LUFS_CHUNK : N;
+  for (long long n = s0; n < s1; ++n) yc[n] = lufs_step(q, __ldg(xc + n), z);
+  endst[(long long)ch * nchunks + ci] = z;
+}
+
+// grid C, one warp; lane 0 verifies the guesses in order and repairs the chunks whose guess was not exact
+__global__ void lufs_fix_kernel(const float* __restrict__ x, long long ld, long long N, int nchunks, LufsCoef q,
+                                float* __restrict__ y, const float* __restrict__ guess, float* __restrict__ endst,
+                                unsigned int* __restrict__ repaired) {
+  if (threadIdx.x != 0) return;
+  const int ch = blockIdx.x;
+  const float* xc = x + (long long)ch * ld;
+  float* yc = y + (long long)ch * N;
+  unsigned int cnt = 0;
+  for (int ci = 1; ci < nchunks; ++ci) {
+    float z = endst[(long long)ch * nchunks + ci - 1];
+    if (__float_as_uint(z) == __float_as_uint(guess[(long long)ch * nchunks + ci])) continue;
+    const long long s0 = (long long)ci * LUFS_CHUNK, s1 = s0 + LUFS_CHUNK < N ? s0 + LUFS_CHUNK : N;
+    for (long long n = s0; n < s1; ++n) yc[n] = lufs_step(q, xc[n], z);
+    endst[(long long)ch * nchunks + ci] = z;
+    ++cnt;
+  }
+  if (cnt) atomicAdd(repaired, cnt);
+}
+
+// grid frames; ms[i] = mean over the block of (channel mean of the tilted signal)^2
+__global__ void __launch_bounds__(LUFS_THREADS) lufs_block_kernel(const float* __restrict__ y, int C, long long N, int blk, int hop,
+                                                                   double* __restrict__ ms) {
+  __shared__ double red[LUFS_THREADS / 32];
+  const long long s = (long long)blockIdx.x * hop;
+  const long long e = s + blk < N ? s + blk : N;
+  double acc = 0.0;
+  for (long long n = s + threadIdx.x; n < e; n += LUFS_THREADS) {
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float* yc = y + (long long)c * N;
+      float v = yc[n];
+      if (n > 0) v = __fadd_rn(v, __fmul_rn(0.02f, __fsub_rn(v, yc[n - 1])));   // y[:,1:] += 0.02*(y[:,1:] - y[:,:-1])
+      sum = c ? __fadd_rn(sum, v) : v;
+    }
+    const double m = (double)__fdiv_rn(sum, (float)C);
+    acc = fma(m, m, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < LUFS_THREADS / 32; ++w) t += red[w];
+    ms[blockIdx.x] = t / (double)(e - s);
+  }
+}
+
+__device__ double lufs_block_sum(double v, double* red /*[32] smem*/) {  // fixed-order sum over the 1024 threads, to all
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int w = 0; w < 32; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(1024) lufs_final_kernel(const double* __restrict__ ms, int frames, const unsigned int* __restrict__ repaired,
+                                                           double* __restrict__ metrics) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < frames; i += 1024) s += ms[i] + 1e-20;
+  const double ungated = -0.691 + 10.0 * log10(lufs_block_sum(s, red) / (double)frames);
+  const double gate = ungated - 10.0;
+  double gs = 0.0, gn = 0.0;
+  for (int i = threadIdx.x; i < frames; i += 1024) {
+    const double m = ms[i] + 1e-20;
+    if (-0.691 + 10.0 * log10(m) >= gate) { gs += m; gn += 1.0; }
+  }
+  gs = lufs_block_sum(gs, red);
+  gn = lufs_block_sum(gn, red);
+  if (threadIdx.x == 0) {
+    metrics[EGR_LUFS_INTEGRATED] = gn > 0.0 ? -0.691 + 10.0 * log10(gs / gn) : ungated;
+    metrics[EGR_LUFS_UNGATED] = ungated;
+    metrics[EGR_LUFS_BLOCKS] = (double)frames;
+    metrics[EGR_LUFS_REPAIRED] = (double)*repaired;
+  }
+}
+
+static void lufs_geometry(int64_t N, int sr, int* blk, int* hop, long long* frames, int* nchunks) {
+  const long r400 = (long)nearbyint(0.400 * (double)sr), r100 = (long)nearbyint(0.100 * (double)sr);  // python round(): half to even
+  *blk = (int)(r400 < 1 ? 1 : r400);
+  *hop = (int)(r100 < 1 ? 1 : r100);
+  *frames = 1 + (N > *blk ? (N - *blk) / *hop : 0);
+  *nchunks = (int)((N + LUFS_CHUNK - 1) / LUFS_CHUNK);
+}
+
+extern "C" size_t egr_eval_lufs_workspace_bytes(int C, int64_t N, int sample_rate) {
+  if (C < 1 || N < 1 || sample_rate < 1) return 0;
+  int blk, hop, nchunks; long long frames;
+  lufs_geometry(N, sample_rate, &blk, &hop, &frames, &nchunks);
+  const size_t y = ((sizeof(float) * (size_t)C * (size_t)N) + 255) / 256 * 256;
+  const size_t st = ((2 * sizeof(float) * (size_t)C * (size_t)nchunks) + 255) / 256 * 256;
+  const size_t ms = ((sizeof(double) * (size_t)frames) + 255) / 256 * 256;
+  return 256 + y + st + ms;
+}
+
+extern "C" int egr_eval_lufs(const float* d_x, int64_t ld, int C, int64_t N, int sample_rate, double* d_metrics, void* d_work,
+                             size_t work_bytes, void* stream) {
+  if (!devinfo().inited) return fail(EGR_ERR_STATE, "egr_eval_lufs: call egr_init first");
+  if (!d_x || !d_metrics || !d_work || C < 1 || C > 64 || N < 1 || ld < N || sample_rate < 1)
+    return fail(EGR_ERR_ARG, "egr_eval_lufs: bad arguments");
+  if (reinterpret_cast<uintptr_t>(d_work) % 256) return fail(EGR_ERR_ARG, "egr_eval_lufs: workspace must be 256-byte aligned");
+  if (work_bytes < egr_eval_lufs_workspace_bytes(C, N, sample_rate)) return fail(EGR_ERR_ARG, "egr_eval_lufs: workspace too small");
+  int blk, hop, nchunks; long long frames;
+  lufs_geometry(N, sample_rate, &blk, &hop, &frames, &nchunks);
+  if (frames > 0x7fffffffLL) return fail(EGR_ERR_UNSUPPORTED, "egr_eval_lufs: too many blocks");
+  // k = exp(-2*pi*fc), fc = 60 / (sr/2): python floats in the reference, used as float32 (weak scalars) in its loop
+  const double fc = 60.0 / ((double)sample_rate * 0.5);
+  const double k = exp(-2.0 * 3.141592653589793 * fc);
+  LufsCoef q;
+  q.c1 = (float)(1.0 - k);
+  q.k = (float)k;
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = reinterpret_cast<char*>(d_work);
+  unsigned int* repaired = reinterpret_cast<unsigned int*>(w);
+  float* y = reinterpret_cast<float*>(w + 256);
+  float* guess = reinterpret_cast<float*>(w + 256 + ((sizeof(float) * (size_t)C * (size_t)N) + 255) / 256 * 256);
+  float* endst = guess + (size_t)C * nchunks;
+  double* ms = reinterpret_cast<double*>(reinterpret_cast<char*>(guess) + ((2 * sizeof(float) * (size_t)C * (size_t)nchunks) + 255) / 256 * 256);
+  EGR_CUDA(cudaMemsetAsync(repaired, 0, 256, st));
+  lufs_hp_kernel<<<dim3((unsigned)((nchunks + 127) / 128), C), 128, 0, st>>>(d_x, ld, N, nchunks, q, y, guess, endst);
+  EGR_CHECK_LAUNCH("lufs_hp_kernel");
+  lufs_fix_kernel<<<C, 32, 0, st>>>(d_x, ld, N, nchunks, q, y, guess, endst, repaired);
+  EGR_CHECK_LAUNCH("lufs_fix_kernel");
+  lufs_block_kernel<<<(unsigned)frames, LUFS_THREADS, 0, st>>>(y, C, N, blk, hop, ms);
+  EGR_CHECK_LAUNCH("lufs_block_kernel");
+  lufs_final_kernel<<<1, 1024, 0, st>>>(ms, (int)frames, repaired, d_metrics);
+  EGR_CHECK_LAUNCH("lufs_final_kernel");
   return EGR_OK;
 }

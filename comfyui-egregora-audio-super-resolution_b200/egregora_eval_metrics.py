@@ -4,8 +4,8 @@ Mirrors the arithmetic of the reference's `Audio_Null_Test.execute` (/root/refer
 :421-467 — trim to the shorter clip, optional least-squares scale, inversion, null = A + B, corr_coef, null_rms_dbfs,
 overshoot_count, clipped_pct, scale_k), of `_si_sdr` (egregora_audio_eval_pack.py:414-429) and of `_stft_mag` +
 `_lsd` (egregora_audio_eval_pack.py:389-411; the same two functions again at egregora_null_test_suite.py:167-189).
-Not here: the LUFS and HF-band options of those nodes (K-weighting IIR path).  One C-ABI call per
-metric group; no CPU fallback.
+and of `integrated_lufs` + `_k_weight` (egregora_null_test_suite.py:125-164).  Not here: the HF-band option
+(`_band_energy_hi_db`, a whole-clip FFT energy ratio).  One C-ABI call per metric group; no CPU fallback.
 """
 from __future__ import annotations
 
@@ -83,3 +83,24 @@ def lsd(ref: torch.Tensor, proc: torch.Tensor, n_fft: int = 2048, hop: int = 512
                                 met.data_ptr(), work.data_ptr(), wb, torch.cuda.current_stream().cuda_stream), "egr_eval_lsd")
     m = met.cpu().tolist()
     return float(m[_abi.K["EGR_LSD_MEAN_DB"]]), float(m[_abi.K["EGR_LSD_P95_DB"]])
+
+
+def integrated_lufs(x: torch.Tensor, sample_rate: int) -> float:
+    """The reference's `integrated_lufs` (egregora_null_test_suite.py:143-164 = egregora_audio_eval_pack.py:153-167) of
+    x [C,N] or [N] float32, host or device: its one-pole high-pass + first-difference tilt (`_k_weight`, float32, bit
+    exact), channel mean, 400 ms / 100 ms blocks, -10 LU relative gate."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("CUDA GPU not detected. The B200-native metrics have no CPU fallback (sm_100a kernels only).")
+    a = x if x.dim() == 2 else x[None, :]
+    if a.dim() != 2 or a.shape[1] == 0:
+        raise RuntimeError(f"audio must be a non-empty [C, N] or [N] tensor; got {tuple(x.shape)}")
+    device = torch.device("cuda", torch.cuda.current_device())
+    lib = _abi.init(device.index or 0)
+    a = a.detach().to(device=device, dtype=torch.float32).contiguous()
+    C, n = a.shape
+    met = torch.zeros(_abi.K["EGR_LUFS_NUM"], dtype=torch.float64, device=device)
+    wb = int(lib.egr_eval_lufs_workspace_bytes(C, n, int(sample_rate)))
+    work = torch.empty(wb, dtype=torch.uint8, device=device)
+    _abi.check(lib.egr_eval_lufs(a.data_ptr(), n, C, n, int(sample_rate), met.data_ptr(), work.data_ptr(), wb,
+                                 torch.cuda.current_stream().cuda_stream), "egr_eval_lufs")
+    return float(met.cpu()[_abi.K["EGR_LUFS_INTEGRATED"]])

@@ -276,8 +276,8 @@ int egr_dfn_mix(const float* d_dry, const float* d_wet, float* d_out, int C, int
 #define EGR_EVAL_CLIPPED_PCT    4  /* :465                                                                     */
 #define EGR_EVAL_SCALE_K        5  /* least-squares scale k, :431-436                                          */
 #define EGR_EVAL_NUM            8
-/* Replaces the arithmetic of Audio_Null_Test.execute (egregora_null_test_suite.py:421-467, without its LUFS / HF-band options; the LSD
- * option is egr_eval_lsd below) and _si_sdr: d_ref / d_proc [C,N] f32 with row strides ld_* (so the "trim both to the shorter"
+/* Replaces the arithmetic of Audio_Null_Test.execute (egregora_null_test_suite.py:421-467, without its HF-band option; the LSD and
+ * LUFS options are egr_eval_lsd / egr_eval_lufs below) and _si_sdr: d_ref / d_proc [C,N] f32 with row strides ld_* (so the "trim both to the shorter"
  * step needs no copy), d_null [C,N] f32 or NULL, d_metrics [EGR_EVAL_NUM] f64 ON THE DEVICE (read it after a stream
  * sync).  The null signal is bit-identical to numpy's; the reductions are deterministic float64 sums. */
 size_t egr_eval_workspace_bytes(void);
@@ -301,6 +301,21 @@ int egr_eval_null_test(const float* d_ref, int64_t ld_ref, const float* d_proc, 
 size_t egr_eval_lsd_workspace_bytes(int64_t N, int n_fft, int hop);
 int egr_eval_lsd(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_t ld_proc, int C, int64_t N, int n_fft,
                  int hop, double* d_metrics, void* d_work, size_t work_bytes, void* stream);
+
+#define EGR_LUFS_INTEGRATED 0  /* integrated_lufs(), egregora_null_test_suite.py:143-164                          */
+#define EGR_LUFS_UNGATED    1  /* lufs_ungated of the same function (:158)                                         */
+#define EGR_LUFS_BLOCKS     2  /* number of 400 ms blocks (:148-150)                                                */
+#define EGR_LUFS_REPAIRED   3  /* chunks whose speculated filter state had to be recomputed (diagnostic)            */
+#define EGR_LUFS_NUM        4
+/* Replaces integrated_lufs + _k_weight (egregora_null_test_suite.py:125-164, identical in egregora_audio_eval_pack.py
+ * :132-167; callers: Audio_Null_Test.execute :455 "null_lufs", the loudness meter :327 and loudness match :373-374):
+ * d_x [C,N] f32 with row stride ld.  The reference's per-sample float32 high-pass recurrence is reproduced BIT-EXACTLY
+ * (speculated per 2048-sample chunk, verified and repaired where needed), as are its float32 tilt and channel mean; the
+ * block mean squares and the gate are float64 (summation order differs from numpy's pairwise sum: ~1e-15 relative).
+ * d_metrics [EGR_LUFS_NUM] f64 ON THE DEVICE. */
+size_t egr_eval_lufs_workspace_bytes(int C, int64_t N, int sample_rate);
+int egr_eval_lufs(const float* d_x, int64_t ld, int C, int64_t N, int sample_rate, double* d_metrics, void* d_work,
+                  size_t work_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,6 +21,7 @@ import pytest
 
 from conftest import GOLDEN, ROOT, load_pkg
 from lsd_cases import signals as lsd_signals
+from lufs_cases import signal as lufs_signal
 
 sys.path.insert(0, str(ROOT / "tests" / "cusim"))
 
@@ -195,6 +196,45 @@ def test_eval_lsd_reference_golden(sim):
     sim.ck(sim.egr_eval_lsd(x.ctypes.data, 20000, x.ctypes.data, 20000, 2, 20000, 2048, 512, met.ctypes.data, wk.ctypes.data, wb, None))
     assert met[0] == float(np.sqrt(np.float32(1e-12))) and met[1] == met[0]
     assert sim.egr_eval_lsd(x.ctypes.data, 20000, x.ctypes.data, 20000, 2, 20000, 640, 160, met.ctypes.data, wk.ctypes.data, wb, None) != 0
+
+
+def _lufs(sim, x, sr):
+    K = sim.K
+    Cc, n = x.shape
+    xd, met = _dev(x), _dev(np.zeros(K["EGR_LUFS_NUM"], np.float64))
+    wb = sim.egr_eval_lufs_workspace_bytes(Cc, n, sr)
+    wk = _dev(wb)
+    sim.ck(sim.egr_eval_lufs(xd.ctypes.data, n, Cc, n, sr, met.ctypes.data, wk.ctypes.data, wb, None))
+    # the filtered signal sits at offset 256 of the workspace (layout of egr_eval_lufs): checked bit for bit below
+    y = wk[256:256 + 4 * Cc * n].view(np.float32).reshape(Cc, n).copy()
+    return met.copy(), y
+
+
+def test_eval_lufs_reference_golden(sim):
+    """egr_eval_lufs: the speculated-and-verified float32 high-pass is bit-identical to the reference's per-sample
+    Python loop (sha256 of the filtered signal before the tilt), the loudness agrees to 1e-9 dB."""
+    from oracle import eval_oracle as O
+    lg = json.loads((GOLDEN / "eval_lufs_golden.json").read_text())
+    K = sim.K
+    for name, c in lg.items():
+        x = lufs_signal(name, c)
+        met, y = _lufs(sim, x, c["sr"])
+        y[:, 1:] += np.float32(0.02) * (y[:, 1:] - y[:, :-1])   # the tilt the block kernel applies on the fly
+        assert hashlib.sha256(np.ascontiguousarray(y).tobytes()).hexdigest() == c["kweight_sha256"], name
+        assert abs(met[K["EGR_LUFS_INTEGRATED"]] - c["lufs"]) <= 1e-9, (name, met)
+        blk, hop = round(0.4 * c["sr"]), round(0.1 * c["sr"])
+        assert int(met[K["EGR_LUFS_BLOCKS"]]) == 1 + max(0, (c["N"] - blk) // hop)
+    # a case built to defeat the speculation: a 1e30 burst leaves a filter state that is still ~8 two chunks later
+    # (k^4096 ~ 1e-28), far above the 1e-3 signal the guess for that chunk is computed from -> the chunk must be
+    # repaired, and the result must stay bit-exact
+    x = np.zeros((1, 3 * 2048 + 100), np.float32)
+    x[0, :5] = 1e30
+    x[0, 2048:] = (np.random.default_rng(1).standard_normal(x.shape[1] - 2048) * 1e-3).astype(np.float32)
+    met, y = _lufs(sim, x, 48000)
+    y[:, 1:] += np.float32(0.02) * (y[:, 1:] - y[:, :-1])
+    assert met[K["EGR_LUFS_REPAIRED"]] >= 1
+    assert np.array_equal(y, O.k_weight(48000, x))
+    assert abs(met[K["EGR_LUFS_INTEGRATED"]] - O.integrated_lufs(x, 48000)) <= 1e-9
 
 
 # ------------------------------------------------------------------------------------------------ path B

@@ -21,6 +21,7 @@ import torch
 
 from conftest import GOLDEN
 from lsd_cases import emulate_kernel_lsd, signals as lsd_signals
+from lufs_cases import signal as lufs_signal
 from oracle import eval_oracle as O
 
 
@@ -125,3 +126,15 @@ def test_lsd_kernel_arithmetic_emulated_matches_reference_golden(lgold):
             assert np.allclose(per[c["probe_idx"]], c["per_probe"], rtol=0, atol=1e-4)
         else:  # noise-floor bins: both implementations are "right"; they only have to be in the same region
             assert abs(mean - c["lsd_mean_db"]) <= 8.0, (name, mean, c["lsd_mean_db"])
+
+
+# ------------------------------------------------------------------------------------------------ LUFS
+def test_lufs_oracle_matches_reference_golden():
+    """oracle.integrated_lufs / k_weight against the reference's functions: the filtered signal bit for bit (sha256),
+    the loudness to 1e-12 (same float64 arithmetic)."""
+    lg = json.loads((GOLDEN / "eval_lufs_golden.json").read_text())
+    for name, c in lg.items():
+        x = lufs_signal(name, c)
+        y = O.k_weight(c["sr"], x)
+        assert hashlib.sha256(np.ascontiguousarray(y).tobytes()).hexdigest() == c["kweight_sha256"], name
+        assert abs(O.integrated_lufs(x, c["sr"]) - c["lufs"]) <= 1e-12, name
