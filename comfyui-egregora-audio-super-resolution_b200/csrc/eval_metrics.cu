@@ -34,6 +34,10 @@
 //                      mean in float32 as numpy does them, mean square in float64
 //   lufs_final_kernel  ungated mean, -10 LU relative gate, gated mean (fixed-order float64 sums)
 //   HBM: read 4*C*N + write 4*C*N (filtered signal) + read 4*C*N x 4 (block overlap, L2).
+//
+// High-band energy ratio (egr_eval_hf_band; _band_energy_hi_db, egregora_null_test_suite.py:190-197): channel mean ->
+// whole-clip FFT through the path-B transform (egr_fft_exec: mixed radix, Bluestein for awkward lengths; no cuFFT) ->
+// |X_k|^2 summed in float64 over all bins and over the bins with rfftfreq(k) >= lo_hz.
 #include <cmath>
 #include "common.cuh"
 #include "select.cuh"
@@ -491,5 +495,69 @@ extern "C" int egr_eval_lufs(const float* d_x, int64_t ld, int C, int64_t N, int
   EGR_CHECK_LAUNCH("lufs_block_kernel");
   lufs_final_kernel<<<1, 1024, 0, st>>>(ms, (int)frames, repaired, d_metrics);
   EGR_CHECK_LAUNCH("lufs_final_kernel");
+  return EGR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ high-band energy
+__global__ void __launch_bounds__(EV_THREADS) hf_pack_kernel(const float* __restrict__ x, long long ld, int C, long long N,
+                                                             float2* __restrict__ z) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < N; t += (long long)gridDim.x * blockDim.x)
+    z[t] = make_float2(ev_mean32(x, ld, C, t), 0.f);
+}
+
+__global__ void __launch_bounds__(EV_THREADS) hf_energy_kernel(const float2* __restrict__ X, long long nbins, double fstep,
+                                                               double lo_hz, double* __restrict__ partials) {
+  double v[3] = {0, 0, 0};  // all bins, bins at or above lo_hz, how many of those
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nbins; k += (long long)gridDim.x * blockDim.x) {
+    const float2 c = X[k];
+    const double p = (double)c.x * (double)c.x + (double)c.y * (double)c.y;
+    v[0] += p;
+    if ((double)k * fstep >= lo_hz) { v[1] += p; v[2] += 1.0; }   // np.fft.rfftfreq: k * (1 / (n * d)), float64
+  }
+  ev_block_reduce<3>(v, partials + (long long)blockIdx.x * 3);
+}
+
+__global__ void hf_final_kernel(const double* __restrict__ partials, int nblk, double* __restrict__ metrics) {
+  if (threadIdx.x != 0) return;
+  double r[3] = {0, 0, 0};
+  for (int b = 0; b < nblk; ++b)
+    for (int i = 0; i < 3; ++i) r[i] += partials[(long long)b * 3 + i];
+  metrics[EGR_HF_RESIDUAL_DB] = 10.0 * log10(r[1] / (r[0] + 1e-20) + 1e-20);
+  metrics[EGR_HF_E_HI] = r[1];
+  metrics[EGR_HF_E_ALL] = r[0];
+  metrics[EGR_HF_BINS_HI] = r[2];
+}
+
+extern "C" size_t egr_eval_hf_band_workspace_bytes(const egr_fft_plan* plan, int64_t N) {
+  if (!plan || N < 1) return 0;
+  const size_t z = (sizeof(float2) * (size_t)N + 255) / 256 * 256;
+  const size_t fw = (egr_fft_plan_workspace_bytes(plan) + 255) / 256 * 256;
+  return z + fw + sizeof(double) * 148 * 8 * 3 + 256;
+}
+
+extern "C" int egr_eval_hf_band(egr_fft_plan* plan, const float* d_x, int64_t ld, int C, int64_t N, int sample_rate, double lo_hz,
+                                double* d_metrics, void* d_work, size_t work_bytes, void* stream) {
+  if (!devinfo().inited) return fail(EGR_ERR_STATE, "egr_eval_hf_band: call egr_init first");
+  if (!plan || !d_x || !d_metrics || !d_work || C < 1 || C > 64 || N < 1 || ld < N || sample_rate < 1)
+    return fail(EGR_ERR_ARG, "egr_eval_hf_band: bad arguments");
+  if (reinterpret_cast<uintptr_t>(d_work) % 256) return fail(EGR_ERR_ARG, "egr_eval_hf_band: workspace must be 256-byte aligned");
+  if (work_bytes < egr_eval_hf_band_workspace_bytes(plan, N)) return fail(EGR_ERR_ARG, "egr_eval_hf_band: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  char* w = reinterpret_cast<char*>(d_work);
+  float2* z = reinterpret_cast<float2*>(w);
+  float* fw = reinterpret_cast<float*>(w + (sizeof(float2) * (size_t)N + 255) / 256 * 256);
+  double* partials = reinterpret_cast<double*>(reinterpret_cast<char*>(fw) + (egr_fft_plan_workspace_bytes(plan) + 255) / 256 * 256);
+  const int nblk = ev_blocks(N);
+  hf_pack_kernel<<<nblk, EV_THREADS, 0, st>>>(d_x, ld, C, N, z);
+  EGR_CHECK_LAUNCH("hf_pack_kernel");
+  int rc = egr_fft_exec(plan, reinterpret_cast<float*>(z), fw, 0, 0, stream);   // plan must be egr_fft_plan_create(N, 1)
+  if (rc) return rc;
+  const long long nbins = N / 2 + 1;
+  const double fstep = 1.0 / ((double)N * (1.0 / (double)sample_rate));
+  const int nb2 = ev_blocks(nbins);
+  hf_energy_kernel<<<nb2, EV_THREADS, 0, st>>>(z, nbins, fstep, lo_hz, partials);
+  EGR_CHECK_LAUNCH("hf_energy_kernel");
+  hf_final_kernel<<<1, 32, 0, st>>>(partials, nb2, d_metrics);
+  EGR_CHECK_LAUNCH("hf_final_kernel");
   return EGR_OK;
 }

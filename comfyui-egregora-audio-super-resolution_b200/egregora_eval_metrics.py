@@ -4,11 +4,12 @@ Mirrors the arithmetic of the reference's `Audio_Null_Test.execute` (/root/refer
 :421-467 — trim to the shorter clip, optional least-squares scale, inversion, null = A + B, corr_coef, null_rms_dbfs,
 overshoot_count, clipped_pct, scale_k), of `_si_sdr` (egregora_audio_eval_pack.py:414-429) and of `_stft_mag` +
 `_lsd` (egregora_audio_eval_pack.py:389-411; the same two functions again at egregora_null_test_suite.py:167-189).
-and of `integrated_lufs` + `_k_weight` (egregora_null_test_suite.py:125-164).  Not here: the HF-band option
-(`_band_energy_hi_db`, a whole-clip FFT energy ratio).  One C-ABI call per metric group; no CPU fallback.
+of `integrated_lufs` + `_k_weight` (egregora_null_test_suite.py:125-164) and of `_band_energy_hi_db` (:190-197) —
+every metric `Audio_Null_Test.execute` can return.  One C-ABI call per metric group; no CPU fallback.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Dict, Tuple
 
 import torch
@@ -104,3 +105,29 @@ def integrated_lufs(x: torch.Tensor, sample_rate: int) -> float:
     _abi.check(lib.egr_eval_lufs(a.data_ptr(), n, C, n, int(sample_rate), met.data_ptr(), work.data_ptr(), wb,
                                  torch.cuda.current_stream().cuda_stream), "egr_eval_lufs")
     return float(met.cpu()[_abi.K["EGR_LUFS_INTEGRATED"]])
+
+
+def hf_band_db(x: torch.Tensor, sample_rate: int, lo_hz: float) -> float:
+    """`_band_energy_hi_db` (egregora_null_test_suite.py:190-197): energy of the channel mean at and above `lo_hz` over
+    its total energy, in dB, from one whole-clip FFT (the hand-written path-B transform).  x [C,N] or [N] float32."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("CUDA GPU not detected. The B200-native metrics have no CPU fallback (sm_100a kernels only).")
+    a = x if x.dim() == 2 else x[None, :]
+    if a.dim() != 2 or a.shape[1] == 0:
+        raise RuntimeError(f"audio must be a non-empty [C, N] or [N] tensor; got {tuple(x.shape)}")
+    device = torch.device("cuda", torch.cuda.current_device())
+    lib = _abi.init(device.index or 0)
+    a = a.detach().to(device=device, dtype=torch.float32).contiguous()
+    C, n = a.shape
+    plan = ctypes.c_void_p()
+    _abi.check(lib.egr_fft_plan_create(n, 1, ctypes.byref(plan)), "egr_fft_plan_create")
+    try:
+        met = torch.zeros(_abi.K["EGR_HF_NUM"], dtype=torch.float64, device=device)
+        wb = int(lib.egr_eval_hf_band_workspace_bytes(plan, n))
+        work = torch.empty(wb, dtype=torch.uint8, device=device)
+        _abi.check(lib.egr_eval_hf_band(plan, a.data_ptr(), n, C, n, int(sample_rate), float(lo_hz), met.data_ptr(),
+                                        work.data_ptr(), wb, torch.cuda.current_stream().cuda_stream), "egr_eval_hf_band")
+        out = float(met.cpu()[_abi.K["EGR_HF_RESIDUAL_DB"]])   # the read-back also orders the plan's destruction after the work
+    finally:
+        lib.egr_fft_plan_destroy(plan)
+    return out

@@ -276,8 +276,8 @@ int egr_dfn_mix(const float* d_dry, const float* d_wet, float* d_out, int C, int
 #define EGR_EVAL_CLIPPED_PCT    4  /* :465                                                                     */
 #define EGR_EVAL_SCALE_K        5  /* least-squares scale k, :431-436                                          */
 #define EGR_EVAL_NUM            8
-/* Replaces the arithmetic of Audio_Null_Test.execute (egregora_null_test_suite.py:421-467, without its HF-band option; the LSD and
- * LUFS options are egr_eval_lsd / egr_eval_lufs below) and _si_sdr: d_ref / d_proc [C,N] f32 with row strides ld_* (so the "trim both to the shorter"
+/* Replaces the arithmetic of Audio_Null_Test.execute (egregora_null_test_suite.py:421-467, the LSD, LUFS and HF-band options are
+ * egr_eval_lsd / egr_eval_lufs / egr_eval_hf_band below) and _si_sdr: d_ref / d_proc [C,N] f32 with row strides ld_* (so the "trim both to the shorter"
  * step needs no copy), d_null [C,N] f32 or NULL, d_metrics [EGR_EVAL_NUM] f64 ON THE DEVICE (read it after a stream
  * sync).  The null signal is bit-identical to numpy's; the reductions are deterministic float64 sums. */
 size_t egr_eval_workspace_bytes(void);
@@ -316,6 +316,19 @@ int egr_eval_lsd(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_
 size_t egr_eval_lufs_workspace_bytes(int C, int64_t N, int sample_rate);
 int egr_eval_lufs(const float* d_x, int64_t ld, int C, int64_t N, int sample_rate, double* d_metrics, void* d_work,
                   size_t work_bytes, void* stream);
+
+#define EGR_HF_RESIDUAL_DB 0  /* 10*log10(e_hi / (e_all + 1e-20) + 1e-20), egregora_null_test_suite.py:190-197       */
+#define EGR_HF_E_HI        1  /* sum |X_k|^2 over bins with rfftfreq(k) >= lo_hz                                      */
+#define EGR_HF_E_ALL       2  /* sum |X_k|^2 over all N/2 + 1 bins                                                    */
+#define EGR_HF_BINS_HI     3
+#define EGR_HF_NUM         4
+/* Replaces _band_energy_hi_db (egregora_null_test_suite.py:190-197; "hf_residual_db" of Audio_Null_Test.execute :462):
+ * channel mean of d_x [C,N] f32 -> length-N FFT with the path-B transform (`plan` must come from
+ * egr_fft_plan_create(N, 1)) -> energy above lo_hz over total energy, float64 sums.  d_metrics [EGR_HF_NUM] f64 ON THE
+ * DEVICE. */
+size_t egr_eval_hf_band_workspace_bytes(const egr_fft_plan* plan, int64_t N);
+int egr_eval_hf_band(egr_fft_plan* plan, const float* d_x, int64_t ld, int C, int64_t N, int sample_rate, double lo_hz,
+                     double* d_metrics, void* d_work, size_t work_bytes, void* stream);
 
 #ifdef __cplusplus
 }

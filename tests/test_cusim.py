@@ -22,6 +22,7 @@ import pytest
 from conftest import GOLDEN, ROOT, load_pkg
 from lsd_cases import signals as lsd_signals
 from lufs_cases import signal as lufs_signal
+from hf_cases import signal as hf_signal
 
 sys.path.insert(0, str(ROOT / "tests" / "cusim"))
 
@@ -235,6 +236,27 @@ def test_eval_lufs_reference_golden(sim):
     assert met[K["EGR_LUFS_REPAIRED"]] >= 1
     assert np.array_equal(y, O.k_weight(48000, x))
     assert abs(met[K["EGR_LUFS_INTEGRATED"]] - O.integrated_lufs(x, 48000)) <= 1e-9
+
+
+def test_eval_hf_band_reference_golden(sim):
+    """egr_eval_hf_band (pack -> path-B FFT, incl. odd and prime lengths -> float64 band sums) against the reference's
+    _band_energy_hi_db: 1e-3 dB (the reference sums |X|^2 in float32, both FFTs are float32), bin mask identical."""
+    hg = json.loads((GOLDEN / "eval_hf_golden.json").read_text())
+    K = sim.K
+    for name, c in hg.items():
+        x = hf_signal(name, c)
+        plan = C.c_void_p()
+        sim.ck(sim.egr_fft_plan_create(c["N"], 1, C.byref(plan)))
+        try:
+            xd, met = _dev(x), _dev(np.zeros(K["EGR_HF_NUM"], np.float64))
+            wb = sim.egr_eval_hf_band_workspace_bytes(plan, c["N"])
+            wk = _dev(wb)
+            sim.ck(sim.egr_eval_hf_band(plan, xd.ctypes.data, c["N"], c["C"], c["N"], c["sr"], float(c["lo_hz"]), met.ctypes.data,
+                                        wk.ctypes.data, wb, None))
+        finally:
+            sim.egr_fft_plan_destroy(plan)
+        assert int(met[K["EGR_HF_BINS_HI"]]) == c["bins_hi"], name
+        assert abs(met[K["EGR_HF_RESIDUAL_DB"]] - c["hf_db"]) <= 1e-3, (name, met, c["hf_db"])
 
 
 # ------------------------------------------------------------------------------------------------ path B

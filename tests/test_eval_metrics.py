@@ -22,6 +22,7 @@ import torch
 from conftest import GOLDEN
 from lsd_cases import emulate_kernel_lsd, signals as lsd_signals
 from lufs_cases import signal as lufs_signal
+from hf_cases import signal as hf_signal
 from oracle import eval_oracle as O
 
 
@@ -138,3 +139,10 @@ def test_lufs_oracle_matches_reference_golden():
         y = O.k_weight(c["sr"], x)
         assert hashlib.sha256(np.ascontiguousarray(y).tobytes()).hexdigest() == c["kweight_sha256"], name
         assert abs(O.integrated_lufs(x, c["sr"]) - c["lufs"]) <= 1e-12, name
+
+
+# ------------------------------------------------------------------------------------------------ HF band ratio
+def test_hf_band_oracle_matches_reference_golden():
+    hg = json.loads((GOLDEN / "eval_hf_golden.json").read_text())
+    for name, c in hg.items():
+        assert abs(O.hf_band_db(hf_signal(name, c), c["sr"], c["lo_hz"]) - c["hf_db"]) <= 1e-9, name
