@@ -27,9 +27,9 @@
 //                      samples starts from a GUESSED state (the recurrence run over the 2048 samples before it, from
 //                      zero — a contraction with k = 0.984 forgets its start long before that) and records guess and
 //                      end state
-//   lufs_fix_kernel    one thread per channel walks the chunk boundaries: where a guess is not bit-identical to the
-//                      true end state of the previous chunk, that chunk is recomputed serially from the true state
-//                      (rare; the count is reported)
+//   lufs_fix_kernel    one CTA per channel finds the first chunk whose guess is not bit-identical to the true end
+//                      state of the previous chunk (none on ordinary audio); from there one thread verifies in order
+//                      and recomputes mismatching chunks serially from the true state (the count is reported)
 //   lufs_block_kernel  one CTA per 400 ms block (100 ms hop): HF tilt y[n] += fl(0.02*(y[n] - y[n-1])) and the channel
 //                      mean in float32 as numpy does them, mean square in float64
 //   lufs_final_kernel  ungated mean, -10 LU relative gate, gated mean (fixed-order float64 sums)
@@ -365,21 +365,31 @@ __global__ void __launch_bounds__(128) lufs_hp_kernel(const float* __restrict__ 
   endst[(long long)ch * nchunks + ci] = z;
 }
 
-// grid C, one warp; lane 0 verifies the guesses in order and repairs the chunks whose guess was not exact
-__global__ void lufs_fix_kernel(const float* __restrict__ x, long long ld, long long N, int nchunks, LufsCoef q,
-                                float* __restrict__ y, const float* __restrict__ guess, float* __restrict__ endst,
-                                unsigned int* __restrict__ repaired) {
-  if (threadIdx.x != 0) return;
+// grid C; all threads look for the first chunk whose guess is not bit-identical to the previous chunk's end state (none on
+// ordinary audio: one parallel pass and out); from there thread 0 verifies in order and repairs — a repaired chunk has a
+// new end state, so its successor is judged against that
+__global__ void __launch_bounds__(LUFS_THREADS) lufs_fix_kernel(const float* __restrict__ x, long long ld, long long N, int nchunks,
+                                                                 LufsCoef q, float* __restrict__ y, const float* __restrict__ guess,
+                                                                 float* __restrict__ endst, unsigned int* __restrict__ repaired) {
+  __shared__ int first;
   const int ch = blockIdx.x;
+  const float* gs = guess + (long long)ch * nchunks;
+  float* es = endst + (long long)ch * nchunks;
+  if (threadIdx.x == 0) first = nchunks;
+  __syncthreads();
+  for (int ci = 1 + threadIdx.x; ci < nchunks; ci += LUFS_THREADS)
+    if (__float_as_uint(es[ci - 1]) != __float_as_uint(gs[ci])) atomicMin(&first, ci);
+  __syncthreads();
+  if (threadIdx.x != 0 || first >= nchunks) return;
   const float* xc = x + (long long)ch * ld;
   float* yc = y + (long long)ch * N;
   unsigned int cnt = 0;
-  for (int ci = 1; ci < nchunks; ++ci) {
-    float z = endst[(long long)ch * nchunks + ci - 1];
-    if (__float_as_uint(z) == __float_as_uint(guess[(long long)ch * nchunks + ci])) continue;
+  for (int ci = first; ci < nchunks; ++ci) {
+    float z = es[ci - 1];
+    if (__float_as_uint(z) == __float_as_uint(gs[ci])) continue;
     const long long s0 = (long long)ci * LUFS_CHUNK, s1 = s0 + LUFS_CHUNK < N ? s0 + LUFS_CHUNK : N;
     for (long long n = s0; n < s1; ++n) yc[n] = lufs_step(q, xc[n], z);
-    endst[(long long)ch * nchunks + ci] = z;
+    es[ci] = z;
     ++cnt;
   }
   if (cnt) atomicAdd(repaired, cnt);
@@ -489,7 +499,7 @@ extern "C" int egr_eval_lufs(const float* d_x, int64_t ld, int C, int64_t N, int
   EGR_CUDA(cudaMemsetAsync(repaired, 0, 256, st));
   lufs_hp_kernel<<<dim3((unsigned)((nchunks + 127) / 128), C), 128, 0, st>>>(d_x, ld, N, nchunks, q, y, guess, endst);
   EGR_CHECK_LAUNCH("lufs_hp_kernel");
-  lufs_fix_kernel<<<C, 32, 0, st>>>(d_x, ld, N, nchunks, q, y, guess, endst, repaired);
+  lufs_fix_kernel<<<C, LUFS_THREADS, 0, st>>>(d_x, ld, N, nchunks, q, y, guess, endst, repaired);
   EGR_CHECK_LAUNCH("lufs_fix_kernel");
   lufs_block_kernel<<<(unsigned)frames, LUFS_THREADS, 0, st>>>(y, C, N, blk, hop, ms);
   EGR_CHECK_LAUNCH("lufs_block_kernel");
