@@ -42,7 +42,7 @@ def golden():
 def cuda_dev():
     import os
     import torch
-    if os.environ.get("EGR_TEST_INTERP"):
+    if os.environ.get("EGR_TEST_INTERP") or os.environ.get("EGR_TEST_CUSIM"):
         return torch.device("cpu")
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")

@@ -3,7 +3,7 @@
 The kernels' real sources (csrc/*.cu) are copied with two textual rewrites and compiled by g++ against the shim:
   kernel<<<grid, block, smem, stream>>>(args);   ->  cusim::launch(dim3(grid), dim3(block), smem, [&]() { kernel(args); });
   extern __shared__ T name[];                     ->  T* name = reinterpret_cast<T*>(cusim::dyn_smem());
-Sources that need tcgen05 / TMA / clusters / half precision are not part of this build.  The result,
+gemm_tc.cu (tcgen05 / TMA) is replaced by the host loops of gemm_tc_ref.cpp; clusters larger than one block are refused.  The result,
 tests/cusim/_build/libegregora_b200_cusim.so, exports the same C ABI for those entry points with HOST pointers in place
 of device pointers; only tests/test_cusim.py loads it.
 """
@@ -17,8 +17,9 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
 CSRC = ROOT / "comfyui-egregora-audio-super-resolution_b200" / "csrc"
-SOURCES = ["core.cu", "wola.cu", "eval_metrics.cu", "dfn_mix.cu", "fft.cu", "fatllama.cu"]
-HEADERS = ["common.cuh", "select.cuh", "fft_plan.cuh", "fft_device.cuh"]
+SOURCES = ["core.cu", "wola.cu", "eval_metrics.cu", "dfn_mix.cu", "fft.cu", "fatllama.cu", "ops.cu", "frontend.cu", "plan.cu"]
+HEADERS = ["common.cuh", "select.cuh", "fft_plan.cuh", "fft_device.cuh", "ops.cuh"]
+SHIM = ["cuda_runtime.h", "cuda_fp16.h", "cooperative_groups.h", "cusim.cpp", "gemm_tc_ref.cpp", "build.py"]
 OUT = HERE / "_build"
 LIB = OUT / "libegregora_b200_cusim.so"
 
@@ -54,8 +55,10 @@ def _split_top(s: str):
 
 
 def rewrite(text: str) -> str:
-    text = re.sub(r"extern\s+__shared__\s+([A-Za-z_][\w:]*)\s+(\w+)\s*\[\s*\]\s*;",
+    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w:]*(?:\s+[A-Za-z_]\w*)*?)\s+(\w+)\s*\[\s*\]\s*;",
                   r"\1* \2 = reinterpret_cast<\1*>(cusim::dyn_smem());", text)
+    # kernels compiled for a fixed thread-block cluster cannot be emulated: their launches become an error return
+    clustered = set(re.findall(r"__cluster_dims__\([^)]*\)\s*(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(", text))
     out, pos = "", 0
     while True:
         k = text.find("<<<", pos)
@@ -85,12 +88,16 @@ def rewrite(text: str) -> str:
         semi = text.index(";", a1)
         assert text[a1:semi].strip() == "", (kernel, text[a1:semi])
         smem = cfg[2] if len(cfg) > 2 else "0"
+        if kernel in clustered:
+            out += text[pos:j] + f'return egr::fail(EGR_ERR_UNSUPPORTED, "cusim: {kernel} needs a thread-block cluster, which the emulator does not provide");'
+            pos = semi + 1
+            continue
         out += text[pos:j] + f"cusim::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}), [&]() {{ {kernel}{text[a0:a1]}; }});"
         pos = semi + 1
 
 
 def build(force: bool = False) -> Path:
-    srcs = [CSRC / s for s in SOURCES + HEADERS] + [HERE / n for n in ("cuda_runtime.h", "cuda_fp16.h", "cusim.cpp", "build.py")]
+    srcs = [CSRC / s for s in SOURCES + HEADERS] + [HERE / n for n in SHIM]
     srcs.append(ROOT / "include" / "egregora_b200.h")
     h = hashlib.sha256()
     for p in srcs:
@@ -109,7 +116,7 @@ def build(force: bool = False) -> Path:
     shutil.copy(ROOT / "include" / "egregora_b200.h", inc / "egregora_b200.h")
     for n in SOURCES + HEADERS:
         (work / (n[:-3] + ".cpp" if n.endswith(".cu") else n)).write_text(rewrite((CSRC / n).read_text()))
-    cpps = [str(work / (n[:-3] + ".cpp")) for n in SOURCES] + [str(HERE / "cusim.cpp")]
+    cpps = [str(work / (n[:-3] + ".cpp")) for n in SOURCES] + [str(HERE / "cusim.cpp"), str(HERE / "gemm_tc_ref.cpp")]
     cmd = [gxx, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
            "-I", str(HERE), "-I", str(work), "-o", str(LIB)] + cpps
     subprocess.run(cmd, check=True)

@@ -5,9 +5,11 @@
 // when all live participants have arrived.  Blocks run one after another.  Nothing in the product loads this: the
 // package's _abi.py binds libegregora_b200.so (nvcc, sm_100a) and raises without a GPU.  This header shadows
 // <cuda_runtime.h> only for the emulator build (tests/cusim/build.py puts this directory first on the include path).
-// Not emulated (sources using them are not built here): tcgen05 / TMA / mbarrier (gemm_tc.cu), thread-block clusters
-// (frontend.cu low-pass, ops.cu fused GroupNorm), half precision.  Timing means nothing; arithmetic differs from the GPU
-// only where nvcc contracts a*b+c into FMA and g++ (-ffp-contract=off) does not.
+// Not emulated: tcgen05 / TMA / mbarrier (gemm_tc.cu is replaced by the plain loops of gemm_tc_ref.cpp, so a whole
+// plan can run) and thread-block clusters larger than one CTA (the low-pass kernel and the fused GroupNorm of large maps
+// return an error instead of launching).  Half precision is _Float16.  Timing means nothing; arithmetic differs from
+// the GPU only where nvcc contracts a*b+c into FMA and g++ (-ffp-contract=off) does not, and in the last bit of libm
+// versus SFU transcendentals.
 #pragma once
 #include <ucontext.h>
 #include <algorithm>
@@ -27,6 +29,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
+#define __align__(n) alignas(n)
 
 struct dim3 {
   unsigned x, y, z;
@@ -79,6 +82,17 @@ inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); retur
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, F, int, size_t) { *n = 8; return cudaSuccess; }
+// CUDA graphs: capture is refused, so egr_plan_run stays on its eager path
+typedef void* cudaGraph_t;
+typedef void* cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal, cudaStreamCaptureModeThreadLocal, cudaStreamCaptureModeRelaxed };
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t* g) { *g = nullptr; return cudaErrorInvalidValue; }
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t*, cudaGraph_t, unsigned long long) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorInvalidValue; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 
 // ------------------------------------------------------------------------------------------------ the emulator
 namespace cusim {
@@ -108,7 +122,7 @@ void yield(State s, unsigned mask);
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 unsigned long long launches();
 
-inline int linear_tid() { Block& b = blk(); const uint3& t = b.f[b.cur].tid; return (int)(t.x + b.bdim.x * (t.y + b.bdim.y * t.z)); }
+inline int linear_tid() { return blk().cur; }
 inline bool lane_alive(int warp, int lane) {
   Block& b = blk();
   const size_t i = (size_t)warp * 32 + lane;
@@ -131,10 +145,31 @@ inline T shuffle(unsigned mask, T v, PICK pick) {
 
 }  // namespace cusim
 
-#define threadIdx (cusim::blk().f[cusim::blk().cur].tid)
-#define blockIdx (cusim::blk().bid)
-#define blockDim (cusim::blk().bdim)
-#define gridDim (cusim::blk().gdim)
+// extended launch: only clusters of ONE block can be emulated (static __shared__ storage is one instance per process)
+enum cudaLaunchAttributeID { cudaLaunchAttributeClusterDimension = 4 };
+struct cudaLaunchAttributeValue { struct { unsigned x, y, z; } clusterDim; };
+struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
+struct cudaLaunchConfig_t {
+  dim3 gridDim, blockDim;
+  size_t dynamicSmemBytes = 0;
+  cudaStream_t stream = nullptr;
+  cudaLaunchAttribute* attrs = nullptr;
+  unsigned numAttrs = 0;
+};
+template <class K, class... A>
+inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, K kernel, A... args) {
+  for (unsigned i = 0; i < cfg->numAttrs; ++i)
+    if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension &&
+        cfg->attrs[i].val.clusterDim.x * cfg->attrs[i].val.clusterDim.y * cfg->attrs[i].val.clusterDim.z != 1)
+      return cudaErrorInvalidValue;
+  cusim::launch(cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, [&]() { kernel(args...); });
+  return cudaSuccess;
+}
+#define __cluster_dims__(...)
+
+// built-in variables: plain globals the scheduler sets before it resumes a fiber (one OS thread runs everything)
+extern uint3 threadIdx, blockIdx;
+extern dim3 blockDim, gridDim;
 
 inline void __syncthreads() { cusim::yield(cusim::WAIT_BLOCK, 0); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { cusim::yield(cusim::WAIT_WARP, mask); }
@@ -156,6 +191,12 @@ inline float __fsub_rn(float a, float b) { return a - b; }
 inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline float __expf(float a) { return expf(a); }
+inline float __sinf(float a) { return sinf(a); }
+inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
+inline void __threadfence() {}
+inline void __threadfence_block() {}
+inline float __cosf(float a) { return cosf(a); }
+inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 inline int __float2int_rn(float f) { return (int)nearbyintf(f); }

@@ -1,6 +1,9 @@
 // cusim scheduler — see cuda_runtime.h in this directory.  TEST INFRASTRUCTURE ONLY.
 #include "cuda_runtime.h"
 
+uint3 threadIdx, blockIdx;
+dim3 blockDim, gridDim;
+
 namespace cusim {
 
 static Block g_blk;
@@ -45,6 +48,7 @@ static void run_block() {
     for (size_t i = 0; i < n; ++i) {
       if (b.f[i].st != READY) continue;
       b.cur = (int)i;
+      threadIdx = b.f[i].tid;
       swapcontext(&b.sched, &b.f[i].uc);
       ran = true;
     }
@@ -94,6 +98,8 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
   Block& b = g_blk;
   b.bdim = block;
   b.gdim = grid;
+  blockDim = block;
+  gridDim = grid;
   b.body = &body;
   b.f.resize(n);
   for (size_t i = 0; i < n; ++i) b.f[i].tid = uint3{(unsigned)(i % block.x), (unsigned)((i / block.x) % block.y), (unsigned)(i / ((size_t)block.x * block.y))};
@@ -101,6 +107,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
     for (unsigned y = 0; y < grid.y; ++y)
       for (unsigned x = 0; x < grid.x; ++x) {
         b.bid = uint3{x, y, z};
+        blockIdx = b.bid;
         run_block();
       }
   b.body = nullptr;

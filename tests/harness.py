@@ -11,6 +11,27 @@ load_pkg()
 from egregora_b200 import _abi, flashsr_model as M, flashsr_plan as P  # noqa: E402
 
 
+_CUSIM = None
+
+
+def cusim_lib():
+    """ctypes handle of the emulator build (tests/cusim/build.py), prototypes declared from _abi.signatures()."""
+    global _CUSIM
+    if _CUSIM is None:
+        import sys
+        from pathlib import Path
+        sys.path.insert(0, str(Path(__file__).resolve().parent / "cusim"))
+        import build as cusim_build
+        lib = C.CDLL(str(cusim_build.build()))
+        for name, (res, args) in _abi.signatures().items():
+            if hasattr(lib, name):
+                fn = getattr(lib, name)
+                fn.restype, fn.argtypes = res, args
+        assert lib.egr_init(0) == 0, lib.egr_last_error()
+        _CUSIM = lib
+    return _CUSIM
+
+
 class MiniPlan:
     def __init__(self, weights=None, spec=None, batch=1):
         self.blob = P.WeightBlob()
@@ -34,6 +55,8 @@ class MiniPlan:
         import os
         if os.environ.get("EGR_TEST_INTERP"):  # dry-run the GPU tests' references through the CPU interpreter
             return self.run_cpu()
+        if os.environ.get("EGR_TEST_CUSIM"):   # run the SIMT kernels' real source under the CPU emulator (tests/cusim)
+            return self.run_sim(first, last)
         self._finish()
         dev = torch.device(device)
         lib = _abi.init(dev.index or 0)
@@ -48,6 +71,25 @@ class MiniPlan:
                                        self.wt.numel(), C.byref(h)), "egr_plan_create")
         _abi.check(lib.egr_plan_run(h, first, last, torch.cuda.current_stream(dev).cuda_stream), "egr_plan_run")
         torch.cuda.synchronize(dev)
+        lib.egr_plan_destroy(h)
+        return self
+
+    def run_sim(self, first=0, last=-1):
+        """The same plan through tests/cusim's build of the library: host memory stands in for device memory, the SIMT
+        kernels execute their real source, tensor-core GEMM ops are evaluated by gemm_tc_ref.cpp's plain loops."""
+        lib = cusim_lib()
+        self._finish()
+        self.ws = torch.zeros(self.ws_bytes + 4096, dtype=torch.uint8)
+        self.wt = torch.frombuffer(bytearray(self.blob.tobytes() or b"\0" * 256), dtype=torch.uint8).clone()
+        for t, x in self.inputs:
+            self.view(t.f32, torch.float32, x.shape).copy_(x)
+            if t.f16 is not None:
+                self.view(t.f16, torch.float16, x.shape).copy_(x.half())
+        h = C.c_void_p()
+        rc = lib.egr_plan_create(self.ops, len(self.be.ops), self.ws.data_ptr(), self.ws.numel(), self.wt.data_ptr(), self.wt.numel(), C.byref(h))
+        assert rc == 0, lib.egr_last_error().decode()
+        rc = lib.egr_plan_run(h, first, last, None)
+        assert rc == 0, lib.egr_last_error().decode()
         lib.egr_plan_destroy(h)
         return self
 

@@ -1,13 +1,19 @@
 """The SIMT kernels' REAL source run on the CPU under tests/cusim (a fiber-per-thread emulation of blocks, shared memory,
 __syncthreads, warp shuffles and atomics — test infrastructure, see tests/cusim/cuda_runtime.h), against the same goldens
 and oracles as the `-m gpu` tests.  Covers: egr_chunk_gather / egr_wola_stitch / egr_resample_poly (bit-exact),
-egr_pcm16_* / egr_absmax, egr_dfn_mix, egr_eval_null_test, egr_eval_lsd, egr_fft_exec and egr_fatllama_run.
+egr_pcm16_* / egr_absmax, egr_dfn_mix, egr_eval_null_test / _lsd / _lufs / _hf_band, egr_fft_exec, egr_fatllama_run, and a
+whole FlashSR plan (tiny spec: front end, VAE, UNet, sampler, vocoder) through egr_plan_create / egr_plan_run, where every
+CUDA-core kernel (GroupNorm, LayerNorm, attention, GEGLU, snake, STFT-mel, element-wise glue, SIMT convs) executes its
+real source and the tensor-core GEMM ops are evaluated by plain loops (tests/cusim/gemm_tc_ref.cpp).  The whole
+`-m gpu` op suite also runs this way on demand: `EGR_TEST_CUSIM=1 pytest tests/test_ops_gpu.py -m gpu` (60 of 65 pass;
+the other five need thread-block clusters, which the emulator refuses loudly).
 
 What this is for: (1) kernels written without GPU time (egr_eval_lsd) execute their actual code — indexing, barriers,
 radix select — before their first hardware run; (2) the emulator reproducing what the B200 already verified for the other
 kernels is the check on the emulator itself.  What it is not: the product never loads this library (there is no CPU
 fallback, tests/test_abi.py::test_no_gpu_fails_loudly), nothing here says anything about speed, and the tcgen05 / TMA /
-cluster kernels (tap-GEMM, GroupNorm, low-pass, snake, attention) are outside its reach — those stay GPU-only.
+cluster kernels (the tap-GEMM itself, the 8-CTA low-pass, GroupNorm on clusters of 2-8 CTAs) are outside its reach —
+those stay GPU-only.
 """
 import ctypes as C
 import hashlib
@@ -309,3 +315,62 @@ def test_fatllama_loop_matches_oracle(Cc, S, U, iters, thr, sim):
     sim.ck(sim.egr_fatllama_run(d_in.ctypes.data, d_out.ctypes.data, Cc, S, U, iters, thr, flags, wk.ctypes.data, wb, None))
     assert d_out.shape == want.shape
     assert float(np.max(np.abs(d_out - want))) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ whole plan
+def test_flashsr_tiny_plan_end_to_end(sim, pkg, monkeypatch):
+    """Tiny-spec FlashSR, one chunk-channel, 1 step, lowpass off (the low-pass kernel needs a cluster), through the real
+    plan executor: waveform RMS error vs the fp32 oracle < 1e-3 (north_star tolerance, as in the GPU test).  GroupNorm
+    runs its one-CTA-per-group form (EGR_GN_NO_CLUSTER, the library's own switch; same sums, different order)."""
+    monkeypatch.setenv("EGR_GN_NO_CLUSTER", "1")
+    import torch
+    from egregora_b200 import flashsr_model as M, flashsr_plan as P
+    from oracle import flashsr_oracle
+    spec = M.tiny_spec()
+    W = M.init_weights(spec, 0)
+    blob = P.WeightBlob()
+    B = 1   # ~50 s under emulation; the GPU test covers B in {1, 2, 3}
+    be = P.build_plan(spec, W, blob, B, 1, False)
+    ws = _dev(be.ws_bytes + 4096)
+    wt = _dev(np.frombuffer(blob.tobytes(), np.uint8))
+    g = torch.Generator().manual_seed(5)
+    wav = (0.1 * torch.randn(B, spec["chunk"], generator=g)).cumsum(1) * 0.05
+    wav = wav - wav.mean(1, keepdim=True)
+    wav = (wav / wav.abs().max() * 0.5).float()
+    fr = spec["chunk"] // spec["mel"]["hop"]
+    noise = torch.randn((B, spec["vae"]["embed_dim"], fr // 8, spec["mel"]["n_mels"] // 8), generator=torch.Generator().manual_seed(4321))
+
+    def put(buf, arr):
+        a = np.ascontiguousarray(arr, np.float32)
+        ws[buf.offset: buf.offset + a.nbytes] = a.view(np.uint8).reshape(-1)
+
+    put(be.inputs["wav"].f32, wav.numpy())
+    put(be.inputs["noise"].f32, noise.permute(0, 2, 3, 1).contiguous().numpy())   # NHWC
+    ops = be.build_ops()
+    h = C.c_void_p()
+    sim.ck(sim.egr_plan_create(ops, len(be.ops), ws.ctypes.data, ws.size, wt.ctypes.data, wt.size, C.byref(h)))
+    try:
+        sim.ck(sim.egr_plan_run(h, 0, -1, None))
+    finally:
+        sim.egr_plan_destroy(h)
+    off = be.output.f32.offset
+    y = ws[off: off + 4 * B * spec["chunk"]].view(np.float32).reshape(B, spec["chunk"])
+    yo, _ = flashsr_oracle.run_flashsr(spec, W, wav, noise, steps=1, lowpass=False)
+    rms = float(np.sqrt(np.mean((y - yo.numpy()) ** 2)))
+    assert np.isfinite(y).all() and rms < 1e-3, rms
+
+
+def test_cluster_kernels_are_refused_not_faked(sim, pkg):
+    """A plan with the low-pass front end must fail loudly under the emulator (no silent wrong numbers)."""
+    from egregora_b200 import flashsr_model as M, flashsr_plan as P
+    spec = M.tiny_spec()
+    blob = P.WeightBlob()
+    be = P.build_plan(spec, M.init_weights(spec, 0), blob, 1, 1, True)
+    ws, wt = _dev(be.ws_bytes + 4096), _dev(np.frombuffer(blob.tobytes(), np.uint8))
+    h = C.c_void_p()
+    sim.ck(sim.egr_plan_create(be.build_ops(), len(be.ops), ws.ctypes.data, ws.size, wt.ctypes.data, wt.size, C.byref(h)))
+    try:
+        assert sim.egr_plan_run(h, 0, -1, None) != 0
+        assert b"cluster" in sim.egr_last_error()
+    finally:
+        sim.egr_plan_destroy(h)
