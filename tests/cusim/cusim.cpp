@@ -43,9 +43,13 @@ static void run_block() {
     makecontext(&f.uc, trampoline, 0);
     f.st = READY;
   }
+  // CUSIM_ORDER=reverse resumes the fibers of a block in descending order: code that misses a barrier tends to give
+  // different results under the two orders (a poor man's racecheck; tests/test_cusim.py runs the new kernels both ways)
+  static const bool reverse = getenv("CUSIM_ORDER") && !strcmp(getenv("CUSIM_ORDER"), "reverse");
   for (;;) {
     bool ran = false;
-    for (size_t i = 0; i < n; ++i) {
+    for (size_t j = 0; j < n; ++j) {
+      const size_t i = reverse ? n - 1 - j : j;
       if (b.f[i].st != READY) continue;
       b.cur = (int)i;
       threadIdx = b.f[i].tid;

@@ -374,3 +374,15 @@ def test_cluster_kernels_are_refused_not_faked(sim, pkg):
         assert b"cluster" in sim.egr_last_error()
     finally:
         sim.egr_plan_destroy(h)
+
+
+def test_new_kernels_do_not_depend_on_thread_order():
+    """The scheduler normally resumes a block's threads in ascending order; CUSIM_ORDER=reverse resumes them in
+    descending order.  Kernels that miss a barrier tend to change their results between the two — the metrics kernels
+    written without GPU time must pass their (partly bit-exact) tests both ways."""
+    import os
+    import subprocess
+    env = dict(os.environ, CUSIM_ORDER="reverse")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(Path(__file__)), "-q", "-x", "-p", "no:cacheprovider", "-k",
+                        "eval_lsd or eval_lufs or eval_hf_band or eval_null_test"], env=env, capture_output=True, text=True, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
