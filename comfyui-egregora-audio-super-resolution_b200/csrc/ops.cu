@@ -824,10 +824,12 @@ __global__ void __launch_bounds__(256) attn_small_kernel(const __half* __restric
 // holds the scaled query in registers, reads whole K / V rows with 16-byte loads (32 FMAs per 4 loads instead of one
 // FMA per 2-byte load), keeps its scores in registers (no probability buffer), and the per-lane partial outputs are
 // combined by a reduce-scatter of 31 shuffles.
-template <int HD>
+// STRIDED: q, k, v are column blocks of one wider [B*S, ld] tensor (the fused q/k/v projection, EGR_FUSE_QKV); the
+// output is always dense [B*S, C].
+template <int HD, bool STRIDED>
 __global__ void __launch_bounds__(256) attn_rows_kernel(const __half* __restrict__ q, const __half* __restrict__ k,
                                                         const __half* __restrict__ v, __half* __restrict__ out, int S,
-                                                        int heads, float scale) {
+                                                        int heads, float scale, int ld) {
   extern __shared__ unsigned char smraw[];
   constexpr int KST = HD + 8;  // halves per staged row
   __half* Ks = reinterpret_cast<__half*>(smraw);
@@ -835,10 +837,12 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(const __half* __restrict
   const int C = heads * HD;
   const int b = blockIdx.z, h = blockIdx.y;
   const long long base = (long long)b * S * C + (long long)h * HD;
+  const int L = STRIDED ? ld : C;                                                        // input row stride
+  const long long ibase = STRIDED ? (long long)b * S * L + (long long)h * HD : base;   // input offset of (b, head)
   for (int i = threadIdx.x; i < S * (HD / 8); i += blockDim.x) {
     const int j = i / (HD / 8), c8 = (i % (HD / 8)) * 8;
-    *reinterpret_cast<uint4*>(Ks + j * KST + c8) = __ldg(reinterpret_cast<const uint4*>(k + base + (long long)j * C + c8));
-    *reinterpret_cast<uint4*>(Vs + j * KST + c8) = __ldg(reinterpret_cast<const uint4*>(v + base + (long long)j * C + c8));
+    *reinterpret_cast<uint4*>(Ks + j * KST + c8) = __ldg(reinterpret_cast<const uint4*>(k + ibase + (long long)j * L + c8));
+    *reinterpret_cast<uint4*>(Vs + j * KST + c8) = __ldg(reinterpret_cast<const uint4*>(v + ibase + (long long)j * L + c8));
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -857,7 +861,7 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(const __half* __restrict
     float qv[HD];
 #pragma unroll
     for (int c8 = 0; c8 < HD; c8 += 8) {
-      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(q + base + (long long)r * C + c8));
+      const uint4 raw = __ldg(reinterpret_cast<const uint4*>(q + ibase + (long long)r * L + c8));
       const __half2* hp = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -950,21 +954,32 @@ int egr::launch_attn_small(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (!q || !k || !v || !o || S <= 0 || heads <= 0 || hd <= 0 || B <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
   const int C_ = heads * hd;
   auto al16 = [](const void* p_) { return reinterpret_cast<uintptr_t>(p_) % 16 == 0; };
+  const int ld = (int)op.i[EGR_I_AUX0];   // 0: dense rows of C halves; otherwise the row stride of a fused q/k/v tensor
+  if (ld != 0 && (ld < C_ || ld % 8 != 0)) return fail(EGR_ERR_ARG, "%s: bad q/k/v row stride %d", op.name, ld);
   if ((hd == 32 || hd == 16) && S <= 512 && C_ % 8 == 0 && al16(q) && al16(k) && al16(v) && getenv("EGR_ATTN_OLD") == nullptr) {
     const size_t sm = (size_t)2 * S * (hd + 8) * sizeof(__half);
     static bool attr2 = false;
     if (!attr2) {
-      EGR_CUDA(cudaFuncSetAttribute(attn_rows_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      EGR_CUDA(cudaFuncSetAttribute(attn_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EGR_CUDA(cudaFuncSetAttribute(attn_rows_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EGR_CUDA(cudaFuncSetAttribute(attn_rows_kernel<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EGR_CUDA(cudaFuncSetAttribute(attn_rows_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      EGR_CUDA(cudaFuncSetAttribute(attn_rows_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       attr2 = true;
     }
     // 16 query rows per block (2 per warp): K/V re-staged per block from L2, many blocks for the short sequences
     const int qblocks = (S + 15) / 16;
-    if (hd == 32) attn_rows_kernel<32><<<dim3(qblocks, heads, B), 256, sm, st>>>(q, k, v, o, S, heads, (float)op.f[EGR_F_ALPHA]);
-    else attn_rows_kernel<16><<<dim3(qblocks, heads, B), 256, sm, st>>>(q, k, v, o, S, heads, (float)op.f[EGR_F_ALPHA]);
+    const float sc_ = (float)op.f[EGR_F_ALPHA];
+    if (ld == 0) {
+      if (hd == 32) attn_rows_kernel<32, false><<<dim3(qblocks, heads, B), 256, sm, st>>>(q, k, v, o, S, heads, sc_, 0);
+      else attn_rows_kernel<16, false><<<dim3(qblocks, heads, B), 256, sm, st>>>(q, k, v, o, S, heads, sc_, 0);
+    } else {
+      if (hd == 32) attn_rows_kernel<32, true><<<dim3(qblocks, heads, B), 256, sm, st>>>(q, k, v, o, S, heads, sc_, ld);
+      else attn_rows_kernel<16, true><<<dim3(qblocks, heads, B), 256, sm, st>>>(q, k, v, o, S, heads, sc_, ld);
+    }
     EGR_CHECK_LAUNCH(op.name);
     return EGR_OK;
   }
+  if (ld != 0) return fail(EGR_ERR_UNSUPPORTED, "%s: strided q/k/v needs the 16/32-dim head kernel", op.name);
   size_t smem = (size_t)2 * S * (hd + 2) * sizeof(__half) + (size_t)8 * S * sizeof(float) + 8 * hd * sizeof(float);
   if (smem > 200 * 1024) return fail(EGR_ERR_UNSUPPORTED, "%s: S=%d hd=%d needs %zu B smem; use the GEMM attention path", op.name, S, hd, smem);
   static bool attr_done = false;

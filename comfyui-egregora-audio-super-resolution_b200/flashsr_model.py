@@ -365,9 +365,12 @@ class FlashSRGraph:
         blk = f"{name}.transformer_blocks.0"
         for a in ("attn1", "attn2"):
             n = be.layernorm(t, f"{blk}.norm{1 if a == 'attn1' else 2}", c, 1e-5)
-            q = be.linear(n, f"{blk}.{a}.to_q", c, c, bias=False, out="f16")
-            k = be.linear(n, f"{blk}.{a}.to_k", c, c, bias=False, out="f16")
-            v = be.linear(n, f"{blk}.{a}.to_v", c, c, bias=False, out="f16")
+            if getattr(be, "fuse_qkv", False) is True and hd in (16, 32):   # plan backend only, opt-in (EGR_FUSE_QKV=1)
+                q, k, v = be.linear_qkv(n, f"{blk}.{a}", c)
+            else:
+                q = be.linear(n, f"{blk}.{a}.to_q", c, c, bias=False, out="f16")
+                k = be.linear(n, f"{blk}.{a}.to_k", c, c, bias=False, out="f16")
+                v = be.linear(n, f"{blk}.{a}.to_v", c, c, bias=False, out="f16")
             o = be.attention(q, k, v, heads=heads, head_dim=hd, v_transposed=False)
             t = be.linear(o, f"{blk}.{a}.to_out.0", c, c, add=t)
         n = be.layernorm(t, f"{blk}.norm3", c, 1e-5)

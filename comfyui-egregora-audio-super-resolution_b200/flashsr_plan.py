@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
@@ -138,6 +139,10 @@ class PlanBackend:
         self.flops = 0.0
         self.tc_flops = 0.0
         self.layer_table: List[dict] = []
+        # EGR_FUSE_QKV=1: the three attention projections of a transformer block as ONE GEMM (N = 3C) whose output the
+        # attention kernel reads as strided column blocks — 2 launches fewer per attention.  Off by default until measured.
+        self.fuse_qkv = os.environ.get("EGR_FUSE_QKV") == "1"
+        self._extra_w: Dict[str, torch.Tensor] = {}   # weights derived at plan time (fused projections)
         self.cutoff_buf: Optional[Buf] = None
         self.debug = False
         self.named: Dict[str, PT] = {}
@@ -186,7 +191,7 @@ class PlanBackend:
 
     def w_taps(self, name: str, kind: str, f16: bool, **kw) -> Tuple[int, int, int]:
         """Returns (offset, ntaps, K) of the packed [taps][N][K] weight."""
-        w = self.Wt[name + ".weight"].float()
+        w = (self._extra_w[name + ".weight"] if name + ".weight" in self._extra_w else self.Wt[name + ".weight"]).float()
         if kind == "conv2d":          # [cout, cin, kh, kw] -> [kh*kw][cout][cin]
             co, ci, kh, kw_ = w.shape
             p = w.permute(2, 3, 0, 1).reshape(kh * kw_, co, ci)
@@ -405,6 +410,14 @@ class PlanBackend:
                    resid=add, act=act, a_elem=elem)
         return o
 
+    def linear_qkv(self, x: PT, prefix, c):
+        """to_q / to_k / to_v of one attention layer as a single [3c, c] projection -> three f16 column-block views."""
+        name = prefix + ".to_qkv"
+        if name + ".weight" not in self._extra_w:
+            self._extra_w[name + ".weight"] = torch.cat([self.Wt[f"{prefix}.to_{s}.weight"] for s in "qkv"], 0)
+        o = self.linear(x, name, c, 3 * c, bias=False, out="f16")
+        return tuple(PT(o.B, o.H, o.W, c, f16=o.f16, ld=3 * c, coff=i * c) for i in range(3))
+
     def groupnorm(self, x: PT, name, c, groups, eps, silu=False):
         assert x.C == c
         a, b = x.parts if x.parts else (x, None)
@@ -479,12 +492,13 @@ class PlanBackend:
                        wstride_n=S, wstride_z=Cc * S, wz_batch=True, w_buf=v.f16)
             return o
         assert not v_transposed and head_dim <= 64
+        assert q.ld == k.ld == v.ld and (q.ld == Cc or head_dim in (16, 32)), "strided q/k/v needs the 16/32-dim head kernel"
         op = RawOp(K["EGR_OP_ATTN_SMALL"], "attn.small")
-        op.i = {"SEQ": S, "HEADS": heads, "HEADDIM": head_dim, "BATCH": B}
+        op.i = {"SEQ": S, "HEADS": heads, "HEADDIM": head_dim, "BATCH": B, "AUX0": q.ld if q.ld != Cc else 0}
         op.f = {"ALPHA": scale}
-        op.x0 = (q.f16, 0, 1, 1, [Cc], [1]); op.reads.append(q.f16)
-        op.x1 = (k.f16, 0, 1, 1, [Cc], [1]); op.reads.append(k.f16)
-        self._ws(op, "AUX", v.f16)
+        op.x0 = (q.f16, 2 * q.coff, 1, 1, [Cc], [1]); op.reads.append(q.f16)
+        op.x1 = (k.f16, 2 * k.coff, 1, 1, [Cc], [1]); op.reads.append(k.f16)
+        self._ws(op, "AUX", v.f16, 2 * v.coff)
         self._ws(op, "OUT16", o.f16, write=True)
         self.emit(op)
         return o

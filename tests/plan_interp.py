@@ -172,9 +172,13 @@ class Interp:
     def attn_small(self, op):
         S, Hh, hd, B = self.i(op, "SEQ"), self.i(op, "HEADS"), self.i(op, "HEADDIM"), self.i(op, "BATCH")
         n = B * S * Hh * hd
-        q = self.flat(op.x0.addr, torch.float16, n).float().view(B, S, Hh, hd).permute(0, 2, 1, 3)
-        k = self.flat(op.x1.addr, torch.float16, n).float().view(B, S, Hh, hd).permute(0, 2, 1, 3)
-        v = self.p(op, "AUX", torch.float16, n).float().view(B, S, Hh, hd).permute(0, 2, 1, 3)
+        ld = self.i(op, "AUX0") or Hh * hd   # row stride of q / k / v (column blocks of a fused projection when > C)
+
+        def rows(t):
+            return torch.as_strided(t, (B * S, Hh * hd), (ld, 1)).float().reshape(B, S, Hh, hd).permute(0, 2, 1, 3)
+        q = rows(self.flat(op.x0.addr, torch.float16))
+        k = rows(self.flat(op.x1.addr, torch.float16))
+        v = rows(self.p(op, "AUX", torch.float16))
         o = torch.softmax(q @ k.transpose(-1, -2) * self.f(op, "ALPHA"), -1) @ v
         self.p(op, "OUT16", torch.float16)[:n] = o.permute(0, 2, 1, 3).reshape(-1).half()
 

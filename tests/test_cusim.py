@@ -317,6 +317,31 @@ def test_fatllama_loop_matches_oracle(Cc, S, U, iters, thr, sim):
     assert float(np.max(np.abs(d_out - want))) <= 1e-5
 
 
+# ------------------------------------------------------------------------------------------------ attention, strided q/k/v
+@pytest.mark.parametrize("S,heads,hd", [(32, 4, 16), (96, 2, 32)])
+def test_attention_reads_fused_qkv_column_blocks(S, heads, hd, sim, pkg):
+    """attn_rows_kernel<HD, STRIDED=true> (the opt-in EGR_FUSE_QKV plan variant): q, k, v as column blocks of one
+    [B*S, 3C] f16 tensor against torch on the same f16-rounded inputs."""
+    import torch
+    from harness import MiniPlan, rel_err
+    from egregora_b200.flashsr_plan import PT
+    Cc, B = heads * hd, 2
+    g = torch.Generator().manual_seed(S)
+    qkv = torch.randn((B, 3 * Cc, 1, S), generator=g)
+    mp = MiniPlan()
+    t = mp.input(qkv, f16=True)
+    q, k, v = (PT(B, 1, S, Cc, f16=t.f16, ld=3 * Cc, coff=i * Cc) for i in range(3))
+    o = mp.be.attention(q, k, v, heads, hd)
+    mp.run_sim()
+
+    def sp(i):
+        x = qkv[:, i * Cc:(i + 1) * Cc].half().float()[:, :, 0].permute(0, 2, 1)
+        return x.reshape(B, S, heads, hd).permute(0, 2, 1, 3)
+    ref = torch.softmax(sp(0) @ sp(1).transpose(-1, -2) * hd ** -0.5, -1) @ sp(2)
+    ref = ref.permute(0, 2, 1, 3).reshape(B, S, Cc).permute(0, 2, 1)
+    assert rel_err(mp.read(o)[:, :, 0], ref) < 2e-3
+
+
 # ------------------------------------------------------------------------------------------------ whole plan
 def test_flashsr_tiny_plan_end_to_end(sim, pkg, monkeypatch):
     """Tiny-spec FlashSR, one chunk-channel, 1 step, lowpass off (the low-pass kernel needs a cluster), through the real

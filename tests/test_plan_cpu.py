@@ -1,6 +1,7 @@
 """CPU-side check of everything the plan builder decides (views, taps, packed weights, crops, buffer reuse):
 the op list is executed by the torch interpreter in tests/plan_interp.py and compared with the fp32 oracle."""
 import numpy as np
+import pytest
 import torch
 
 from conftest import load_pkg
@@ -21,12 +22,20 @@ def _inputs(spec, B, seed=5):
     return wav, noise
 
 
-def test_tiny_plan_matches_oracle_through_interpreter():
+@pytest.mark.parametrize("fuse_qkv", [False, True])
+def test_tiny_plan_matches_oracle_through_interpreter(fuse_qkv, monkeypatch):
+    """fuse_qkv: the opt-in plan variant (EGR_FUSE_QKV=1) that runs the three attention projections as one GEMM and
+    feeds the attention op strided column blocks — 64 ops fewer, same numbers."""
+    if fuse_qkv:
+        monkeypatch.setenv("EGR_FUSE_QKV", "1")
+    else:
+        monkeypatch.delenv("EGR_FUSE_QKV", raising=False)
     spec = M.tiny_spec()
     W = M.init_weights(spec, 0)
     B, steps, lp = 1, 1, True
     blob = P.WeightBlob()
     be = P.build_plan(spec, W, blob, B, steps, lp)
+    assert any(o.name.endswith(".to_qkv") for o in be.ops) == fuse_qkv
     it = Interp(_abi.K, be.build_ops(), be.ws_bytes, blob.tobytes())
     wav, noise = _inputs(spec, B)
 
