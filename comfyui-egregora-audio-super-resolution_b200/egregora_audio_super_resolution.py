@@ -166,6 +166,22 @@ def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_SPAN_CACHE: Dict[Tuple[Tuple[Tuple[int, int], ...], str], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def _span_tensors(spans, device: torch.device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(starts int64, lens int32) of a span list on the device; cached, so a clip length pays its two small
+    host-to-device copies once instead of on every gather and every stitch."""
+    key = (tuple((int(s), int(l)) for s, l in spans), str(device))
+    hit = _SPAN_CACHE.get(key)
+    if hit is None:
+        if len(_SPAN_CACHE) > 256:
+            _SPAN_CACHE.clear()
+        hit = _SPAN_CACHE[key] = (torch.tensor([s for s, _ in key[0]], dtype=torch.int64).to(device),
+                                  torch.tensor([l for _, l in key[0]], dtype=torch.int32).to(device))
+    return hit
+
+
 def gather_chunks(x_dev: torch.Tensor, spans, win: int) -> torch.Tensor:
     """[C,total] device f32 -> [n,C,win] (slice + right zero pad of every span in one launch)."""
     lib = _abi.init(x_dev.device.index or 0)
@@ -174,8 +190,7 @@ def gather_chunks(x_dev: torch.Tensor, spans, win: int) -> torch.Tensor:
     out = torch.empty((n, C, win), dtype=torch.float32, device=x_dev.device)
     if n == 0:
         return out
-    starts = torch.tensor([s for s, _ in spans], dtype=torch.int64).to(x_dev.device, non_blocking=True)
-    lens = torch.tensor([l for _, l in spans], dtype=torch.int32).to(x_dev.device, non_blocking=True)
+    starts, lens = _span_tensors(spans, x_dev.device)
     x_dev = x_dev.contiguous()
     _abi.check(lib.egr_chunk_gather(x_dev.data_ptr(), C, total, starts.data_ptr(), lens.data_ptr(), n, win,
                                     out.data_ptr(), _stream_ptr()), "egr_chunk_gather")
@@ -189,8 +204,7 @@ def wola_stitch(preds_dev: torch.Tensor, spans, total: int, win: int) -> torch.T
     lib = _abi.init(preds_dev.device.index or 0)
     n, C, l_pred = preds_dev.shape
     out = torch.empty((C, total), dtype=torch.float32, device=preds_dev.device)
-    starts = torch.tensor([s for s, _ in spans], dtype=torch.int64).to(preds_dev.device, non_blocking=True)
-    lens = torch.tensor([l for _, l in spans], dtype=torch.int32).to(preds_dev.device, non_blocking=True)
+    starts, lens = _span_tensors(spans, preds_dev.device)
     w = _device_window(win, preds_dev.device)
     preds_dev = preds_dev.contiguous()
     _abi.check(lib.egr_wola_stitch(preds_dev.data_ptr(), l_pred, starts.data_ptr(), lens.data_ptr(), n, C, total,
