@@ -98,7 +98,7 @@ def signatures() -> dict:
         "egr_eval_workspace_bytes": (C.c_size_t, []),
         "egr_eval_null_test": (C.c_int, [f32p, i64, f32p, i64, i32, i64, i32, i32, f32p, vp, vp, C.c_size_t, vp]),
         "egr_eval_lsd_workspace_bytes": (C.c_size_t, [i64, i32, i32]),
-        "egr_eval_lsd": (C.c_int, [f32p, i64, f32p, i64, i32, i64, i32, i32, vp, vp, C.c_size_t, vp]),
+        "egr_eval_lsd": (C.c_int, [f32p, i64, f32p, i64, i32, i64, i32, i32, C.c_float, vp, vp, C.c_size_t, vp]),
         "egr_eval_lufs_workspace_bytes": (C.c_size_t, [i32, i64, i32]),
         "egr_eval_lufs": (C.c_int, [f32p, i64, i32, i64, i32, vp, vp, C.c_size_t, vp]),
         "egr_eval_hf_band_workspace_bytes": (C.c_size_t, [vp, i64]),

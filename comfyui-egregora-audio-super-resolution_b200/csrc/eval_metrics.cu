@@ -75,6 +75,12 @@ __device__ __forceinline__ float ev_mean32(const float* __restrict__ x, long lon
   for (int c = 1; c < C; ++c) s = __fadd_rn(s, __ldg(x + (long long)c * ld + t));
   return __fdiv_rn(s, (float)C);
 }
+// channel mean of (x * k) with the product rounded to float32 first, as (B * k).astype(np.float32).mean(axis=0)
+__device__ __forceinline__ float ev_mean32_scaled(const float* __restrict__ x, long long ld, int C, long long t, float k) {
+  float s = __fmul_rn(__ldg(x + t), k);
+  for (int c = 1; c < C; ++c) s = __fadd_rn(s, __fmul_rn(__ldg(x + (long long)c * ld + t), k));
+  return __fdiv_rn(s, (float)C);
+}
 __device__ __forceinline__ double ev_mean64(const float* __restrict__ x, long long ld, int C, long long t) {
   double s = (double)__ldg(x + t);
   for (int c = 1; c < C; ++c) s += (double)__ldg(x + (long long)c * ld + t);
@@ -213,7 +219,7 @@ __device__ __forceinline__ float2 lsd_cmul(float2 a, float2 b) { return make_flo
 template <class EMIT>
 __device__ __forceinline__ void lsd_frame_logmag(const float* __restrict__ x, long long ld, int C, long long N, long long start,
                                                  int n_fft, const float* __restrict__ window, const float2* __restrict__ tw,
-                                                 float2* bufA, float2* bufB, EMIT emit) {
+                                                 float2* bufA, float2* bufB, float gain, EMIT emit) {
   const int M = n_fft >> 1;
   for (int m = threadIdx.x; m < M; m += LSD_THREADS) {
     float v[2];
@@ -221,7 +227,7 @@ __device__ __forceinline__ void lsd_frame_logmag(const float* __restrict__ x, lo
     for (int u = 0; u < 2; ++u) {
       const int j = 2 * m + u;
       const long long t = start + j;
-      v[u] = t < N ? __fmul_rn(ev_mean32(x, ld, C, t), __ldg(window + j)) : 0.f;
+      v[u] = t < N ? __fmul_rn(gain == 1.0f ? ev_mean32(x, ld, C, t) : ev_mean32_scaled(x, ld, C, t, gain), __ldg(window + j)) : 0.f;
     }
     bufA[m] = make_float2(v[0], v[1]);
   }
@@ -259,7 +265,8 @@ __global__ void __launch_bounds__(LSD_THREADS) eval_lsd_frames_kernel(const floa
                                                                        const float* __restrict__ B, long long ldb, int C,
                                                                        long long N, int n_fft, int hop,
                                                                        const float* __restrict__ window,
-                                                                       const float2* __restrict__ tw, float* __restrict__ per) {
+                                                                       const float2* __restrict__ tw, float* __restrict__ per,
+                                                                       float proc_gain) {
   extern __shared__ float2 lsd_sm[];
   __shared__ double red[LSD_THREADS / 32];
   const int M = n_fft >> 1;
@@ -267,9 +274,9 @@ __global__ void __launch_bounds__(LSD_THREADS) eval_lsd_frames_kernel(const floa
   float2* bufB = lsd_sm + M;
   float* LA = reinterpret_cast<float*>(lsd_sm + 2 * M);  // [M+1]
   const long long start = (long long)blockIdx.x * hop;
-  lsd_frame_logmag(A, lda, C, N, start, n_fft, window, tw, bufA, bufB, [&](int k, float l) { LA[k] = l; });
+  lsd_frame_logmag(A, lda, C, N, start, n_fft, window, tw, bufA, bufB, 1.0f, [&](int k, float l) { LA[k] = l; });
   double acc = 0.0;  // every thread meets the bins k it wrote itself (same k -> thread mapping in both calls)
-  lsd_frame_logmag(B, ldb, C, N, start, n_fft, window, tw, bufA, bufB, [&](int k, float l) {
+  lsd_frame_logmag(B, ldb, C, N, start, n_fft, window, tw, bufA, bufB, proc_gain, [&](int k, float l) {
     const float d = __fsub_rn(LA[k], l);
     acc += (double)__fmul_rn(d, d);
   });
@@ -312,7 +319,7 @@ extern "C" size_t egr_eval_lsd_workspace_bytes(int64_t N, int n_fft, int hop) {
 }
 
 extern "C" int egr_eval_lsd(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_t ld_proc, int C, int64_t N, int n_fft,
-                            int hop, double* d_metrics, void* d_work, size_t work_bytes, void* stream) {
+                            int hop, float proc_gain, double* d_metrics, void* d_work, size_t work_bytes, void* stream) {
   if (!devinfo().inited) return fail(EGR_ERR_STATE, "egr_eval_lsd: call egr_init first");
   if (!d_ref || !d_proc || !d_metrics || !d_work || C < 1 || C > 64 || N < 1 || ld_ref < N || ld_proc < N || hop < 1)
     return fail(EGR_ERR_ARG, "egr_eval_lsd: bad arguments");
@@ -330,7 +337,7 @@ extern "C" int egr_eval_lsd(const float* d_ref, int64_t ld_ref, const float* d_p
   EGR_CHECK_LAUNCH("eval_lsd_tables_kernel");
   const size_t smem = sizeof(float2) * (size_t)n_fft + sizeof(float) * (size_t)(n_fft / 2 + 1);
   if (smem > 48 * 1024) EGR_CUDA(cudaFuncSetAttribute(eval_lsd_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  eval_lsd_frames_kernel<<<(unsigned)frames, LSD_THREADS, smem, st>>>(d_ref, ld_ref, d_proc, ld_proc, C, N, n_fft, hop, window, tw, per);
+  eval_lsd_frames_kernel<<<(unsigned)frames, LSD_THREADS, smem, st>>>(d_ref, ld_ref, d_proc, ld_proc, C, N, n_fft, hop, window, tw, per, proc_gain);
   EGR_CHECK_LAUNCH("eval_lsd_frames_kernel");
   eval_lsd_final_kernel<<<1, 1024, 0, st>>>(per, (int)frames, d_metrics);
   EGR_CHECK_LAUNCH("eval_lsd_final_kernel");

@@ -58,10 +58,11 @@ def si_sdr(ref: torch.Tensor, est: torch.Tensor) -> float:
     return null_test(r, e, want_null=False)[1]["si_sdr_db"]
 
 
-def lsd(ref: torch.Tensor, proc: torch.Tensor, n_fft: int = 2048, hop: int = 512) -> Tuple[float, float]:
+def lsd(ref: torch.Tensor, proc: torch.Tensor, n_fft: int = 2048, hop: int = 512, proc_gain: float = 1.0) -> Tuple[float, float]:
     """Log-spectral distance (lsd_mean_db, lsd_p95_db) of `proc` against `ref`, as Metrics_LSD_SISDR.execute computes
     it (egregora_audio_eval_pack.py:453-467): channel means, both trimmed to the shorter clip, `_stft_mag` frames
-    (symmetric Hann, no centring), `_lsd`.  ref, proc: [C,N] or [N] float32, host or device."""
+    (symmetric Hann, no centring), `_lsd`.  ref, proc: [C,N] or [N] float32, host or device.  proc_gain: the null test's
+    least-squares scale (its `B = (B * k).astype(float32)` step, :436) when the LSD is taken after it."""
     if not torch.cuda.is_available():
         raise RuntimeError("CUDA GPU not detected. The B200-native metrics have no CPU fallback (sm_100a kernels only).")
     r = ref if ref.dim() == 2 else ref[None, :]
@@ -80,7 +81,7 @@ def lsd(ref: torch.Tensor, proc: torch.Tensor, n_fft: int = 2048, hop: int = 512
     met = torch.zeros(_abi.K["EGR_LSD_NUM"], dtype=torch.float64, device=device)
     wb = int(lib.egr_eval_lsd_workspace_bytes(n, int(n_fft), int(hop)))
     work = torch.empty(max(wb, 256), dtype=torch.uint8, device=device)
-    _abi.check(lib.egr_eval_lsd(a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], C, n, int(n_fft), int(hop),
+    _abi.check(lib.egr_eval_lsd(a.data_ptr(), a.shape[1], b.data_ptr(), b.shape[1], C, n, int(n_fft), int(hop), float(proc_gain),
                                 met.data_ptr(), work.data_ptr(), wb, torch.cuda.current_stream().cuda_stream), "egr_eval_lsd")
     m = met.cpu().tolist()
     return float(m[_abi.K["EGR_LSD_MEAN_DB"]]), float(m[_abi.K["EGR_LSD_P95_DB"]])
@@ -131,3 +132,29 @@ def hf_band_db(x: torch.Tensor, sample_rate: int, lo_hz: float) -> float:
     finally:
         lib.egr_fft_plan_destroy(plan)
     return out
+
+
+def audio_null_test(ref: torch.Tensor, proc: torch.Tensor, sample_rate: int, *, invert_b: bool = True,
+                    least_squares_scale: bool = False, compute_corr: bool = True, compute_null_rms: bool = True,
+                    compute_null_lufs: bool = True, compute_lsd: bool = True, compute_hf_residual: bool = False,
+                    n_fft: int = 2048, hop: int = 512, hf_band_hz: float = 8000) -> Tuple[torch.Tensor, Dict[str, float]]:
+    """Everything `Audio_Null_Test.execute` computes (egregora_null_test_suite.py:421-467), same keyword names, same
+    metric keys, same toggles; ref / proc are [C,N] float32 at `sample_rate` (already aligned and matched, as the node's
+    second input says).  Returns (null [C,N] device tensor, metrics dict)."""
+    null, m = null_test(ref, proc, invert_b=invert_b, least_squares_scale=least_squares_scale)
+    out: Dict[str, float] = {}
+    if compute_corr:
+        out["corr_coef"] = m["corr_coef"]
+    if compute_null_rms:
+        out["null_rms_dbfs"] = m["null_rms_dbfs"]
+    if compute_null_lufs:
+        out["null_lufs"] = integrated_lufs(null, sample_rate)
+    if compute_lsd:   # of the channel means of A and of the scaled B (:439-440, :456-458); a sign does not change |X|
+        gain = float(torch.tensor(m["scale_k"], dtype=torch.float32)) if least_squares_scale else 1.0
+        out["lsd_mean_db"], out["lsd_p95_db"] = lsd(ref, proc, n_fft, hop, proc_gain=gain)
+    if compute_hf_residual:
+        out["hf_residual_db"] = hf_band_db(null, sample_rate, hf_band_hz)
+    out["overshoot_count"] = m["overshoot_count"]
+    out["clipped_pct"] = m["clipped_pct"]
+    out["scale_k"] = m["scale_k"]
+    return null, out

@@ -297,10 +297,11 @@ int egr_eval_null_test(const float* d_ref, int64_t ld_ref, const float* d_proc, 
  * then the mean and the 95th percentile over frames into d_metrics [EGR_LSD_NUM] f64 ON THE DEVICE.  n_fft must be a
  * power of two in [64, 8192] (the nodes' default is 2048); other sizes return an error, nothing falls back.  Two float32
  * FFTs agree to rounding, so bins that hold real signal agree to ~1e-5 dB; bins that hold only rounding noise are noise
- * in the reference too (tests state the tolerance per case). */
+ * in the reference too (tests state the tolerance per case).  proc_gain: 1, or the null test's least-squares scale k as
+ * float32 — every proc sample is multiplied by it (rounded to float32) before the channel mean, as (B * k).astype(f32). */
 size_t egr_eval_lsd_workspace_bytes(int64_t N, int n_fft, int hop);
 int egr_eval_lsd(const float* d_ref, int64_t ld_ref, const float* d_proc, int64_t ld_proc, int C, int64_t N, int n_fft,
-                 int hop, double* d_metrics, void* d_work, size_t work_bytes, void* stream);
+                 int hop, float proc_gain, double* d_metrics, void* d_work, size_t work_bytes, void* stream);
 
 #define EGR_LUFS_INTEGRATED 0  /* integrated_lufs(), egregora_null_test_suite.py:143-164                          */
 #define EGR_LUFS_UNGATED    1  /* lufs_ungated of the same function (:158)                                         */

@@ -187,7 +187,7 @@ def test_eval_lsd_reference_golden(sim):
         a, b, met = _dev(A), _dev(B), _dev(np.zeros(K["EGR_LSD_NUM"], np.float64))
         wb = sim.egr_eval_lsd_workspace_bytes(n, c["n_fft"], c["hop"])
         wk = _dev(wb)
-        sim.ck(sim.egr_eval_lsd(a.ctypes.data, A.shape[1], b.ctypes.data, B.shape[1], c["C"], n, c["n_fft"], c["hop"],
+        sim.ck(sim.egr_eval_lsd(a.ctypes.data, A.shape[1], b.ctypes.data, B.shape[1], c["C"], n, c["n_fft"], c["hop"], 1.0,
                                 met.ctypes.data, wk.ctypes.data, wb, None))
         assert int(met[K["EGR_LSD_FRAMES"]]) == c["frames"]
         if c["band"] >= 1.0:
@@ -200,9 +200,9 @@ def test_eval_lsd_reference_golden(sim):
     met = _dev(np.zeros(4, np.float64))
     wb = sim.egr_eval_lsd_workspace_bytes(20000, 2048, 512)
     wk = _dev(wb)
-    sim.ck(sim.egr_eval_lsd(x.ctypes.data, 20000, x.ctypes.data, 20000, 2, 20000, 2048, 512, met.ctypes.data, wk.ctypes.data, wb, None))
+    sim.ck(sim.egr_eval_lsd(x.ctypes.data, 20000, x.ctypes.data, 20000, 2, 20000, 2048, 512, 1.0, met.ctypes.data, wk.ctypes.data, wb, None))
     assert met[0] == float(np.sqrt(np.float32(1e-12))) and met[1] == met[0]
-    assert sim.egr_eval_lsd(x.ctypes.data, 20000, x.ctypes.data, 20000, 2, 20000, 640, 160, met.ctypes.data, wk.ctypes.data, wb, None) != 0
+    assert sim.egr_eval_lsd(x.ctypes.data, 20000, x.ctypes.data, 20000, 2, 20000, 640, 160, 1.0, met.ctypes.data, wk.ctypes.data, wb, None) != 0
 
 
 def _lufs(sim, x, sr):
@@ -263,6 +263,49 @@ def test_eval_hf_band_reference_golden(sim):
             sim.egr_fft_plan_destroy(plan)
         assert int(met[K["EGR_HF_BINS_HI"]]) == c["bins_hi"], name
         assert abs(met[K["EGR_HF_RESIDUAL_DB"]] - c["hf_db"]) <= 1e-3, (name, met, c["hf_db"])
+
+
+def test_full_null_test_reference_golden(sim):
+    """Audio_Null_Test.execute with every toggle on (goldens from the reference node): the same sequence of C-ABI calls
+    `egregora_eval_metrics.audio_null_test` makes — null test, LUFS of the null, LSD of A vs the scaled B, HF band of the
+    null — through the emulator."""
+    G = json.loads((GOLDEN / "null_full_golden.json").read_text())
+    K = sim.K
+    for name, c in G.items():
+        rng = np.random.default_rng(sum(map(ord, name)))
+        t = np.arange(c["N"]) / c["sr"]
+        A = (0.3 * np.sin(2 * np.pi * 440 * t) + 0.1 * rng.standard_normal((c["C"], c["N"]))).astype(np.float32)
+        B = (c["gain"] * A + c["noise"] * rng.standard_normal((c["C"], c["N"]))).astype(np.float32)
+        n, Cc, ref = c["N"], c["C"], c["metrics"]
+        a, b, null, met = _dev(A), _dev(B), _dev(np.zeros((Cc, n), np.float32)), _dev(np.zeros(K["EGR_EVAL_NUM"], np.float64))
+        wb = sim.egr_eval_workspace_bytes()
+        wk = _dev(wb)
+        sim.ck(sim.egr_eval_null_test(a.ctypes.data, n, b.ctypes.data, n, Cc, n, int(c["invert_b"]), int(c["least_squares_scale"]),
+                                      null.ctypes.data, met.ctypes.data, wk.ctypes.data, wb, None))
+        assert abs(met[K["EGR_EVAL_CORR"]] - ref["corr_coef"]) <= 3e-6
+        assert abs(met[K["EGR_EVAL_NULL_RMS_DBFS"]] - ref["null_rms_dbfs"]) <= 1e-9 * abs(ref["null_rms_dbfs"])
+        assert int(met[K["EGR_EVAL_OVERSHOOT"]]) == ref["overshoot_count"]
+        assert abs(met[K["EGR_EVAL_CLIPPED_PCT"]] - ref["clipped_pct"]) <= 1e-12
+        k = float(met[K["EGR_EVAL_SCALE_K"]])
+        assert abs(k - ref["scale_k"]) <= 1e-9 * abs(ref["scale_k"])
+        lufs, _ = _lufs(sim, null, c["sr"])
+        assert abs(lufs[K["EGR_LUFS_INTEGRATED"]] - ref["null_lufs"]) <= 1e-9
+        lm = _dev(np.zeros(K["EGR_LSD_NUM"], np.float64))
+        wb = sim.egr_eval_lsd_workspace_bytes(n, 2048, 512)
+        wk = _dev(wb)
+        gain = float(np.float32(k)) if c["least_squares_scale"] else 1.0
+        sim.ck(sim.egr_eval_lsd(a.ctypes.data, n, b.ctypes.data, n, Cc, n, 2048, 512, gain, lm.ctypes.data, wk.ctypes.data, wb, None))
+        assert abs(lm[K["EGR_LSD_MEAN_DB"]] - ref["lsd_mean_db"]) <= 1e-4 and abs(lm[K["EGR_LSD_P95_DB"]] - ref["lsd_p95_db"]) <= 1e-4
+        plan = C.c_void_p()
+        sim.ck(sim.egr_fft_plan_create(n, 1, C.byref(plan)))
+        try:
+            hm = _dev(np.zeros(K["EGR_HF_NUM"], np.float64))
+            wb = sim.egr_eval_hf_band_workspace_bytes(plan, n)
+            wk = _dev(wb)
+            sim.ck(sim.egr_eval_hf_band(plan, null.ctypes.data, n, Cc, n, c["sr"], 8000.0, hm.ctypes.data, wk.ctypes.data, wb, None))
+        finally:
+            sim.egr_fft_plan_destroy(plan)
+        assert abs(hm[K["EGR_HF_RESIDUAL_DB"]] - ref["hf_residual_db"]) <= 1e-3
 
 
 # ------------------------------------------------------------------------------------------------ path B

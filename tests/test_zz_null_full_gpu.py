@@ -1,0 +1,33 @@
+"""`egregora_eval_metrics.audio_null_test` — everything the reference's Audio_Null_Test.execute returns
+(egregora_null_test_suite.py:421-467), every toggle on — against goldens produced by the reference node
+(tests/golden/make_null_full_golden.py).  Composes egr_eval_null_test (validated on the B200) with egr_eval_lufs / _lsd /
+_hf_band (emulator-verified, first hardware run): collected last, xfail(strict=False)."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="LUFS / LSD / HF-band kernels not yet run on hardware (GPU budget spent); XPASS = verified")]
+
+
+def test_audio_null_test_matches_reference_node(cuda_dev, pkg):
+    from egregora_b200 import egregora_eval_metrics as M
+    G = json.loads((GOLDEN / "null_full_golden.json").read_text())
+    for name, c in G.items():
+        rng = np.random.default_rng(sum(map(ord, name)))
+        t = np.arange(c["N"]) / c["sr"]
+        A = (0.3 * np.sin(2 * np.pi * 440 * t) + 0.1 * rng.standard_normal((c["C"], c["N"]))).astype(np.float32)
+        B = (c["gain"] * A + c["noise"] * rng.standard_normal((c["C"], c["N"]))).astype(np.float32)
+        null, m = M.audio_null_test(torch.from_numpy(A), torch.from_numpy(B), c["sr"], invert_b=c["invert_b"],
+                                    least_squares_scale=c["least_squares_scale"], compute_hf_residual=True)
+        ref = c["metrics"]
+        assert set(m) == set(ref), (sorted(m), sorted(ref))
+        tol = {"corr_coef": 3e-6, "null_rms_dbfs": 1e-7, "null_lufs": 1e-7, "lsd_mean_db": 1e-4, "lsd_p95_db": 1e-4,
+               "hf_residual_db": 1e-3, "overshoot_count": 0, "clipped_pct": 1e-12, "scale_k": 1e-8}
+        for k, v in ref.items():
+            assert abs(m[k] - v) <= tol[k], (name, k, m[k], v)
+        assert tuple(null.shape) == (c["C"], c["N"])
