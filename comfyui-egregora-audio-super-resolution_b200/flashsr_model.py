@@ -350,7 +350,10 @@ class FlashSRGraph:
     def _unet_res(self, be, x, emb_act, name, cin, cout):
         u = self.s["unet"]
         h = be.groupnorm(x, f"{name}.in_layers.0", cin, u["groups"], u["eps"], silu=True)
-        e = be.linear(emb_act, f"{name}.emb_layers.1", 4 * u["model_channels"], cout, small=True)
+        if isinstance(emb_act, dict):   # plan backend, EGR_FUSE_EMB=1: all blocks' projections came out of one GEMV
+            e = emb_act[name]
+        else:
+            e = be.linear(emb_act, f"{name}.emb_layers.1", 4 * u["model_channels"], cout, small=True)
         h = be.conv2d(h, f"{name}.in_layers.2", cin, cout, 3, rowbias=e)
         h = be.groupnorm(h, f"{name}.out_layers.0", cout, u["groups"], u["eps"], silu=True)
         sc = x if cin == cout else be.conv2d(x, f"{name}.skip_connection", cin, cout, 1)
@@ -387,6 +390,8 @@ class FlashSRGraph:
         te = be.time_embedding(t_value, mc)
         te = be.linear(te, "unet.time_embed.0", mc, 4 * mc, small=True, act="silu")
         te = be.linear(te, "unet.time_embed.2", 4 * mc, 4 * mc, small=True, act="silu")  # SiLU of emb_layers.0 folded in
+        if getattr(be, "fuse_emb", False) is True:
+            te = be.linear_emb_all(te, 4 * mc)
         hs = []
         h = be.conv2d(x, "unet.input_blocks.0.0", u["in_channels"], mc, 3)
         hs.append((h, mc))

@@ -142,6 +142,9 @@ class PlanBackend:
         # EGR_FUSE_QKV=1: the three attention projections of a transformer block as ONE GEMM (N = 3C) whose output the
         # attention kernel reads as strided column blocks — 2 launches fewer per attention.  Off by default until measured.
         self.fuse_qkv = os.environ.get("EGR_FUSE_QKV") == "1"
+        # EGR_FUSE_EMB=1: the time-embedding projections of ALL UNet ResBlocks (emb_layers.1, M = 1 GEMVs that depend on
+        # nothing but the step's embedding) as one GEMV per diffusion step; each block's conv takes its slice as row bias.
+        self.fuse_emb = os.environ.get("EGR_FUSE_EMB") == "1"
         self._extra_w: Dict[str, torch.Tensor] = {}   # weights derived at plan time (fused projections)
         self.cutoff_buf: Optional[Buf] = None
         self.debug = False
@@ -182,6 +185,8 @@ class PlanBackend:
     # ------------------------------------------------------------------ weights
     def w_bias(self, name) -> Optional[int]:
         key = name + ".bias"
+        if key in self._extra_w:
+            return self.blob.put("f32:" + key, self._extra_w[key].float().numpy())
         if key not in self.Wt:
             return None
         return self.blob.put("f32:" + key, self.Wt[key].float().numpy())
@@ -293,7 +298,7 @@ class PlanBackend:
         if bias_off is not None:
             self._wt(op, "BIAS", bias_off)
         if rowbias is not None:
-            self._ws(op, "ROWBIAS", rowbias.f32)
+            self._ws(op, "ROWBIAS", rowbias.f32, 4 * rowbias.coff)
         if resid is not None:
             assert resid.f32 is not None and resid.parts is None and resid.ld == resid.C
             self._ws(op, "RESID", resid.f32)
@@ -409,6 +414,22 @@ class PlanBackend:
                    Wo=W, Ho=H, Bo=B, out_pt=o, out16=want16, out32=not want16, bias_off=self.w_bias(name) if bias else None,
                    resid=add, act=act, a_elem=elem)
         return o
+
+    def linear_emb_all(self, emb: PT, cin) -> Dict[str, PT]:
+        """emb_layers.1 of every UNet ResBlock in one GEMV: {block name: [1,1,1,cout] f32 slice of the joint output}."""
+        names = sorted(k[:-len(".emb_layers.1.weight")] for k in self.Wt if k.startswith("unet.") and k.endswith(".emb_layers.1.weight"))
+        key = "unet.emb_layers_all"
+        if key + ".weight" not in self._extra_w:
+            self._extra_w[key + ".weight"] = torch.cat([self.Wt[n + ".emb_layers.1.weight"] for n in names], 0)
+            self._extra_w[key + ".bias"] = torch.cat([self.Wt[n + ".emb_layers.1.bias"] for n in names], 0)
+        total = int(self._extra_w[key + ".weight"].shape[0])
+        o = self.linear(emb, key, cin, total, small=True)
+        out, off = {}, 0
+        for n in names:
+            c = int(self.Wt[n + ".emb_layers.1.weight"].shape[0])
+            out[n] = PT(o.B, 1, 1, c, f32=o.f32, ld=total, coff=off)
+            off += c
+        return out
 
     def linear_qkv(self, x: PT, prefix, c):
         """to_q / to_k / to_v of one attention layer as a single [3c, c] projection -> three f16 column-block views."""

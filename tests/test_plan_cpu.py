@@ -22,20 +22,23 @@ def _inputs(spec, B, seed=5):
     return wav, noise
 
 
-@pytest.mark.parametrize("fuse_qkv", [False, True])
-def test_tiny_plan_matches_oracle_through_interpreter(fuse_qkv, monkeypatch):
-    """fuse_qkv: the opt-in plan variant (EGR_FUSE_QKV=1) that runs the three attention projections as one GEMM and
-    feeds the attention op strided column blocks — 64 ops fewer, same numbers."""
-    if fuse_qkv:
-        monkeypatch.setenv("EGR_FUSE_QKV", "1")
-    else:
-        monkeypatch.delenv("EGR_FUSE_QKV", raising=False)
+@pytest.mark.parametrize("fuse_qkv,fuse_emb", [(False, False), (True, True)])
+def test_tiny_plan_matches_oracle_through_interpreter(fuse_qkv, fuse_emb, monkeypatch):
+    """The opt-in plan variants: EGR_FUSE_QKV=1 runs the three attention projections as one GEMM and feeds the attention
+    op strided column blocks (64 ops fewer); EGR_FUSE_EMB=1 runs the time-embedding projections of all ResBlocks as one
+    GEMV per step (21 fewer at full size) — same numbers."""
+    for var, on in (("EGR_FUSE_QKV", fuse_qkv), ("EGR_FUSE_EMB", fuse_emb)):
+        if on:
+            monkeypatch.setenv(var, "1")
+        else:
+            monkeypatch.delenv(var, raising=False)
     spec = M.tiny_spec()
     W = M.init_weights(spec, 0)
     B, steps, lp = 1, 1, True
     blob = P.WeightBlob()
     be = P.build_plan(spec, W, blob, B, steps, lp)
     assert any(o.name.endswith(".to_qkv") for o in be.ops) == fuse_qkv
+    assert any(o.name == "unet.emb_layers_all" for o in be.ops) == fuse_emb
     it = Interp(_abi.K, be.build_ops(), be.ws_bytes, blob.tobytes())
     wav, noise = _inputs(spec, B)
 

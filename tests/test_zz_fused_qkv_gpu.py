@@ -3,7 +3,8 @@
 924 -> 860 ops).  Off by default: written after the round's GPU budget was spent, so it is unmeasured; its numerics are
 pinned on the CPU (plan interpreter: tests/test_plan_cpu.py, real kernel under the emulator: tests/test_cusim.py).  These
 are the first hardware runs — collected last, xfail(strict=False); XPASS = verified, then measure with
-`EGR_FUSE_QKV=1 python bench.py` against the default."""
+`EGR_FUSE_QKV=1 EGR_FUSE_EMB=1 python bench.py` against the default (EGR_FUSE_EMB: the 22 ResBlock time-embedding GEMVs as
+one per diffusion step; both together 924 -> 839 ops)."""
 import pytest
 import torch
 
@@ -32,16 +33,21 @@ def test_attention_reads_fused_qkv_column_blocks(S, heads, hd, cuda_dev, pkg):
     assert rel_err(mp.read(o)[:, :, 0], ref) < 2e-3
 
 
-def test_tiny_e2e_with_fused_qkv(cuda_dev, pkg, monkeypatch):
+@pytest.mark.parametrize("emb", [False, True])
+def test_tiny_e2e_with_fused_qkv(cuda_dev, pkg, monkeypatch, emb):
+    """emb: additionally EGR_FUSE_EMB=1 (all ResBlock time-embedding projections as one GEMV per step)."""
     from egregora_b200 import flashsr_model as M
     from egregora_b200.flashsr_engine import FlashSREngine
     from oracle import flashsr_oracle as O
     monkeypatch.setenv("EGR_FUSE_QKV", "1")
+    if emb:
+        monkeypatch.setenv("EGR_FUSE_EMB", "1")
     spec = M.tiny_spec()
     W = M.init_weights(spec, 0)
     eng = FlashSREngine(cuda_dev, spec, W, max_batch=2)
     be, _ = eng.plan(2, 1, True)
     assert any(o.name.endswith(".to_qkv") for o in be.ops)
+    assert any(o.name == "unet.emb_layers_all" for o in be.ops) == emb
     g = torch.Generator().manual_seed(9)
     wav = (0.1 * torch.randn(2, spec["chunk"], generator=g)).cumsum(1) * 0.05
     wav = wav - wav.mean(1, keepdim=True)

@@ -8,4 +8,4 @@ timeout 900 python -m pytest tests/ -x -q -m gpu -p no:cacheprovider > gpurun_ou
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -n 2 gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"; cat gpurun_out/bench.json; tail -n 3 gpurun_out/bench.err
 # opt-in plan variants, to be compared with the default bench line above
-EGR_BENCH_CPU=0 EGR_BENCH_PATHB=0 EGR_FUSE_QKV=1 timeout 600 python bench.py > gpurun_out/bench_fuse_qkv.json 2> gpurun_out/bench_fuse_qkv.err; echo "bench (EGR_FUSE_QKV=1) exit $?"; cat gpurun_out/bench_fuse_qkv.json
+EGR_BENCH_CPU=0 EGR_BENCH_PATHB=0 EGR_FUSE_QKV=1 EGR_FUSE_EMB=1 timeout 600 python bench.py > gpurun_out/bench_fused.json 2> gpurun_out/bench_fused.err; echo "bench (EGR_FUSE_QKV=1 EGR_FUSE_EMB=1) exit $?"; cat gpurun_out/bench_fused.json
