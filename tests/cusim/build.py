@@ -54,11 +54,12 @@ def _split_top(s: str):
     return parts
 
 
-def rewrite(text: str) -> str:
+def rewrite(text: str, clusters: bool = False) -> str:
     text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w:]*(?:\s+[A-Za-z_]\w*)*?)\s+(\w+)\s*\[\s*\]\s*;",
                   r"\1* \2 = reinterpret_cast<\1*>(cusim::dyn_smem());", text)
     # kernels compiled for a fixed thread-block cluster cannot be emulated: their launches become an error return
-    clustered = set(re.findall(r"__cluster_dims__\([^)]*\)\s*(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(", text))
+    clustered = {m.group(2): m.group(1).split(",")[0].strip()
+                 for m in re.finditer(r"__cluster_dims__\(([^)]*)\)\s*(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(", text)}
     out, pos = "", 0
     while True:
         k = text.find("<<<", pos)
@@ -88,15 +89,20 @@ def rewrite(text: str) -> str:
         semi = text.index(";", a1)
         assert text[a1:semi].strip() == "", (kernel, text[a1:semi])
         smem = cfg[2] if len(cfg) > 2 else "0"
-        if kernel in clustered:
-            out += text[pos:j] + f'return egr::fail(EGR_ERR_UNSUPPORTED, "cusim: {kernel} needs a thread-block cluster, which the emulator does not provide");'
+        if kernel in clustered and not clusters:
+            out += text[pos:j] + f'return egr::fail(EGR_ERR_UNSUPPORTED, "cusim: {kernel} needs a thread-block cluster, which this build of the emulator does not provide");'
             pos = semi + 1
             continue
-        out += text[pos:j] + f"cusim::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}), [&]() {{ {kernel}{text[a0:a1]}; }});"
+        ncl = clustered.get(kernel, "1")
+        out += text[pos:j] + f"cusim::launch(dim3({cfg[0]}), dim3({cfg[1]}), (size_t)({smem}), [&]() {{ {kernel}{text[a0:a1]}; }}, {ncl});"
         pos = semi + 1
 
 
-def build(force: bool = False) -> Path:
+def build(force: bool = False, clusters: bool = False) -> Path:
+    """clusters=True: the slower variant in which thread-block clusters work (CUSIM_CLUSTERS, see cuda_runtime.h)."""
+    global OUT, LIB
+    OUT = HERE / ("_build_clusters" if clusters else "_build")
+    LIB = OUT / ("libegregora_b200_cusim_clusters.so" if clusters else "libegregora_b200_cusim.so")
     srcs = [CSRC / s for s in SOURCES + HEADERS] + [HERE / n for n in SHIM]
     srcs.append(ROOT / "include" / "egregora_b200.h")
     h = hashlib.sha256()
@@ -115,9 +121,10 @@ def build(force: bool = False) -> Path:
     inc.mkdir(exist_ok=True)
     shutil.copy(ROOT / "include" / "egregora_b200.h", inc / "egregora_b200.h")
     for n in SOURCES + HEADERS:
-        (work / (n[:-3] + ".cpp" if n.endswith(".cu") else n)).write_text(rewrite((CSRC / n).read_text()))
+        (work / (n[:-3] + ".cpp" if n.endswith(".cu") else n)).write_text(rewrite((CSRC / n).read_text(), clusters))
     cpps = [str(work / (n[:-3] + ".cpp")) for n in SOURCES] + [str(HERE / "cusim.cpp"), str(HERE / "gemm_tc_ref.cpp")]
-    cmd = [gxx, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
+    extra = ["-DCUSIM_CLUSTERS", "-pthread"] if clusters else []
+    cmd = [gxx, "-O2", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w"] + extra + [
            "-I", str(HERE), "-I", str(work), "-o", str(LIB)] + cpps
     subprocess.run(cmd, check=True)
     stamp.write_text(h.hexdigest())
@@ -125,4 +132,5 @@ def build(force: bool = False) -> Path:
 
 
 if __name__ == "__main__":
-    print(build(force=True))
+    import sys
+    print(build(force=True, clusters="--clusters" in sys.argv))

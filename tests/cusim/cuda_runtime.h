@@ -6,8 +6,10 @@
 // package's _abi.py binds libegregora_b200.so (nvcc, sm_100a) and raises without a GPU.  This header shadows
 // <cuda_runtime.h> only for the emulator build (tests/cusim/build.py puts this directory first on the include path).
 // Not emulated: tcgen05 / TMA / mbarrier (gemm_tc.cu is replaced by the plain loops of gemm_tc_ref.cpp, so a whole
-// plan can run) and thread-block clusters larger than one CTA (the low-pass kernel and the fused GroupNorm of large maps
-// return an error instead of launching).  Half precision is _Float16.  Timing means nothing; arithmetic differs from
+// plan can run).  Thread-block clusters exist only in the CUSIM_CLUSTERS build variant: there every CTA of a cluster is an
+// OS thread running its own fiber scheduler, `__shared__` is thread_local (so each CTA has its own copy), cluster.sync()
+// is a pthread barrier and map_shared_rank() adds the constant distance between two threads' TLS blocks.  thread_local
+// access is slow, so the default build has no clusters (the low-pass kernel and GroupNorm on 2-8 CTAs return an error).  Half precision is _Float16.  Timing means nothing; arithmetic differs from
 // the GPU only where nvcc contracts a*b+c into FMA and g++ (-ffp-contract=off) does not, and in the last bit of libm
 // versus SFU transcendentals.
 #pragma once
@@ -28,7 +30,12 @@
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
-#define __shared__ static
+#ifdef CUSIM_CLUSTERS
+#define CUSIM_TLS thread_local
+#else
+#define CUSIM_TLS
+#endif
+#define __shared__ static CUSIM_TLS
 #define __align__(n) alignas(n)
 
 struct dim3 {
@@ -97,7 +104,7 @@ inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 // ------------------------------------------------------------------------------------------------ the emulator
 namespace cusim {
 
-enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
+enum State { READY, WAIT_BLOCK, WAIT_WARP, WAIT_CLUSTER, DONE };
 
 struct Fiber {
   ucontext_t uc;
@@ -119,7 +126,12 @@ struct Block {
 Block& blk();                  // the block being executed
 void* dyn_smem();              // dynamic shared memory of the running block
 void yield(State s, unsigned mask);
-void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
+// cluster > 1 (CUSIM_CLUSTERS build only): consecutive x-blocks form a cluster; returns false when it cannot be done
+bool launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body, unsigned cluster = 1);
+unsigned cluster_size();
+unsigned cluster_rank();
+void cluster_sync();
+ptrdiff_t cluster_delta(unsigned rank);   // bytes from this CTA's shared memory to the same object in CTA `rank`
 unsigned long long launches();
 
 inline int linear_tid() { return blk().cur; }
@@ -145,7 +157,7 @@ inline T shuffle(unsigned mask, T v, PICK pick) {
 
 }  // namespace cusim
 
-// extended launch: only clusters of ONE block can be emulated (static __shared__ storage is one instance per process)
+// extended launch (cluster dimension along x only)
 enum cudaLaunchAttributeID { cudaLaunchAttributeClusterDimension = 4 };
 struct cudaLaunchAttributeValue { struct { unsigned x, y, z; } clusterDim; };
 struct cudaLaunchAttribute { cudaLaunchAttributeID id; cudaLaunchAttributeValue val; };
@@ -158,18 +170,19 @@ struct cudaLaunchConfig_t {
 };
 template <class K, class... A>
 inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* cfg, K kernel, A... args) {
+  unsigned ncl = 1;
   for (unsigned i = 0; i < cfg->numAttrs; ++i)
-    if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension &&
-        cfg->attrs[i].val.clusterDim.x * cfg->attrs[i].val.clusterDim.y * cfg->attrs[i].val.clusterDim.z != 1)
+    if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension && (cfg->attrs[i].val.clusterDim.y != 1 || cfg->attrs[i].val.clusterDim.z != 1))
       return cudaErrorInvalidValue;
-  cusim::launch(cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, [&]() { kernel(args...); });
-  return cudaSuccess;
+    else if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension)
+      ncl = cfg->attrs[i].val.clusterDim.x;
+  return cusim::launch(cfg->gridDim, cfg->blockDim, cfg->dynamicSmemBytes, [&]() { kernel(args...); }, ncl) ? cudaSuccess : cudaErrorInvalidValue;
 }
 #define __cluster_dims__(...)
 
 // built-in variables: plain globals the scheduler sets before it resumes a fiber (one OS thread runs everything)
-extern uint3 threadIdx, blockIdx;
-extern dim3 blockDim, gridDim;
+extern CUSIM_TLS uint3 threadIdx, blockIdx;
+extern CUSIM_TLS dim3 blockDim, gridDim;
 
 inline void __syncthreads() { cusim::yield(cusim::WAIT_BLOCK, 0); }
 inline void __syncwarp(unsigned mask = 0xffffffffu) { cusim::yield(cusim::WAIT_WARP, mask); }

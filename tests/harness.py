@@ -15,14 +15,16 @@ _CUSIM = None
 
 
 def cusim_lib():
-    """ctypes handle of the emulator build (tests/cusim/build.py), prototypes declared from _abi.signatures()."""
+    """ctypes handle of the emulator build (tests/cusim/build.py), prototypes declared from _abi.signatures().
+    EGR_TEST_CUSIM=clusters picks the slower variant in which thread-block clusters work."""
     global _CUSIM
     if _CUSIM is None:
         import sys
         from pathlib import Path
         sys.path.insert(0, str(Path(__file__).resolve().parent / "cusim"))
         import build as cusim_build
-        lib = C.CDLL(str(cusim_build.build()))
+        import os
+        lib = C.CDLL(str(cusim_build.build(clusters=os.environ.get("EGR_TEST_CUSIM") == "clusters")))
         for name, (res, args) in _abi.signatures().items():
             if hasattr(lib, name):
                 fn = getattr(lib, name)

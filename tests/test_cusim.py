@@ -6,14 +6,14 @@ whole FlashSR plan (tiny spec: front end, VAE, UNet, sampler, vocoder) through e
 CUDA-core kernel (GroupNorm, LayerNorm, attention, GEGLU, snake, STFT-mel, element-wise glue, SIMT convs) executes its
 real source and the tensor-core GEMM ops are evaluated by plain loops (tests/cusim/gemm_tc_ref.cpp).  The whole
 `-m gpu` op suite also runs this way on demand: `EGR_TEST_CUSIM=1 pytest tests/test_ops_gpu.py -m gpu` (60 of 65 pass;
-the other five need thread-block clusters, which the emulator refuses loudly).
+the other five need thread-block clusters, which the default build refuses loudly and the slower
+`EGR_TEST_CUSIM=clusters` variant runs: 65 of 65).
 
 What this is for: (1) kernels written without GPU time (egr_eval_lsd) execute their actual code — indexing, barriers,
 radix select — before their first hardware run; (2) the emulator reproducing what the B200 already verified for the other
 kernels is the check on the emulator itself.  What it is not: the product never loads this library (there is no CPU
 fallback, tests/test_abi.py::test_no_gpu_fails_loudly), nothing here says anything about speed, and the tcgen05 / TMA /
-cluster kernels (the tap-GEMM itself, the 8-CTA low-pass, GroupNorm on clusters of 2-8 CTAs) are outside its reach —
-those stay GPU-only.
+kernel (the tap-GEMM) is outside its reach — that one stays GPU-only.
 """
 import ctypes as C
 import hashlib
@@ -442,6 +442,19 @@ def test_cluster_kernels_are_refused_not_faked(sim, pkg):
         assert b"cluster" in sim.egr_last_error()
     finally:
         sim.egr_plan_destroy(h)
+
+
+def test_cluster_kernels_under_the_cluster_variant():
+    """The CUSIM_CLUSTERS build (every CTA of a cluster an OS thread, `__shared__` thread_local, cluster.sync a pthread
+    barrier, map_shared_rank the distance between two threads' TLS blocks) runs the two cluster kernels of the hot path:
+    GroupNorm on clusters of 2 / 4 / 8 CTAs exchanging moments through distributed shared memory, and the 8-CTA
+    zero-phase low-pass with its three-level scan — the GPU op tests for them, through the emulator."""
+    import os
+    import subprocess
+    env = dict(os.environ, EGR_TEST_CUSIM="clusters")
+    r = subprocess.run([sys.executable, "-m", "pytest", str(ROOT / "tests" / "test_ops_gpu.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "cluster_sizes or lowpass"], env=env, capture_output=True, text=True, cwd=str(ROOT))
+    assert r.returncode == 0 and " passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
 def test_new_kernels_do_not_depend_on_thread_order():
