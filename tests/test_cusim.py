@@ -35,10 +35,13 @@ sys.path.insert(0, str(ROOT / "tests" / "cusim"))
 pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="g++ is needed to build the emulator")
 
 
+POISON = False   # True: scratch buffers start as 0xFF bytes (NaN as float / double), like torch.empty on a used GPU heap
+
+
 def _dev(nbytes_or_array):
     """256-byte aligned host buffer standing in for device memory; accepts a byte count or an array to copy."""
     if isinstance(nbytes_or_array, (int, np.integer)):
-        raw = np.zeros(int(nbytes_or_array) + 256, np.uint8)
+        raw = np.full(int(nbytes_or_array) + 256, 0xFF if POISON else 0, np.uint8)
         off = (-raw.ctypes.data) % 256
         return raw[off:off + int(nbytes_or_array)]
     a = np.ascontiguousarray(nbytes_or_array)
@@ -442,6 +445,19 @@ def test_cluster_kernels_are_refused_not_faked(sim, pkg):
         assert b"cluster" in sim.egr_last_error()
     finally:
         sim.egr_plan_destroy(h)
+
+
+def test_metrics_kernels_do_not_depend_on_a_zeroed_workspace(sim, monkeypatch):
+    """The host mirrors hand the kernels torch.empty workspaces.  Re-run the metrics tests with every scratch buffer
+    poisoned (0xFF bytes = NaN): a kernel that reads workspace it has not written shows up as a NaN or a wrong number."""
+    import test_cusim as me
+    monkeypatch.setattr(me, "POISON", True)
+    assert _dev(16)[0] == 0xFF
+    test_eval_null_test_reference_golden(sim)
+    test_eval_lsd_reference_golden(sim)
+    test_eval_lufs_reference_golden(sim)
+    test_eval_hf_band_reference_golden(sim)
+    test_dfn_mix_reference_golden(sim)
 
 
 def test_cluster_kernels_under_the_cluster_variant():
