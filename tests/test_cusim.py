@@ -403,6 +403,7 @@ def test_flashsr_tiny_plan_end_to_end(sim, pkg, monkeypatch):
     B = 1   # ~50 s under emulation; the GPU test covers B in {1, 2, 3}
     be = P.build_plan(spec, W, blob, B, 1, False)
     ws = _dev(be.ws_bytes + 4096)
+    ws[:] = 0xFF   # the engine hands the plan a torch.empty workspace: every byte a NaN until some op writes it
     wt = _dev(np.frombuffer(blob.tobytes(), np.uint8))
     g = torch.Generator().manual_seed(5)
     wav = (0.1 * torch.randn(B, spec["chunk"], generator=g)).cumsum(1) * 0.05
