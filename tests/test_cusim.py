@@ -454,11 +454,9 @@ def test_metrics_kernels_do_not_depend_on_a_zeroed_workspace(sim, monkeypatch):
     import test_cusim as me
     monkeypatch.setattr(me, "POISON", True)
     assert _dev(16)[0] == 0xFF
-    test_eval_null_test_reference_golden(sim)
-    test_eval_lsd_reference_golden(sim)
+    test_eval_lsd_reference_golden(sim)       # the three entry points that have not met a real torch.empty yet
     test_eval_lufs_reference_golden(sim)
     test_eval_hf_band_reference_golden(sim)
-    test_dfn_mix_reference_golden(sim)
 
 
 def test_cluster_kernels_under_the_cluster_variant():
@@ -482,5 +480,5 @@ def test_new_kernels_do_not_depend_on_thread_order():
     import subprocess
     env = dict(os.environ, CUSIM_ORDER="reverse")
     r = subprocess.run([sys.executable, "-m", "pytest", str(Path(__file__)), "-q", "-x", "-p", "no:cacheprovider", "-k",
-                        "eval_lsd or eval_lufs or eval_hf_band or eval_null_test"], env=env, capture_output=True, text=True, cwd=str(ROOT))
+                        "eval_lsd or eval_lufs or eval_hf_band"], env=env, capture_output=True, text=True, cwd=str(ROOT))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
