@@ -103,6 +103,7 @@ def signatures() -> dict:
         "egr_eval_lufs": (C.c_int, [f32p, i64, i32, i64, i32, vp, vp, C.c_size_t, vp]),
         "egr_eval_hf_band_workspace_bytes": (C.c_size_t, [vp, i64]),
         "egr_eval_hf_band": (C.c_int, [vp, f32p, i64, i32, i64, i32, C.c_double, vp, vp, C.c_size_t, vp]),
+        "egr_noise_fill": (C.c_int, [C.c_uint64, i64, i64, i64, f32p, vp]),
         "egr_resample_poly": (C.c_int, [f32p, i32, i64, i32, i32, f32p, i32, i64, i64, f32p, vp]),
         "egr_plan_create": (C.c_int, [C.POINTER(Op), i32, vp, C.c_size_t, vp, C.c_size_t, C.POINTER(vp)]),
         "egr_plan_run": (C.c_int, [vp, i32, i32, vp]),
@@ -120,6 +121,7 @@ def signatures() -> dict:
         "egr_pcm16_quantize": (C.c_int, [f32p, vp, i64, vp]),
         "egr_pcm16_to_float": (C.c_int, [vp, f32p, i64, C.c_float, vp]),
         "egr_absmax": (C.c_int, [f32p, i64, f32p, vp]),
+        "egr_scale_if_above": (C.c_int, [f32p, i64, f32p, C.c_float, C.c_float, vp]),
     }
 
 

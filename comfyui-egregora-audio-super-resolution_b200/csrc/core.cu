@@ -145,3 +145,76 @@ extern "C" int egr_pcm16_to_float(const int16_t* d_in, float* d_out, int64_t n, 
   EGR_CHECK_LAUNCH("pcm16_deq_kernel");
   return EGR_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Diffusion start noise x_T.  Counter-based (Philox4x32-10, Salmon et al. 2011) so that the value of element e of
+// chunk-channel row r depends on (seed, r, e) only: a rank that owns rows [lo, hi) of a clip generates exactly the
+// numbers a single-GPU run uses for those rows, whatever the world size or sub-batch split.  Four uniforms per
+// counter -> two Box-Muller pairs.  u = ((bits >> 8) + 1) * 2^-24 in (0, 1].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void noise_fill_kernel(uint32_t k0, uint32_t k1, int64_t row0, int64_t n_rows, int64_t row_elems,
+                                  float* __restrict__ out) {
+  const int64_t quads = (row_elems + 3) >> 2;
+  const int64_t total = n_rows * quads;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / quads, q = i - r * quads;
+    const uint64_t row = (uint64_t)(row0 + r);
+    uint32_t x[4];
+    philox4x32_10((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)row, (uint32_t)(row >> 32), k0, k1, x);
+    float z[4];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      const float u1 = (float)((x[2 * p] >> 8) + 1u) * 5.9604644775390625e-8f;      // 2^-24
+      const float u2 = (float)((x[2 * p + 1] >> 8) + 1u) * 5.9604644775390625e-8f;
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float s, c;
+      sincospif(2.0f * u2, &s, &c);
+      z[2 * p] = rad * c; z[2 * p + 1] = rad * s;
+    }
+    float* dst = out + r * row_elems + 4 * q;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (4 * q + u < row_elems) dst[u] = z[u];
+  }
+}
+
+extern "C" int egr_noise_fill(uint64_t seed, int64_t row0, int64_t n_rows, int64_t row_elems, float* d_out, void* stream) {
+  if (!d_out || n_rows < 0 || row_elems <= 0 || row0 < 0) return fail(EGR_ERR_ARG, "egr_noise_fill: bad arguments");
+  if (n_rows == 0) return EGR_OK;
+  const int64_t total = n_rows * ((row_elems + 3) >> 2);
+  noise_fill_kernel<<<grid_for(total, 1), 256, 0, (cudaStream_t)stream>>>((uint32_t)seed, (uint32_t)(seed >> 32), row0, n_rows,
+                                                                         row_elems, d_out);
+  EGR_CHECK_LAUNCH("noise_fill_kernel");
+  return EGR_OK;
+}
+
+// x *= scale iff *d_ref > threshold — the "rescale integer-scaled data by 2^(8*sw-1) when its peak exceeds 1" rule of
+// the reference's patched write_audio (egregora_fat_llama_gpu.py:195-200), decided on the device from egr_absmax's
+// result so the node body never reads the peak back to the host.
+__global__ void scale_if_above_kernel(float* __restrict__ x, int64_t n, const float* __restrict__ ref, float threshold, float scale) {
+  if (!(__ldg(ref) > threshold)) return;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] *= scale;
+}
+
+extern "C" int egr_scale_if_above(float* d_x, int64_t n, const float* d_ref, float threshold, float scale, void* stream) {
+  if (!d_x || !d_ref || n < 0) return fail(EGR_ERR_ARG, "egr_scale_if_above: bad arguments");
+  if (n == 0) return EGR_OK;
+  scale_if_above_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(d_x, n, d_ref, threshold, scale);
+  EGR_CHECK_LAUNCH("scale_if_above_kernel");
+  return EGR_OK;
+}

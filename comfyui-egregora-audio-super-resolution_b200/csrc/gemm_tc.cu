@@ -895,10 +895,13 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   const int n_outer = halo ? kchunks : g.ntaps * kchunks;
   const int n_inner = halo ? g.ntaps : 1;
 
-  // ---- split-K: only when the whole launch (all batch items) has too few 128x128 output blocks to fill the GPU.
-  // The reduction order is fixed for a given launch geometry (deterministic); a different batch size may pick a
-  // different split count, i.e. a different f32 summation order (differences at the 1e-6 relative level).
-  const int units = tiles1 * ceil_div(g.N, 128);
+  // ---- split-K: a constant of the LAYER, not of the launch.  The split count fixes the f32 summation order of
+  // every output element, so it is derived from the geometry of ONE batch item (output tiles of a single item x
+  // n-tiles): a chunk-channel then gets bit-identical results whether it runs alone or inside a batch of 8.  (The
+  // first version sized the split for the whole launch; alone-vs-batched outputs differed by ~7e-4 RMS through the
+  // f16 operand roundings downstream.)  EGR_TC_SPLIT_POLICY=launch restores that rule for A/B timing only.
+  static const bool split_by_launch = getenv("EGR_TC_SPLIT_POLICY") && !strcmp(getenv("EGR_TC_SPLIT_POLICY"), "launch");
+  const int units = (split_by_launch ? tiles1 : tiles_w128 * tiles_h) * ceil_div(g.N, 128);
   int splits = 1;
   if (!g.wz_batch && env_int("EGR_TC_NO_SPLITK", 0) == 0) {
     splits = sms / (units > 0 ? units : 1);

@@ -42,7 +42,16 @@ def _make_audio(sr: int, samples_cs) -> Dict[str, Any]:
     t = samples_cs if isinstance(samples_cs, torch.Tensor) else torch.from_numpy(np.asarray(samples_cs, np.float32))
     if t.dim() == 1:
         t = t[None, :]
-    t = t.detach().to(device="cpu", dtype=torch.float32)
+    t = t.detach()
+    if t.is_cuda:
+        # device result -> a fresh PINNED host tensor (torch's caching host allocator): the copy runs at PCIe speed
+        # instead of being staged through the driver's bounce buffers as a pageable destination is (c3: 230 MB)
+        host = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
+        host.copy_(t.to(torch.float32), non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        t = host
+    else:
+        t = t.to(dtype=torch.float32)
     return {"waveform": t.unsqueeze(0).contiguous(), "sample_rate": int(sr)}
 
 
@@ -223,14 +232,34 @@ def _require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def get_engine(device: Optional[torch.device] = None):
-    """Process-level FlashSR engine (the reference rebuilds its runner on every run(), ref :393)."""
+def get_engine(device: Optional[torch.device] = None, ckpt_dir: Optional[str] = None):
+    """Process-level FlashSR engine (the reference rebuilds its runner — three torch.load + H2D of every weight —
+    on every run(), ref :393).  Weights come from the reference's checkpoint files (flashsr_weights.py: ref :260-265,
+    :282-320, :346-359); a missing file raises the reference's RuntimeError, random weights are never substituted
+    unless EGREGORA_FLASHSR_RANDOM_INIT=1 says so explicitly (tests / bench)."""
     from .flashsr_engine import FlashSREngine
+    from . import flashsr_weights
     device = device or _require_cuda()
-    key = (device.index or 0, os.environ.get("EGREGORA_FLASHSR_WEIGHTS", ""))
+    d = flashsr_weights.resolve_ckpt_dir(ckpt_dir)
+    key = (device.index or 0, str(d), flashsr_weights.random_init_allowed(), os.environ.get("EGREGORA_FLASHSR_RANDOM_SEED", "0"))
     if key not in _ENGINES:
-        _ENGINES[key] = FlashSREngine(device)
+        weights, tag = flashsr_weights.weights_for_node(ckpt_dir)
+        eng = FlashSREngine(device, weights=weights)
+        eng.weights_tag = tag
+        _ENGINES[key] = eng
     return _ENGINES[key]
+
+
+def _call_model(chunk_model, chunks: torch.Tensor, row0: int) -> torch.Tensor:
+    """chunk_model(chunks [N,win]) or chunk_model(chunks, row0=...) when it declares that keyword: row0 is the global
+    chunk-channel index of chunks[0] inside the clip (the FlashSR engine keys its diffusion noise on it, so a rank that
+    runs spans [lo,hi) produces the same numbers a single-GPU run does)."""
+    import inspect
+    try:
+        takes = "row0" in inspect.signature(chunk_model).parameters
+    except (TypeError, ValueError):
+        takes = False
+    return chunk_model(chunks, row0=row0) if takes else chunk_model(chunks)
 
 
 def upscale_48k(x_dev: torch.Tensor, chunk_model, *, shard: bool = True) -> torch.Tensor:
@@ -244,7 +273,7 @@ def upscale_48k(x_dev: torch.Tensor, chunk_model, *, shard: bool = True) -> torc
     world = dist.get_world_size() if (shard and dist.is_available() and dist.is_initialized()) else 1
     if world == 1 or n == 0:
         chunks = gather_chunks(x_dev, spans, win)
-        preds = chunk_model(chunks.view(n * C, win)) if n else chunks
+        preds = _call_model(chunk_model, chunks.view(n * C, win), 0) if n else chunks
         preds = preds.view(n, C, -1) if n else preds
         return wola_stitch(preds, spans, total, win)
     # contiguous blocks of ceil(n/world) spans per rank; pad the tail ranks so one all_gather suffices
@@ -255,7 +284,7 @@ def upscale_48k(x_dev: torch.Tensor, chunk_model, *, shard: bool = True) -> torc
     chunks = gather_chunks(x_dev, mine, win)
     local = torch.zeros((per, C, win), dtype=torch.float32, device=x_dev.device)
     if hi > lo:
-        y = chunk_model(chunks.view((hi - lo) * C, win)).view(hi - lo, C, -1)
+        y = _call_model(chunk_model, chunks.view((hi - lo) * C, win), lo * C).view(hi - lo, C, -1)
         if y.shape[-1] != win:
             raise RuntimeError("sharded stitch needs the chunk model to return full windows")
         local[: hi - lo] = y
@@ -286,16 +315,18 @@ class EgregoraAudioSuperResolution:
     NUM_STEPS = int(os.environ.get("EGREGORA_FLASHSR_STEPS", "1"))
     SEED = int(os.environ.get("EGREGORA_FLASHSR_SEED", "4321"))
 
+    CKPT_DIR: Optional[str] = None   # flashsr_min --ckpt-dir; None = ComfyUI/models/audio/flashsr (ref :265)
+
     def run(self, audio=None, lowpass_input=False, output_sr="48000"):
         in_cs, in_sr = _from_audio_dict(audio)
         device = _require_cuda()
-        engine = get_engine(device)
+        engine = get_engine(device, self.CKPT_DIR)
         x_dev = in_cs.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
         if in_sr != REQ_SR:
             x_dev = _resample_hq(x_dev, in_sr, REQ_SR)
             in_sr = REQ_SR
         steps, seed, lp = int(self.NUM_STEPS), int(self.SEED), bool(lowpass_input)
-        out_48k = upscale_48k(x_dev, lambda chunks: engine.infer(chunks, lowpass=lp, steps=steps, seed=seed))
+        out_48k = upscale_48k(x_dev, lambda chunks, row0=0: engine.infer(chunks, lowpass=lp, steps=steps, seed=seed, row0=row0))
         tgt_sr = int(output_sr)
         if tgt_sr != in_sr:
             return (_make_audio(tgt_sr, _resample_hq(out_48k, in_sr, tgt_sr)),)

@@ -10,8 +10,21 @@ from __future__ import annotations
 
 import torch
 
-from .egregora_fat_llama_gpu import (CATEGORY, FUNCTION, RETURN_TYPES, _ensure_gpu_stack,
-                                     _normalize_audio_input, fat_llama_device)
+from .egregora_fat_llama_gpu import (CATEGORY, FUNCTION, RETURN_TYPES, _normalize_audio_input, _to_host,
+                                     fat_llama_device)
+
+
+def _ensure_device() -> torch.device:
+    """The reference's CPU node needs no GPU (egregora_fat_llama_cpu.py:77-134: fat_llama_fftw + pyFFTW).  This build
+    ships no CPU arithmetic at all (north_star: "no CPU fallback"), so on a machine without CUDA this node ID cannot
+    run — say exactly that instead of the GPU node's "use the CPU node" hint, which would point back here."""
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "Fat Llama — CPU/FFTW: this B200-native build of the pack keeps the node ID for existing graphs but runs it "
+            "on the CUDA kernels of the GPU node; it ships no CPU/FFTW implementation and no CUDA GPU was detected. "
+            "Install the original pack (fat-llama-fftw) for CPU-only machines."
+        )
+    return torch.device("cuda", torch.cuda.current_device())
 
 
 class EgregoraFatLlamaCPU:
@@ -38,11 +51,11 @@ class EgregoraFatLlamaCPU:
 
     def run(self, target_format, max_iterations, threshold_value, target_bitrate_kbps, AUDIO=None,
             audio_path="", audio_url=""):
-        device = _ensure_gpu_stack()
+        device = _ensure_device()
         cs, in_sr = _normalize_audio_input(AUDIO, audio_path, audio_url)
         out, sr = fat_llama_device(cs.to(device=device, dtype=torch.float32), in_sr, int(max_iterations),
                                    float(threshold_value), int(target_bitrate_kbps), True, True)
-        return ({"waveform": out.to("cpu").unsqueeze(0).contiguous(), "sample_rate": int(sr)},)
+        return ({"waveform": _to_host(out).unsqueeze(0).contiguous(), "sample_rate": int(sr)},)
 
 
 NODE_CLASS_MAPPINGS = {"EgregoraFatLlamaCPU": EgregoraFatLlamaCPU}

@@ -44,10 +44,14 @@ def _to_cs(x) -> np.ndarray:
 
 
 def _read_pcm_wav(path: str) -> Tuple[np.ndarray, int]:
-    """Minimal WAV reader (PCM 8/16/24/32-bit) -> float32 frames-first, like sf.read(dtype='float32')."""
-    with wave.open(path, "rb") as w:
-        sr, ch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
-        raw = w.readframes(n)
+    """WAV reader (PCM 8/16/24/32-bit) -> float32 frames-first, like sf.read(dtype='float32')."""
+    try:
+        with wave.open(path, "rb") as w:
+            sr, ch, sw, n = w.getframerate(), w.getnchannels(), w.getsampwidth(), w.getnframes()
+            raw = w.readframes(n)
+    except (wave.Error, EOFError, OSError) as e:
+        raise RuntimeError(f"Failed to read audio file {path}: {e} (without the soundfile package only PCM WAV files "
+                           "can be decoded; FLAC/OGG/float WAV need `pip install soundfile`)") from e
     if sw == 2:
         x = np.frombuffer(raw, "<i2").astype(np.float32) / 32768.0
     elif sw == 4:
@@ -60,9 +64,24 @@ def _read_pcm_wav(path: str) -> Tuple[np.ndarray, int]:
     elif sw == 1:
         x = (np.frombuffer(raw, np.uint8).astype(np.float32) - 128.0) / 128.0
     else:
-        raise RuntimeError(f"unsupported WAV sample width {sw}")
+        raise RuntimeError(f"Failed to read audio file {path}: unsupported WAV sample width {sw}")
     x = x.astype(np.float32)
     return (x.reshape(-1, ch) if ch > 1 else x), sr
+
+
+def _read_audio_file(path: str) -> Tuple[np.ndarray, int]:
+    """sf.read(path, dtype='float32', always_2d=False) of the reference (:62-66, :74-78) — through soundfile itself when
+    it is importable (any libsndfile format: WAV incl. float / extensible, FLAC, OGG), else the stdlib PCM-WAV reader.
+    Failures are RuntimeErrors, the pack's only error type."""
+    try:
+        import soundfile as sf  # type: ignore
+    except Exception:
+        return _read_pcm_wav(path)
+    try:
+        y, sr = sf.read(path, dtype="float32", always_2d=False)
+    except Exception as e:
+        raise RuntimeError(f"Failed to read audio file {path}: {e}") from e
+    return np.asarray(y, np.float32), int(sr)
 
 
 def _normalize_audio_input(AUDIO=None, audio_path: str = "", audio_url: str = "") -> Tuple[torch.Tensor, int]:
@@ -84,7 +103,7 @@ def _normalize_audio_input(AUDIO=None, audio_path: str = "", audio_url: str = ""
         p = Path(audio_path)
         if not p.exists():
             raise RuntimeError(f"audio_path not found: {audio_path}")
-        y, sr = _read_pcm_wav(str(p))
+        y, sr = _read_audio_file(str(p))
         return torch.from_numpy(_to_cs(y)), int(sr)
     if audio_url:
         import requests
@@ -92,7 +111,7 @@ def _normalize_audio_input(AUDIO=None, audio_path: str = "", audio_url: str = ""
         r.raise_for_status()
         p = Path(tempfile.gettempdir()) / f"eg_url_{int(time.time() * 1000)}.wav"
         p.write_bytes(r.content)
-        y, sr = _read_pcm_wav(str(p))
+        y, sr = _read_audio_file(str(p))
         return torch.from_numpy(_to_cs(y)), int(sr)
     raise RuntimeError("No AUDIO provided.")
 
@@ -139,10 +158,11 @@ def fat_llama_device(x_dev: torch.Tensor, sr: int, max_iterations: int, threshol
     _abi.check(lib.egr_fatllama_run(samples.data_ptr(), y.data_ptr(), C, S, U, int(max_iterations),
                                     float(threshold_value), flags, work.data_ptr(), int(wbytes), st), "egr_fatllama_run")
     # patched write_audio (:188-208): integer-scaled data is brought back to [-1,1] by 2**(8*sw-1)
+    # — decided and applied on the device (the branch needs max|y|; reading it back would stall the stream)
     peak = torch.empty((1,), dtype=torch.float32, device=dev)
     _abi.check(lib.egr_absmax(y.data_ptr(), C * S * U, peak.data_ptr(), st), "egr_absmax")
-    if float(peak.item()) > 1.0:
-        y = y / float(2 ** (8 * SAMPLE_WIDTH - 1))
+    _abi.check(lib.egr_scale_if_above(y.data_ptr(), C * S * U, peak.data_ptr(), 1.0, 1.0 / float(2 ** (8 * SAMPLE_WIDTH - 1)), st),
+               "egr_scale_if_above")
     # output file (PCM-16) + sf.read(float32) (:291)
     q2 = torch.empty((C, S * U), dtype=torch.int16, device=dev)
     _abi.check(lib.egr_pcm16_quantize(y.data_ptr(), q2.data_ptr(), C * S * U, st), "egr_pcm16_quantize")
@@ -151,6 +171,14 @@ def fat_llama_device(x_dev: torch.Tensor, sr: int, max_iterations: int, threshol
     if return_prequant:
         return out, sr * U, y
     return out, sr * U
+
+
+def _to_host(t: torch.Tensor) -> torch.Tensor:
+    """device [C,T] -> fresh pinned CPU tensor (PCIe-speed copy, one sync — the only one of the node body)."""
+    host = torch.empty(t.shape, dtype=torch.float32, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host
 
 
 class EgregoraFatLlamaGPU:
@@ -187,8 +215,7 @@ class EgregoraFatLlamaGPU:
         x_dev = cs.to(device=device, dtype=torch.float32)
         out, sr = fat_llama_device(x_dev, in_sr, int(max_iterations), float(threshold_value),
                                    int(target_bitrate_kbps), bool(toggle_normalize), bool(toggle_autoscale))
-        wf = out.to("cpu").unsqueeze(0).contiguous()  # [1,C,T]
-        return ({"waveform": wf, "sample_rate": int(sr)},)
+        return ({"waveform": _to_host(out).unsqueeze(0).contiguous(), "sample_rate": int(sr)},)  # [1,C,T]
 
 
 NODE_CLASS_MAPPINGS = {"EgregoraFatLlamaGPU": EgregoraFatLlamaGPU}

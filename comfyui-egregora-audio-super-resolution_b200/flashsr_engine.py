@@ -58,15 +58,17 @@ class FlashSREngine:
         be = build_plan(self.spec, self.weights, self.blob, batch, steps, lowpass, debug=self.debug)
         need = be.ws_bytes + 4096
         if self.ws is None or self.ws.numel() < need:
+            # a larger workspace: every existing plan holds absolute addresses into the old one, so all handles are
+            # rebuilt.  Forget them BEFORE anything can raise (allocation, plan creation): a failed re-plan must not
+            # leave freed handles behind for the next infer() / close() to use.
             torch.cuda.synchronize(self.device)
-            for _, h in self.plans.values():
+            old, self.plans = self.plans, {}
+            for _, h in old.values():
                 self.lib.egr_plan_destroy(h)
             self.ws = None
             self.ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            rebuilt = {}
-            for k, (obe, _) in self.plans.items():
-                rebuilt[k] = (obe, self._create(obe))
-            self.plans = rebuilt
+            for k, (obe, _) in old.items():
+                self.plans[k] = (obe, self._create(obe))
         self.plans[key] = (be, self._create(be))
         return self.plans[key]
 
@@ -86,22 +88,32 @@ class FlashSREngine:
         return x.permute(0, 3, 1, 2).contiguous().cpu()
 
     # ------------------------------------------------------------------ inference
-    def make_noise(self, n: int, seed: int) -> torch.Tensor:
-        """x_T [n, z, T/8, F/8] from a CPU generator, so the oracle can be fed the same tensor."""
+    def noise_shape(self, n: int) -> Tuple[int, int, int, int]:
         s = self.spec
-        g = torch.Generator().manual_seed(int(seed))
         fr = s["chunk"] // s["mel"]["hop"]
-        return torch.randn((n, s["vae"]["embed_dim"], fr // 8, s["mel"]["n_mels"] // 8), generator=g)
+        return (n, s["vae"]["embed_dim"], fr // 8, s["mel"]["n_mels"] // 8)
+
+    def make_noise(self, n: int, seed: int, row0: int = 0) -> torch.Tensor:
+        """x_T [n, z, T/8, F/8] (NCHW, on the device) for chunk-channel rows row0 .. row0+n-1 of a clip.  Counter-based
+        (egr_noise_fill): a row's noise depends on (seed, global row index) only — not on the batch it runs in, not on
+        how a clip is split over sub-batches or ranks — and no host RNG sits on the critical path."""
+        shape = self.noise_shape(n)
+        out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        if n:
+            _abi.check(self.lib.egr_noise_fill(int(seed) & 0xFFFFFFFFFFFFFFFF, int(row0), n, out[0].numel(), out.data_ptr(),
+                                               torch.cuda.current_stream(self.device).cuda_stream), "egr_noise_fill")
+        return out
 
     def infer(self, x: torch.Tensor, lowpass: bool = False, steps: int = 1, seed: int = 4321,
-              noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """x [N, chunk] f32 on the engine's device -> [N, chunk]."""
+              noise: Optional[torch.Tensor] = None, row0: int = 0) -> torch.Tensor:
+        """x [N, chunk] f32 on the engine's device -> [N, chunk].  `row0`: global index of x[0] among the clip's
+        chunk-channels (selects its diffusion noise when `noise` is not supplied)."""
         if x.dim() != 2 or x.shape[1] != self.spec["chunk"]:
             raise RuntimeError(f"FlashSR expects [N, {self.spec['chunk']}] chunks, got {tuple(x.shape)}")
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
         N = x.shape[0]
         if noise is None:
-            noise = self.make_noise(N, seed)
+            noise = self.make_noise(N, seed, row0)
         noise = noise.to(self.device, torch.float32).permute(0, 2, 3, 1).contiguous()  # NHWC
         out = torch.empty_like(x)
         caller = torch.cuda.current_stream(self.device)

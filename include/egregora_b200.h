@@ -68,6 +68,12 @@ int egr_wola_stitch(const float* d_chunks, int l_pred, const int64_t* d_starts, 
 int egr_resample_poly(const float* d_x, int C, int64_t n_in, int up, int down, const float* d_hflip,
                       int hpp, int64_t y_first, int64_t n_out, float* d_y, void* stream);
 
+/* Diffusion start noise x_T of the FlashSR sampler (upstream draws it inside forward(), call site
+ * egregora_audio_super_resolution.py:366-369).  Counter-based Philox4x32-10 + Box-Muller: element e
+ * of chunk-channel row (row0 + r) depends on (seed, row0 + r, e) only, so a rank that owns rows [lo, hi) of a clip
+ * produces exactly the numbers the single-GPU run uses for those rows.  d_out [n_rows, row_elems] f32, standard normal. */
+int egr_noise_fill(uint64_t seed, int64_t row0, int64_t n_rows, int64_t row_elems, float* d_out, void* stream);
+
 /* ------------------------------------------------------------------------------------------ */
 /* path A model: a plan is a straight-line list of ops over one workspace + one weight blob     */
 /* ------------------------------------------------------------------------------------------ */
@@ -242,6 +248,9 @@ int  egr_pcm16_quantize(const float* d_in, int16_t* d_out, int64_t n, void* stre
 int  egr_pcm16_to_float(const int16_t* d_in, float* d_out, int64_t n, float scale, void* stream);
 /* max |x| over n f32 values -> d_out[0] (f32). */
 int  egr_absmax(const float* d_in, int64_t n, float* d_out, void* stream);
+/* d_x[i] *= scale for all i iff d_ref[0] > threshold, decided on the device: the patched write_audio of the reference
+ * (egregora_fat_llama_gpu.py:195-200) divides integer-scaled data by 2^(8*sample_width-1) when its peak exceeds 1. */
+int  egr_scale_if_above(float* d_x, int64_t n, const float* d_ref, float threshold, float scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* next row: adaptive wet/dry mix of Egregora_DeepFilterNet_Denoise        */

@@ -10,6 +10,10 @@ PKG_DIR = ROOT / "comfyui-egregora-audio-super-resolution_b200"
 GOLDEN = ROOT / "tests" / "golden"
 if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
+# No FlashSR checkpoint exists in this environment: tests that go through the node run on seeded random weights and say so
+# explicitly (the node itself raises without this switch; tests/test_weights.py and test_checkpoint_gpu.py cover loading).
+import os  # noqa: E402
+os.environ.setdefault("EGREGORA_FLASHSR_RANDOM_INIT", "1")
 
 
 def load_pkg():
@@ -50,3 +54,17 @@ def cuda_dev():
     from egregora_b200 import _abi
     _abi.init(0)
     return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="session")
+def synthetic_ckpt_dir(tmp_path_factory):
+    """Full-size synthetic checkpoint files in upstream naming (tools/make_synthetic_ckpt.py) -> (dir, weights)."""
+    load_pkg()
+    sys.path.insert(0, str(ROOT / "tools"))
+    import make_synthetic_ckpt as S
+    from egregora_b200 import flashsr_model as M
+    spec = M.default_spec()
+    W = M.init_weights(spec, 7)
+    d = tmp_path_factory.mktemp("flashsr_ckpt")
+    S.write(d, spec, W)
+    return d, W

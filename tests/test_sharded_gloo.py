@@ -24,10 +24,17 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _chunk_model(c: torch.Tensor) -> torch.Tensor:
-    # position-dependent, non-linear, deterministic: any mis-ordered or mis-padded chunk shows up in the stitch
+SEED = 4321
+
+
+def _chunk_model(c: torch.Tensor, row0: int = 0) -> torch.Tensor:
+    # position-dependent, non-linear, deterministic: any mis-ordered or mis-padded chunk shows up in the stitch.
+    # It also CONSUMES NOISE keyed by the global chunk-channel row, as the FlashSR engine does (egr_noise_fill's numpy
+    # restatement): a sharded driver that restarted its rows at 0 on every rank would change the stitched output.
+    from oracle import noise_oracle as NO
     ramp = torch.linspace(0.5, 1.5, c.shape[1], dtype=torch.float32)
-    return torch.tanh(c * 3.0) * ramp + 0.01 * c.flip(1)
+    z = torch.from_numpy(NO.noise_rows(SEED, row0, c.shape[0], 4096))
+    return torch.tanh(c * 3.0) * ramp + 0.01 * c.flip(1) + 0.05 * z.repeat(1, c.shape[1] // 4096 + 1)[:, :c.shape[1]]
 
 
 def _worker(rank: int, world: int, port: int, total: int, channels: int, out_dir: str):
@@ -49,9 +56,10 @@ def _worker(rank: int, world: int, port: int, total: int, channels: int, out_dir
         lst = [(preds[k].numpy(), s, L) for k, (s, L) in enumerate(spans)]
         return torch.from_numpy(O.wola_stitch(lst, total_, win))
 
-    def model(c):
+    def model(c, row0=0):
         calls["rows"] += c.shape[0]
-        return _chunk_model(c)
+        calls.setdefault("row0s", []).append(int(row0))
+        return _chunk_model(c, row0)
 
     N.gather_chunks, N.wola_stitch = gather_chunks, wola_stitch
     x = torch.from_numpy((np.random.default_rng(7).standard_normal((channels, total)) * 0.2).astype(np.float32))
@@ -70,7 +78,15 @@ def test_two_rank_sharded_driver_matches_reference_driver(tmp_path, total, chann
     sys.path.insert(0, str(ROOT))
     from oracle import driver_oracle as O
     x = (np.random.default_rng(7).standard_normal((channels, total)) * 0.2).astype(np.float32)
-    want, _ = O.run_driver(x, 48000, lambda c: _chunk_model(torch.from_numpy(np.ascontiguousarray(c))).numpy())
+    # single-process reference driver: one model call per span, rows numbered span-major (span k, channel c -> k*C + c)
+    state = {"row": 0}
+
+    def ref_model(c):
+        y = _chunk_model(torch.from_numpy(np.ascontiguousarray(c)), state["row"]).numpy()
+        state["row"] += c.shape[0]
+        return y
+
+    want, _ = O.run_driver(x, 48000, ref_model)
     win, hop = O.win_hop()
     n = len(O.iter_chunks(total, win, hop))
     rows = 0
