@@ -17,6 +17,13 @@ exactly c2's single chunk).  Random-init weights of the spec'd architecture and 
               device time of exactly those launches (egr_plan_run_code, CUDA events on the launching stream)
   cpu_baseline / --impl reference : the fp32 oracle port of the same path on the host cores (the upstream
               FlashSR_Inference package and its weights cannot be installed here) — baseline only.
+  c3        : BASELINE.json configs[2] for real — 10 min stereo, 130 spans x 2 channels, 4 diffusion steps, through
+              node.run() with a pinned host clip, STRONG scaling over the N ranks (each rank uploads and runs its own span
+              block, ONE all_gather_into_tensor, stitch on every rank), with per-phase device times
+  chain_c5  : configs[4] — stub "wet" signal -> adaptive DFN mix -> FlashSR (4 steps) -> Fat-Llama (50 it), 5 min stereo,
+              node to node with host AUDIO dicts; path B runs on rank 0 after the gather (replicas only)
+  gpu_eager_baseline : the same fp32 torch graph as the CPU port, eager on the same GPU (cuDNN / cuBLAS, TF32 allowed)
+              — the library-call comparator of SURVEY 8(d), baseline only
 """
 from __future__ import annotations
 
@@ -256,6 +263,142 @@ def bench_fatllama(dev, pk):
             "cpu_baseline": {"value": audio_s / t_cpu, "unit": "sec audio / sec", "cores": 1, "kind": "port",
                              "sample": f"numpy/scipy.fft float32 port, 1 channel x {k} iterations at N={S}, scaled to {C} ch x {iters} it"}}
 
+# ------------------------------------------------------------------------------------------------ c3 / c5 / eager legs
+def synth_long(total: int, channels: int, sr: int = 48000, seed: int = 1234):
+    """SURVEY 8(d) signal at clip length without a 28.8 M-point host FFT per channel: one 2^21-sample band-limited block per
+    channel, tiled with a per-tile gain ramp (timing input; the parity tests use synth_audio itself)."""
+    import torch
+    blk = 1 << 21
+    base = synth_audio(blk, channels, sr, seed)
+    reps = -(-total // blk)
+    gains = torch.linspace(0.6, 1.0, reps)
+    x = (base[:, None, :] * gains[None, :, None]).reshape(channels, reps * blk)[:, :total]
+    return x.contiguous()
+
+
+def _max_over_ranks(val: float, dev, world):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([val], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def bench_c3(N, node_cls, dev, world, sync_all, reps=2):
+    """configs[2]: 10 min stereo 48 kHz, 4 diffusion steps, the span batch sharded over the ranks.  Everything through
+    node.run() with a pinned HOST clip: H2D of the rank's span block, chunk gather, model, all-gather, stitch, D2H."""
+    import torch
+    total, C, steps = 28_800_000, 2, 4
+    x_host = synth_long(total, C).pin_memory()
+    audio = {"waveform": x_host[None], "sample_rate": N.REQ_SR}
+    node = node_cls()
+    node.NUM_STEPS = steps
+    win, hop = N._win_hop()
+    n_spans = len(N._iter_chunks(total, win, hop))
+    for _ in range(2):   # builds the sub-batch plans, then captures their graphs
+        node.run(audio=audio, lowpass_input=False, output_sr="48000")
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        (res,) = node.run(audio=audio, lowpass_input=False, output_sr="48000")
+    e1.record()
+    sync_all()
+    t = _max_over_ranks(e0.elapsed_time(e1) / 1e3 / reps, dev, world)
+    assert res["waveform"].shape == (1, C, total)
+    # one instrumented pass: CUDA events between the phases of upscale_48k
+    node._marks = []
+    e0.record()
+    (res,) = node.run(audio=audio, lowpass_input=False, output_sr="48000")
+    e1.record()
+    sync_all()
+    phases, prev = {}, e0
+    for name, ev in node._marks:
+        phases[name + "_ms"] = _max_over_ranks(prev.elapsed_time(ev), dev, world)
+        prev = ev
+    phases["d2h_ms"] = _max_over_ranks(prev.elapsed_time(e1), dev, world)
+    node._marks = None
+    per = -(-n_spans // world)
+    limiting = max(phases, key=phases.get)
+    return {"workload": "c3: FlashSR 10 min stereo 48 kHz, 130 spans x 2 channels = 260 chunk-channels, 4 diffusion steps, "
+                        "through node.run() with a pinned host clip", "scaling": "strong", "n_gpus": world,
+            "value": total / N.REQ_SR / t, "unit": UNIT, "seconds": t, "spans": n_spans, "spans_per_rank": per,
+            "chunk_channels_per_rank": per * C, "phases_max_over_ranks": phases, "limiting_phase": limiting,
+            "h2d_bytes_per_rank": int(min(per * hop + win - hop, total) * C * 4), "d2h_bytes_per_rank": int(total * C * 4),
+            "all_gather_bytes": int(world * per * C * win * 4) if world > 1 else 0}
+
+
+def bench_c5(N, node_cls, dev, world, rank, sync_all):
+    """configs[4]: DeepFilterNet3 denoise -> FlashSR (4 steps) -> Fat-Llama (50 it), 5 min stereo 48 kHz.  The DFN3 model is
+    third-party and absent: `wet` is a stub; its adaptive wet/dry mix, the reference's own part of that node
+    (egregora_audio_enhance_extras.py:607-724), runs for real.  Node to node with host AUDIO dicts, as a graph does."""
+    import torch
+    from egregora_b200 import egregora_dfn_mix as D, egregora_fat_llama_gpu as G
+    total, C = 14_400_000, 2
+    dry = synth_long(total, C, seed=99).pin_memory()
+    wet = (0.85 * dry + 0.01 * synth_long(total, C, seed=7)).pin_memory()
+    node = node_cls()
+    node.NUM_STEPS = 4
+    fl = G.EgregoraFatLlamaGPU()
+
+    def chain():
+        mixed = D.adaptive_mix(dry, wet, 48000)                                             # device [C,T]
+        (up,) = node.run(audio={"waveform": mixed[None], "sample_rate": 48000}, lowpass_input=False, output_sr="48000")
+        if rank == 0:   # path B does not shard (one FFT spans the clip): replicas only, rank 0 carries it
+            (out,) = fl.run("wav", 50, 0.6, 1411, True, True, AUDIO=up)
+            return out
+        return up
+
+    chain()
+    chain()
+    sync_all()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = chain()
+    e1.record()
+    sync_all()
+    t = _max_over_ranks(e0.elapsed_time(e1) / 1e3, dev, world)
+    assert out["waveform"].shape == (1, C, total) and bool(torch.isfinite(out["waveform"][0, :, ::997]).all())
+    return {"workload": "c5: stub wet -> adaptive DFN mix -> FlashSR (4 steps) -> Fat-Llama (50 it, thr 0.6), 5 min stereo 48 kHz, "
+                        "node to node", "n_gpus": world, "value": total / 48000 / t, "unit": "sec audio / sec", "seconds": t,
+            "note": "DeepFilterNet3 itself is third-party and absent: wet is a stub, the mix is real; path B on rank 0 after the gather"}
+
+
+def bench_gpu_eager(engine, dev):
+    """the fp32 torch graph (the oracle port — upstream is eager fp32 torch too) run EAGER ON THE SAME GPU through
+    cuDNN / cuBLAS with TF32 allowed.  Baseline only; its low-pass is scipy on the host, as upstream's is."""
+    import torch
+    from oracle import flashsr_oracle as O
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    spec, out = engine.spec, {}
+    be = O.TorchBackend(spec, engine.weights, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for B, lowpass, reps in ((1, True, 3), (1, False, 3), (8, False, 2)):
+        wav = synth_audio(spec["chunk"], 1).expand(B, -1).contiguous().to(dev)
+        noise = engine.make_noise(B, 4321)
+        try:
+            for _ in range(2):
+                O.run_flashsr(spec, None, wav, noise, steps=1, lowpass=lowpass, backend=be)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(reps):
+                O.run_flashsr(spec, None, wav, noise, steps=1, lowpass=lowpass, backend=be)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            t = e0.elapsed_time(e1) / 1e3 / reps
+            out[f"b{B}_lowpass_{'on' if lowpass else 'off'}"] = {"ms": 1e3 * t, "rtf": B * spec["chunk"] / spec["sr"] / t}
+        except Exception as e:  # pragma: no cover
+            out[f"b{B}_lowpass_{'on' if lowpass else 'off'}"] = {"error": str(e)[:200]}
+    del be
+    torch.cuda.empty_cache()
+    out["what"] = ("fp32 torch eager (cuDNN/cuBLAS, TF32 allowed, cudnn.benchmark) of the same graph on the same GPU, 1 step, "
+                   "output copied to the host; baseline only")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import torch
@@ -270,6 +413,11 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    # no FlashSR checkpoint exists here: seeded random weights of the spec'd architecture, said so in `data`.
+    # The node itself never does this silently (flashsr_weights.py); a real checkpoint directory wins when present.
+    os.environ.setdefault("EGREGORA_FLASHSR_RANDOM_INIT", "1")
+    import warnings
+    warnings.filterwarnings("ignore", category=RuntimeWarning, message="FlashSR: EGREGORA_FLASHSR_RANDOM_INIT")
     load_pkg()
     from egregora_b200 import _abi, egregora_audio_super_resolution as N
     K = _abi.K
@@ -283,7 +431,7 @@ def run_b200(args):
     audio_s = total / N.REQ_SR
     x_host = synth_audio(total, 1).pin_memory()
     x_dev = x_host.to(dev)
-    chunk_model = lambda c: engine.infer(c, lowpass=True, steps=1, seed=4321)  # noqa: E731
+    chunk_model = lambda c, row0=0: engine.infer(c, lowpass=True, steps=1, seed=4321, row0=row0)  # noqa: E731
 
     def sync_all():
         if world > 1:
@@ -331,6 +479,19 @@ def run_b200(args):
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = float(t_dev.item()), float(t_e2e.item())
     assert res["waveform"].shape == (1, 1, total) and bool(torch.isfinite(res["waveform"]).all())
+
+    # ---- the BASELINE multi-GPU configs, on every rank (they hold the collective)
+    c3 = c5 = None
+    if os.environ.get("EGR_BENCH_C3", "1") == "1":
+        try:
+            c3 = bench_c3(N, N.EgregoraAudioSuperResolution, dev, world, sync_all)
+        except Exception as e:  # pragma: no cover
+            c3 = {"error": repr(e)[:300]}
+    if os.environ.get("EGR_BENCH_C5", "1") == "1":
+        try:
+            c5 = bench_c5(N, N.EgregoraAudioSuperResolution, dev, world, rank, sync_all)
+        except Exception as e:  # pragma: no cover
+            c5 = {"error": repr(e)[:300]}
 
     if rank == 0:
         pk = peaks()
@@ -412,6 +573,12 @@ def run_b200(args):
                 tc_, a_ = oracle_chunk_seconds(engine.spec, engine.weights, frac, threads)
             cpu = {"value": a_ / tc_, "unit": UNIT, "cores": threads, "kind": "port",
                    "sample": f"one {a_:.2f} s mono chunk (chunk/{frac}), 1 step, lowpass on, fp32 torch oracle port, {tc_:.1f} s"}
+        eager = None
+        if world == 1 and os.environ.get("EGR_BENCH_EAGER", "1") == "1":
+            try:
+                eager = bench_gpu_eager(engine, dev)
+            except Exception as e:  # pragma: no cover
+                eager = {"error": repr(e)[:300]}
         path_b = None
         if world == 1 and os.environ.get("EGR_BENCH_PATHB", "1") == "1":
             try:
@@ -423,16 +590,18 @@ def run_b200(args):
             "metric": METRIC, "value": args.steps * audio_s / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands / f32 accumulate (f32 activations between layers)",
-            "data": "synthetic band-limited 48 kHz audio (SURVEY.md 8d); random-init weights of the spec'd architecture",
+            "data": "synthetic band-limited 48 kHz audio (SURVEY.md 8d); random-init weights of the spec'd architecture "
+                    f"(engine weights: {getattr(engine, 'weights_tag', '?')})",
             "config": {"workload": WORKLOAD, "clip_samples": total, "chunks": world, "chunk_channels_per_gpu": 1, "steps_diffusion": 1,
                        "lowpass_input": True, "parallelism": f"chunk-sharded dp{world}" + (" + 1 NCCL all-gather" if world > 1 else ""),
                        "l2": f"no explicit flush: per-step working set (weights {engine.d_weights.numel() / 1e6:.0f} MB + "
                              f"workspace {ws_mb:.0f} MB) exceeds the 126 MB L2"},
             "e2e": {"value": args.steps * audio_s / t_e2e, "unit": UNIT, "ms_per_step": 1e3 * t_e2e / args.steps,
-                    "h2d_bytes_per_step": int(x_host.numel() * 4) + world * (int(engine.make_noise(1, 0).numel()) * 4 + 24),
+                    "h2d_bytes_per_step": int(x_host.numel() * 4),   # the diffusion noise is generated on the device
                     "d2h_bytes_per_step": int(total * 4)},
             "gpu_launches": gpu_launches,
-            "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "batched": extra, "path_b": path_b,
+            "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_baseline": eager, "c3": c3, "chain_c5": c5,
+            "batched": extra, "path_b": path_b,
         }
         print(json.dumps(out), flush=True)
     if world > 1:

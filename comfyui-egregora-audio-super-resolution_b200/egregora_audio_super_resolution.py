@@ -262,35 +262,66 @@ def _call_model(chunk_model, chunks: torch.Tensor, row0: int) -> torch.Tensor:
     return chunk_model(chunks, row0=row0) if takes else chunk_model(chunks)
 
 
-def upscale_48k(x_dev: torch.Tensor, chunk_model, *, shard: bool = True) -> torch.Tensor:
-    """The hot loop of run(): spans -> gather -> model on every chunk-channel -> WOLA.
-    `chunk_model([N,win] device f32) -> [N,L_pred]`.  Sharded over ranks when torch.distributed is up."""
+def _mark(marks, name: str):
+    """bench.py's phase clock: a CUDA event on the current stream after each phase (no-op when marks is None)."""
+    if marks is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append((name, ev))
+
+
+def upscale_48k(x: torch.Tensor, chunk_model, *, shard: bool = True, device: Optional[torch.device] = None,
+                marks: Optional[list] = None) -> torch.Tensor:
+    """The hot loop of run(): spans -> gather -> model on every chunk-channel -> [all-gather] -> WOLA (ref :400-420).
+    `x` [C,total] f32 at 48 kHz, on the device or on the host (then `device` says where to run): a sharded run uploads
+    only the samples its own spans cover.  `chunk_model([N,win] device f32[, row0]) -> [N,L_pred]`.
+    Sharded over ranks when torch.distributed is up: contiguous blocks of ceil(n/world) spans per rank,
+    ONE all_gather_into_tensor of the per-rank chunk outputs, stitch on every rank."""
     win, hop = _win_hop()
-    C, total = x_dev.shape
+    C, total = x.shape
     spans = _iter_chunks(total, win, hop)
     n = len(spans)
+    dev = x.device if x.is_cuda else (device or _require_cuda())
     import torch.distributed as dist
     world = dist.get_world_size() if (shard and dist.is_available() and dist.is_initialized()) else 1
     if world == 1 or n == 0:
+        x_dev = x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        _mark(marks, "h2d")
         chunks = gather_chunks(x_dev, spans, win)
+        _mark(marks, "gather")
         preds = _call_model(chunk_model, chunks.view(n * C, win), 0) if n else chunks
         preds = preds.view(n, C, -1) if n else preds
-        return wola_stitch(preds, spans, total, win)
+        _mark(marks, "model")
+        out = wola_stitch(preds, spans, total, win)
+        _mark(marks, "stitch")
+        return out
     # contiguous blocks of ceil(n/world) spans per rank; pad the tail ranks so one all_gather suffices
     rank = dist.get_rank()
     per = -(-n // world)
     lo, hi = min(rank * per, n), min((rank + 1) * per, n)
     mine = spans[lo:hi]
-    chunks = gather_chunks(x_dev, mine, win)
-    local = torch.zeros((per, C, win), dtype=torch.float32, device=x_dev.device)
+    local = torch.zeros((per, C, win), dtype=torch.float32, device=dev)
     if hi > lo:
+        # only the samples this rank's spans cover cross PCIe (1/world of the clip plus one overlap)
+        s0, s1 = mine[0][0], mine[-1][0] + mine[-1][1]
+        x_dev = x[:, s0:s1].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        _mark(marks, "h2d")
+        chunks = gather_chunks(x_dev, [(s - s0, L) for s, L in mine], win)
+        _mark(marks, "gather")
         y = _call_model(chunk_model, chunks.view((hi - lo) * C, win), lo * C).view(hi - lo, C, -1)
         if y.shape[-1] != win:
             raise RuntimeError("sharded stitch needs the chunk model to return full windows")
         local[: hi - lo] = y
-    gathered = torch.empty((world * per, C, win), dtype=torch.float32, device=x_dev.device)
+    else:
+        _mark(marks, "h2d")
+        _mark(marks, "gather")
+    _mark(marks, "model")
+    gathered = torch.empty((world * per, C, win), dtype=torch.float32, device=dev)
     dist.all_gather_into_tensor(gathered, local)
-    return wola_stitch(gathered[:n], spans, total, win)
+    _mark(marks, "all_gather")
+    out = wola_stitch(gathered[:n], spans, total, win)
+    _mark(marks, "stitch")
+    return out
 
 
 # --------------------------------------------------------------------------------------------- node
@@ -321,12 +352,13 @@ class EgregoraAudioSuperResolution:
         in_cs, in_sr = _from_audio_dict(audio)
         device = _require_cuda()
         engine = get_engine(device, self.CKPT_DIR)
-        x_dev = in_cs.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+        x = in_cs
         if in_sr != REQ_SR:
-            x_dev = _resample_hq(x_dev, in_sr, REQ_SR)
+            x = _resample_hq(x, in_sr, REQ_SR)
             in_sr = REQ_SR
         steps, seed, lp = int(self.NUM_STEPS), int(self.SEED), bool(lowpass_input)
-        out_48k = upscale_48k(x_dev, lambda chunks, row0=0: engine.infer(chunks, lowpass=lp, steps=steps, seed=seed, row0=row0))
+        out_48k = upscale_48k(x, lambda chunks, row0=0: engine.infer(chunks, lowpass=lp, steps=steps, seed=seed, row0=row0),
+                              device=device, marks=getattr(self, "_marks", None))
         tgt_sr = int(output_sr)
         if tgt_sr != in_sr:
             return (_make_audio(tgt_sr, _resample_hq(out_48k, in_sr, tgt_sr)),)

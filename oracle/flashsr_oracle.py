@@ -229,11 +229,12 @@ class TorchBackend:
 
 
 def run_flashsr(spec, weights, wav: torch.Tensor, noise: torch.Tensor, steps=1, lowpass=False, device="cpu",
-                trace=None, dtype=torch.float32):
-    """wav [B,chunk] f32, noise [B,z,T/8,F/8] (NCHW) -> [B,chunk]."""
+                trace=None, dtype=torch.float32, backend=None):
+    """wav [B,chunk] f32, noise [B,z,T/8,F/8] (NCHW) -> [B,chunk].  `backend`: a TorchBackend to reuse (its weights are
+    already on its device — bench.py's GPU-eager baseline builds it once, as an eager user would)."""
     import sys
     M = sys.modules["egregora_b200.flashsr_model"]
-    be = TorchBackend(spec, weights, device, dtype)
+    be = backend if backend is not None else TorchBackend(spec, weights, device, dtype)
     be.trace = trace
     with torch.inference_mode():
         y = M.FlashSRGraph(spec).forward(be, wav.to(be.dev, dtype), noise.to(be.dev, dtype), steps=steps, lowpass=lowpass)

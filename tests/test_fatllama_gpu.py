@@ -20,13 +20,7 @@ TOL = 1e-5
 LSB = 1.0 / 32768.0
 
 
-def _audio(C, S, seed, sr=16000):
-    rng = np.random.default_rng(seed)
-    t = np.arange(S) / sr
-    x = 0.05 * rng.standard_normal((C, S))
-    for h, a in ((220.0, 0.3), (440.0, 0.15), (1760.0, 0.05)):
-        x += a * np.sin(2 * np.pi * h * t + rng.uniform(0, 6.28, (C, 1)))
-    return np.clip(x, -1, 1).astype(np.float32)
+from fatllama_cases import audio as _audio  # noqa: E402
 
 
 def _run_abi(samples_cs: np.ndarray, U, iters, thr, normalize=True, autoscale=True):
@@ -120,18 +114,35 @@ def test_cpu_node_id_uses_same_kernels(cuda_dev):
     assert np.max(np.abs(res["waveform"][0].numpy() - want)) <= LSB * 1.0001
 
 
-def test_full_size_c4_properties(cuda_dev):
-    """BASELINE config c4 (3 min stereo 44.1 kHz, 300 iterations, thr 0.6, autoscale on) at full size.  With
-    integer-scaled samples every non-zero sample and bin passes the 0.6 gate, so the loop is a projection that
-    keeps the signal: y = 2x up to float32 rounding of 300 round trips, and the node output is x / max|x|
-    re-quantised (size-independent properties; the numpy oracle needs ~4 minutes at this size)."""
-    S = 7938000
-    x = _audio(2, S, seed=44, sr=44100)
-    xq = O.pcm16_read(O.pcm16_write(x))
-    out, sr, pre = G.fat_llama_device(torch.from_numpy(x).cuda(), 44100, 300, 0.6, 1411, True, True, return_prequant=True)
+def test_full_size_c4_vs_float64_fixture(cuda_dev):
+    """BASELINE config c4 (3 min stereo 44.1 kHz, 300 iterations, thr 0.6, normalize + autoscale on) at FULL size against
+    the float64 oracle: tests/golden/fatllama_c4_golden.npz holds the oracle's pre-quantisation output at 21 990 sample
+    positions (both edges + a seeded random draw) plus 64 block sums / sums of squares per channel as a checksum of the
+    whole clip (tests/golden/make_fatllama_c4_golden.py, ~10 min of host time, committed).  Tolerance: north_star's 1e-5
+    per sample, pre-quantisation; after the PCM-16 wire format at most 1 LSB."""
+    import hashlib
+    from conftest import GOLDEN
+    from fatllama_cases import C4, audio, c4_sample_index
+    g = np.load(GOLDEN / "fatllama_c4_golden.npz")
+    c = C4
+    x = audio(c["C"], c["S"], c["seed"], c["sr"])
+    assert np.array_equal(np.frombuffer(hashlib.sha256(x.tobytes()).digest(), np.uint8), g["in_sha"]), "input clip differs from the fixture's"
+    idx = c4_sample_index(c["S"])
+    assert np.array_equal(idx, g["idx"])
+    out, sr, pre = G.fat_llama_device(torch.from_numpy(x).cuda(), c["sr"], c["iters"], c["thr"], c["kbps"], True, True, return_prequant=True)
     torch.cuda.synchronize()
-    assert sr == 44100 and out.shape == (2, S)
-    pre = pre.cpu().numpy()
-    want = xq / np.max(np.abs(xq))         # autoscale restores each channel's own peak, normalise divides by the global one
-    assert np.max(np.abs(pre - want)) < 5e-5
-    assert float(np.max(np.abs(out.cpu().numpy()))) <= 1.0
+    assert sr == c["sr"] and out.shape == (c["C"], c["S"])
+    pre64 = pre.double()
+    err = float((pre64[:, torch.from_numpy(idx).cuda()].cpu() - torch.from_numpy(g["pre"])).abs().max())
+    assert err < TOL, err
+    # checksum of the whole clip: per-block mean error and mean-square error (float64 sums on the device)
+    edges = g["edges"]
+    for k in range(c["C"]):
+        for b in range(len(edges) - 1):
+            seg = pre64[k, int(edges[b]):int(edges[b + 1])]
+            n = seg.numel()
+            assert abs(float(seg.sum()) - float(g["blk"][k, b])) / n < 1e-6
+            assert abs(float((seg * seg).sum()) - float(g["blk2"][k, b])) / n < 1e-6
+    want_q = O.pcm16_read(O.pcm16_write(g["pre"].astype(np.float32)))
+    got_q = out[:, torch.from_numpy(idx).cuda()].cpu().numpy()
+    assert np.max(np.abs(got_q - want_q)) <= LSB * 1.0001

@@ -63,7 +63,7 @@ def _worker(rank: int, world: int, port: int, total: int, channels: int, out_dir
 
     N.gather_chunks, N.wola_stitch = gather_chunks, wola_stitch
     x = torch.from_numpy((np.random.default_rng(7).standard_normal((channels, total)) * 0.2).astype(np.float32))
-    y = N.upscale_48k(x, model)
+    y = N.upscale_48k(x, model, device=torch.device("cpu"))
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), y.numpy())
     np.save(os.path.join(out_dir, f"rows{rank}.npy"), np.array([calls["rows"]]))
     dist.barrier()

@@ -1,7 +1,7 @@
 """egr_eval_hf_band on the device (_band_energy_hi_db, egregora_null_test_suite.py:190-197) through
 `egregora_eval_metrics.hf_band_db`, against goldens made by the reference function (tests/golden/make_eval_hf_golden.py).
 Written after this round's GPU budget was spent; verified under the CPU emulator (tests/test_cusim.py); collected last and
-xfail(strict=False) like the LSD / LUFS hardware tests."""
+verified on hardware at the end of round 1 (plain tests since round 2) like the LSD / LUFS hardware tests."""
 import json
 
 import numpy as np
@@ -11,8 +11,7 @@ import torch
 from conftest import GOLDEN
 from hf_cases import signal
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="egr_eval_hf_band not yet run on hardware (GPU budget spent); XPASS = verified")]
+pytestmark = pytest.mark.gpu
 
 
 def test_hf_band_kernel_matches_reference_golden(cuda_dev, pkg):

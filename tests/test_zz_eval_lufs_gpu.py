@@ -4,7 +4,7 @@ reference functions (tests/golden/make_eval_lufs_golden.py).
 
 STATUS: written after this round's GPU budget was spent.  The kernels' real source runs under the CPU emulator
 (tests/test_cusim.py::test_eval_lufs_reference_golden: filtered signal bit-identical to the reference, loudness to 1e-9
-dB); the tests below are the first hardware run, collected last and xfail(strict=False) like the LSD ones.
+dB); the tests below are the first hardware run, collected last and verified on hardware at the end of round 1 (plain tests since round 2) like the LSD ones.
 """
 import json
 
@@ -14,8 +14,7 @@ import torch
 from conftest import GOLDEN
 from lufs_cases import signal
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="egr_eval_lufs not yet run on hardware (GPU budget spent); XPASS = verified")]
+pytestmark = pytest.mark.gpu
 
 
 def test_lufs_kernel_matches_reference_golden(cuda_dev, pkg):

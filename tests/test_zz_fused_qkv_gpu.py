@@ -2,7 +2,7 @@
 (N = 3C) whose output attn_rows_kernel<HD, STRIDED=true> reads as column blocks — 64 launches fewer per UNet pass (c2 plan:
 924 -> 860 ops).  Off by default: written after the round's GPU budget was spent, so it is unmeasured; its numerics are
 pinned on the CPU (plan interpreter: tests/test_plan_cpu.py, real kernel under the emulator: tests/test_cusim.py).  These
-are the first hardware runs — collected last, xfail(strict=False); XPASS = verified, then measure with
+are the first hardware runs — collected last, verified on hardware at the end of round 1 (plain tests since round 2); XPASS = verified, then measure with
 `EGR_FUSE_QKV=1 EGR_FUSE_EMB=1 python bench.py` against the default (EGR_FUSE_EMB: the 22 ResBlock time-embedding GEMVs as
 one per diffusion step; both together 924 -> 839 ops)."""
 import pytest
@@ -10,8 +10,7 @@ import torch
 
 from harness import MiniPlan, rel_err
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="EGR_FUSE_QKV path not yet run on hardware (GPU budget spent); XPASS = verified")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("S,heads,hd", [(32, 4, 16), (128, 2, 32), (512, 8, 32)])

@@ -1,7 +1,7 @@
 """`egregora_eval_metrics.audio_null_test` — everything the reference's Audio_Null_Test.execute returns
 (egregora_null_test_suite.py:421-467), every toggle on — against goldens produced by the reference node
 (tests/golden/make_null_full_golden.py).  Composes egr_eval_null_test (validated on the B200) with egr_eval_lufs / _lsd /
-_hf_band (emulator-verified, first hardware run): collected last, xfail(strict=False)."""
+_hf_band (emulator-verified, first hardware run): collected last, verified on hardware at the end of round 1 (plain tests since round 2)."""
 import json
 
 import numpy as np
@@ -10,8 +10,7 @@ import torch
 
 from conftest import GOLDEN
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="LUFS / LSD / HF-band kernels not yet run on hardware (GPU budget spent); XPASS = verified")]
+pytestmark = pytest.mark.gpu
 
 
 def test_audio_null_test_matches_reference_node(cuda_dev, pkg):
