@@ -9,6 +9,8 @@ import torch
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+import os  # noqa: E402
+os.environ.setdefault("EGREGORA_FLASHSR_RANDOM_INIT", "1")   # no checkpoint in this environment
 import bench  # noqa: E402
 
 bench.load_pkg()

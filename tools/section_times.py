@@ -4,6 +4,8 @@ from pathlib import Path
 import torch
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
+import os
+os.environ.setdefault("EGREGORA_FLASHSR_RANDOM_INIT", "1")   # no checkpoint in this environment
 import bench
 bench.load_pkg()
 from egregora_b200 import _abi, egregora_audio_super_resolution as N
