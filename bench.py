@@ -482,17 +482,21 @@ def run_b200(args):
 
     # ---- the BASELINE multi-GPU configs, on every rank (they hold the collective)
     c3 = c5 = None
+    log = lambda m: (print(f"[bench rank {rank}] {m}", file=sys.stderr, flush=True) if os.environ.get("EGR_BENCH_VERBOSE") else None)  # noqa: E731
+    log("c2 done; c3 leg")
     if os.environ.get("EGR_BENCH_C3", "1") == "1":
         try:
             c3 = bench_c3(N, N.EgregoraAudioSuperResolution, dev, world, sync_all)
         except Exception as e:  # pragma: no cover
             c3 = {"error": repr(e)[:300]}
+    log("c5 leg")
     if os.environ.get("EGR_BENCH_C5", "1") == "1":
         try:
             c5 = bench_c5(N, N.EgregoraAudioSuperResolution, dev, world, rank, sync_all)
         except Exception as e:  # pragma: no cover
             c5 = {"error": repr(e)[:300]}
 
+    log("rank-0 legs")
     if rank == 0:
         pk = peaks()
         lib = engine.lib
@@ -610,6 +614,8 @@ def run_b200(args):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()   # a native crash in any leg prints the Python stack to stderr instead of dying silently
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
