@@ -497,6 +497,7 @@ def run_b200(args):
             c5 = {"error": repr(e)[:300]}
 
     log("rank-0 legs")
+    be, handle = engine.plan(1, 1, True)   # the c3 / c5 legs grew the workspace: every plan handle was rebuilt
     if rank == 0:
         pk = peaks()
         lib = engine.lib

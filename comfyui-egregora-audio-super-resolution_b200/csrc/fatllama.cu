@@ -30,7 +30,9 @@ int fft2_inverse_from_positions(const Fft2Plan* p, float2* d_pos, float2* d_out,
 
 struct FlDev {
   int R1, R2, cw, cw_shift;
-  float inv_m;  // 1/M, rounded once from double on the host
+  float inv_m;     // 1/M, rounded once from double on the host
+  float inv_m_lo;  // 1/M - inv_m: the loop feeds its own output back 300 times, so a scale that is off by a CONSTANT
+                   // relative 3e-8 (the rounding of 1/M) compounds into a gain drift of 1e-5; v*hi + v*lo has no bias
   long long M;
   Radices rd1, rd2;
   const float2 *tw1, *tw2, *twM_lo, *twM_hi, *twN_lo, *twN_hi, *twH;
@@ -47,6 +49,7 @@ static FlDev fl_dev(const Fft2Plan* p) {
   d.cw_shift = 0;
   while ((1 << d.cw_shift) < d.cw) ++d.cw_shift;
   d.inv_m = (float)(1.0 / (double)p->M);
+  d.inv_m_lo = (float)(1.0 / (double)p->M - (double)d.inv_m);
   return d;
 }
 
@@ -294,13 +297,13 @@ __global__ void __launch_bounds__(MINB == 4 ? 256 : 320, MINB) fl_row_kernel(FlD
   }
   __syncthreads();
   fft_inverse<false>(sm, g, d.rd2, tws);
-  const float sc = d.inv_m;
+  const float sc = d.inv_m, sl = d.inv_m_lo;
   for (int i = threadIdx.x; i < R2; i += T) {
     float2 v = k1a ? cmulc(sA[i], cmulf(hiA[i >> 6], loA[i & 63])) : sA[i];
-    rowA[i] = make_float2(v.x * sc, v.y * sc);
+    rowA[i] = make_float2(fmaf(v.x, sc, v.x * sl), fmaf(v.y, sc, v.y * sl));
     if (two) {
       v = cmulc(sB[i], cmulf(hiB[i >> 6], loB[i & 63]));
-      rowB[i] = make_float2(v.x * sc, v.y * sc);
+      rowB[i] = make_float2(fmaf(v.x, sc, v.x * sl), fmaf(v.y, sc, v.y * sl));
     }
   }
 }

@@ -65,7 +65,9 @@ struct TcKernelArgs {
   int mt, halo, n_iss, kchunks, n_outer, n_inner, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin;
   int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
   FastDiv d_splits, d_tiles_n, d_tiles_w, d_tiles_h, d_kchunks, d_bw, d_bh, d_c4n;
-  int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (<= 256)
+  int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (x splits when folded)
+  int fold;      // split-K folded into ONE work item: each split accumulates into its own TMEM region, summed in the epilogue
+  int nbuf;      // accumulator buffers in TMEM: 2 when 2 * acc_cols <= 512, else 1
   int vec_ok, need_crop, epi_plain;
   float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
   unsigned int* counters;  // one per output tile, zero between launches
@@ -153,6 +155,14 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld16b(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
@@ -210,12 +220,13 @@ struct WorkItem {
 
 __device__ __forceinline__ void decode_work(const TcKernelArgs& ka, int w, WorkItem& wi) {
   const GemmArgs& g = ka.g;
-  int t = fdiv(w, ka.d_splits);
-  wi.ks = w - t * ka.splits;
+  int t = w;
+  wi.ks = 0;
+  if (!ka.fold) { t = fdiv(w, ka.d_splits); wi.ks = w - t * ka.splits; }
   wi.tm = fdiv(t, ka.d_tiles_n);
   wi.tn = t - wi.tm * ka.tiles_n;
-  wi.o_begin = wi.ks * ka.outer_per_split;
-  wi.o_end = min(ka.n_outer, wi.o_begin + ka.outer_per_split);
+  if (ka.fold) { wi.o_begin = 0; wi.o_end = ka.n_outer; }   // all splits of the tile, streamed back to back
+  else { wi.o_begin = wi.ks * ka.outer_per_split; wi.o_end = min(ka.n_outer, wi.o_begin + ka.outer_per_split); }
   wi.mt_eff = 0;
 #pragma unroll
   for (int m = 0; m < 2; ++m) {
@@ -484,12 +495,18 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
       for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
         WorkItem wi;
         decode_work(ka, w, wi);
-        const int buf = it & 1;
-        const uint32_t acc = tmem_base + (uint32_t)(buf * ka.acc_cols) + c_off;
-        mbar_wait(accE_u + 8 * buf, (((uint32_t)(it >> 1)) & 1u) ^ 1u);  // epilogue has drained this buffer
+        const int buf = ka.nbuf == 2 ? (it & 1) : 0;
+        const int use = ka.nbuf == 2 ? (it >> 1) : it;
+        uint32_t acc = tmem_base + (uint32_t)(buf * ka.acc_cols) + c_off;
+        mbar_wait(accE_u + 8 * buf, (((uint32_t)use) & 1u) ^ 1u);  // epilogue has drained this buffer
         tc_fence_after();
-        uint32_t first = 0;  // 0 until the first MMA of this item has been issued (accumulate flag)
+        uint32_t first = 0;  // 0 until the first MMA of this item (of this split when folded) has been issued
+        int in_split = 0;    // folded split-K: outer steps issued into the current split's accumulator
         for (int io = wi.o_begin; io < wi.o_end; ++io) {
+          if (ka.fold && in_split == ka.outer_per_split) {   // next split: its own TMEM region, accumulation restarts
+            in_split = 0; first = 0; acc += (uint32_t)(ka.mt * BN);
+          }
+          ++in_split;
           if (ka.halo) mbar_wait(fullA_u + 8 * sa, pa);  // otherwise A rides on the B barriers (same stage index)
           const uint32_t aBase = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
           for (int ii = 0; ii < ka.n_inner; ++ii) {
@@ -546,14 +563,14 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
     for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
       WorkItem wi;
       decode_work(ka, w, wi);
-      const int buf = it & 1;
+      const int buf = ka.nbuf == 2 ? (it & 1) : 0;
       const int n0 = wi.tn * BN;
-      mbar_wait(accF_u + 8 * buf, ((uint32_t)(it >> 1)) & 1u);
+      mbar_wait(accF_u + 8 * buf, ((uint32_t)(ka.nbuf == 2 ? (it >> 1) : it)) & 1u);
       tc_fence_after();
       if (tr && threadIdx.x == 64 && it < 6) tr[2 + 2 * it] = clock64();
       const int tile_id = wi.tm * ka.tiles_n + wi.tn;
       const size_t pstride = (size_t)ka.mt * TILE_M * BN;
-      float* part = ka.splits > 1 ? ka.partial + ((size_t)tile_id * ka.splits + wi.ks) * pstride : nullptr;
+      float* part = (ka.splits > 1 && !ka.fold) ? ka.partial + ((size_t)tile_id * ka.splits + wi.ks) * pstride : nullptr;
       const bool vecpath = ka.vec_ok && !part && !g.transposed;
       const int ntot = wi.mt_eff * nblk;
       const int last_bi = ntot - 1 - ((ntot - 1 - eset) & 1);  // last block of this set (< eset when it has none)
@@ -591,6 +608,24 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ka.acc_cols + m * BN + cb);
         const int ncols = min(32, BN - cb);  // BN is a multiple of 16
         if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
+        if (ka.fold) {
+          // folded split-K: the splits' accumulators are added in split order — the same f32 additions, in the same
+          // order, as the last-arriver reduction of the global-partial path, so both modes give the same bits
+          tc_wait_ld();
+          for (int sp = 1; sp < ka.splits; ++sp) {
+            const uint32_t ta2 = taddr + (uint32_t)(sp * ka.mt * BN);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {   // 16 columns at a time: a 32-register temporary would spill
+              if (hf * 16 < ncols) {
+                uint32_t r2[16];
+                tc_ld16b(ta2 + (uint32_t)(hf * 16), r2);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[hf * 16 + j] = __float_as_uint(__uint_as_float(r[hf * 16 + j]) + __uint_as_float(r2[j]));
+              }
+            }
+          }
+        }
         const int nb = n0 + cb;
         const int n = nb + c4;
         const bool col_ok = c4 < ncols && n < g.N;
@@ -913,9 +948,23 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   const int ops = ceil_div(n_outer, splits);
   splits = ceil_div(n_outer, ops);  // no empty split
 
+  // ---- folded split-K.  The split count is a constant of the layer (bit-identical results at any batch size), but a
+  // batched launch has enough output tiles to fill the GPU without spreading one tile's reduction over several CTAs.
+  // Then ONE work item streams all the splits of its tile back to back, each split into its own TMEM accumulator
+  // region, and the epilogue adds the regions in split order: the same f32 additions in the same order as the
+  // last-arriver reduction over global partial tiles — without the partial traffic, the atomics and the extra CTAs.
+  // Needs splits * BLOCK_N <= 512 TMEM columns and enough (tile, n-block) items to occupy the SMs.
+  int fold = 0, fold_bn = 0;
+  if (splits > 1 && env_int("EGR_TC_NO_FOLD", 0) == 0) {
+    for (int c = 16; c <= 128; c += 16)
+      if (g.N % c == 0 && splits * c <= 512) fold_bn = c;
+    if (fold_bn && (long long)tiles1 * (g.N / fold_bn) * 4 >= (long long)sms * 3) fold = 1;
+  }
+
   // ---- BLOCK_N and sub-tiles per CTA: cheapest (waves x per-item cycles) under a coarse cost model
   int bn = 0, mt = 1;
-  {
+  if (fold) { bn = fold_bn; mt = 1; }
+  else {
     const int cands[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
     double best = 1e30;
     for (int c : cands) {
@@ -940,7 +989,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     }
     if (bn == 0) return bail(fail(EGR_ERR_ARG, "%s: no BLOCK_N fits N=%d", op.name, g.N));
   }
-  if (env_int("EGR_TC_BN", 0) > 0 && g.N % env_int("EGR_TC_BN", 0) == 0) { bn = env_int("EGR_TC_BN", 0); if (mt * bn > 256) mt = 1; }
+  if (!fold && env_int("EGR_TC_BN", 0) > 0 && g.N % env_int("EGR_TC_BN", 0) == 0) { bn = env_int("EGR_TC_BN", 0); if (mt * bn > 256) mt = 1; }
   g.block_n = bn;
 
   ka.mt = mt; ka.halo = halo ? 1 : 0; ka.kchunks = kchunks; ka.tmin = tmin;
@@ -952,8 +1001,10 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   ka.tiles_m = halo ? ka.tiles_w * tiles_h * tiles_b : ceil_div(tiles1, mt);
   ka.tiles_n = g.N / bn;
   ka.splits = splits; ka.outer_per_split = ops;
-  ka.n_work = ka.tiles_m * ka.tiles_n * splits;
-  ka.acc_cols = mt * bn;
+  ka.fold = fold;
+  ka.n_work = ka.tiles_m * ka.tiles_n * (fold ? 1 : splits);
+  ka.acc_cols = mt * bn * (fold ? splits : 1);
+  ka.nbuf = 2 * ka.acc_cols <= 512 ? 2 : 1;
   ka.d_splits = make_fastdiv(splits); ka.d_tiles_n = make_fastdiv(ka.tiles_n); ka.d_tiles_w = make_fastdiv(ka.tiles_w);
   ka.d_tiles_h = make_fastdiv(tiles_h); ka.d_kchunks = make_fastdiv(kchunks); ka.d_bw = make_fastdiv(g.bw);
   ka.d_bh = make_fastdiv(g.bh); ka.d_c4n = make_fastdiv(bn / 4);
@@ -997,8 +1048,8 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   p->smem_bytes = SA * ka.a_stage_bytes + SB * ka.b_stage_bytes + 8 * STAGE_BYTES_PER_WARP + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
   if (p->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: %d B of shared memory needed", op.name, p->smem_bytes));
   p->grid = ka.n_work < sms ? ka.n_work : sms;
-  p->partial_bytes = splits > 1 ? (size_t)ka.tiles_m * ka.tiles_n * splits * mt * TILE_M * bn * sizeof(float) : 0;
-  p->n_counters = splits > 1 ? ka.tiles_m * ka.tiles_n : 0;
+  p->partial_bytes = (splits > 1 && !fold) ? (size_t)ka.tiles_m * ka.tiles_n * splits * mt * TILE_M * bn * sizeof(float) : 0;
+  p->n_counters = (splits > 1 && !fold) ? ka.tiles_m * ka.tiles_n : 0;
   // vector epilogue needs 16-byte aligned groups of 4 columns
   bool vec = !g.transposed && (g.N % 4 == 0) && (g.out_pix_stride % 4 == 0) && (g.out_h_stride % 4 == 0) && (g.out_batch_stride % 4 == 0) &&
              (g.out_offset % 4 == 0) && (g.out_lo % 4 == 0) && (g.out_hi % 4 == 0) && (g.rowbias_stride % 4 == 0);
@@ -1042,7 +1093,7 @@ extern "C" int egr_debug_tc_trace(unsigned long long* h_out, int n) {
 }
 
 int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
-  if (p->ka.splits > 1 && (!p->ka.partial || !p->ka.counters))
+  if (p->ka.splits > 1 && !p->ka.fold && (!p->ka.partial || !p->ka.counters))
     return fail(EGR_ERR_STATE, "%s: split-K scratch not bound", p->name);
   TcKernelArgs ka = p->ka;
   ka.trace = g_trace_dev;
@@ -1053,7 +1104,7 @@ int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
 
 void egr::tc_describe(const TcPrepared* p, int* o) {
   o[0] = p->ka.g.block_n; o[1] = p->ka.mt; o[2] = p->ka.splits; o[3] = p->ka.halo; o[4] = p->ka.n_work; o[5] = p->grid;
-  o[6] = p->ka.SA; o[7] = p->ka.SB;
+  o[6] = p->ka.SA; o[7] = p->ka.SB + 100 * p->ka.fold;
 }
 
 void egr::tc_free(TcPrepared* p) { delete p; }

@@ -24,14 +24,11 @@ def _inputs(spec, B, seed=5):
 
 @pytest.mark.parametrize("fuse_qkv,fuse_emb", [(False, False), (True, True)])
 def test_tiny_plan_matches_oracle_through_interpreter(fuse_qkv, fuse_emb, monkeypatch):
-    """The opt-in plan variants: EGR_FUSE_QKV=1 runs the three attention projections as one GEMM and feeds the attention
+    """The two plan variants (fused is the default since round 2): EGR_FUSE_QKV=1 runs the three attention projections as one GEMM and feeds the attention
     op strided column blocks (64 ops fewer); EGR_FUSE_EMB=1 runs the time-embedding projections of all ResBlocks as one
     GEMV per step (21 fewer at full size) — same numbers."""
     for var, on in (("EGR_FUSE_QKV", fuse_qkv), ("EGR_FUSE_EMB", fuse_emb)):
-        if on:
-            monkeypatch.setenv(var, "1")
-        else:
-            monkeypatch.delenv(var, raising=False)
+        monkeypatch.setenv(var, "1" if on else "0")
     spec = M.tiny_spec()
     W = M.init_weights(spec, 0)
     B, steps, lp = 1, 1, True

@@ -39,8 +39,7 @@ def test_tiny_e2e_with_fused_qkv(cuda_dev, pkg, monkeypatch, emb):
     from egregora_b200.flashsr_engine import FlashSREngine
     from oracle import flashsr_oracle as O
     monkeypatch.setenv("EGR_FUSE_QKV", "1")
-    if emb:
-        monkeypatch.setenv("EGR_FUSE_EMB", "1")
+    monkeypatch.setenv("EGR_FUSE_EMB", "1" if emb else "0")
     spec = M.tiny_spec()
     W = M.init_weights(spec, 0)
     eng = FlashSREngine(cuda_dev, spec, W, max_batch=2)
