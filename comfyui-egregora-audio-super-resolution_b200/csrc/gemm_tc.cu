@@ -28,329 +28,36 @@
 //
 // The single-thread producer / issuer loops are kept free of integer divisions and of dynamically indexed local
 // arrays: a clock trace of the previous version showed ~1400 cycles per k-step spent in exactly that scalar code.
-#include <cuda.h>
-#include <cstdlib>
-#include "ops.cuh"
+#include "gemm_tc.cuh"
 
 namespace egr {
-
-static constexpr int TILE_M = 128;
-static constexpr int KBLK = 64;  // f16 elements per smem row = 128 B = one swizzle span
-static constexpr int A_BOX_BYTES = TILE_M * KBLK * 2;
-static constexpr int HALO_BOX_ROWS = 64;
-static constexpr int STAGE_LD = 36;  // floats per row of the epilogue staging tile (16-byte aligned, conflict-free)
-static constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_LD * 4;
-static constexpr int MAX_SPLITS = 16;
-
-// division by a launch-time constant as multiply-high + shift (the scalar loops and the per-row index math run
-// on single threads: a 32-bit hardware-less division costs ~100+ cycles there)
-struct FastDiv {
-  unsigned int mul, shr, d;
-};
-static inline FastDiv make_fastdiv(int d) {
-  FastDiv f;
-  f.d = (unsigned int)(d < 1 ? 1 : d);
-  if (f.d == 1) { f.mul = 0; f.shr = 0; return f; }
-  unsigned int l = 0;
-  while ((1ull << l) < f.d) ++l;  // ceil(log2 d)
-  f.shr = l;
-  f.mul = (unsigned int)(((1ull << 32) * ((1ull << l) - f.d)) / f.d + 1);
-  return f;
-}
-
-struct TcKernelArgs {
-  GemmArgs g;
-  Taps taps;
-  short tapw[EGR_MAX_TAPS];  // tap offset along dimW (halo mode)
-  int mt, halo, n_iss, kchunks, n_outer, n_inner, nboxA, boxA_bytes, a_stage_bytes, b_stage_bytes, SA, SB, tmin;
-  int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
-  FastDiv d_splits, d_tiles_n, d_tiles_w, d_tiles_h, d_kchunks, d_bw, d_bh, d_c4n;
-  int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (x splits when folded)
-  int fold;      // split-K folded into ONE work item: each split accumulates into its own TMEM region, summed in the epilogue
-  int nbuf;      // accumulator buffers in TMEM: 2 when 2 * acc_cols <= 512, else 1
-  int vec_ok, need_crop, epi_plain;
-  float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
-  unsigned int* counters;  // one per output tile, zero between launches
-  unsigned long long* trace;  // debug: clock64() stamps of CTA 0 when non-null
-};
-
-struct TcPrepared {
-  CUtensorMap tmA, tmB;
-  TcKernelArgs ka;
-  int smem_bytes;
-  int grid;
-  size_t partial_bytes;
-  int n_counters;
-  char name[48];
-};
-
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static PFN_encodeTiled g_encode = nullptr;
-
 }  // namespace egr
-
-using namespace egr;
-
-// ------------------------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld16b(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld16x256_x4(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld16x256_x2(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// one lane of a fully converged warp; the surrounding code stays warp-uniform so that descriptors and addresses live
-// in uniform registers (a lane==0 guard around the whole loop makes ptxas wrap every UTCHMMA / UTMALDG in a
-// per-lane "waterfall" loop of R2UR moves, ~100 cycles per instruction)
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), LBO unused (=1),
-// descriptor version 1 (Blackwell), layout type 2 (SWIZZLE_128B).  cf. cute::UMMA::SmemDescriptor.
-// The 128-byte swizzle XOR is applied by the hardware to the ABSOLUTE shared-memory address (bits 4-6 ^= bits 7-9),
-// exactly as TMA wrote it, so a start address moved by whole 128-byte rows (halo mode) or by 32 bytes inside the
-// span (k advance) needs no "base offset" field — measured on B200: setting it breaks the row-shifted reads.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-// n / d for 0 <= n < 2^31 (Granlund-Montgomery round-up variant: q = (mulhi(n, mul) + n) >> shr, 33-bit safe form)
-__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
-  if (f.d == 1) return n;
-  const unsigned int t = __umulhi((unsigned int)n, f.mul);
-  return (int)((t + (((unsigned int)n - t) >> 1)) >> (f.shr - 1));
-}
-
-// ------------------------------------------------------------------------------------------------ work decoding
-struct WorkItem {
-  int tm, tn, ks;
-  int o_begin, o_end;  // outer-step range of this split
-  int mt_eff;          // valid sub-tiles
-  int w0[2], h0[2], b0[2];
-};
-
-__device__ __forceinline__ void decode_work(const TcKernelArgs& ka, int w, WorkItem& wi) {
-  const GemmArgs& g = ka.g;
-  int t = w;
-  wi.ks = 0;
-  if (!ka.fold) { t = fdiv(w, ka.d_splits); wi.ks = w - t * ka.splits; }
-  wi.tm = fdiv(t, ka.d_tiles_n);
-  wi.tn = t - wi.tm * ka.tiles_n;
-  if (ka.fold) { wi.o_begin = 0; wi.o_end = ka.n_outer; }   // all splits of the tile, streamed back to back
-  else { wi.o_begin = wi.ks * ka.outer_per_split; wi.o_end = min(ka.n_outer, wi.o_begin + ka.outer_per_split); }
-  wi.mt_eff = 0;
-#pragma unroll
-  for (int m = 0; m < 2; ++m) {
-    wi.w0[m] = wi.h0[m] = wi.b0[m] = 0;
-    if (m >= ka.mt) continue;
-    bool valid;
-    int q;
-    if (ka.halo) {  // CTA tile = mt*128 consecutive positions along W inside one (h, b) row
-      q = wi.tm;
-      const int q1 = fdiv(q, ka.d_tiles_w);
-      wi.w0[m] = (q - q1 * ka.tiles_w) * (TILE_M * ka.mt) + TILE_M * m; q = q1;
-      valid = wi.w0[m] < g.Wo;
-    } else {
-      q = wi.tm * ka.mt + m;
-      valid = q < ka.tiles1;
-      const int q1 = fdiv(q, ka.d_tiles_w);
-      wi.w0[m] = (q - q1 * ka.tiles_w) * g.bw; q = q1;
-    }
-    const int q2 = fdiv(q, ka.d_tiles_h);
-    wi.h0[m] = (q - q2 * ka.tiles_h) * g.bh;
-    wi.b0[m] = q2 * g.bb;
-    if (valid) wi.mt_eff = m + 1;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ epilogue math
-struct RowInfo {
-  long long base;   // output index of column 0 of this row (non-transposed) / of n = 0 (transposed)
-  long long flat0;  // in-batch flat index of column 0 (crop test)
-  int b;
-  int ok;
-};
-
-__device__ __forceinline__ RowInfo row_info(const TcKernelArgs& ka, const WorkItem& wi, int m, int row) {
-  const GemmArgs& g = ka.g;
-  int w, h, b;
-  if (ka.halo) { w = wi.w0[m] + row; h = wi.h0[m]; b = wi.b0[m]; }
-  else {
-    const int t = fdiv(row, ka.d_bw), wl = row - t * g.bw;
-    const int t2 = fdiv(t, ka.d_bh);
-    w = wi.w0[m] + wl; h = wi.h0[m] + (t - t2 * g.bh); b = wi.b0[m] + t2;
-  }
-  RowInfo r;
-  r.ok = (w < g.Wo) && (h < g.Ho) && (b < g.Bo);
-  r.b = b;
-  const long long pix = (long long)h * g.Wo + w;
-  if (g.transposed) {
-    r.flat0 = 0;
-    r.base = (long long)b * g.out_batch_stride + pix + g.out_offset;
-  } else {
-    r.flat0 = (long long)h * g.out_h_stride + (long long)w * g.out_pix_stride + g.out_offset;
-    r.base = (long long)b * g.out_batch_stride + r.flat0;
-  }
-  return r;
-}
-
-// final value of 4 consecutive columns n..n+3 of one row (vector path: alignment checked on the host)
-__device__ __forceinline__ void finish4(const GemmArgs& g, float4 acc, long long idx, int n, const float* rb) {
-  float v[4] = {acc.x * g.alpha, acc.y * g.alpha, acc.z * g.alpha, acc.w * g.alpha};
-  if (g.bias) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-    v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
-  }
-  if (rb) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(rb + n));
-    v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
-  }
-  if (g.act) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = egr_apply_act(v[u], g.act);
-  }
-  if (g.resid) {
-    const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid + idx));
-    v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
-  }
-  if (g.resid2) {
-    const float4 rv = __ldg(reinterpret_cast<const float4*>(g.resid2 + idx));
-    v[0] += rv.x; v[1] += rv.y; v[2] += rv.z; v[3] += rv.w;
-  }
-#pragma unroll
-  for (int u = 0; u < 4; ++u) v[u] *= g.post;
-  if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
-  if (g.out16) {
-    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
-    uint2 pk;
-    pk.x = *reinterpret_cast<unsigned*>(&h0);
-    pk.y = *reinterpret_cast<unsigned*>(&h1);
-    *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
-  }
-}
-__device__ __forceinline__ void finish1(const GemmArgs& g, float acc, long long idx, int n, const float* rb) {
-  float v = acc * g.alpha;
-  if (g.bias) v += g.bias[n];
-  if (rb) v += rb[n];
-  v = egr_apply_act(v, g.act);
-  if (g.resid) v += g.resid[idx];
-  if (g.resid2) v += g.resid2[idx];
-  v *= g.post;
-  if (g.out32) g.out32[idx] = v;
-  if (g.out16) g.out16[idx] = __float2half_rn(v);
-}
 
 // ------------------------------------------------------------------------------------------------ the kernel
 __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                           const __grid_constant__ CUtensorMap tmB,
                                                           const __grid_constant__ TcKernelArgs ka) {
   extern __shared__ uint8_t smem_raw[];
-  const GemmArgs& g = ka.g;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int BN = g.block_n;
-  uint8_t* ringA = smem;
-  uint8_t* ringB = ringA + (size_t)ka.SA * ka.a_stage_bytes;
-  float* stage_all = reinterpret_cast<float*>(ringB + (size_t)ka.SB * ka.b_stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stage_all) + 8 * STAGE_BYTES_PER_WARP);
-  uint64_t* fullA = bars;
-  uint64_t* emptyA = fullA + ka.SA;
-  uint64_t* fullB = emptyA + ka.SA;
-  uint64_t* emptyB = fullB + ka.SB;
-  uint64_t* acc_full = emptyB + ka.SB;   // [2]
-  uint64_t* acc_empty = acc_full + 2;    // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint32_t* last_flag = tmem_slot + 1;
+  TcSmemView sv;
+  sv.ringA = smem;
+  sv.ringB = sv.ringA + (size_t)ka.SA * ka.a_stage_bytes;
+  sv.stage_all = reinterpret_cast<float*>(sv.ringB + (size_t)ka.SB * ka.b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sv.stage_all) + 8 * STAGE_BYTES_PER_WARP);
+  sv.fullA = bars;
+  sv.emptyA = sv.fullA + ka.SA;
+  sv.fullB = sv.emptyA + ka.SA;
+  sv.emptyB = sv.fullB + ka.SB;
+  sv.acc_full = sv.emptyB + ka.SB;   // [2]
+  sv.acc_empty = sv.acc_full + 2;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sv.acc_empty + 2);
+  sv.last_flag = tmem_slot + 1;
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
 #ifdef EGR_TC_TRACE  // debug build only (make TRACE=1): clock stamps of CTA 0; the optimiser drops all of it otherwise
   unsigned long long* tr = (ka.trace && blockIdx.x == 0) ? ka.trace : nullptr;
   if (tr && threadIdx.x == 0) tr[0] = clock64();
@@ -366,15 +73,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
-  if (threadIdx.x == 0) {
-    // halo mode: A and B rings advance at different rates and have their own barriers; otherwise the A stage rides
-    // on the B barriers (both producers arrive on fullB, one wait and one commit per k-step for the issuers)
-    for (int s = 0; s < ka.SA; ++s) { mbar_init(&fullA[s], 1); mbar_init(&emptyA[s], (uint32_t)ka.n_iss); }
-    for (int s = 0; s < ka.SB; ++s) { mbar_init(&fullB[s], ka.halo ? 1u : 2u); mbar_init(&emptyB[s], (uint32_t)ka.n_iss); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], (uint32_t)ka.n_iss); mbar_init(&acc_empty[s], 8); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
+  if (threadIdx.x == 0) tc_init_barriers(ka, sv);
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -385,461 +84,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
   if (tr && threadIdx.x == 0) tr[1] = clock64();
 
-  if (warp == 0) {
-    // ============================================================ A producer (whole warp, one elected lane issues)
-    if (tr && lane == 0) tr[5] = clock64();
-    const uint32_t ringA_u = smem_u32(ringA);
-    const uint32_t fullA_u = smem_u32(ka.halo ? fullA : fullB), emptyA_u = smem_u32(ka.halo ? emptyA : emptyB);
-    int sa = 0;
-    uint32_t pa = 0;  // ring phase
-    int tcount = 0;
-    for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x) {
-      WorkItem wi;
-      decode_work(ka, w, wi);
-      const int nA = ka.halo ? ka.nboxA : wi.mt_eff;
-      // per-sub-tile base coordinates, selected without dynamic register indexing
-      int cb[2][5];
-#pragma unroll
-      for (int m = 0; m < 2; ++m)
-#pragma unroll
-        for (int d = 0; d < 5; ++d)
-          cb[m][d] = (g.dimW == d ? wi.w0[m] : 0) + (g.dimH == d ? wi.h0[m] : 0) + (g.dimB == d ? wi.b0[m] : 0);
-      int tap = 0, kc = wi.o_begin;
-      if (!ka.halo) { tap = fdiv(wi.o_begin, ka.d_kchunks); kc = wi.o_begin - tap * ka.kchunks; }
-      if (tr && lane == 0 && tcount == 0) tr[6] = clock64();
-      for (int io = wi.o_begin; io < wi.o_end; ++io) {
-        mbar_wait(emptyA_u + 8 * sa, pa ^ 1u);
-        if (tr && lane == 0 && tcount == 0) tr[7] = clock64();
-        const uint32_t dstA = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
-        if (elect_one()) {
-          if (tr && tcount < 250) tr[16 + 2 * tcount] = clock64();
-          mbar_expect_tx(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
-          if (ka.halo) {
-            int c[5];
-#pragma unroll
-            for (int d = 0; d < 5; ++d) c[d] = cb[0][d] + (g.dimW == d ? ka.tmin : 0);
-            c[0] = kc * KBLK;
-            for (int bx = 0; bx < nA; ++bx) {
-              const int sh = bx * HALO_BOX_ROWS;
-              tma_load_5d(dstA + (uint32_t)bx * (uint32_t)ka.boxA_bytes, &tmA, fullA_u + 8 * sa, c[0],
-                          c[1] + (g.dimW == 1 ? sh : 0), c[2] + (g.dimW == 2 ? sh : 0), c[3] + (g.dimW == 3 ? sh : 0),
-                          c[4] + (g.dimW == 4 ? sh : 0));
-            }
-          } else {
-            int t[5];
-#pragma unroll
-            for (int d = 0; d < 5; ++d) t[d] = ka.taps.t[tap][d];
-            t[0] += kc * KBLK;
-#pragma unroll
-            for (int m = 0; m < 2; ++m) {
-              if (m < nA)
-                tma_load_5d(dstA + (uint32_t)m * A_BOX_BYTES, &tmA, fullA_u + 8 * sa, t[0] + cb[m][0], t[1] + cb[m][1],
-                            t[2] + cb[m][2], t[3] + cb[m][3], t[4] + cb[m][4]);
-            }
-          }
-          if (tr && tcount < 250) tr[16 + 2 * tcount + 1] = clock64();
-        }
-        __syncwarp();
-        ++tcount;
-        if (++sa == ka.SA) { sa = 0; pa ^= 1u; }
-        if (++kc == ka.kchunks && !ka.halo) { kc = 0; ++tap; }
-      }
-    }
-  } else if (warp == 6) {
-    // ============================================================ B producer (weights / batch-indexed operand)
-    const uint32_t ringB_u = smem_u32(ringB), fullB_u = smem_u32(fullB), emptyB_u = smem_u32(emptyB);
-    int sb = 0;
-    uint32_t pb = 0;
-    for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x) {
-      WorkItem wi;
-      decode_work(ka, w, wi);
-      const int n0 = wi.tn * BN;
-      int tap = 0, kc = wi.o_begin;
-      if (!ka.halo) { tap = fdiv(wi.o_begin, ka.d_kchunks); kc = wi.o_begin - tap * ka.kchunks; }
-      for (int io = wi.o_begin; io < wi.o_end; ++io) {
-        for (int ii = 0; ii < ka.n_inner; ++ii) {
-          mbar_wait(emptyB_u + 8 * sb, pb ^ 1u);
-          if (elect_one()) {
-            mbar_expect_tx(fullB_u + 8 * sb, (uint32_t)ka.b_stage_bytes);
-            const int z = g.wz_batch ? wi.b0[0] : (ka.halo ? ii : tap);
-            tma_load_3d(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, &tmB, fullB_u + 8 * sb, kc * KBLK, n0, z);
-          }
-          __syncwarp();
-          if (++sb == ka.SB) { sb = 0; pb ^= 1u; }
-        }
-        if (++kc == ka.kchunks && !ka.halo) { kc = 0; ++tap; }
-      }
-    }
-  } else if (warp == 1 || warp == 7) {
-    // ============================================================ MMA issuers (whole warp, one elected lane issues)
-    // A UTCHMMA costs ~55 issue cycles whatever its N, and every k-step adds a barrier wait and a commit on top, so
-    // one issuing thread cannot keep the tensor pipe busy at N <= 128.  With two issuers each owns half of the CTA
-    // tile (a sub-tile when MT = 2, a BLOCK_N/2 column half when MT = 1): disjoint TMEM accumulators, so no ordering
-    // between them is needed; stages are released when both have committed (empty barriers count n_iss arrivals).
-    const int u = warp == 1 ? 0 : 1;
-    if (u < ka.n_iss) {
-      const bool split_n = (ka.n_iss == 2 && ka.mt == 1);
-      const int NI = split_n ? (BN >> 1) : BN;  // N of one instruction
-      const int m_lo = (ka.n_iss == 2 && ka.mt == 2) ? u : 0;
-      const int m_hi = (ka.n_iss == 2 && ka.mt == 2) ? u + 1 : ka.mt;
-      const uint32_t b_off = split_n ? (uint32_t)(u * NI * 128) : 0u;  // rows of the B stage owned by this issuer
-      const uint32_t c_off = split_n ? (uint32_t)(u * NI) : 0u;          // accumulator columns owned by this issuer
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(NI >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-      const uint32_t ringA_u = smem_u32(ringA), ringB_u = smem_u32(ringB);
-      const uint32_t fullA_u = smem_u32(fullA), emptyA_u = smem_u32(emptyA), fullB_u = smem_u32(fullB), emptyB_u = smem_u32(emptyB);
-      const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0;
-      int it = 0, tcount = 0;
-      for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
-        WorkItem wi;
-        decode_work(ka, w, wi);
-        const int buf = ka.nbuf == 2 ? (it & 1) : 0;
-        const int use = ka.nbuf == 2 ? (it >> 1) : it;
-        uint32_t acc = tmem_base + (uint32_t)(buf * ka.acc_cols) + c_off;
-        mbar_wait(accE_u + 8 * buf, (((uint32_t)use) & 1u) ^ 1u);  // epilogue has drained this buffer
-        tc_fence_after();
-        uint32_t first = 0;  // 0 until the first MMA of this item (of this split when folded) has been issued
-        int in_split = 0;    // folded split-K: outer steps issued into the current split's accumulator
-        for (int io = wi.o_begin; io < wi.o_end; ++io) {
-          if (ka.fold && in_split == ka.outer_per_split) {   // next split: its own TMEM region, accumulation restarts
-            in_split = 0; first = 0; acc += (uint32_t)(ka.mt * BN);
-          }
-          ++in_split;
-          if (ka.halo) mbar_wait(fullA_u + 8 * sa, pa);  // otherwise A rides on the B barriers (same stage index)
-          const uint32_t aBase = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
-          for (int ii = 0; ii < ka.n_inner; ++ii) {
-            mbar_wait(fullB_u + 8 * sb, pb);
-            tc_fence_after();
-            const uint64_t bdesc = make_smem_desc(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes + b_off);
-            const uint32_t shift = ka.halo ? (uint32_t)((ka.tapw[ii] - ka.tmin) * 128) : 0u;
-            const bool lastB = (ii == ka.n_inner - 1);
-            if (elect_one()) {
-              if (tr && u == 0 && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
-#pragma unroll
-              for (int m = 0; m < 2; ++m) {
-                if (m >= m_lo && m < m_hi && m < wi.mt_eff) {
-                  const uint64_t adesc = make_smem_desc(aBase + shift + (uint32_t)m * A_BOX_BYTES);
-#pragma unroll
-                  for (int k = 0; k < KBLK / 16; ++k) {
-                    // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
-                    tc_mma_f16(acc + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
-                  }
-                }
-              }
-              tc_commit(emptyB_u + 8 * sb);
-              if (lastB) {
-                if (ka.halo) tc_commit(emptyA_u + 8 * sa);
-                if (io == wi.o_end - 1) tc_commit(accF_u + 8 * buf);
-                if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
-              }
-            }
-            __syncwarp();
-            first = 1;
-            if (++sb == ka.SB) { sb = 0; pb ^= 1u; }
-          }
-          ++tcount;
-          if (++sa == ka.SA) { sa = 0; pa ^= 1u; }
-        }
-      }
-    }
-  } else if ((warp >= 2 && warp <= 5) || warp >= 8) {
-    // ============================================================ epilogue: warps 2..5 (set 0) and 8..11 (set 1)
-    // A warp may only read TMEM lanes 32*(warp%4)..+31, so each lane group has one warp per set; the two warps
-    // take alternate 32-column blocks of the tile.  The store pass is ALU-latency bound inside a single warp
-    // (address math, predicates, FMAs on a dependent chain): a second warp per scheduler hides that latency.
-    const int lg = warp & 3;
-    const int eset = warp >= 8 ? 1 : 0;
-    const int ew = eset * 4 + (eset ? warp - 8 : warp - 2);   // 0..7
-    const int et = ew * 32 + lane;                             // epilogue thread id 0..255
-    float* stg = stage_all + (size_t)ew * (32 * STAGE_LD);
-    const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
-    const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // vector pass: 4 rows x 8 float4 per instruction
-    const int nblk = (BN + 31) >> 5;
-    const bool has_resid = g.resid != nullptr, has_bias = g.bias != nullptr, has_out16 = g.out16 != nullptr;
-    const bool has_resid2 = g.resid2 != nullptr;
-    int it = 0;
-    for (int w = blockIdx.x; w < ka.n_work; w += gridDim.x, ++it) {
-      WorkItem wi;
-      decode_work(ka, w, wi);
-      const int buf = ka.nbuf == 2 ? (it & 1) : 0;
-      const int n0 = wi.tn * BN;
-      mbar_wait(accF_u + 8 * buf, ((uint32_t)(ka.nbuf == 2 ? (it >> 1) : it)) & 1u);
-      tc_fence_after();
-      if (tr && threadIdx.x == 64 && it < 6) tr[2 + 2 * it] = clock64();
-      const int tile_id = wi.tm * ka.tiles_n + wi.tn;
-      const size_t pstride = (size_t)ka.mt * TILE_M * BN;
-      float* part = (ka.splits > 1 && !ka.fold) ? ka.partial + ((size_t)tile_id * ka.splits + wi.ks) * pstride : nullptr;
-      const bool vecpath = ka.vec_ok && !part && !g.transposed;
-      const int ntot = wi.mt_eff * nblk;
-      const int last_bi = ntot - 1 - ((ntot - 1 - eset) & 1);  // last block of this set (< eset when it has none)
-      if (last_bi < eset) {  // nothing to read for this warp: hand the buffer back right away
-        tc_fence_before();
-        if (lane == 0) mbar_arrive(accE_u + 8 * buf);
-      }
-      // NOTE: r[] and the other per-block arrays must only be indexed by compile-time constants (fully unrolled
-      // loops): one dynamic index sends the whole array to local memory.
-      int m_prev = -1;
-      RowInfo ri;
-      uint32_t any_ok = 0;
-      long long base_l0 = 0, flat_l0 = 0;
-      int roff = 0, foff = 0;
-      int off[8];
-      for (int bi = eset; bi < ntot; bi += 2) {
-        const int m = bi >= nblk ? 1 : 0;
-        const int cb = (bi - m * nblk) * 32;
-        if (m != m_prev) {
-          m_prev = m;
-          ri = row_info(ka, wi, m, lg * 32 + lane);  // this thread's own row
-          any_ok = __ballot_sync(0xffffffffu, ri.ok);
-          base_l0 = __shfl_sync(0xffffffffu, ri.base, 0);
-          flat_l0 = __shfl_sync(0xffffffffu, ri.flat0, 0);
-          roff = (int)(ri.base - base_l0);   // row offsets inside the tile (host checked: fit 32 bits)
-          foff = (int)(ri.flat0 - flat_l0);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = 4 * i + rsub;
-            off[i] = __shfl_sync(0xffffffffu, roff, rr);
-            if (!((any_ok >> rr) & 1u)) off[i] = -1;
-          }
-        }
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ka.acc_cols + m * BN + cb);
-        const int ncols = min(32, BN - cb);  // BN is a multiple of 16
-        if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
-        if (ka.fold) {
-          // folded split-K: the splits' accumulators are added in split order — the same f32 additions, in the same
-          // order, as the last-arriver reduction of the global-partial path, so both modes give the same bits
-          tc_wait_ld();
-          for (int sp = 1; sp < ka.splits; ++sp) {
-            const uint32_t ta2 = taddr + (uint32_t)(sp * ka.mt * BN);
-#pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {   // 16 columns at a time: a 32-register temporary would spill
-              if (hf * 16 < ncols) {
-                uint32_t r2[16];
-                tc_ld16b(ta2 + (uint32_t)(hf * 16), r2);
-                tc_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[hf * 16 + j] = __float_as_uint(__uint_as_float(r[hf * 16 + j]) + __uint_as_float(r2[j]));
-              }
-            }
-          }
-        }
-        const int nb = n0 + cb;
-        const int n = nb + c4;
-        const bool col_ok = c4 < ncols && n < g.N;
-        // bias / residual loads of the vector path are issued under the TMEM load
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 rv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vecpath && any_ok) {
-          if (col_ok && has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
-          if (has_resid) {
-            if (!ka.need_crop) {  // predicated loads, no per-cell branches
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (col_ok && off[i] >= 0) rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
-              if (has_resid2) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (col_ok && off[i] >= 0) {
-                    const float4 r2 = __ldg(reinterpret_cast<const float4*>(g.resid2 + base_l0 + off[i] + n));
-                    rv[i].x += r2.x; rv[i].y += r2.y; rv[i].z += r2.z; rv[i].w += r2.w;
-                  }
-              }
-            } else {              // cropped cells (transposed-conv margins) may lie outside the residual tensor
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const long long fl = flat_l0 + __shfl_sync(0xffffffffu, foff, 4 * i + rsub) + n;
-                if (col_ok && off[i] >= 0 && fl >= g.out_lo && fl < g.out_hi) {
-                  rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
-                  if (has_resid2) {
-                    const float4 r2 = __ldg(reinterpret_cast<const float4*>(g.resid2 + base_l0 + off[i] + n));
-                    rv[i].x += r2.x; rv[i].y += r2.y; rv[i].z += r2.z; rv[i].w += r2.w;
-                  }
-                }
-              }
-            }
-          }
-        }
-        tc_wait_ld();
-        if (bi == last_bi) {  // last TMEM read of this buffer by this warp: hand it back to the MMA warps
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(accE_u + 8 * buf);
-        }
-        if (!any_ok) continue;
-        if (g.transposed && !part) {
-          // out[b][n][pix]: consecutive rows are consecutive addresses -> already coalesced per column
-          if (ri.ok) {
-            const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols && nb + j < g.N) finish1(g, __uint_as_float(r[j]), ri.base + (long long)(nb + j) * g.out_n_stride, nb + j, rb);
-          }
-          continue;
-        }
-        // transpose through shared memory: thread = row  ->  8 lanes per row, 4 rows per instruction
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          if (j < ncols)
-            *reinterpret_cast<float4*>(stg + lane * STAGE_LD + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                               __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-        __syncwarp();
-        if (part) {
-          // raw partial sums, row-major [mt*128][BN]
-          if (c4 < ncols) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 4 * i + rsub;
-              if (off[i] >= 0)
-                __stcg(reinterpret_cast<float4*>(part + ((size_t)(m * TILE_M + lg * 32 + rr)) * BN + cb + c4),
-                       *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4));
-            }
-          }
-        } else if (vecpath) {
-          // 4 rows x 128 contiguous bytes per store instruction
-          if (ka.epi_plain) {
-            // plain f32 output (+bias, +residual): branch-free passes, only the store is predicated, so the passes
-            // interleave (the general variant below serialises on its per-pass uniform branches)
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              float4 a[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(stg + (4 * (4 * half + i) + rsub) * STAGE_LD + c4);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int k = 4 * half + i;
-                float4 o;
-                o.x = fmaf(a[i].x, g.alpha, bias4.x) + rv[k].x; o.y = fmaf(a[i].y, g.alpha, bias4.y) + rv[k].y;
-                o.z = fmaf(a[i].z, g.alpha, bias4.z) + rv[k].z; o.w = fmaf(a[i].w, g.alpha, bias4.w) + rv[k].w;
-                if (col_ok && off[k] >= 0) {
-                  *reinterpret_cast<float4*>(g.out32 + base_l0 + off[k] + n) = o;
-                  if (has_out16) {  // f16 copy for a following tensor-core layer (uniform flag)
-                    __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<unsigned*>(&h0);
-                    pk.y = *reinterpret_cast<unsigned*>(&h1);
-                    *reinterpret_cast<uint2*>(g.out16 + base_l0 + off[k] + n) = pk;
-                  }
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = 4 * i + rsub;
-              const int fo = __shfl_sync(0xffffffffu, foff, rr);   // convergent: before any per-lane skip
-              const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
-              bool ok = col_ok && off[i] >= 0;
-              if (ka.need_crop) {
-                const long long fl = flat_l0 + fo + n;
-                ok = ok && fl >= g.out_lo && fl < g.out_hi;
-              }
-              if (ok) {
-                const float4 a = *reinterpret_cast<const float4*>(stg + rr * STAGE_LD + c4);
-                float x[4] = {fmaf(a.x, g.alpha, bias4.x), fmaf(a.y, g.alpha, bias4.y), fmaf(a.z, g.alpha, bias4.z), fmaf(a.w, g.alpha, bias4.w)};
-                if (g.rowbias) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(g.rowbias + (long long)bb * g.rowbias_stride + n));
-                  x[0] += b4.x; x[1] += b4.y; x[2] += b4.z; x[3] += b4.w;
-                }
-                if (g.act) {
-#pragma unroll
-                  for (int u = 0; u < 4; ++u) x[u] = egr_apply_act(x[u], g.act);
-                }
-                x[0] = (x[0] + rv[i].x) * g.post; x[1] = (x[1] + rv[i].y) * g.post;
-                x[2] = (x[2] + rv[i].z) * g.post; x[3] = (x[3] + rv[i].w) * g.post;
-                const long long idx = base_l0 + off[i] + n;
-                if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(x[0], x[1], x[2], x[3]);
-                if (g.out16) {
-                  __half2 h0 = __floats2half2_rn(x[0], x[1]), h1 = __floats2half2_rn(x[2], x[3]);
-                  uint2 pk;
-                  pk.x = *reinterpret_cast<unsigned*>(&h0);
-                  pk.y = *reinterpret_cast<unsigned*>(&h1);
-                  *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
-                }
-              }
-            }
-          }
-        } else {
-          // scalar path (odd alignments): lane = column, one row per pass
-#pragma unroll 4
-          for (int rr = 0; rr < 32; ++rr) {
-            const int o = __shfl_sync(0xffffffffu, roff, rr);
-            const int fo = __shfl_sync(0xffffffffu, foff, rr);
-            const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
-            const int nn = nb + lane;
-            const long long fl = flat_l0 + fo + nn;
-            if (((any_ok >> rr) & 1u) && lane < ncols && nn < g.N && fl >= g.out_lo && fl < g.out_hi) {
-              const float* rb = g.rowbias ? g.rowbias + (long long)bb * g.rowbias_stride : nullptr;
-              finish1(g, stg[rr * STAGE_LD + lane], base_l0 + o + nn, nn, rb);
-            }
-          }
-        }
-        __syncwarp();
-      }
-      if (part) {
-        // split-K: the last CTA to finish this output tile reduces all partials in split order
-        __threadfence();
-        epi_bar_sync();
-        if (et == 0) {
-          const unsigned int old = atomicAdd(ka.counters + tile_id, 1u);
-          const unsigned int last = (old == (unsigned int)(ka.splits - 1)) ? 1u : 0u;
-          if (last) ka.counters[tile_id] = 0u;  // ready for the next launch
-          *last_flag = last;
-        }
-        epi_bar_sync();
-        const bool is_last = *last_flag != 0u;
-        epi_bar_sync();  // everyone has read the flag before a later item may overwrite it
-        if (is_last) {
-          __threadfence();
-          // all 128 epilogue threads share the valid elements, whatever TMEM lane group produced them
-          const float* pt = ka.partial + (size_t)tile_id * ka.splits * pstride;
-          const int c4n = BN >> 2;
-          const int total = wi.mt_eff * TILE_M * c4n;
-          for (int e = et; e < total; e += 256) {
-            const int row = fdiv(e, ka.d_c4n), c = (e - row * c4n) * 4;
-            const int m = row >> 7;
-            const RowInfo ri = row_info(ka, wi, m, row & 127);
-            const int n = n0 + c;
-            if (!ri.ok || n >= g.N) continue;
-            const float* pe = pt + (size_t)row * BN + c;
-            float4 acc = __ldcg(reinterpret_cast<const float4*>(pe));
-            int sidx = 1;
-            for (; sidx + 4 <= ka.splits; sidx += 4) {  // four independent loads in flight, summed in split order
-              const float4 v0 = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)sidx * pstride));
-              const float4 v1 = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)(sidx + 1) * pstride));
-              const float4 v2 = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)(sidx + 2) * pstride));
-              const float4 v3 = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)(sidx + 3) * pstride));
-              acc.x += v0.x; acc.y += v0.y; acc.z += v0.z; acc.w += v0.w;
-              acc.x += v1.x; acc.y += v1.y; acc.z += v1.z; acc.w += v1.w;
-              acc.x += v2.x; acc.y += v2.y; acc.z += v2.z; acc.w += v2.w;
-              acc.x += v3.x; acc.y += v3.y; acc.z += v3.z; acc.w += v3.w;
-            }
-            for (; sidx < ka.splits; ++sidx) {
-              const float4 v = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)sidx * pstride));
-              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
-            const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
-            if (g.transposed) {
-              for (int u = 0; u < 4 && n + u < g.N; ++u) finish1(g, a4[u], ri.base + (long long)(n + u) * g.out_n_stride, n + u, rb);
-            } else if (ka.vec_ok) {
-              const long long fl = ri.flat0 + n;
-              if (fl >= g.out_lo && fl < g.out_hi) finish4(g, acc, ri.base + n, n, rb);
-            } else {
-              for (int u = 0; u < 4 && n + u < g.N; ++u) {
-                const long long fl = ri.flat0 + n + u;
-                if (fl >= g.out_lo && fl < g.out_hi) finish1(g, a4[u], ri.base + n + u, n + u, rb);
-              }
-            }
-          }
-        }
-      }
-      if (tr && threadIdx.x == 64 && it < 6) tr[3 + 2 * it] = clock64();
-    }
-  }
+  tc_roles(&tmA, &tmB, ka, sv, tmem_base, (int)blockIdx.x, (int)gridDim.x, tr);
+
   tc_fence_before();
   __syncthreads();
 #ifdef EGR_TC_TRACE
