@@ -1,0 +1,774 @@
+// mega.cu — the UNet of the FlashSR plan as ONE persistent kernel.
+//
+// Why.  A denoising step is ~440 ops over feature maps of 32 .. 2048 pixels per chunk-channel: 1 % of the pass's FLOPs,
+// yet 4.7 ms of a 16.5 ms pass at batch 1 and 9.7 ms per step at batch 8 (round-2 measurements) — every op is a kernel
+// whose useful work is a few microseconds behind a launch, a prologue (barrier set-up, TMEM allocation, descriptor
+// fetch) and a drain.  Its weights (360 MB of f16) stream in 55 us at HBM speed; nothing else bounds the section.
+//
+// What.  One CTA per SM (cooperative launch, 384 threads) walks an op table in global memory.  Between dependent ops
+// the CTAs meet at a grid barrier (one atomic round trip through L2, ~1.5 us) instead of at a kernel boundary; the
+// planner marks the ops whose successor does not depend on them (the q/k/v projections, independent casts), which skip
+// it.  TMEM is allocated once per launch, tensor maps and per-op arguments are prefetched from the table.
+//   GEMM ops run the SAME warp roles as gemm_tc_kernel (gemm_tc.cuh: TMA producers, tcgen05 issuers, TMEM epilogue,
+//   split-K with per-layer constant splits) — only the barriers are re-initialised per op;
+//   the CUDA-core ops (GroupNorm over a virtual concat, LayerNorm, short-sequence attention, GEGLU, casts, the DDIM
+//   update, the time-embedding GEMVs) are grid-strided bodies on warps 0-7 with the arithmetic of their stand-alone
+//   kernels in ops.cu.
+// Results are deterministic and independent of the batch a chunk-channel runs in (fixed reduction orders, geometry-only
+// work splits), like the per-op path.
+#include <vector>
+#include "gemm_tc.cuh"
+#include "mega.cuh"
+
+namespace egr {
+
+enum { MOP_GEMM_TC = 1, MOP_GEMV, MOP_GN_STATS, MOP_GN_APPLY, MOP_LAYERNORM, MOP_ATTN, MOP_GEGLU, MOP_CAT, MOP_AXPBY, MOP_TIME_EMBED };
+
+struct __align__(16) MegaOp {
+  int code, sync_after, tc, pad;
+  union {
+    struct { View a; GemmArgs g; int npix; } gemv;
+    struct { CatArgs a; const float* gamma; const float* beta; float eps; int silu; float* out32; __half* out16; double* part; int nsl; } gn;
+    struct { const float* x; long long rows; int C; float eps; const float* gamma; const float* beta; __half* out16; float* out32; } ln;
+    struct { const __half* q; const __half* k; const __half* v; __half* out; int S, heads, hd, B, ld, qblocks; float scale; } attn;
+    struct { const float* x; long long rows; int D; __half* out; } geglu;
+    struct { const float* x0; const float* x1; int C0, C1; long long rows, ld0, ld1; float* o32; __half* o16; } cat;
+    struct { const float* x; const float* y; float a, b; long long n; float* o32; __half* o16; } axpby;
+    struct { float t; int dim; float* out; } temb;
+  } u;
+};
+static_assert(sizeof(MegaOp) % 16 == 0 && sizeof(MegaOp) <= 512, "MegaOp is copied to shared memory in 16-byte words");
+static_assert(sizeof(TcKernelArgs) % 8 == 0, "TcKernelArgs is copied to shared memory in 8-byte words");
+
+struct MegaRun {
+  int first = 0, last = 0, n_ops = 0, n_tc = 0, n_sync = 0;
+  MegaOp* d_ops = nullptr;
+  TcKernelArgs* d_kas = nullptr;
+  CUtensorMap* d_maps = nullptr;   // [n_tc][2], 128-byte entries
+  unsigned int* d_bar = nullptr;   // [0] arrival count, [1] generation
+  int smem_bytes = 0;
+  int grid = 0;
+};
+
+static constexpr int MEGA_THREADS = 384;
+static constexpr int MEGA_SIMT = 256;        // CUDA-core ops run on warps 0..7
+static constexpr int MEGA_MAX_STAGES = 10;   // ring depth bound of tc_prepare
+static constexpr int MEGA_BAR_BYTES = 1024;  // 4 x 10 ring barriers + 4 accumulator barriers, padded
+
+}  // namespace egr
+
+using namespace egr;
+
+// ------------------------------------------------------------------------------------------------ synchronisation
+__device__ __forceinline__ void simt_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+// Sense-reversing grid barrier (state returns to "count 0" after every use, so a captured graph can replay the launch).
+// Memory: every thread's earlier global writes are ordered before the arrival by bar.sync + the arriving thread's gpu-scope
+// fence; on the way out the gpu-scope fence of thread 0 also drops the SM's L1 lines (the data other SMs wrote is read
+// from L2), and both sides fence the generic -> async proxy edge because the next op's TMA loads read what plain stores
+// of the previous op produced.
+__device__ __forceinline__ bool grid_sync(unsigned int* bar, int ncta) {
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncthreads();
+  __shared__ unsigned int s_abort;
+  if (threadIdx.x == 0) {
+    unsigned int gen, now, dead = 0;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+    __threadfence();
+    const unsigned int prev = atomicAdd(bar, 1u);
+    if (prev == (unsigned int)ncta - 1u) {
+      atomicExch(bar, 0u);
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      // watchdog: a CTA that never arrives (a bug, never a legal state) must not hang the GPU — after ~2^25 polls
+      // (seconds) the launch is abandoned: bar[2] is raised, every CTA leaves its op loop, the host reports it
+      unsigned int spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory");
+        if (((++spins) & 0xFFFu) == 0u) {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dead) : "l"(bar + 2) : "memory");
+          if (spins > (1u << 25)) { atomicExch(bar + 2, 1u); dead = 1; }
+          if (dead) break;
+        }
+      } while (now == gen);
+    }
+    if (!dead) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dead) : "l"(bar + 2) : "memory");
+    s_abort = dead;
+    __threadfence();
+  }
+  __syncthreads();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  return s_abort != 0u;
+}
+
+// ------------------------------------------------------------------------------------------------ CUDA-core op bodies
+// (threads 0..255 of every CTA; activations are read with ld.global.cg — they were written by other SMs during this launch)
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
+__device__ __noinline__ void mega_gemv(const MegaOp& op, int cta, int ncta) {
+  const GemmArgs& g = op.u.gemv.g;
+  const View& a = op.u.gemv.a;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int npix = op.u.gemv.npix;
+  for (int n = cta * 8 + warp; n < g.N; n += ncta * 8) {
+    const float* wrow = reinterpret_cast<const float*>(g.W) + (long long)n * g.wstride_n;
+    for (int p = 0; p < npix; ++p) {
+      const int w = p % g.Wo, h = (p / g.Wo) % g.Ho, b = p / (g.Wo * g.Ho);
+      const float* x = reinterpret_cast<const float*>(a.p) + (long long)w * a.stride[g.dimW] + (long long)h * a.stride[g.dimH] +
+                       (long long)b * a.stride[g.dimB];
+      float acc = 0.f;
+      for (int k = lane * 4; k < g.K; k += 128) {
+        const float4 xv = ldcg4(x + k);
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(wrow + k));
+        acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc); acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) epilogue_store(g, b, (long long)h * g.Wo + w, n, acc);
+    }
+  }
+}
+
+__device__ __forceinline__ const float* gn_src(const CatArgs& a, int b, long long p, int c) {
+  return c < a.C0 ? a.x0 + ((long long)b * a.P + p) * a.C0 + c : a.x1 + ((long long)b * a.P + p) * a.C1 + (c - a.C0);
+}
+
+// unit = (item b, group gi, pixel slice sl): f32 partial moments per thread, combined in f64 in a fixed order
+__device__ __noinline__ void mega_gn_stats(const MegaOp& op, int cta, int ncta, double (*red)[8]) {
+  const CatArgs& a = op.u.gn.a;
+  const int C = a.C0 + a.C1, cpg = C / a.G, q4 = cpg >> 2, nsl = op.u.gn.nsl;
+  const int units = a.B * a.G * nsl;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int unit = cta; unit < units; unit += ncta) {
+    const int sl = unit % nsl, gi = (unit / nsl) % a.G, b = unit / (nsl * a.G);
+    const int p_lo = (int)(a.P * sl / nsl), p_hi = (int)(a.P * (sl + 1) / nsl);
+    const int n4 = (p_hi - p_lo) * q4;
+    float s = 0.f, ss = 0.f;
+    for (int u = tid; u < n4; u += MEGA_SIMT) {
+      const int pl = u / q4;
+      const int c = gi * cpg + (u - pl * q4) * 4;
+      const float4 v = ldcg4(gn_src(a, b, p_lo + pl, c));
+      s += (v.x + v.y) + (v.z + v.w);
+      ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+    }
+    const double ds = warp_sum((double)s), dss = warp_sum((double)ss);
+    if (lane == 0) { red[0][warp] = ds; red[1][warp] = dss; }
+    simt_sync();
+    if (tid == 0) {
+      double t = 0.0, tt = 0.0;
+      for (int w = 0; w < 8; ++w) { t += red[0][w]; tt += red[1][w]; }
+      double* dst = op.u.gn.part + (((long long)b * a.G + gi) * nsl + sl) * 2;
+      dst[0] = t; dst[1] = tt;
+    }
+    simt_sync();
+  }
+}
+
+__device__ __noinline__ void mega_gn_apply(const MegaOp& op, int cta, int ncta, float* stat) {
+  const CatArgs& a = op.u.gn.a;
+  const int C = a.C0 + a.C1, cpg = C / a.G, q4 = cpg >> 2, nsl = op.u.gn.nsl;
+  const int units = a.B * a.G * nsl;
+  const int tid = threadIdx.x;
+  const int silu = op.u.gn.silu;
+  float* out32 = op.u.gn.out32;
+  __half* out16 = op.u.gn.out16;
+  for (int unit = cta; unit < units; unit += ncta) {
+    const int sl = unit % nsl, gi = (unit / nsl) % a.G, b = unit / (nsl * a.G);
+    if (tid == 0) {
+      const double* src = op.u.gn.part + ((long long)b * a.G + gi) * nsl * 2;
+      double t = 0.0, tt = 0.0;
+      for (int r = 0; r < nsl; ++r) { t += __ldcg(src + 2 * r); tt += __ldcg(src + 2 * r + 1); }
+      const double cnt = (double)cpg * (double)a.P;
+      const double mean = t / cnt;
+      double var = tt / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stat[0] = (float)mean;
+      stat[1] = (float)(1.0 / sqrt(var + (double)op.u.gn.eps));
+    }
+    simt_sync();
+    const float mean = stat[0], rstd = stat[1];
+    const int p_lo = (int)(a.P * sl / nsl), p_hi = (int)(a.P * (sl + 1) / nsl);
+    const int n4 = (p_hi - p_lo) * q4;
+    for (int u = tid; u < n4; u += MEGA_SIMT) {
+      const int pl = u / q4;
+      const int c = gi * cpg + (u - pl * q4) * 4;
+      const int p = p_lo + pl;
+      const float4 v = ldcg4(gn_src(a, b, p, c));
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(op.u.gn.gamma + c));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(op.u.gn.beta + c));
+      float r[4] = {fmaf(v.x, rstd * g4.x, b4.x - mean * (rstd * g4.x)), fmaf(v.y, rstd * g4.y, b4.y - mean * (rstd * g4.y)),
+                    fmaf(v.z, rstd * g4.z, b4.z - mean * (rstd * g4.z)), fmaf(v.w, rstd * g4.w, b4.w - mean * (rstd * g4.w))};
+      if (silu) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = egr_silu(r[k]);
+      }
+      const long long o = ((long long)b * a.P + p) * C + c;
+      if (out32) *reinterpret_cast<float4*>(out32 + o) = make_float4(r[0], r[1], r[2], r[3]);
+      if (out16) {
+        __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&h0);
+        pk.y = *reinterpret_cast<unsigned*>(&h1);
+        *reinterpret_cast<uint2*>(out16 + o) = pk;
+      }
+    }
+    simt_sync();   // stat[] is rewritten by the next unit
+  }
+}
+
+__device__ __noinline__ void mega_layernorm(const MegaOp& op, int cta, int ncta) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = op.u.ln.C;
+  const float* gamma = op.u.ln.gamma;
+  const float* beta = op.u.ln.beta;
+  for (long long row = (long long)cta * 8 + warp; row < op.u.ln.rows; row += (long long)ncta * 8) {
+    const float* xr = op.u.ln.x + row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __ldcg(xr + c);
+    const float mean = warp_sum(s) / C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = __ldcg(xr + c) - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(warp_sum(v) / C + op.u.ln.eps);
+    for (int c = lane; c < C; c += 32) {
+      const float y = (__ldcg(xr + c) - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+      if (op.u.ln.out16) op.u.ln.out16[row * C + c] = __float2half_rn(y);
+      if (op.u.ln.out32) op.u.ln.out32[row * C + c] = y;
+    }
+  }
+}
+
+// attn_rows_kernel of ops.cu with (q block, head, item) taken from a virtual block index: K / V of one (item, head) staged
+// in shared memory as f16, one warp per query row, lanes split the keys in both phases, reduce-scatter of the outputs
+template <int HD>
+__device__ __noinline__ void mega_attn(const MegaOp& op, int cta, int ncta, unsigned char* smraw) {
+  constexpr int KST = HD + 8;
+  const int S = op.u.attn.S, heads = op.u.attn.heads, B = op.u.attn.B, qblocks = op.u.attn.qblocks;
+  const __half* q = op.u.attn.q;
+  const __half* k = op.u.attn.k;
+  const __half* v = op.u.attn.v;
+  __half* out = op.u.attn.out;
+  const float scale = op.u.attn.scale;
+  __half* Ks = reinterpret_cast<__half*>(smraw);
+  __half* Vs = Ks + (size_t)S * KST;
+  const int C = heads * HD;
+  const int L = op.u.attn.ld ? op.u.attn.ld : C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_block = (S + qblocks - 1) / qblocks;
+  const int njj = (S + 31) >> 5;
+  const int nvb = qblocks * heads * B;
+  auto row8 = [](const __half* p, float* x) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw.x));
+    const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+    const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&raw.z));
+    const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&raw.w));
+    x[0] = f0.x; x[1] = f0.y; x[2] = f1.x; x[3] = f1.y; x[4] = f2.x; x[5] = f2.y; x[6] = f3.x; x[7] = f3.y;
+  };
+  int staged = -1;   // (item, head) whose K / V currently sit in shared memory
+  for (int vb = cta; vb < nvb; vb += ncta) {
+    const int qb = vb % qblocks, h = (vb / qblocks) % heads, b = vb / (qblocks * heads);
+    const long long base = (long long)b * S * C + (long long)h * HD;
+    const long long ibase = (long long)b * S * L + (long long)h * HD;
+    if (staged != b * heads + h) {
+      simt_sync();   // the previous virtual block's readers are done with Ks / Vs
+      for (int i = threadIdx.x; i < S * (HD / 8); i += MEGA_SIMT) {
+        const int j = i / (HD / 8), c8 = (i % (HD / 8)) * 8;
+        *reinterpret_cast<uint4*>(Ks + j * KST + c8) = __ldcg(reinterpret_cast<const uint4*>(k + ibase + (long long)j * L + c8));
+        *reinterpret_cast<uint4*>(Vs + j * KST + c8) = __ldcg(reinterpret_cast<const uint4*>(v + ibase + (long long)j * L + c8));
+      }
+      staged = b * heads + h;
+      simt_sync();
+    }
+    const int r_lo = qb * rows_per_block, r_hi = min(S, r_lo + rows_per_block);
+    for (int r = r_lo + warp; r < r_hi; r += 8) {
+      float qv[HD];
+#pragma unroll
+      for (int c8 = 0; c8 < HD; c8 += 8) {
+        const uint4 raw = __ldcg(reinterpret_cast<const uint4*>(q + ibase + (long long)r * L + c8));
+        const __half2* hp = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float2 f = __half22float2(hp[u]);
+          qv[c8 + 2 * u] = f.x * scale; qv[c8 + 2 * u + 1] = f.y * scale;
+        }
+      }
+      float sc[16];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        sc[jj] = -INFINITY;
+        const int j = jj * 32 + lane;
+        if (jj < njj && j < S) {
+          float dot = 0.f;
+#pragma unroll
+          for (int c8 = 0; c8 < HD; c8 += 8) {
+            float x[8];
+            row8(Ks + j * KST + c8, x);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dot = fmaf(qv[c8 + u], x[u], dot);
+          }
+          sc[jj] = dot;
+          mx = fmaxf(mx, dot);
+        }
+      }
+      mx = warp_max(mx);
+      float o[HD];
+#pragma unroll
+      for (int d = 0; d < HD; ++d) o[d] = 0.f;
+      float sum = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) {
+        const int j = jj * 32 + lane;
+        if (jj < njj && j < S) {
+          const float p = __expf(sc[jj] - mx);
+          sum += p;
+#pragma unroll
+          for (int c8 = 0; c8 < HD; c8 += 8) {
+            float x[8];
+            row8(Vs + j * KST + c8, x);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) o[c8 + u] = fmaf(p, x[u], o[c8 + u]);
+          }
+        }
+      }
+      const float inv = 1.0f / warp_sum(sum);
+      if (HD == 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float mine = (lane & 16) ? o[16 + i] : o[i], send = (lane & 16) ? o[i] : o[16 + i];
+          o[i] = mine + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] += __shfl_xor_sync(0xffffffffu, o[i], 16);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mine = (lane & 8) ? o[8 + i] : o[i], send = (lane & 8) ? o[i] : o[8 + i];
+        o[i] = mine + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float mine = (lane & 4) ? o[4 + i] : o[i], send = (lane & 4) ? o[i] : o[4 + i];
+        o[i] = mine + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const float mine = (lane & 2) ? o[2 + i] : o[i], send = (lane & 2) ? o[i] : o[2 + i];
+        o[i] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      {
+        const float mine = (lane & 1) ? o[1] : o[0], send = (lane & 1) ? o[0] : o[1];
+        o[0] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+      }
+      const int d = HD == 32 ? lane : (lane & 15);
+      if (HD == 32 || lane < 16) out[base + (long long)r * C + d] = __float2half_rn(o[0] * inv);
+    }
+  }
+}
+
+__device__ __noinline__ void mega_geglu(const MegaOp& op, int cta, int ncta) {
+  const int D = op.u.geglu.D;
+  const long long total = op.u.geglu.rows * D;
+  const float* x = op.u.geglu.x;
+  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < total; i += (long long)ncta * MEGA_SIMT) {
+    const long long r = i / D; const int d = (int)(i % D);
+    const float a = __ldcg(x + r * 2 * D + d), g = __ldcg(x + r * 2 * D + D + d);
+    op.u.geglu.out[i] = __float2half_rn(a * (0.5f * g * (1.0f + erff(g * 0.70710678118654752f))));
+  }
+}
+
+__device__ __noinline__ void mega_cat(const MegaOp& op, int cta, int ncta) {
+  const int C0 = op.u.cat.C0, C = C0 + op.u.cat.C1;
+  const long long total = op.u.cat.rows * C;
+  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < total; i += (long long)ncta * MEGA_SIMT) {
+    const long long r = i / C; const int c = (int)(i % C);
+    const float v = c < C0 ? __ldcg(op.u.cat.x0 + r * op.u.cat.ld0 + c) : __ldcg(op.u.cat.x1 + r * op.u.cat.ld1 + (c - C0));
+    if (op.u.cat.o32) op.u.cat.o32[i] = v;
+    if (op.u.cat.o16) op.u.cat.o16[i] = __float2half_rn(v);
+  }
+}
+
+__device__ __noinline__ void mega_axpby(const MegaOp& op, int cta, int ncta) {
+  const float a = op.u.axpby.a, b = op.u.axpby.b;
+  const float* x = op.u.axpby.x;
+  const float* y = op.u.axpby.y;
+  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < op.u.axpby.n; i += (long long)ncta * MEGA_SIMT) {
+    const float v = y ? fmaf(a, __ldcg(x + i), b * __ldcg(y + i)) : fmaf(a, __ldcg(x + i), b);
+    if (op.u.axpby.o32) op.u.axpby.o32[i] = v;
+    if (op.u.axpby.o16) op.u.axpby.o16[i] = __float2half_rn(v);
+  }
+}
+
+__device__ __noinline__ void mega_time_embed(const MegaOp& op, int cta) {
+  if (cta != 0) return;
+  const int half = op.u.temb.dim / 2;
+  for (int i = threadIdx.x; i < half; i += MEGA_SIMT) {
+    const float fr = expf(-9.210340371976184f * (float)i / (float)half);
+    const float a = op.u.temb.t * fr;
+    op.u.temb.out[i] = cosf(a);
+    op.u.temb.out[half + i] = sinf(a);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp* __restrict__ ops, int n_ops,
+                                                                    const TcKernelArgs* __restrict__ kas,
+                                                                    const CUtensorMap* __restrict__ maps,
+                                                                    unsigned int* __restrict__ bar) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(16) MegaOp s_op;
+  __shared__ __align__(16) TcKernelArgs s_ka;
+  __shared__ double s_red[2][8];
+  __shared__ float s_stat[2];
+  __shared__ uint32_t s_tmem, s_last;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int cta = (int)blockIdx.x, ncta = (int)gridDim.x;
+
+  // barriers live at a FIXED place (the ring geometry changes from op to op); the rings follow, 1024-byte aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint8_t* rings = smem + MEGA_BAR_BYTES;
+  TcSmemView sv;
+  sv.fullA = bars;
+  sv.emptyA = bars + MEGA_MAX_STAGES;
+  sv.fullB = bars + 2 * MEGA_MAX_STAGES;
+  sv.emptyB = bars + 3 * MEGA_MAX_STAGES;
+  sv.acc_full = bars + 4 * MEGA_MAX_STAGES;
+  sv.acc_empty = sv.acc_full + 2;
+  sv.last_flag = &s_last;
+
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+  int bars_live = 0;   // SA / SB / counts of the barriers currently initialised (0 = none yet)
+  int live_SA = 0, live_SB = 0;
+
+  for (int i = 0; i < n_ops; ++i) {
+    // ---- fetch the op (and its GEMM arguments) into shared memory
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(ops + i);
+      uint4* dst = reinterpret_cast<uint4*>(&s_op);
+      if (tid < (int)(sizeof(MegaOp) / 16)) dst[tid] = __ldg(src + tid);
+    }
+    __syncthreads();
+    const int code = s_op.code;
+    if (code == MOP_GEMM_TC) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(kas + s_op.tc);
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_ka);
+      for (int w = tid; w < (int)(sizeof(TcKernelArgs) / 8); w += MEGA_THREADS) dst[w] = __ldg(src + w);
+      if (tid == 64) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(maps + 2 * s_op.tc) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(maps + 2 * s_op.tc + 1) : "memory");
+      }
+      __syncthreads();
+      const TcKernelArgs& ka = s_ka;
+      sv.ringA = rings;
+      sv.ringB = sv.ringA + (size_t)ka.SA * ka.a_stage_bytes;
+      sv.stage_all = reinterpret_cast<float*>(sv.ringB + (size_t)ka.SB * ka.b_stage_bytes);
+      if (tid == 0) {
+        if (bars_live) {
+          for (int s = 0; s < live_SA; ++s) { mbar_inval(&sv.fullA[s]); mbar_inval(&sv.emptyA[s]); }
+          for (int s = 0; s < live_SB; ++s) { mbar_inval(&sv.fullB[s]); mbar_inval(&sv.emptyB[s]); }
+          for (int s = 0; s < 2; ++s) { mbar_inval(&sv.acc_full[s]); mbar_inval(&sv.acc_empty[s]); }
+        }
+        tc_init_barriers(ka, sv);
+      }
+      bars_live = 1; live_SA = ka.SA; live_SB = ka.SB;
+      tc_fence_before();
+      __syncthreads();
+      tc_fence_after();
+      tc_roles(maps + 2 * s_op.tc, maps + 2 * s_op.tc + 1, ka, sv, tmem_base, cta, ncta, nullptr);
+      tc_fence_before();
+    } else if (tid < MEGA_SIMT) {
+      switch (code) {
+        case MOP_GEMV: mega_gemv(s_op, cta, ncta); break;
+        case MOP_GN_STATS: mega_gn_stats(s_op, cta, ncta, s_red); break;
+        case MOP_GN_APPLY: mega_gn_apply(s_op, cta, ncta, s_stat); break;
+        case MOP_LAYERNORM: mega_layernorm(s_op, cta, ncta); break;
+        case MOP_ATTN:
+          if (s_op.u.attn.hd == 32) mega_attn<32>(s_op, cta, ncta, rings);
+          else mega_attn<16>(s_op, cta, ncta, rings);
+          break;
+        case MOP_GEGLU: mega_geglu(s_op, cta, ncta); break;
+        case MOP_CAT: mega_cat(s_op, cta, ncta); break;
+        case MOP_AXPBY: mega_axpby(s_op, cta, ncta); break;
+        case MOP_TIME_EMBED: mega_time_embed(s_op, cta); break;
+        default: break;
+      }
+    }
+    const int sync_after = s_op.sync_after;   // read before the next fetch overwrites s_op
+    if (sync_after) {
+      if (grid_sync(bar, ncta)) break;   // watchdog fired somewhere: abandon the launch
+    } else {
+      __syncthreads();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int mega_nsl(const CatArgs& a) {
+  // pixel slices per (item, group): ~8192 elements each, at most 16 — a function of the op's geometry only
+  const long long elems = a.P * ((a.C0 + a.C1) / a.G);
+  long long n = (elems + 8191) / 8192;
+  if (n > 16) n = 16;
+  if (n > a.P) n = a.P;
+  return (int)(n < 1 ? 1 : n);
+}
+
+bool egr::mega_supports(const egr_op& op) {
+  switch (op.code) {
+    case EGR_OP_GEMM_TC: case EGR_OP_LAYERNORM: case EGR_OP_GEGLU: case EGR_OP_TIME_EMBED:
+      return true;
+    case EGR_OP_GEMM_SIMT:   // only the M <= 8 GEMV form (time-embedding MLP, per-block embedding projections)
+      return op.i[EGR_I_WO] * op.i[EGR_I_HO] * op.i[EGR_I_BO] <= 8 && op.i[EGR_I_NTAPS] == 1 && op.x0.elem == 0 && (op.i[EGR_I_K] & 3) == 0 &&
+             op.i[EGR_I_WZ_BATCH] == 0;
+    case EGR_OP_GN_STATS: case EGR_OP_GN_APPLY: {
+      const long long C = op.i[EGR_I_C0] + op.i[EGR_I_C1], G = op.i[EGR_I_GROUPS];
+      return G > 0 && C % G == 0 && ((C / G) & 3) == 0;
+    }
+    case EGR_OP_ATTN_SMALL: {
+      const long long hd = op.i[EGR_I_HEADDIM];
+      return (hd == 16 || hd == 32) && op.i[EGR_I_SEQ] <= 512;
+    }
+    case EGR_OP_ELTWISE: {
+      const int m = (int)op.i[EGR_I_MODE];
+      return m == EGR_ELT_CAST16 || m == EGR_ELT_COPY32 || m == EGR_ELT_AXPBY || m == EGR_ELT_SCALE_SHIFT;
+    }
+    default: return false;
+  }
+}
+
+int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, int first, int last, MegaRun** out) {
+  *out = nullptr;
+  int rc = tc_global_init();
+  if (rc) return rc;
+  static bool attr = false;
+  if (!attr) {
+    EGR_CUDA(cudaFuncSetAttribute(unet_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  std::vector<MegaOp> mops;
+  std::vector<TcKernelArgs> kas;
+  std::vector<CUtensorMap> maps;
+  size_t ring_bytes = 0;
+  for (int i = first; i < last; ++i) {
+    const egr_op& op = ops[i];
+    MegaOp m;
+    memset(&m, 0, sizeof(m));
+    m.sync_after = (op.flags & EGR_FLAG_NOSYNC) ? 0 : 1;
+    auto bad = [&](const char* why) { return fail(EGR_ERR_UNSUPPORTED, "%s: not supported inside the persistent UNet kernel (%s)", op.name, why); };
+    switch (op.code) {
+      case EGR_OP_GEMM_TC: {
+        const TcPrepared* p = tc[i];
+        if (!p) return bad("unprepared GEMM");
+        if (p->ka.halo) return bad("halo mode");
+        m.code = MOP_GEMM_TC;
+        m.tc = (int)kas.size();
+        kas.push_back(p->ka);
+        maps.push_back(p->tmA);
+        maps.push_back(p->tmB);
+        const size_t need = (size_t)p->ka.SA * p->ka.a_stage_bytes + (size_t)p->ka.SB * p->ka.b_stage_bytes;
+        ring_bytes = need > ring_bytes ? need : ring_bytes;
+        if (p->ka.SA > MEGA_MAX_STAGES || p->ka.SB > MEGA_MAX_STAGES) return bad("ring deeper than the barrier block");
+        break;
+      }
+      case EGR_OP_GEMM_SIMT: {
+        Taps taps;
+        rc = gemm_args_from_op(sp, op, &m.u.gemv.g, &taps, &m.u.gemv.a);
+        if (rc) return rc;
+        const GemmArgs& g = m.u.gemv.g;
+        const View& a = m.u.gemv.a;
+        const long long npix = (long long)g.Wo * g.Ho * g.Bo;
+        bool zero_taps = true;
+        for (int t = 0; t < g.ntaps; ++t)
+          for (int d = 0; d < 5; ++d) zero_taps = zero_taps && taps.t[t][d] == 0;
+        auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+        if (!(npix <= 8 && g.ntaps == 1 && zero_taps && a.elem == 0 && a.stride[0] == 1 && g.K <= a.dim[0] && (g.K & 3) == 0 && al16(a.p) &&
+              al16(g.W) && (g.wstride_n & 3) == 0 && (a.stride[g.dimW] & 3) == 0 && (a.stride[g.dimH] & 3) == 0 && (a.stride[g.dimB] & 3) == 0 &&
+              !g.wz_batch))
+          return bad("only the M <= 8 GEMV form of the CUDA-core GEMM");
+        m.code = MOP_GEMV;
+        m.u.gemv.npix = (int)npix;
+        break;
+      }
+      case EGR_OP_GN_STATS:
+      case EGR_OP_GN_APPLY: {
+        rc = cat_args(sp, op, &m.u.gn.a);
+        if (rc) return rc;
+        const CatArgs& a = m.u.gn.a;
+        if (((a.C0 + a.C1) / a.G) & 3) return bad("channels per group not a multiple of 4");
+        m.u.gn.part = (double*)resolve(sp, op.ptr[EGR_P_STATS]);
+        m.u.gn.nsl = mega_nsl(a);
+        if (!m.u.gn.part) return bad("null stats buffer");
+        if (m.u.gn.nsl > 1 + (int)op.i[EGR_I_AUX1]) return bad("stats buffer smaller than the slice partials");
+        if (op.code == EGR_OP_GN_STATS) { m.code = MOP_GN_STATS; break; }
+        m.code = MOP_GN_APPLY;
+        m.u.gn.gamma = (const float*)resolve(sp, op.ptr[EGR_P_GAMMA]);
+        m.u.gn.beta = (const float*)resolve(sp, op.ptr[EGR_P_BETA]);
+        m.u.gn.out32 = (float*)resolve(sp, op.ptr[EGR_P_OUT32]);
+        m.u.gn.out16 = (__half*)resolve(sp, op.ptr[EGR_P_OUT16]);
+        m.u.gn.eps = (float)op.f[EGR_F_EPS];
+        m.u.gn.silu = (int)op.i[EGR_I_MODE];
+        if (!m.u.gn.gamma || !m.u.gn.beta || (!m.u.gn.out32 && !m.u.gn.out16)) return bad("null pointer");
+        break;
+      }
+      case EGR_OP_LAYERNORM: {
+        m.code = MOP_LAYERNORM;
+        m.u.ln.x = (const float*)resolve(sp, op.x0.addr);
+        m.u.ln.rows = op.i[EGR_I_ROWS];
+        m.u.ln.C = (int)op.i[EGR_I_COLS];
+        m.u.ln.eps = (float)op.f[EGR_F_EPS];
+        m.u.ln.gamma = (const float*)resolve(sp, op.ptr[EGR_P_GAMMA]);
+        m.u.ln.beta = (const float*)resolve(sp, op.ptr[EGR_P_BETA]);
+        m.u.ln.out16 = (__half*)resolve(sp, op.ptr[EGR_P_OUT16]);
+        m.u.ln.out32 = (float*)resolve(sp, op.ptr[EGR_P_OUT32]);
+        if (!m.u.ln.x || !m.u.ln.gamma || !m.u.ln.beta || (!m.u.ln.out16 && !m.u.ln.out32) || m.u.ln.rows <= 0 || m.u.ln.C <= 0) return bad("bad arguments");
+        break;
+      }
+      case EGR_OP_ATTN_SMALL: {
+        m.code = MOP_ATTN;
+        m.u.attn.q = (const __half*)resolve(sp, op.x0.addr);
+        m.u.attn.k = (const __half*)resolve(sp, op.x1.addr);
+        m.u.attn.v = (const __half*)resolve(sp, op.ptr[EGR_P_AUX]);
+        m.u.attn.out = (__half*)resolve(sp, op.ptr[EGR_P_OUT16]);
+        m.u.attn.S = (int)op.i[EGR_I_SEQ]; m.u.attn.heads = (int)op.i[EGR_I_HEADS]; m.u.attn.hd = (int)op.i[EGR_I_HEADDIM];
+        m.u.attn.B = (int)op.i[EGR_I_BATCH]; m.u.attn.ld = (int)op.i[EGR_I_AUX0];
+        m.u.attn.scale = (float)op.f[EGR_F_ALPHA];
+        m.u.attn.qblocks = (m.u.attn.S + 15) / 16;
+        const int C_ = m.u.attn.heads * m.u.attn.hd;
+        auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
+        if (!m.u.attn.q || !m.u.attn.k || !m.u.attn.v || !m.u.attn.out) return bad("null pointer");
+        if (!((m.u.attn.hd == 32 || m.u.attn.hd == 16) && m.u.attn.S <= 512 && C_ % 8 == 0 && al16(m.u.attn.q) && al16(m.u.attn.k) && al16(m.u.attn.v)))
+          return bad("attention shape outside the 16/32-dim head, S <= 512 kernel");
+        if (m.u.attn.ld != 0 && (m.u.attn.ld < C_ || m.u.attn.ld % 8 != 0)) return bad("bad q/k/v row stride");
+        const size_t need = (size_t)2 * m.u.attn.S * (m.u.attn.hd + 8) * sizeof(__half);
+        ring_bytes = need > ring_bytes ? need : ring_bytes;
+        break;
+      }
+      case EGR_OP_GEGLU: {
+        m.code = MOP_GEGLU;
+        m.u.geglu.x = (const float*)resolve(sp, op.x0.addr);
+        m.u.geglu.out = (__half*)resolve(sp, op.ptr[EGR_P_OUT16]);
+        m.u.geglu.rows = op.i[EGR_I_ROWS]; m.u.geglu.D = (int)op.i[EGR_I_COLS];
+        if (!m.u.geglu.x || !m.u.geglu.out || m.u.geglu.rows <= 0 || m.u.geglu.D <= 0) return bad("bad arguments");
+        break;
+      }
+      case EGR_OP_TIME_EMBED: {
+        m.code = MOP_TIME_EMBED;
+        m.u.temb.out = (float*)resolve(sp, op.ptr[EGR_P_OUT32]);
+        m.u.temb.dim = (int)op.i[EGR_I_COLS];
+        m.u.temb.t = (float)op.f[EGR_F_A];
+        if (!m.u.temb.out || m.u.temb.dim <= 0 || (m.u.temb.dim & 1)) return bad("bad arguments");
+        break;
+      }
+      case EGR_OP_ELTWISE: {
+        const int mode = (int)op.i[EGR_I_MODE];
+        const float* x0 = (const float*)resolve(sp, op.x0.addr);
+        const float* x1 = (const float*)resolve(sp, op.x1.addr);
+        float* o32 = (float*)resolve(sp, op.ptr[EGR_P_OUT32]);
+        __half* o16 = (__half*)resolve(sp, op.ptr[EGR_P_OUT16]);
+        if (!x0 || (!o32 && !o16)) return bad("bad arguments");
+        if (mode == EGR_ELT_CAST16 || mode == EGR_ELT_COPY32) {
+          m.code = MOP_CAT;
+          m.u.cat.x0 = x0; m.u.cat.x1 = x1;
+          m.u.cat.C0 = (int)op.i[EGR_I_C0]; m.u.cat.C1 = (int)op.i[EGR_I_C1];
+          m.u.cat.rows = op.i[EGR_I_ROWS];
+          m.u.cat.ld0 = op.i[EGR_I_AUX0] ? op.i[EGR_I_AUX0] : m.u.cat.C0;
+          m.u.cat.ld1 = op.i[EGR_I_AUX1] ? op.i[EGR_I_AUX1] : m.u.cat.C1;
+          m.u.cat.o32 = o32; m.u.cat.o16 = o16;
+          if (m.u.cat.C1 > 0 && !x1) return bad("null x1");
+        } else if (mode == EGR_ELT_AXPBY || mode == EGR_ELT_SCALE_SHIFT) {
+          m.code = MOP_AXPBY;
+          m.u.axpby.x = x0; m.u.axpby.y = mode == EGR_ELT_AXPBY ? x1 : nullptr;
+          if (mode == EGR_ELT_AXPBY && !x1) return bad("null x1");
+          m.u.axpby.a = (float)op.f[EGR_F_A]; m.u.axpby.b = (float)op.f[EGR_F_B];
+          m.u.axpby.n = op.i[EGR_I_ROWS];
+          m.u.axpby.o32 = o32; m.u.axpby.o16 = o16;
+        } else {
+          return bad("eltwise mode");
+        }
+        break;
+      }
+      default: return bad("op code");
+    }
+    mops.push_back(m);
+  }
+  if (mops.empty()) return EGR_OK;
+  mops.back().sync_after = 1;   // the launch ends on a full barrier (nothing of the next kernel may overtake)
+  MegaRun* r = new MegaRun();
+  r->first = first; r->last = last; r->n_ops = (int)mops.size(); r->n_tc = (int)kas.size();
+  for (const MegaOp& m : mops) r->n_sync += m.sync_after;
+  auto bail = [&](int code) { mega_free(r); return code; };
+  if (cudaMalloc(&r->d_ops, mops.size() * sizeof(MegaOp)) != cudaSuccess) return bail(fail(EGR_ERR_CUDA, "mega: cudaMalloc of the op table failed"));
+  if (cudaMemcpy(r->d_ops, mops.data(), mops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(EGR_ERR_CUDA, "mega: op table copy failed"));
+  if (!kas.empty()) {
+    if (cudaMalloc(&r->d_kas, kas.size() * sizeof(TcKernelArgs)) != cudaSuccess || cudaMalloc(&r->d_maps, maps.size() * sizeof(CUtensorMap)) != cudaSuccess)
+      return bail(fail(EGR_ERR_CUDA, "mega: cudaMalloc of the GEMM tables failed"));
+    if (cudaMemcpy(r->d_kas, kas.data(), kas.size() * sizeof(TcKernelArgs), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(r->d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(EGR_ERR_CUDA, "mega: GEMM table copy failed"));
+  }
+  if (cudaMalloc(&r->d_bar, 256) != cudaSuccess || cudaMemset(r->d_bar, 0, 256) != cudaSuccess) return bail(fail(EGR_ERR_CUDA, "mega: barrier allocation failed"));
+  r->smem_bytes = 1024 + MEGA_BAR_BYTES + (int)ring_bytes + 8 * STAGE_BYTES_PER_WARP;
+  if (r->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "mega: %d B of shared memory needed", r->smem_bytes));
+  const int sms = devinfo().sm_count ? devinfo().sm_count : 148;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, unet_mega_kernel, MEGA_THREADS, r->smem_bytes) != cudaSuccess || per_sm < 1)
+    return bail(fail(EGR_ERR_CUDA, "mega: the persistent kernel does not fit an SM (%d B shared memory)", r->smem_bytes));
+  r->grid = sms;
+  *out = r;
+  return EGR_OK;
+}
+
+int egr::mega_launch(const MegaRun* r, cudaStream_t st) {
+  // barrier state is re-armed by a memset node, so an aborted launch cannot poison the next one
+  EGR_CUDA(cudaMemsetAsync(r->d_bar, 0, 8, st));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(r->grid);
+  cfg.blockDim = dim3(MEGA_THREADS);
+  cfg.dynamicSmemBytes = (size_t)r->smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: they meet at grid barriers
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const MegaOp* ops = r->d_ops;
+  const TcKernelArgs* kas = r->d_kas;
+  const CUtensorMap* maps = r->d_maps;
+  unsigned int* bar = r->d_bar;
+  int n = r->n_ops;
+  EGR_CUDA(cudaLaunchKernelEx(&cfg, unet_mega_kernel, ops, n, kas, maps, bar));
+  EGR_CHECK_LAUNCH("unet_mega_kernel");
+  return EGR_OK;
+}
+
+void egr::mega_describe(const MegaRun* r, int* o) {
+  o[0] = r->first; o[1] = r->last; o[2] = r->n_ops; o[3] = r->n_tc; o[4] = r->n_sync; o[5] = r->smem_bytes; o[6] = r->grid;
+}
+
+int egr::mega_aborted(const MegaRun* r) {
+  unsigned int v = 0;
+  if (cudaMemcpy(&v, r->d_bar + 2, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return (int)v;
+}
+
+void egr::mega_free(MegaRun* r) {
+  if (!r) return;
+  if (r->d_ops) cudaFree(r->d_ops);
+  if (r->d_kas) cudaFree(r->d_kas);
+  if (r->d_maps) cudaFree(r->d_maps);
+  if (r->d_bar) cudaFree(r->d_bar);
+  delete r;
+}

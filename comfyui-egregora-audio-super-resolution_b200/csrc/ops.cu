@@ -49,29 +49,6 @@ int gemm_args_from_op(const Spaces& s, const egr_op& op, GemmArgs* g, Taps* taps
 
 using namespace egr;
 
-// ------------------------------------------------------------------------------------------------
-// shared scalar epilogue: out = act(alpha*acc + bias + rowbias) + resid, with the transposed-conv crop
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_store(const GemmArgs& g, int b, long long pix, int n, float acc) {
-  float v = acc * g.alpha;
-  if (g.bias) v += g.bias[n];
-  if (g.rowbias) v += g.rowbias[(long long)b * g.rowbias_stride + n];
-  v = egr_apply_act(v, g.act);
-  long long idx;
-  if (g.transposed) {
-    idx = (long long)b * g.out_batch_stride + (long long)n * g.out_n_stride + pix + g.out_offset;
-  } else {
-    long long flat = pix * g.out_pix_stride + g.out_offset + n;
-    if (flat < g.out_lo || flat >= g.out_hi) return;
-    idx = (long long)b * g.out_batch_stride + flat;
-  }
-  if (g.resid) v += g.resid[idx];
-  if (g.resid2) v += g.resid2[idx];
-  v *= g.post;
-  if (g.out32) g.out32[idx] = v;
-  if (g.out16) g.out16[idx] = __float2half_rn(v);
-}
-
 __device__ __forceinline__ float load_view(const View& a, const long long c[5]) {
   long long off = 0;
 #pragma unroll
@@ -405,11 +382,6 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
 // innermost, pixels contiguous per batch item: element (b,p,c) at base + (b*P + p)*Cx + c.
 // stats: f64 [B][G][2] = (sum, sumsq), must be zeroed first (EGR_OP_ZERO).
 // ------------------------------------------------------------------------------------------------
-struct CatArgs {
-  const float* x0; const float* x1;
-  int C0, C1, G, B;
-  long long P;  // pixels per batch item
-};
 
 // Deterministic (no atomics, fixed summation order) and independent of the batch size: block (slab, b) reduces its
 // slab of pixels to per-group f64 partial sums; gn_finalize_kernel adds the slabs in index order.
@@ -622,20 +594,6 @@ static int gn_cluster_size(const CatArgs& a) {
 static bool gn_use_fused(const CatArgs& a) {
   const int C = a.C0 + a.C1, cpg = C / a.G;
   return a.P <= 4096 && (cpg & 3) == 0 && getenv("EGR_GN_NO_FUSED") == nullptr;
-}
-
-static int cat_args(const Spaces& s, const egr_op& op, CatArgs* a) {
-  a->x0 = (const float*)resolve(s, op.x0.addr);
-  a->x1 = (const float*)resolve(s, op.x1.addr);
-  a->C0 = (int)op.i[EGR_I_C0]; a->C1 = (int)op.i[EGR_I_C1];
-  a->G = (int)op.i[EGR_I_GROUPS]; a->B = (int)op.i[EGR_I_BATCH];
-  a->P = op.i[EGR_I_ROWS];
-  const int C = a->C0 + a->C1;
-  if (!a->x0 || a->C0 <= 0 || (a->C1 > 0 && !a->x1)) return fail(EGR_ERR_ARG, "%s: bad inputs", op.name);
-  if ((a->C0 & 3) || (a->C1 & 3)) return fail(EGR_ERR_ARG, "%s: channel counts must be multiples of 4", op.name);
-  if (a->G <= 0 || C % a->G) return fail(EGR_ERR_ARG, "%s: C=%d not divisible by groups=%d", op.name, C, a->G);
-  if (a->B <= 0 || a->B > 65535 || a->P <= 0) return fail(EGR_ERR_ARG, "%s: bad batch/pixels", op.name);
-  return EGR_OK;
 }
 
 static int slab_for(long long P, int* nslabs) {

@@ -84,3 +84,50 @@ __device__ __forceinline__ float egr_apply_act(float v, int act) {
   if (act == EGR_ACT_TANH) return tanhf(v);
   return v;
 }
+
+// ------------------------------------------------------------------------------------------------
+// shared scalar epilogue: out = act(alpha*acc + bias + rowbias) + resid, with the transposed-conv crop
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_store(const egr::GemmArgs& g, int b, long long pix, int n, float acc) {
+  float v = acc * g.alpha;
+  if (g.bias) v += g.bias[n];
+  if (g.rowbias) v += g.rowbias[(long long)b * g.rowbias_stride + n];
+  v = egr_apply_act(v, g.act);
+  long long idx;
+  if (g.transposed) {
+    idx = (long long)b * g.out_batch_stride + (long long)n * g.out_n_stride + pix + g.out_offset;
+  } else {
+    long long flat = pix * g.out_pix_stride + g.out_offset + n;
+    if (flat < g.out_lo || flat >= g.out_hi) return;
+    idx = (long long)b * g.out_batch_stride + flat;
+  }
+  if (g.resid) v += g.resid[idx];
+  if (g.resid2) v += g.resid2[idx];
+  v *= g.post;
+  if (g.out32) g.out32[idx] = v;
+  if (g.out16) g.out16[idx] = __float2half_rn(v);
+}
+
+
+// GroupNorm input: a virtual channel-concat of x0 (C0 channels) and x1 (C1 channels), f32, channels innermost
+struct CatArgs {
+  const float* x0; const float* x1;
+  int C0, C1, G, B;
+  long long P;  // pixels per batch item
+};
+
+static inline int cat_args(const egr::Spaces& s, const egr_op& op, CatArgs* a) {
+  a->x0 = (const float*)egr::resolve(s, op.x0.addr);
+  a->x1 = (const float*)egr::resolve(s, op.x1.addr);
+  a->C0 = (int)op.i[EGR_I_C0]; a->C1 = (int)op.i[EGR_I_C1];
+  a->G = (int)op.i[EGR_I_GROUPS]; a->B = (int)op.i[EGR_I_BATCH];
+  a->P = op.i[EGR_I_ROWS];
+  const int C = a->C0 + a->C1;
+  if (!a->x0 || a->C0 <= 0 || (a->C1 > 0 && !a->x1)) return egr::fail(EGR_ERR_ARG, "%s: bad inputs", op.name);
+  if ((a->C0 & 3) || (a->C1 & 3)) return egr::fail(EGR_ERR_ARG, "%s: channel counts must be multiples of 4", op.name);
+  if (a->G <= 0 || C % a->G) return egr::fail(EGR_ERR_ARG, "%s: C=%d not divisible by groups=%d", op.name, C, a->G);
+  if (a->B <= 0 || a->B > 65535 || a->P <= 0) return egr::fail(EGR_ERR_ARG, "%s: bad batch/pixels", op.name);
+  return EGR_OK;
+}
+
+

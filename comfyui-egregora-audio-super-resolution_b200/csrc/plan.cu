@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <vector>
 #include "ops.cuh"
+#include "mega.cuh"
 
 using namespace egr;
 
@@ -13,6 +14,8 @@ struct egr_plan {
   std::vector<TcPrepared*> tc;  // per op, nullptr unless GEMM_TC
   Spaces sp;
   void* scratch = nullptr;      // split-K partial tiles followed by the per-tile arrival counters (library-owned)
+  std::vector<MegaRun*> runs;   // persistent-kernel runs (mega.cu): consecutive ops flagged EGR_FLAG_MEGA
+  std::vector<int> run_at;      // per op: index into `runs` of the run that STARTS here, else -1
   // whole-plan CUDA graph: the op list is static (fixed addresses, shapes, launch geometry), so after one eager pass
   // the ~900 launches are captured once and replayed with a single cudaGraphLaunch
   cudaGraphExec_t graph_exec = nullptr;
@@ -89,8 +92,66 @@ extern "C" int egr_plan_create(const egr_op* h_ops, int n_ops, void* d_workspace
     for (TcPrepared* t : p->tc)
       if (t && tc_partial_bytes(t) > 0) tc_bind_scratch(t, static_cast<float*>(p->scratch), counters);
   }
+  // persistent-kernel runs: maximal stretches of flagged ops the megakernel supports (the UNet of every diffusion step)
+  p->run_at.assign(n_ops, -1);
+  if (getenv("EGR_NO_MEGA") == nullptr) {
+    int i = 0;
+    while (i < n_ops) {
+      int j = i;
+      while (j < n_ops && (p->ops[j].flags & EGR_FLAG_MEGA) && mega_supports(p->ops[j])) ++j;
+      if (j - i >= 4) {
+        MegaRun* r = nullptr;
+        int rc = mega_build(p->sp, p->ops.data(), p->tc.data(), i, j, &r);
+        if (rc) { egr_plan_destroy(p); return rc; }
+        if (r) { p->run_at[i] = (int)p->runs.size(); p->runs.push_back(r); }
+      }
+      i = j > i ? j : i + 1;
+    }
+  }
   *out = p;
   return EGR_OK;
+}
+
+// ops [first, last) in stream order; a persistent-kernel run that lies wholly inside the range is ONE launch
+static int run_range(const egr_plan* plan, int first, int last, cudaStream_t st) {
+  for (int i = first; i < last;) {
+    const int r = plan->run_at[i];
+    if (r >= 0) {
+      int d[8];
+      mega_describe(plan->runs[r], d);
+      if (d[1] <= last) {
+        int rc = mega_launch(plan->runs[r], st);
+        if (rc) return rc;
+        i = d[1];
+        continue;
+      }
+    }
+    int rc = run_op(plan, i, st);
+    if (rc) return rc;
+    ++i;
+  }
+  return EGR_OK;
+}
+
+// debug hook (not in the public header): persistent-kernel runs of a plan -> out[0] = count, then 7 ints per run
+// (first, last, ops, gemm ops, grid barriers, smem bytes, grid), at most `max_runs` of them
+extern "C" int egr_debug_mega_info(const egr_plan* plan, int* out, int max_runs) {
+  if (!plan || !out) return -1;
+  out[0] = (int)plan->runs.size();
+  for (int r = 0; r < (int)plan->runs.size() && r < max_runs; ++r) {
+    int d[8];
+    mega_describe(plan->runs[r], d);
+    for (int k = 0; k < 7; ++k) out[1 + 7 * r + k] = d[k];
+  }
+  return 0;
+}
+
+// debug hook: number of persistent-kernel launches of this plan that a barrier watchdog abandoned (must be 0)
+extern "C" int egr_debug_mega_aborted(const egr_plan* plan) {
+  if (!plan) return -1;
+  int n = 0;
+  for (MegaRun* r : plan->runs) n += mega_aborted(r) > 0;
+  return n;
 }
 
 // debug hook (not in the public header): tile configuration the library chose for op `op_index`
@@ -118,8 +179,7 @@ extern "C" int egr_plan_run(egr_plan* plan, int first, int last, void* stream) {
     const unsigned long long before = launch_count();
     cudaGraph_t graph = nullptr;
     if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      int rc = EGR_OK;
-      for (int i = first; i < last && rc == EGR_OK; ++i) rc = run_op(plan, i, st);
+      int rc = run_range(plan, first, last, st);
       cudaError_t e = cudaStreamEndCapture(st, &graph);
       if (rc == EGR_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&plan->graph_exec, graph, 0) == cudaSuccess) {
         plan->launches_per_run = launch_count() - before;
@@ -142,8 +202,8 @@ extern "C" int egr_plan_run(egr_plan* plan, int first, int last, void* stream) {
       plan->full_runs = -1000000;
     }
   }
-  for (int i = first; i < last; ++i) {
-    int rc = run_op(plan, i, st);
+  {
+    int rc = run_range(plan, first, last, st);
     if (rc) return rc;
   }
   if (full) ++plan->full_runs;
@@ -179,7 +239,12 @@ extern "C" void egr_plan_destroy(egr_plan* plan) {
   if (!plan) return;
   for (TcPrepared* t : plan->tc)
     if (t) tc_free(t);
+  for (MegaRun* r : plan->runs) mega_free(r);
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
   if (plan->scratch) cudaFree(plan->scratch);
   delete plan;
 }
+
+// debug hook (not in the public header): 1 when the whole-plan CUDA graph has been instantiated, 0 when the plan runs
+// eagerly (before its second full pass, or because capture failed)
+extern "C" int egr_debug_plan_graphed(const egr_plan* plan) { return plan && plan->graph_exec ? 1 : 0; }

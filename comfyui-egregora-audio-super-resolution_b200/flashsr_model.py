@@ -483,12 +483,17 @@ class FlashSRGraph:
         mel_lr = be.stft_mel(wav)
         z_lr = self.vae_encode(be, mel_lr)
         x = noise
+        region = getattr(be, "region", None)   # plan backend: the denoising loop is one persistent-kernel region
+        if region is not None:
+            region("unet", True)
         for (t, a_t, a_prev) in ddim_schedule(d["T"], d["cosine_s"], steps):
             v = self.unet(be, be.concat(x, z_lr), t)
             # v-prediction: x0 = sqrt(a)x - sqrt(1-a)v ; eps = sqrt(a)v + sqrt(1-a)x ; x' = sqrt(a')x0 + sqrt(1-a')eps
             sa, s1a = math.sqrt(a_t), math.sqrt(1.0 - a_t)
             sp, s1p = math.sqrt(a_prev), math.sqrt(1.0 - a_prev)
             x = be.axpby(x, v, sp * sa + s1p * s1a, -sp * s1a + s1p * sa)
+        if region is not None:
+            region("unet", False)
         mel_hat = self.vae_decode(be, x)
         y = self.vocoder(be, be.mel_as_sequence(mel_hat), be.wav_as_sequence(wav))
         return be.sequence_as_wav(y)

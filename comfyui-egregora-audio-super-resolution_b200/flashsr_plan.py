@@ -67,6 +67,7 @@ class RawOp:
         self.reads: List[Buf] = []
         self.writes: List[Buf] = []
         self.index = -1
+        self.flags = 0
 
 
 class WeightBlob:
@@ -150,6 +151,9 @@ class PlanBackend:
         self.cutoff_buf: Optional[Buf] = None
         self.debug = False
         self.named: Dict[str, PT] = {}
+        # ops emitted while a region is open carry EGR_FLAG_MEGA: the library may run the whole stretch (the UNet of every
+        # diffusion step) as ONE persistent kernel (csrc/mega.cu).  EGR_NO_MEGA=1 (read by the library) keeps one launch per op.
+        self.mega_region = False
 
     # ------------------------------------------------------------------ buffers / ops
     def buf(self, nbytes, tag="", persistent=False) -> Buf:
@@ -166,9 +170,16 @@ class PlanBackend:
             self.named[tag] = t
         return t
 
+    def region(self, name: str, on: bool):
+        """FlashSRGraph brackets the denoising loop with region("unet", True/False)."""
+        if name == "unet":
+            self.mega_region = bool(on)
+
     def emit(self, op: RawOp) -> RawOp:
         idx = len(self.ops)
         op.index = idx
+        if self.mega_region:
+            op.flags |= K["EGR_FLAG_MEGA"]
         for b in op.reads + op.writes:
             if b.first is None:
                 b.first = idx
@@ -786,6 +797,7 @@ class PlanBackend:
         for n, r in enumerate(self.ops):
             o = arr[n]
             o.code = r.code
+            o.flags = r.flags
             o.name = r.name.encode()[:47]
 
             def fill(t, v):

@@ -95,9 +95,13 @@ typedef struct egr_tensor {
   int64_t  stride[5];
 } egr_tensor;
 
+/* egr_op.flags */
+#define EGR_FLAG_MEGA   1   /* member of a run of ops the library may execute as ONE persistent kernel (the UNet) */
+#define EGR_FLAG_NOSYNC 2   /* inside such a run: the next op does not depend on this one (no grid barrier after it) */
+
 typedef struct egr_op {
   int32_t    code;      /* EGR_OP_* */
-  int32_t    flags;
+  int32_t    flags;     /* EGR_FLAG_* */
   egr_tensor x0;        /* primary input view   */
   egr_tensor x1;        /* secondary input view */
   uint64_t   ptr[10];   /* EGR_P_* */

@@ -18,7 +18,7 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parents[1]
 CSRC = ROOT / "comfyui-egregora-audio-super-resolution_b200" / "csrc"
 SOURCES = ["core.cu", "wola.cu", "eval_metrics.cu", "dfn_mix.cu", "fft.cu", "fatllama.cu", "ops.cu", "frontend.cu", "plan.cu"]
-HEADERS = ["common.cuh", "select.cuh", "fft_plan.cuh", "fft_device.cuh", "ops.cuh"]
+HEADERS = ["common.cuh", "select.cuh", "fft_plan.cuh", "fft_device.cuh", "ops.cuh", "mega.cuh"]
 SHIM = ["cuda_runtime.h", "cuda_fp16.h", "cooperative_groups.h", "cusim.cpp", "gemm_tc_ref.cpp", "build.py"]
 OUT = HERE / "_build"
 LIB = OUT / "libegregora_b200_cusim.so"

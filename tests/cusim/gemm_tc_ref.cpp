@@ -6,6 +6,7 @@
 // executor) run on the CPU around it.
 #include <vector>
 #include "ops.cuh"
+#include "mega.cuh"
 
 namespace egr {
 
@@ -87,5 +88,14 @@ size_t tc_partial_bytes(const TcPrepared*) { return 0; }
 int tc_num_counters(const TcPrepared*) { return 0; }
 void tc_bind_scratch(TcPrepared*, float*, unsigned int*) {}
 void tc_describe(const TcPrepared*, int* o) { for (int i = 0; i < 8; ++i) o[i] = 0; }
+
+// The persistent UNet kernel (csrc/mega.cu) is built on the tcgen05 warp roles: not emulated.  Flagged ops run one by one.
+struct MegaRun { int unused; };
+bool mega_supports(const egr_op&) { return false; }
+int mega_build(const Spaces&, const egr_op*, TcPrepared* const*, int, int, MegaRun** out) { *out = nullptr; return EGR_OK; }
+int mega_launch(const MegaRun*, cudaStream_t) { return fail(EGR_ERR_UNSUPPORTED, "cusim: no persistent kernel"); }
+void mega_describe(const MegaRun*, int* o) { for (int i = 0; i < 8; ++i) o[i] = 0; }
+int mega_aborted(const MegaRun*) { return 0; }
+void mega_free(MegaRun*) {}
 
 }  // namespace egr
