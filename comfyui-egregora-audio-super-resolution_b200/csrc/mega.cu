@@ -54,6 +54,7 @@ static constexpr int MEGA_THREADS = 384;
 static constexpr int MEGA_SIMT = 256;        // CUDA-core ops run on warps 0..7
 static constexpr int MEGA_MAX_STAGES = 10;   // ring depth bound of tc_prepare
 static constexpr int MEGA_BAR_BYTES = 1024;  // 4 x 10 ring barriers + 4 accumulator barriers, padded
+static constexpr int MEGA_DYN_SMEM_MAX = 227 * 1024 - 2048;   // 227 KB per CTA minus the kernel's static shared memory
 
 }  // namespace egr
 
@@ -555,7 +556,8 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
   if (rc) return rc;
   static bool attr = false;
   if (!attr) {
-    EGR_CUDA(cudaFuncSetAttribute(unet_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // static shared memory (op / argument copies, reduction scratch) counts against the same 227 KB
+    EGR_CUDA(cudaFuncSetAttribute(unet_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEGA_DYN_SMEM_MAX));
     attr = true;
   }
   std::vector<MegaOp> mops;
@@ -721,7 +723,7 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
   }
   if (cudaMalloc(&r->d_bar, 256) != cudaSuccess || cudaMemset(r->d_bar, 0, 256) != cudaSuccess) return bail(fail(EGR_ERR_CUDA, "mega: barrier allocation failed"));
   r->smem_bytes = 1024 + MEGA_BAR_BYTES + (int)ring_bytes + 8 * STAGE_BYTES_PER_WARP;
-  if (r->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "mega: %d B of shared memory needed", r->smem_bytes));
+  if (r->smem_bytes > MEGA_DYN_SMEM_MAX) return bail(fail(EGR_ERR_UNSUPPORTED, "mega: %d B of shared memory needed", r->smem_bytes));
   const int sms = devinfo().sm_count ? devinfo().sm_count : 148;
   int per_sm = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, unet_mega_kernel, MEGA_THREADS, r->smem_bytes) != cudaSuccess || per_sm < 1)
