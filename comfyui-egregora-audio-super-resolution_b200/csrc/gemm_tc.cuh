@@ -32,7 +32,7 @@ static inline FastDiv make_fastdiv(int d) {
   return f;
 }
 
-struct TcKernelArgs {
+struct alignas(16) TcKernelArgs {   // (16-byte multiple: the persistent kernel copies it with 16-byte cp.async)
   GemmArgs g;
   Taps taps;
   short tapw[EGR_MAX_TAPS];  // tap offset along dimW (halo mode)

@@ -38,14 +38,16 @@ struct __align__(16) MegaOp {
   } u;
 };
 static_assert(sizeof(MegaOp) % 16 == 0 && sizeof(MegaOp) <= 512, "MegaOp is copied to shared memory in 16-byte words");
-static_assert(sizeof(TcKernelArgs) % 8 == 0, "TcKernelArgs is copied to shared memory in 8-byte words");
+static_assert(sizeof(TcKernelArgs) % 16 == 0, "TcKernelArgs is copied to shared memory in 16-byte words");
 
 struct MegaRun {
   int first = 0, last = 0, n_ops = 0, n_tc = 0, n_sync = 0;
   MegaOp* d_ops = nullptr;
   TcKernelArgs* d_kas = nullptr;
   CUtensorMap* d_maps = nullptr;   // [n_tc][2], 128-byte entries
-  unsigned int* d_bar = nullptr;   // [0] arrival count, [1] generation
+  unsigned int* d_bar = nullptr;   // [0] arrival counter, [2] watchdog flag
+  int* d_tc_of = nullptr;          // per op: index of its GEMM argument block, -1 for a CUDA-core op
+  unsigned long long* d_trace = nullptr;   // EGR_MEGA_TRACE=1: clock64 stamps of CTA 0, 4 per op
   int smem_bytes = 0;
   int grid = 0;
 };
@@ -54,7 +56,7 @@ static constexpr int MEGA_THREADS = 384;
 static constexpr int MEGA_SIMT = 256;        // CUDA-core ops run on warps 0..7
 static constexpr int MEGA_MAX_STAGES = 10;   // ring depth bound of tc_prepare
 static constexpr int MEGA_BAR_BYTES = 1024;  // 4 x 10 ring barriers + 4 accumulator barriers, padded
-static constexpr int MEGA_DYN_SMEM_MAX = 227 * 1024 - 2048;   // 227 KB per CTA minus the kernel's static shared memory
+static constexpr int MEGA_DYN_SMEM_MAX = 227 * 1024 - 4096;   // 227 KB per CTA minus the kernel's static shared memory
 
 }  // namespace egr
 
@@ -63,44 +65,34 @@ using namespace egr;
 // ------------------------------------------------------------------------------------------------ synchronisation
 __device__ __forceinline__ void simt_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
-// Sense-reversing grid barrier (state returns to "count 0" after every use, so a captured graph can replay the launch).
-// Memory: every thread's earlier global writes are ordered before the arrival by bar.sync + the arriving thread's gpu-scope
-// fence; on the way out the gpu-scope fence of thread 0 also drops the SM's L1 lines (the data other SMs wrote is read
-// from L2), and both sides fence the generic -> async proxy edge because the next op's TMA loads read what plain stores
-// of the previous op produced.
-__device__ __forceinline__ bool grid_sync(unsigned int* bar, int ncta) {
+// Grid barrier: one monotonically increasing arrival counter per launch (zeroed by a memset node before the launch).
+// A CTA arrives with a fire-and-forget release reduction and waits until the counter reaches epoch * ncta: one L2 round
+// trip after the last arrival, no returned atomics, no second word.
+// Memory: every thread's earlier global writes are ordered before the arrival by bar.sync + the release of the arriving
+// thread; the acquire load on the way out (gpu scope: it also drops the SM's L1 lines, so data other SMs wrote is read
+// from L2) + bar.sync orders every thread's later reads after it; both sides fence the generic -> async proxy edge,
+// because the next op's TMA loads read what plain stores of the previous op produced.
+// Watchdog: a CTA that never arrives (a bug, never a legal state) must not hang the GPU — after ~2^25 polls (seconds) the
+// waiter raises bar[2] and bumps the counter past every later target: the launch drains (with garbage) and the host
+// reports it (egr_debug_mega_aborted).
+__device__ __forceinline__ void grid_sync(unsigned int* bar, unsigned int target) {
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncthreads();
-  __shared__ unsigned int s_abort;
   if (threadIdx.x == 0) {
-    unsigned int gen, now, dead = 0;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-    __threadfence();
-    const unsigned int prev = atomicAdd(bar, 1u);
-    if (prev == (unsigned int)ncta - 1u) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      // watchdog: a CTA that never arrives (a bug, never a legal state) must not hang the GPU — after ~2^25 polls
-      // (seconds) the launch is abandoned: bar[2] is raised, every CTA leaves its op loop, the host reports it
-      unsigned int spins = 0;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory");
-        if (((++spins) & 0xFFFu) == 0u) {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dead) : "l"(bar + 2) : "memory");
-          if (spins > (1u << 25)) { atomicExch(bar + 2, 1u); dead = 1; }
-          if (dead) break;
-        }
-      } while (now == gen);
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+    unsigned int now, spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar) : "memory");
+      if (now >= target) break;
+      if (++spins > (1u << 25)) {
+        atomicExch(bar + 2, 1u);
+        atomicAdd(bar, 0x40000000u);
+        break;
+      }
     }
-    if (!dead) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(dead) : "l"(bar + 2) : "memory");
-    s_abort = dead;
-    __threadfence();
   }
   __syncthreads();
   asm volatile("fence.proxy.async;" ::: "memory");
-  return s_abort != 0u;
 }
 
 // ------------------------------------------------------------------------------------------------ CUDA-core op bodies
@@ -222,8 +214,32 @@ __device__ __noinline__ void mega_layernorm(const MegaOp& op, int cta, int ncta)
   const int C = op.u.ln.C;
   const float* gamma = op.u.ln.gamma;
   const float* beta = op.u.ln.beta;
+  constexpr int NJ = 20;   // a row of up to 640 channels lives in registers: ONE trip to L2 instead of three
   for (long long row = (long long)cta * 8 + warp; row < op.u.ln.rows; row += (long long)ncta * 8) {
     const float* xr = op.u.ln.x + row * C;
+    if (C <= 32 * NJ) {
+      float xv[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) { const int c = lane + 32 * j; xv[j] = c < C ? __ldcg(xr + c) : 0.f; }
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) if (lane + 32 * j < C) s += xv[j];
+      const float mean = warp_sum(s) / C;
+      float v = 0.f;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) if (lane + 32 * j < C) { const float d = xv[j] - mean; v = fmaf(d, d, v); }
+      const float rstd = rsqrtf(warp_sum(v) / C + op.u.ln.eps);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const int c = lane + 32 * j;
+        if (c < C) {
+          const float y = (xv[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
+          if (op.u.ln.out16) op.u.ln.out16[row * C + c] = __float2half_rn(y);
+          if (op.u.ln.out32) op.u.ln.out32[row * C + c] = y;
+        }
+      }
+      continue;
+    }
     float s = 0.f;
     for (int c = lane; c < C; c += 32) s += __ldcg(xr + c);
     const float mean = warp_sum(s) / C;
@@ -413,13 +429,29 @@ __device__ __noinline__ void mega_time_embed(const MegaOp& op, int cta) {
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// op i (and, for a GEMM, its argument block) -> shared-memory slot, asynchronously: issued while op i-1 executes
+__device__ __forceinline__ void fetch_op(const MegaOp* ops, const TcKernelArgs* kas, const int* tc_of, int i, MegaOp* s_op, TcKernelArgs* s_ka) {
+  constexpr int NOP = (int)(sizeof(MegaOp) / 16), NKA = (int)(sizeof(TcKernelArgs) / 16);
+  const int t = threadIdx.x;
+  if (t < NOP) cp_async16(reinterpret_cast<uint4*>(s_op) + t, reinterpret_cast<const uint4*>(ops + i) + t);
+  const int tc = __ldg(tc_of + i);   // -1 for a CUDA-core op
+  if (tc >= 0 && t >= 64 && t < 64 + NKA) cp_async16(reinterpret_cast<uint4*>(s_ka) + (t - 64), reinterpret_cast<const uint4*>(kas + tc) + (t - 64));
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp* __restrict__ ops, int n_ops,
                                                                     const TcKernelArgs* __restrict__ kas,
                                                                     const CUtensorMap* __restrict__ maps,
-                                                                    unsigned int* __restrict__ bar) {
+                                                                    const int* __restrict__ tc_of,
+                                                                    unsigned int* __restrict__ bar,
+                                                                    unsigned long long* __restrict__ trace) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(16) MegaOp s_op;
-  __shared__ __align__(16) TcKernelArgs s_ka;
+  __shared__ __align__(16) MegaOp s_ops[2];
+  __shared__ __align__(16) TcKernelArgs s_kas[2];
   __shared__ double s_red[2][8];
   __shared__ float s_stat[2];
   __shared__ uint32_t s_tmem, s_last;
@@ -439,36 +471,31 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
   sv.acc_empty = sv.acc_full + 2;
   sv.last_flag = &s_last;
 
+  fetch_op(ops, kas, tc_of, 0, &s_ops[0], &s_kas[0]);
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
-  int bars_live = 0;   // SA / SB / counts of the barriers currently initialised (0 = none yet)
-  int live_SA = 0, live_SB = 0;
+  int bars_live = 0, live_SA = 0, live_SB = 0;   // the barriers currently initialised (0 = none yet)
+  unsigned int epoch = 0;                         // grid barriers passed so far
+  unsigned long long* tr = (trace && cta == 0 && tid == 0) ? trace : nullptr;
 
   for (int i = 0; i < n_ops; ++i) {
-    // ---- fetch the op (and its GEMM arguments) into shared memory
-    {
-      const uint4* src = reinterpret_cast<const uint4*>(ops + i);
-      uint4* dst = reinterpret_cast<uint4*>(&s_op);
-      if (tid < (int)(sizeof(MegaOp) / 16)) dst[tid] = __ldg(src + tid);
-    }
-    __syncthreads();
-    const int code = s_op.code;
+    const MegaOp& op = s_ops[i & 1];
+    const TcKernelArgs& ka = s_kas[i & 1];
+    if (i + 1 < n_ops) fetch_op(ops, kas, tc_of, i + 1, &s_ops[(i + 1) & 1], &s_kas[(i + 1) & 1]);   // lands while this op runs
+    if (tr) tr[4 * i] = clock64();
+    const int code = op.code;
     if (code == MOP_GEMM_TC) {
-      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(kas + s_op.tc);
-      unsigned long long* dst = reinterpret_cast<unsigned long long*>(&s_ka);
-      for (int w = tid; w < (int)(sizeof(TcKernelArgs) / 8); w += MEGA_THREADS) dst[w] = __ldg(src + w);
       if (tid == 64) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(maps + 2 * s_op.tc) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(maps + 2 * s_op.tc + 1) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(maps + 2 * op.tc) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(maps + 2 * op.tc + 1) : "memory");
       }
-      __syncthreads();
-      const TcKernelArgs& ka = s_ka;
       sv.ringA = rings;
       sv.ringB = sv.ringA + (size_t)ka.SA * ka.a_stage_bytes;
       sv.stage_all = reinterpret_cast<float*>(sv.ringB + (size_t)ka.SB * ka.b_stage_bytes);
@@ -484,31 +511,36 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
-      tc_roles(maps + 2 * s_op.tc, maps + 2 * s_op.tc + 1, ka, sv, tmem_base, cta, ncta, nullptr);
+      if (tr) tr[4 * i + 1] = clock64();
+      tc_roles(maps + 2 * op.tc, maps + 2 * op.tc + 1, ka, sv, tmem_base, cta, ncta, nullptr);
       tc_fence_before();
     } else if (tid < MEGA_SIMT) {
+      if (tr) tr[4 * i + 1] = clock64();
       switch (code) {
-        case MOP_GEMV: mega_gemv(s_op, cta, ncta); break;
-        case MOP_GN_STATS: mega_gn_stats(s_op, cta, ncta, s_red); break;
-        case MOP_GN_APPLY: mega_gn_apply(s_op, cta, ncta, s_stat); break;
-        case MOP_LAYERNORM: mega_layernorm(s_op, cta, ncta); break;
+        case MOP_GEMV: mega_gemv(op, cta, ncta); break;
+        case MOP_GN_STATS: mega_gn_stats(op, cta, ncta, s_red); break;
+        case MOP_GN_APPLY: mega_gn_apply(op, cta, ncta, s_stat); break;
+        case MOP_LAYERNORM: mega_layernorm(op, cta, ncta); break;
         case MOP_ATTN:
-          if (s_op.u.attn.hd == 32) mega_attn<32>(s_op, cta, ncta, rings);
-          else mega_attn<16>(s_op, cta, ncta, rings);
+          if (op.u.attn.hd == 32) mega_attn<32>(op, cta, ncta, rings);
+          else mega_attn<16>(op, cta, ncta, rings);
           break;
-        case MOP_GEGLU: mega_geglu(s_op, cta, ncta); break;
-        case MOP_CAT: mega_cat(s_op, cta, ncta); break;
-        case MOP_AXPBY: mega_axpby(s_op, cta, ncta); break;
-        case MOP_TIME_EMBED: mega_time_embed(s_op, cta); break;
+        case MOP_GEGLU: mega_geglu(op, cta, ncta); break;
+        case MOP_CAT: mega_cat(op, cta, ncta); break;
+        case MOP_AXPBY: mega_axpby(op, cta, ncta); break;
+        case MOP_TIME_EMBED: mega_time_embed(op, cta); break;
         default: break;
       }
     }
-    const int sync_after = s_op.sync_after;   // read before the next fetch overwrites s_op
-    if (sync_after) {
-      if (grid_sync(bar, ncta)) break;   // watchdog fired somewhere: abandon the launch
+    if (tr) tr[4 * i + 2] = clock64();
+    asm volatile("cp.async.wait_all;" ::: "memory");   // the next op's descriptor has landed (this thread's part)
+    if (op.sync_after) {
+      epoch += 1;
+      grid_sync(bar, epoch * (unsigned int)ncta);
     } else {
       __syncthreads();
     }
+    if (tr) tr[4 * i + 3] = clock64();
   }
   tc_fence_before();
   __syncthreads();
@@ -519,9 +551,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
 
 // ------------------------------------------------------------------------------------------------ host side
 static int mega_nsl(const CatArgs& a) {
-  // pixel slices per (item, group): ~8192 elements each, at most 16 — a function of the op's geometry only
+  // pixel slices per (item, group): ~2048 elements each (two 16-byte loads per thread, all in flight at once), at most
+  // 16 — a function of the op's geometry only
   const long long elems = a.P * ((a.C0 + a.C1) / a.G);
-  long long n = (elems + 8191) / 8192;
+  long long n = (elems + 2047) / 2048;
   if (n > 16) n = 16;
   if (n > a.P) n = a.P;
   return (int)(n < 1 ? 1 : n);
@@ -722,6 +755,18 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
       return bail(fail(EGR_ERR_CUDA, "mega: GEMM table copy failed"));
   }
   if (cudaMalloc(&r->d_bar, 256) != cudaSuccess || cudaMemset(r->d_bar, 0, 256) != cudaSuccess) return bail(fail(EGR_ERR_CUDA, "mega: barrier allocation failed"));
+  {
+    std::vector<int> tc_of(mops.size());
+    for (size_t k = 0; k < mops.size(); ++k) tc_of[k] = mops[k].code == MOP_GEMM_TC ? mops[k].tc : -1;
+    if (cudaMalloc(&r->d_tc_of, tc_of.size() * sizeof(int)) != cudaSuccess ||
+        cudaMemcpy(r->d_tc_of, tc_of.data(), tc_of.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
+      return bail(fail(EGR_ERR_CUDA, "mega: op index table allocation failed"));
+  }
+  if (getenv("EGR_MEGA_TRACE")) {
+    if (cudaMalloc(&r->d_trace, mops.size() * 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(r->d_trace, 0, mops.size() * 4 * sizeof(unsigned long long)) != cudaSuccess)
+      return bail(fail(EGR_ERR_CUDA, "mega: trace allocation failed"));
+  }
   r->smem_bytes = 1024 + MEGA_BAR_BYTES + (int)ring_bytes + 8 * STAGE_BYTES_PER_WARP;
   if (r->smem_bytes > MEGA_DYN_SMEM_MAX) return bail(fail(EGR_ERR_UNSUPPORTED, "mega: %d B of shared memory needed", r->smem_bytes));
   const int sms = devinfo().sm_count ? devinfo().sm_count : 148;
@@ -750,14 +795,29 @@ int egr::mega_launch(const MegaRun* r, cudaStream_t st) {
   const TcKernelArgs* kas = r->d_kas;
   const CUtensorMap* maps = r->d_maps;
   unsigned int* bar = r->d_bar;
+  const int* tc_of = r->d_tc_of;
+  unsigned long long* trace = r->d_trace;
   int n = r->n_ops;
-  EGR_CUDA(cudaLaunchKernelEx(&cfg, unet_mega_kernel, ops, n, kas, maps, bar));
+  EGR_CUDA(cudaLaunchKernelEx(&cfg, unet_mega_kernel, ops, n, kas, maps, tc_of, bar, trace));
   EGR_CHECK_LAUNCH("unet_mega_kernel");
   return EGR_OK;
 }
 
 void egr::mega_describe(const MegaRun* r, int* o) {
   o[0] = r->first; o[1] = r->last; o[2] = r->n_ops; o[3] = r->n_tc; o[4] = r->n_sync; o[5] = r->smem_bytes; o[6] = r->grid;
+}
+
+// debug: copy the clock trace of the last launch (4 stamps per op: start, body start, body end, after the barrier) and
+// the op codes; returns the number of ops, 0 when tracing is off
+int egr::mega_trace(const MegaRun* r, unsigned long long* h_stamps, int* h_codes, int max_ops) {
+  if (!r->d_trace) return 0;
+  const int n = r->n_ops < max_ops ? r->n_ops : max_ops;
+  cudaDeviceSynchronize();
+  if (cudaMemcpy(h_stamps, r->d_trace, (size_t)n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  std::vector<MegaOp> mo(n);
+  if (cudaMemcpy(mo.data(), r->d_ops, (size_t)n * sizeof(MegaOp), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  for (int k = 0; k < n; ++k) h_codes[k] = mo[k].code;
+  return n;
 }
 
 int egr::mega_aborted(const MegaRun* r) {
@@ -772,5 +832,7 @@ void egr::mega_free(MegaRun* r) {
   if (r->d_kas) cudaFree(r->d_kas);
   if (r->d_maps) cudaFree(r->d_maps);
   if (r->d_bar) cudaFree(r->d_bar);
+  if (r->d_tc_of) cudaFree(r->d_tc_of);
+  if (r->d_trace) cudaFree(r->d_trace);
   delete r;
 }

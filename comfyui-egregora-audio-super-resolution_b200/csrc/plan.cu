@@ -146,6 +146,12 @@ extern "C" int egr_debug_mega_info(const egr_plan* plan, int* out, int max_runs)
   return 0;
 }
 
+// debug hook (EGR_MEGA_TRACE=1): clock trace of run `run` -> number of ops copied
+extern "C" int egr_debug_mega_trace(const egr_plan* plan, int run, unsigned long long* h_stamps, int* h_codes, int max_ops) {
+  if (!plan || run < 0 || run >= (int)plan->runs.size()) return -1;
+  return mega_trace(plan->runs[run], h_stamps, h_codes, max_ops);
+}
+
 // debug hook: number of persistent-kernel launches of this plan that a barrier watchdog abandoned (must be 0)
 extern "C" int egr_debug_mega_aborted(const egr_plan* plan) {
   if (!plan) return -1;

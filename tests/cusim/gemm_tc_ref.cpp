@@ -96,6 +96,7 @@ int mega_build(const Spaces&, const egr_op*, TcPrepared* const*, int, int, MegaR
 int mega_launch(const MegaRun*, cudaStream_t) { return fail(EGR_ERR_UNSUPPORTED, "cusim: no persistent kernel"); }
 void mega_describe(const MegaRun*, int* o) { for (int i = 0; i < 8; ++i) o[i] = 0; }
 int mega_aborted(const MegaRun*) { return 0; }
+int mega_trace(const MegaRun*, unsigned long long*, int*, int) { return 0; }
 void mega_free(MegaRun*) {}
 
 }  // namespace egr
