@@ -40,6 +40,7 @@ struct alignas(16) TcKernelArgs {   // (16-byte multiple: the persistent kernel 
   int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
   FastDiv d_splits, d_tiles_n, d_tiles_w, d_tiles_h, d_kchunks, d_bw, d_bh, d_c4n;
   int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (x splits when folded)
+  int defer;     // split-K partials are reduced by a separate, grid-wide pass (tc_reduce_distributed: the persistent kernel)
   int fold;      // split-K folded into ONE work item: each split accumulates into its own TMEM region, summed in the epilogue
   int nbuf;      // accumulator buffers in TMEM: 2 when 2 * acc_cols <= 512, else 1
   int vec_ok, need_crop, epi_plain;
@@ -303,6 +304,55 @@ __device__ __forceinline__ void finish1(const GemmArgs& g, float acc, long long 
   if (g.out16) g.out16[idx] = __float2half_rn(v);
 }
 
+// ------------------------------------------------------------------------------------------------ deferred split-K
+// The last-arriver reduction above runs on ONE CTA per output tile: 16 partial tiles of 64 KB pulled through a single
+// SM, a few loads in flight per thread — 30-45 us for the UNet's big-K layers, most of their time (round-2 trace of the
+// persistent kernel).  With a grid barrier at hand the reduction is a separate pass over ALL threads of the grid: every
+// thread owns at most a few float4 of the output, issues the loads of all its splits at once and adds them in split
+// order (the same additions in the same order: identical bits), then applies the epilogue.
+__device__ __forceinline__ void tc_reduce_distributed(const TcKernelArgs& ka, long long gtid, long long gthreads) {
+  const GemmArgs& g = ka.g;
+  const int BN = g.block_n, c4n = BN >> 2;
+  const size_t pstride = (size_t)ka.mt * TILE_M * BN;
+  const long long per_tile = (long long)ka.mt * TILE_M * c4n;
+  const long long total = (long long)ka.tiles_m * ka.tiles_n * per_tile;
+  int cur_tile = -1;
+  WorkItem wi;
+  for (long long e = gtid; e < total; e += gthreads) {
+    const int tile_id = (int)(e / per_tile);
+    const int r = (int)(e - (long long)tile_id * per_tile);
+    if (tile_id != cur_tile) { decode_work(ka, tile_id * ka.splits, wi); cur_tile = tile_id; }
+    const int row = fdiv(r, ka.d_c4n), c = (r - row * c4n) * 4;
+    const int m = row >> 7;
+    if (m >= wi.mt_eff) continue;
+    const RowInfo ri = row_info(ka, wi, m, row & 127);
+    const int n = wi.tn * BN + c;
+    if (!ri.ok || n >= g.N) continue;
+    const float* pe = ka.partial + (size_t)tile_id * ka.splits * pstride + (size_t)row * BN + c;
+    float4 v[MAX_SPLITS];
+#pragma unroll
+    for (int sp = 0; sp < MAX_SPLITS; ++sp)
+      if (sp < ka.splits) v[sp] = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)sp * pstride));
+    float4 acc = v[0];
+#pragma unroll
+    for (int sp = 1; sp < MAX_SPLITS; ++sp)
+      if (sp < ka.splits) { acc.x += v[sp].x; acc.y += v[sp].y; acc.z += v[sp].z; acc.w += v[sp].w; }
+    const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
+    const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+    if (g.transposed) {
+      for (int u = 0; u < 4 && n + u < g.N; ++u) finish1(g, a4[u], ri.base + (long long)(n + u) * g.out_n_stride, n + u, rb);
+    } else if (ka.vec_ok) {
+      const long long fl = ri.flat0 + n;
+      if (fl >= g.out_lo && fl < g.out_hi) finish4(g, acc, ri.base + n, n, rb);
+    } else {
+      for (int u = 0; u < 4 && n + u < g.N; ++u) {
+        const long long fl = ri.flat0 + n + u;
+        if (fl >= g.out_lo && fl < g.out_hi) finish1(g, a4[u], ri.base + n + u, n + u, rb);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the warp roles
 // Shared-memory objects of one CTA (the two hosts lay them out differently).
 struct TcSmemView {
@@ -322,6 +372,16 @@ __device__ __forceinline__ void tc_init_barriers(const TcKernelArgs& ka, const T
   for (int s = 0; s < 2; ++s) { mbar_init(&sv.acc_full[s], (uint32_t)ka.n_iss); mbar_init(&sv.acc_empty[s], 8); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// the same, one barrier per calling thread (k = 0 .. 2*SA + 2*SB + 3); fences + CTA barrier are the caller's business
+__device__ __forceinline__ void tc_init_barrier_k(const TcKernelArgs& ka, const TcSmemView& sv, int k) {
+  if (k < ka.SA) mbar_init(&sv.fullA[k], 1);
+  else if ((k -= ka.SA) < ka.SA) mbar_init(&sv.emptyA[k], (uint32_t)ka.n_iss);
+  else if ((k -= ka.SA) < ka.SB) mbar_init(&sv.fullB[k], ka.halo ? 1u : 2u);
+  else if ((k -= ka.SB) < ka.SB) mbar_init(&sv.emptyB[k], (uint32_t)ka.n_iss);
+  else if ((k -= ka.SB) < 2) mbar_init(&sv.acc_full[k], (uint32_t)ka.n_iss);
+  else if ((k -= 2) < 2) mbar_init(&sv.acc_empty[k], 8);
 }
 
 // All 12 warps of the CTA call this with initialised barriers and allocated TMEM; CTA `cta` of `ncta` takes the work items
@@ -732,7 +792,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
         }
         __syncwarp();
       }
-      if (part) {
+      if (part && !ka.defer) {
         // split-K: the last CTA to finish this output tile reduces all partials in split order
         __threadfence();
         epi_bar_sync();

@@ -22,10 +22,12 @@
 
 namespace egr {
 
-enum { MOP_GEMM_TC = 1, MOP_GEMV, MOP_GN_STATS, MOP_GN_APPLY, MOP_LAYERNORM, MOP_ATTN, MOP_GEGLU, MOP_CAT, MOP_AXPBY, MOP_TIME_EMBED };
+enum { MOP_GEMM_TC = 1, MOP_GEMV, MOP_GN_STATS, MOP_GN_APPLY, MOP_LAYERNORM, MOP_ATTN, MOP_GEGLU, MOP_CAT, MOP_AXPBY, MOP_TIME_EMBED, MOP_SPLITK_REDUCE };
 
 struct __align__(16) MegaOp {
   int code, sync_after, tc, pad;
+  const void* pf_ptr;      // weights of the NEXT weight-reading op: prefetched into L2 while this op runs (static data,
+  long long pf_bytes;      // so always legal) — the layer's first TMA loads then hit L2 instead of paying HBM latency
   union {
     struct { View a; GemmArgs g; int npix; } gemv;
     struct { CatArgs a; const float* gamma; const float* beta; float eps; int silu; float* out32; __half* out16; double* part; int nsl; } gn;
@@ -428,6 +430,10 @@ __device__ __noinline__ void mega_time_embed(const MegaOp& op, int cta) {
   }
 }
 
+__device__ __noinline__ void mega_splitk_reduce(const TcKernelArgs& ka, int cta, int ncta) {
+  tc_reduce_distributed(ka, (long long)cta * MEGA_SIMT + threadIdx.x, (long long)ncta * MEGA_SIMT);
+}
+
 // ------------------------------------------------------------------------------------------------ the kernel
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -491,6 +497,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
     if (i + 1 < n_ops) fetch_op(ops, kas, tc_of, i + 1, &s_ops[(i + 1) & 1], &s_kas[(i + 1) & 1]);   // lands while this op runs
     if (tr) tr[4 * i] = clock64();
     const int code = op.code;
+    if (op.pf_bytes > 0) {
+      const long long lines = (op.pf_bytes + 127) >> 7;
+      const char* base = reinterpret_cast<const char*>(op.pf_ptr);
+      for (long long l = (long long)cta * MEGA_THREADS + tid; l < lines; l += (long long)ncta * MEGA_THREADS)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)) : "memory");
+    }
     if (code == MOP_GEMM_TC) {
       if (tid == 64) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(maps + 2 * op.tc) : "memory");
@@ -499,13 +511,26 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
       sv.ringA = rings;
       sv.ringB = sv.ringA + (size_t)ka.SA * ka.a_stage_bytes;
       sv.stage_all = reinterpret_cast<float*>(sv.ringB + (size_t)ka.SB * ka.b_stage_bytes);
-      if (tid == 0) {
-        if (bars_live) {
-          for (int s = 0; s < live_SA; ++s) { mbar_inval(&sv.fullA[s]); mbar_inval(&sv.emptyA[s]); }
-          for (int s = 0; s < live_SB; ++s) { mbar_inval(&sv.fullB[s]); mbar_inval(&sv.emptyB[s]); }
-          for (int s = 0; s < 2; ++s) { mbar_inval(&sv.acc_full[s]); mbar_inval(&sv.acc_empty[s]); }
+      {
+        // one barrier per thread: retire the previous GEMM's set, arm this one's (counts depend on the op)
+        const int nprev = bars_live ? 2 * live_SA + 2 * live_SB + 4 : 0, nnew = 2 * ka.SA + 2 * ka.SB + 4;
+        if (tid < nprev) {
+          int k = tid;
+          uint64_t* b;
+          if (k < live_SA) b = &sv.fullA[k];
+          else if ((k -= live_SA) < live_SA) b = &sv.emptyA[k];
+          else if ((k -= live_SA) < live_SB) b = &sv.fullB[k];
+          else if ((k -= live_SB) < live_SB) b = &sv.emptyB[k];
+          else if ((k -= live_SB) < 2) b = &sv.acc_full[k];
+          else b = &sv.acc_empty[k - 2];
+          mbar_inval(b);
         }
-        tc_init_barriers(ka, sv);
+        __syncthreads();
+        if (tid < nnew) {
+          tc_init_barrier_k(ka, sv, tid);
+          asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
       }
       bars_live = 1; live_SA = ka.SA; live_SB = ka.SB;
       tc_fence_before();
@@ -529,6 +554,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
         case MOP_CAT: mega_cat(op, cta, ncta); break;
         case MOP_AXPBY: mega_axpby(op, cta, ncta); break;
         case MOP_TIME_EMBED: mega_time_embed(op, cta); break;
+        case MOP_SPLITK_REDUCE: mega_splitk_reduce(ka, cta, ncta); break;
         default: break;
       }
     }
@@ -611,6 +637,7 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
         m.code = MOP_GEMM_TC;
         m.tc = (int)kas.size();
         kas.push_back(p->ka);
+        if (p->ka.splits > 1 && !p->ka.fold && getenv("EGR_MEGA_NO_DEFER") == nullptr) kas.back().defer = 1;
         maps.push_back(p->tmA);
         maps.push_back(p->tmB);
         const size_t need = (size_t)p->ka.SA * p->ka.a_stage_bytes + (size_t)p->ka.SB * p->ka.b_stage_bytes;
@@ -738,8 +765,32 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
       default: return bad("op code");
     }
     mops.push_back(m);
+    if (m.code == MOP_GEMM_TC && kas[m.tc].defer) {   // the grid-wide reduction + epilogue of a split-K layer
+      MegaOp rd;
+      memset(&rd, 0, sizeof(rd));
+      rd.code = MOP_SPLITK_REDUCE;
+      rd.tc = m.tc;
+      rd.sync_after = m.sync_after;
+      mops.back().sync_after = 1;
+      mops.push_back(rd);
+    }
   }
   if (mops.empty()) return EGR_OK;
+  // weight prefetch chain: op k prefetches the weights the next weight-reading op after it will stream
+  {
+    const void* nxt_ptr = nullptr; long long nxt_bytes = 0;
+    for (int k = (int)mops.size() - 1; k >= 0; --k) {
+      mops[k].pf_ptr = nxt_ptr; mops[k].pf_bytes = nxt_ptr ? nxt_bytes : 0;
+      if (mops[k].code == MOP_GEMM_TC) {
+        const GemmArgs& g = kas[mops[k].tc].g;
+        if (!g.wz_batch) { nxt_ptr = g.W; nxt_bytes = (long long)g.ntaps * (g.wstride_z > 0 ? g.wstride_z : g.wstride_n * g.N) * 2; }
+      } else if (mops[k].code == MOP_GEMV) {
+        const GemmArgs& g = mops[k].u.gemv.g;
+        nxt_ptr = g.W; nxt_bytes = (long long)g.N * g.wstride_n * 4;
+      }
+      if (getenv("EGR_MEGA_NO_PREFETCH")) { nxt_ptr = nullptr; nxt_bytes = 0; }
+    }
+  }
   mops.back().sync_after = 1;   // the launch ends on a full barrier (nothing of the next kernel may overtake)
   MegaRun* r = new MegaRun();
   r->first = first; r->last = last; r->n_ops = (int)mops.size(); r->n_tc = (int)kas.size();
@@ -757,7 +808,7 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
   if (cudaMalloc(&r->d_bar, 256) != cudaSuccess || cudaMemset(r->d_bar, 0, 256) != cudaSuccess) return bail(fail(EGR_ERR_CUDA, "mega: barrier allocation failed"));
   {
     std::vector<int> tc_of(mops.size());
-    for (size_t k = 0; k < mops.size(); ++k) tc_of[k] = mops[k].code == MOP_GEMM_TC ? mops[k].tc : -1;
+    for (size_t k = 0; k < mops.size(); ++k) tc_of[k] = (mops[k].code == MOP_GEMM_TC || mops[k].code == MOP_SPLITK_REDUCE) ? mops[k].tc : -1;
     if (cudaMalloc(&r->d_tc_of, tc_of.size() * sizeof(int)) != cudaSuccess ||
         cudaMemcpy(r->d_tc_of, tc_of.data(), tc_of.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess)
       return bail(fail(EGR_ERR_CUDA, "mega: op index table allocation failed"));

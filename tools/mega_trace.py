@@ -36,10 +36,17 @@ stamps = (C.c_ulonglong * (4 * n_ops))()
 codes = (C.c_int * n_ops)()
 lib.egr_debug_mega_trace.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_int), C.c_int]
 n = lib.egr_debug_mega_trace(h, 0, stamps, codes, n_ops)
-NAMES = {1: "gemm_tc", 2: "gemv", 3: "gn_stats", 4: "gn_apply", 5: "layernorm", 6: "attn", 7: "geglu", 8: "cat", 9: "axpby", 10: "time_embed"}
+NAMES = {1: "gemm_tc", 2: "gemv", 3: "gn_stats", 4: "gn_apply", 5: "layernorm", 6: "attn", 7: "geglu", 8: "cat", 9: "axpby", 10: "time_embed", 11: "splitk_red"}
 mhz = 1965.0
 agg = collections.OrderedDict()
-names = [o.name for o in be.ops if o.flags & 1][:n]
+flagged = [o.name for o in be.ops if o.flags & 1]
+names, fi = [], 0
+for k in range(n):   # a deferred split-K layer is two table entries (GEMM, reduction) for one plan op
+    if codes[k] == 11:
+        names.append(names[-1] + " [reduce]")
+    else:
+        names.append(flagged[fi] if fi < len(flagged) else "?")
+        fi += 1
 rows = []
 for k in range(n):
     t0, t1, t2, t3 = (stamps[4 * k + j] for j in range(4))
