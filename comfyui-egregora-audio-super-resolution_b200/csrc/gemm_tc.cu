@@ -204,7 +204,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   if (splits > 1 && env_int("EGR_TC_NO_FOLD", 0) == 0) {
     for (int c = 16; c <= 128; c += 16)
       if (g.N % c == 0 && splits * c <= 512) fold_bn = c;
-    if (fold_bn && (long long)tiles1 * (g.N / fold_bn) * 4 >= (long long)sms * 3) fold = 1;
+    if (fold_bn && (long long)tiles1 * (g.N / fold_bn) * 2 >= (long long)sms) fold = 1;   // at least half the SMs get an item
   }
 
   // ---- BLOCK_N and sub-tiles per CTA: cheapest (waves x per-item cycles) under a coarse cost model

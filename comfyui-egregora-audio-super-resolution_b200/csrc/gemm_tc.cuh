@@ -329,25 +329,57 @@ __device__ __forceinline__ void tc_reduce_distributed(const TcKernelArgs& ka, lo
     const int n = wi.tn * BN + c;
     if (!ri.ok || n >= g.N) continue;
     const float* pe = ka.partial + (size_t)tile_id * ka.splits * pstride + (size_t)row * BN + c;
+    const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
+    const bool vec = !g.transposed && ka.vec_ok;
+    const long long fl = ri.flat0 + n;
+    const bool keep = vec && fl >= g.out_lo && fl < g.out_hi;
+    // every load this element needs is in flight before the first addition: the partials of all splits, and (vector
+    // path) bias / row bias / residuals — one trip to L2 / HBM instead of a chain of them
     float4 v[MAX_SPLITS];
 #pragma unroll
     for (int sp = 0; sp < MAX_SPLITS; ++sp)
       if (sp < ka.splits) v[sp] = __ldcg(reinterpret_cast<const float4*>(pe + (size_t)sp * pstride));
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), r4 = b4, s4 = b4, t4 = b4;
+    if (keep) {
+      if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+      if (rb) r4 = __ldcg(reinterpret_cast<const float4*>(rb + n));
+      if (g.resid) s4 = __ldcg(reinterpret_cast<const float4*>(g.resid + ri.base + n));
+      if (g.resid2) t4 = __ldcg(reinterpret_cast<const float4*>(g.resid2 + ri.base + n));
+    }
     float4 acc = v[0];
 #pragma unroll
     for (int sp = 1; sp < MAX_SPLITS; ++sp)
       if (sp < ka.splits) { acc.x += v[sp].x; acc.y += v[sp].y; acc.z += v[sp].z; acc.w += v[sp].w; }
-    const float* rb = g.rowbias ? g.rowbias + (long long)ri.b * g.rowbias_stride : nullptr;
     const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
-    if (g.transposed) {
+    if (vec) {
+      if (keep) {   // finish4's arithmetic, operand for operand
+        float o[4] = {acc.x * g.alpha, acc.y * g.alpha, acc.z * g.alpha, acc.w * g.alpha};
+        if (g.bias) { o[0] += b4.x; o[1] += b4.y; o[2] += b4.z; o[3] += b4.w; }
+        if (rb) { o[0] += r4.x; o[1] += r4.y; o[2] += r4.z; o[3] += r4.w; }
+        if (g.act) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) o[u] = egr_apply_act(o[u], g.act);
+        }
+        if (g.resid) { o[0] += s4.x; o[1] += s4.y; o[2] += s4.z; o[3] += s4.w; }
+        if (g.resid2) { o[0] += t4.x; o[1] += t4.y; o[2] += t4.z; o[3] += t4.w; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] *= g.post;
+        const long long idx = ri.base + n;
+        if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(o[0], o[1], o[2], o[3]);
+        if (g.out16) {
+          __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+          uint2 pk;
+          pk.x = *reinterpret_cast<unsigned*>(&h0);
+          pk.y = *reinterpret_cast<unsigned*>(&h1);
+          *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
+        }
+      }
+    } else if (g.transposed) {
       for (int u = 0; u < 4 && n + u < g.N; ++u) finish1(g, a4[u], ri.base + (long long)(n + u) * g.out_n_stride, n + u, rb);
-    } else if (ka.vec_ok) {
-      const long long fl = ri.flat0 + n;
-      if (fl >= g.out_lo && fl < g.out_hi) finish4(g, acc, ri.base + n, n, rb);
     } else {
       for (int u = 0; u < 4 && n + u < g.N; ++u) {
-        const long long fl = ri.flat0 + n + u;
-        if (fl >= g.out_lo && fl < g.out_hi) finish1(g, a4[u], ri.base + n + u, n + u, rb);
+        const long long fl1 = ri.flat0 + n + u;
+        if (fl1 >= g.out_lo && fl1 < g.out_hi) finish1(g, a4[u], ri.base + n + u, n + u, rb);
       }
     }
   }

@@ -32,7 +32,7 @@ struct __align__(16) MegaOp {
     struct { View a; GemmArgs g; int npix; } gemv;
     struct { CatArgs a; const float* gamma; const float* beta; float eps; int silu; float* out32; __half* out16; double* part; int nsl; } gn;
     struct { const float* x; long long rows; int C; float eps; const float* gamma; const float* beta; __half* out16; float* out32; } ln;
-    struct { const __half* q; const __half* k; const __half* v; __half* out; int S, heads, hd, B, ld, qblocks; float scale; } attn;
+    struct { const __half* q; const __half* k; const __half* v; __half* out; int S, heads, hd, B, ld, qblocks; float scale; int mma; } attn;
     struct { const float* x; long long rows; int D; __half* out; } geglu;
     struct { const float* x0; const float* x1; int C0, C1; long long rows, ld0, ld1; float* o32; __half* o16; } cat;
     struct { const float* x; const float* y; float a, b; long long n; float* o32; __half* o16; } axpby;
@@ -55,7 +55,8 @@ struct MegaRun {
 };
 
 static constexpr int MEGA_THREADS = 384;
-static constexpr int MEGA_SIMT = 256;        // CUDA-core ops run on warps 0..7
+static constexpr int MEGA_SIMT = 384;        // CUDA-core ops run on all 12 warps
+static constexpr int MEGA_NW = MEGA_SIMT / 32;
 static constexpr int MEGA_MAX_STAGES = 10;   // ring depth bound of tc_prepare
 static constexpr int MEGA_BAR_BYTES = 1024;  // 4 x 10 ring barriers + 4 accumulator barriers, padded
 static constexpr int MEGA_DYN_SMEM_MAX = 227 * 1024 - 4096;   // 227 KB per CTA minus the kernel's static shared memory
@@ -65,7 +66,7 @@ static constexpr int MEGA_DYN_SMEM_MAX = 227 * 1024 - 4096;   // 227 KB per CTA 
 using namespace egr;
 
 // ------------------------------------------------------------------------------------------------ synchronisation
-__device__ __forceinline__ void simt_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+__device__ __forceinline__ void simt_sync() { asm volatile("bar.sync 2, 384;" ::: "memory"); }
 
 // Grid barrier: one monotonically increasing arrival counter per launch (zeroed by a memset node before the launch).
 // A CTA arrives with a fire-and-forget release reduction and waits until the counter reaches epoch * ncta: one L2 round
@@ -106,7 +107,7 @@ __device__ __noinline__ void mega_gemv(const MegaOp& op, int cta, int ncta) {
   const View& a = op.u.gemv.a;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int npix = op.u.gemv.npix;
-  for (int n = cta * 8 + warp; n < g.N; n += ncta * 8) {
+  for (int n = cta * MEGA_NW + warp; n < g.N; n += ncta * MEGA_NW) {
     const float* wrow = reinterpret_cast<const float*>(g.W) + (long long)n * g.wstride_n;
     for (int p = 0; p < npix; ++p) {
       const int w = p % g.Wo, h = (p / g.Wo) % g.Ho, b = p / (g.Wo * g.Ho);
@@ -129,7 +130,7 @@ __device__ __forceinline__ const float* gn_src(const CatArgs& a, int b, long lon
 }
 
 // unit = (item b, group gi, pixel slice sl): f32 partial moments per thread, combined in f64 in a fixed order
-__device__ __noinline__ void mega_gn_stats(const MegaOp& op, int cta, int ncta, double (*red)[8]) {
+__device__ __noinline__ void mega_gn_stats(const MegaOp& op, int cta, int ncta, double (*red)[MEGA_NW]) {
   const CatArgs& a = op.u.gn.a;
   const int C = a.C0 + a.C1, cpg = C / a.G, q4 = cpg >> 2, nsl = op.u.gn.nsl;
   const int units = a.B * a.G * nsl;
@@ -151,7 +152,7 @@ __device__ __noinline__ void mega_gn_stats(const MegaOp& op, int cta, int ncta, 
     simt_sync();
     if (tid == 0) {
       double t = 0.0, tt = 0.0;
-      for (int w = 0; w < 8; ++w) { t += red[0][w]; tt += red[1][w]; }
+      for (int w = 0; w < MEGA_NW; ++w) { t += red[0][w]; tt += red[1][w]; }
       double* dst = op.u.gn.part + (((long long)b * a.G + gi) * nsl + sl) * 2;
       dst[0] = t; dst[1] = tt;
     }
@@ -217,12 +218,20 @@ __device__ __noinline__ void mega_layernorm(const MegaOp& op, int cta, int ncta)
   const float* gamma = op.u.ln.gamma;
   const float* beta = op.u.ln.beta;
   constexpr int NJ = 20;   // a row of up to 640 channels lives in registers: ONE trip to L2 instead of three
-  for (long long row = (long long)cta * 8 + warp; row < op.u.ln.rows; row += (long long)ncta * 8) {
+  for (long long row = (long long)cta * MEGA_NW + warp; row < op.u.ln.rows; row += (long long)ncta * MEGA_NW) {
     const float* xr = op.u.ln.x + row * C;
     if (C <= 32 * NJ) {
-      float xv[NJ];
+      // every load of the row — x, gamma, beta — is issued before the first use: the stores below would otherwise
+      // serialise the parameter loads behind them (one cold miss per element: 8.7 us per row in the round-2 trace)
+      float xv[NJ], gv[NJ], bv[NJ];
 #pragma unroll
-      for (int j = 0; j < NJ; ++j) { const int c = lane + 32 * j; xv[j] = c < C ? __ldcg(xr + c) : 0.f; }
+      for (int j = 0; j < NJ; ++j) {
+        const int c = lane + 32 * j;
+        const bool in = c < C;
+        xv[j] = in ? __ldcg(xr + c) : 0.f;
+        gv[j] = in ? __ldg(gamma + c) : 0.f;
+        bv[j] = in ? __ldg(beta + c) : 0.f;
+      }
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) if (lane + 32 * j < C) s += xv[j];
@@ -231,13 +240,15 @@ __device__ __noinline__ void mega_layernorm(const MegaOp& op, int cta, int ncta)
 #pragma unroll
       for (int j = 0; j < NJ; ++j) if (lane + 32 * j < C) { const float d = xv[j] - mean; v = fmaf(d, d, v); }
       const float rstd = rsqrtf(warp_sum(v) / C + op.u.ln.eps);
+      __half* const o16 = op.u.ln.out16;
+      float* const o32 = op.u.ln.out32;
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int c = lane + 32 * j;
         if (c < C) {
-          const float y = (xv[j] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c);
-          if (op.u.ln.out16) op.u.ln.out16[row * C + c] = __float2half_rn(y);
-          if (op.u.ln.out32) op.u.ln.out32[row * C + c] = y;
+          const float y = (xv[j] - mean) * rstd * gv[j] + bv[j];
+          if (o16) o16[row * C + c] = __float2half_rn(y);
+          if (o32) o32[row * C + c] = y;
         }
       }
       continue;
@@ -299,7 +310,7 @@ __device__ __noinline__ void mega_attn(const MegaOp& op, int cta, int ncta, unsi
       simt_sync();
     }
     const int r_lo = qb * rows_per_block, r_hi = min(S, r_lo + rows_per_block);
-    for (int r = r_lo + warp; r < r_hi; r += 8) {
+    for (int r = r_lo + warp; r < r_hi; r += MEGA_NW) {
       float qv[HD];
 #pragma unroll
       for (int c8 = 0; c8 < HD; c8 += 8) {
@@ -386,25 +397,177 @@ __device__ __noinline__ void mega_attn(const MegaOp& op, int cta, int ncta, unsi
   }
 }
 
+// ------------------------------------------------------------------------------------------------ attention on HMMA
+// Flash-style self-attention for the UNet's short sequences (S <= 512, 16/32-dim heads) inside the persistent kernel: K / V
+// of one (item, head) are staged in shared memory as f16 (rows past S zero-filled up to a multiple of 16), every warp owns
+// 16 query rows: S = Q K^T by mma.sync m16n8k16 (Q fragments straight from global memory, K fragments are 32-bit shared
+// loads), online softmax over 16-key chunks in f32, O += P V with P re-packed from the score fragments and V fragments
+// fetched by ldmatrix.trans.  Replaces the CUDA-core row kernel here: 2.1 GFLOP per attention at batch 8 took 90-230 us
+// on the FMA pipe (round-2 trace), a quarter of the UNet's time.
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2h(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int HD>
+__device__ __noinline__ void mega_attn_mma(const MegaOp& op, int cta, int ncta, unsigned char* smraw) {
+  constexpr int KST = HD + 8;          // halves per staged row: 16-byte aligned, ldmatrix rows hit distinct bank groups
+  constexpr int KS = HD / 16;          // k-steps of Q K^T
+  constexpr int NT = HD / 8;           // n-tiles of P V
+  const int S = op.u.attn.S, heads = op.u.attn.heads, B = op.u.attn.B, qblocks = op.u.attn.qblocks;
+  const __half* q = op.u.attn.q;
+  const __half* k = op.u.attn.k;
+  const __half* v = op.u.attn.v;
+  __half* out = op.u.attn.out;
+  const float scale = op.u.attn.scale * 1.4426950408889634f;   // scores in log2 units: exp2f below
+  const int S16 = (S + 15) & ~15;
+  __half* Ks = reinterpret_cast<__half*>(smraw);
+  __half* Vs = Ks + (size_t)S16 * KST;
+  const int C = heads * HD;
+  const int L = op.u.attn.ld ? op.u.attn.ld : C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qr = lane >> 2, qc = (lane & 3) * 2;   // fragment row / column pair of this lane
+  const int tiles = S16 >> 4;                       // 16-row query tiles per (item, head)
+  const int tiles_per_vb = (tiles + qblocks - 1) / qblocks;
+  const int nvb = qblocks * heads * B;
+  int staged = -1;
+  for (int vb = cta; vb < nvb; vb += ncta) {
+    const int qb = vb % qblocks, h = (vb / qblocks) % heads, b = vb / (qblocks * heads);
+    const long long base = (long long)b * S * C + (long long)h * HD;
+    const long long ibase = (long long)b * S * L + (long long)h * HD;
+    if (staged != b * heads + h) {
+      simt_sync();
+      for (int i = threadIdx.x; i < S16 * (HD / 8); i += MEGA_SIMT) {
+        const int j = i / (HD / 8), c8 = (i % (HD / 8)) * 8;
+        uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+        if (j < S) {
+          kv = __ldcg(reinterpret_cast<const uint4*>(k + ibase + (long long)j * L + c8));
+          vv = __ldcg(reinterpret_cast<const uint4*>(v + ibase + (long long)j * L + c8));
+        }
+        *reinterpret_cast<uint4*>(Ks + j * KST + c8) = kv;
+        *reinterpret_cast<uint4*>(Vs + j * KST + c8) = vv;
+      }
+      staged = b * heads + h;
+      simt_sync();
+    }
+    const int t_lo = qb * tiles_per_vb, t_hi = min(tiles, t_lo + tiles_per_vb);
+    for (int t = t_lo + warp; t < t_hi; t += MEGA_NW) {
+      const int r0 = t * 16 + qr, r1 = r0 + 8;      // the two query rows this lane holds fragments of
+      uint32_t qa[KS][4];
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const int c0 = ks * 16 + qc;
+        qa[ks][0] = r0 < S ? __ldcg(reinterpret_cast<const uint32_t*>(q + ibase + (long long)r0 * L + c0)) : 0u;
+        qa[ks][1] = r1 < S ? __ldcg(reinterpret_cast<const uint32_t*>(q + ibase + (long long)r1 * L + c0)) : 0u;
+        qa[ks][2] = r0 < S ? __ldcg(reinterpret_cast<const uint32_t*>(q + ibase + (long long)r0 * L + c0 + 8)) : 0u;
+        qa[ks][3] = r1 < S ? __ldcg(reinterpret_cast<const uint32_t*>(q + ibase + (long long)r1 * L + c0 + 8)) : 0u;
+      }
+      float o[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) { o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f; }
+      float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+      for (int j0 = 0; j0 < S16; j0 += 16) {
+        // scores of 16 keys: two n8 tiles
+        float s[2][4];
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+          s[nb][0] = s[nb][1] = s[nb][2] = s[nb][3] = 0.f;
+          const __half* kr = Ks + (j0 + nb * 8 + qr) * KST + qc;
+#pragma unroll
+          for (int ks = 0; ks < KS; ++ks)
+            mma16816(s[nb], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16), *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+        }
+        // scale, mask the zero-filled keys, running maximum per row (a row lives in the 4 lanes of a quad)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool ok = j0 + nb * 8 + qc + e < S;
+            s[nb][e] = ok ? s[nb][e] * scale : -INFINITY;
+            s[nb][2 + e] = ok ? s[nb][2 + e] * scale : -INFINITY;
+            mx0 = fmaxf(mx0, s[nb][e]); mx1 = fmaxf(mx1, s[nb][2 + e]);
+          }
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float n0 = fmaxf(m0, mx0), n1 = fmaxf(m1, mx1);   // finite from the first chunk on (key 0 is never masked)
+        const float f0 = exp2f(m0 - n0), f1 = exp2f(m1 - n1);
+        m0 = n0; m1 = n1;
+        float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            s[nb][e] = exp2f(s[nb][e] - n0); ps0 += s[nb][e];
+            s[nb][2 + e] = exp2f(s[nb][2 + e] - n1); ps1 += s[nb][2 + e];
+          }
+        }
+        l0 = l0 * f0 + ps0; l1 = l1 * f1 + ps1;   // per-lane partial row sums; combined across the quad at the end
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) { o[nt][0] *= f0; o[nt][1] *= f0; o[nt][2] *= f1; o[nt][3] *= f1; }
+        // P (16 x 16 keys) as the A operand: score fragments re-packed to f16
+        uint32_t pa[4];
+        pa[0] = pack2h(s[0][0], s[0][1]); pa[1] = pack2h(s[0][2], s[0][3]);
+        pa[2] = pack2h(s[1][0], s[1][1]); pa[3] = pack2h(s[1][2], s[1][3]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          uint32_t b0, b1;
+          const uint32_t addr = smem_u32(Vs + (j0 + (lane & 15)) * KST + nt * 8);
+          asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+          mma16816(o[nt], pa, b0, b1);
+        }
+      }
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (r0 < S) *reinterpret_cast<uint32_t*>(out + base + (long long)r0 * C + nt * 8 + qc) = pack2h(o[nt][0] * i0, o[nt][1] * i0);
+        if (r1 < S) *reinterpret_cast<uint32_t*>(out + base + (long long)r1 * C + nt * 8 + qc) = pack2h(o[nt][2] * i1, o[nt][3] * i1);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint2 pack4h(float a, float b, float c, float d) {
+  __half2 h0 = __floats2half2_rn(a, b), h1 = __floats2half2_rn(c, d);
+  uint2 pk;
+  pk.x = *reinterpret_cast<unsigned*>(&h0);
+  pk.y = *reinterpret_cast<unsigned*>(&h1);
+  return pk;
+}
+__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752f)); }
+
+// the element-wise bodies move 16 bytes per access (the planner's channel counts are multiples of 4; build checks it)
 __device__ __noinline__ void mega_geglu(const MegaOp& op, int cta, int ncta) {
-  const int D = op.u.geglu.D;
-  const long long total = op.u.geglu.rows * D;
+  const int D = op.u.geglu.D, D4 = D >> 2;
+  const long long total4 = op.u.geglu.rows * D4;
   const float* x = op.u.geglu.x;
-  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < total; i += (long long)ncta * MEGA_SIMT) {
-    const long long r = i / D; const int d = (int)(i % D);
-    const float a = __ldcg(x + r * 2 * D + d), g = __ldcg(x + r * 2 * D + D + d);
-    op.u.geglu.out[i] = __float2half_rn(a * (0.5f * g * (1.0f + erff(g * 0.70710678118654752f))));
+  __half* out = op.u.geglu.out;
+  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < total4; i += (long long)ncta * MEGA_SIMT) {
+    const long long r = i / D4; const int d = (int)(i - r * D4) * 4;
+    const float4 a = ldcg4(x + r * 2 * D + d), g = ldcg4(x + r * 2 * D + D + d);
+    *reinterpret_cast<uint2*>(out + r * D + d) = pack4h(a.x * gelu_erf(g.x), a.y * gelu_erf(g.y), a.z * gelu_erf(g.z), a.w * gelu_erf(g.w));
   }
 }
 
 __device__ __noinline__ void mega_cat(const MegaOp& op, int cta, int ncta) {
-  const int C0 = op.u.cat.C0, C = C0 + op.u.cat.C1;
-  const long long total = op.u.cat.rows * C;
-  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < total; i += (long long)ncta * MEGA_SIMT) {
-    const long long r = i / C; const int c = (int)(i % C);
-    const float v = c < C0 ? __ldcg(op.u.cat.x0 + r * op.u.cat.ld0 + c) : __ldcg(op.u.cat.x1 + r * op.u.cat.ld1 + (c - C0));
-    if (op.u.cat.o32) op.u.cat.o32[i] = v;
-    if (op.u.cat.o16) op.u.cat.o16[i] = __float2half_rn(v);
+  const int C0 = op.u.cat.C0, C = C0 + op.u.cat.C1, C4 = C >> 2;
+  const long long total4 = op.u.cat.rows * C4;
+  const float* x0 = op.u.cat.x0; const float* x1 = op.u.cat.x1;
+  const long long ld0 = op.u.cat.ld0, ld1 = op.u.cat.ld1;
+  float* o32 = op.u.cat.o32; __half* o16 = op.u.cat.o16;
+  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < total4; i += (long long)ncta * MEGA_SIMT) {
+    const long long r = i / C4; const int c = (int)(i - r * C4) * 4;
+    const float4 v = c < C0 ? ldcg4(x0 + r * ld0 + c) : ldcg4(x1 + r * ld1 + (c - C0));
+    if (o32) *reinterpret_cast<float4*>(o32 + r * C + c) = v;
+    if (o16) *reinterpret_cast<uint2*>(o16 + r * C + c) = pack4h(v.x, v.y, v.z, v.w);
   }
 }
 
@@ -412,10 +575,19 @@ __device__ __noinline__ void mega_axpby(const MegaOp& op, int cta, int ncta) {
   const float a = op.u.axpby.a, b = op.u.axpby.b;
   const float* x = op.u.axpby.x;
   const float* y = op.u.axpby.y;
-  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < op.u.axpby.n; i += (long long)ncta * MEGA_SIMT) {
-    const float v = y ? fmaf(a, __ldcg(x + i), b * __ldcg(y + i)) : fmaf(a, __ldcg(x + i), b);
-    if (op.u.axpby.o32) op.u.axpby.o32[i] = v;
-    if (op.u.axpby.o16) op.u.axpby.o16[i] = __float2half_rn(v);
+  float* o32 = op.u.axpby.o32; __half* o16 = op.u.axpby.o16;
+  const long long n4 = op.u.axpby.n >> 2;
+  for (long long i = (long long)cta * MEGA_SIMT + threadIdx.x; i < n4; i += (long long)ncta * MEGA_SIMT) {
+    const float4 xv = ldcg4(x + 4 * i);
+    float4 v;
+    if (y) {
+      const float4 yv = ldcg4(y + 4 * i);
+      v = make_float4(fmaf(a, xv.x, b * yv.x), fmaf(a, xv.y, b * yv.y), fmaf(a, xv.z, b * yv.z), fmaf(a, xv.w, b * yv.w));
+    } else {
+      v = make_float4(fmaf(a, xv.x, b), fmaf(a, xv.y, b), fmaf(a, xv.z, b), fmaf(a, xv.w, b));
+    }
+    if (o32) *reinterpret_cast<float4*>(o32 + 4 * i) = v;
+    if (o16) *reinterpret_cast<uint2*>(o16 + 4 * i) = pack4h(v.x, v.y, v.z, v.w);
   }
 }
 
@@ -458,7 +630,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(16) MegaOp s_ops[2];
   __shared__ __align__(16) TcKernelArgs s_kas[2];
-  __shared__ double s_red[2][8];
+  __shared__ double s_red[2][MEGA_NW];
   __shared__ float s_stat[2];
   __shared__ uint32_t s_tmem, s_last;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -512,20 +684,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
       sv.ringB = sv.ringA + (size_t)ka.SA * ka.a_stage_bytes;
       sv.stage_all = reinterpret_cast<float*>(sv.ringB + (size_t)ka.SB * ka.b_stage_bytes);
       {
-        // one barrier per thread: retire the previous GEMM's set, arm this one's (counts depend on the op)
-        const int nprev = bars_live ? 2 * live_SA + 2 * live_SB + 4 : 0, nnew = 2 * ka.SA + 2 * ka.SB + 4;
-        if (tid < nprev) {
-          int k = tid;
-          uint64_t* b;
-          if (k < live_SA) b = &sv.fullA[k];
-          else if ((k -= live_SA) < live_SA) b = &sv.emptyA[k];
-          else if ((k -= live_SA) < live_SB) b = &sv.fullB[k];
-          else if ((k -= live_SB) < live_SB) b = &sv.emptyB[k];
-          else if ((k -= live_SB) < 2) b = &sv.acc_full[k];
-          else b = &sv.acc_empty[k - 2];
-          mbar_inval(b);
-        }
-        __syncthreads();
+        // one barrier per thread: arm this op's set (counts depend on the op).  The previous GEMM's barriers are idle by
+        // now — every TMA transaction and every tcgen05.commit arrival was consumed before its epilogue finished — and
+        // mbarrier.init simply rewrites the 64-bit state word.
+        const int nnew = 2 * ka.SA + 2 * ka.SB + 4;
         if (tid < nnew) {
           tc_init_barrier_k(ka, sv, tid);
           asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -539,7 +701,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
       if (tr) tr[4 * i + 1] = clock64();
       tc_roles(maps + 2 * op.tc, maps + 2 * op.tc + 1, ka, sv, tmem_base, cta, ncta, nullptr);
       tc_fence_before();
-    } else if (tid < MEGA_SIMT) {
+    } else {
       if (tr) tr[4 * i + 1] = clock64();
       switch (code) {
         case MOP_GEMV: mega_gemv(op, cta, ncta); break;
@@ -547,8 +709,13 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
         case MOP_GN_APPLY: mega_gn_apply(op, cta, ncta, s_stat); break;
         case MOP_LAYERNORM: mega_layernorm(op, cta, ncta); break;
         case MOP_ATTN:
-          if (op.u.attn.hd == 32) mega_attn<32>(op, cta, ncta, rings);
-          else mega_attn<16>(op, cta, ncta, rings);
+          if (op.u.attn.mma) {
+            if (op.u.attn.hd == 32) mega_attn_mma<32>(op, cta, ncta, rings);
+            else mega_attn_mma<16>(op, cta, ncta, rings);
+          } else {
+            if (op.u.attn.hd == 32) mega_attn<32>(op, cta, ncta, rings);
+            else mega_attn<16>(op, cta, ncta, rings);
+          }
           break;
         case MOP_GEGLU: mega_geglu(op, cta, ncta); break;
         case MOP_CAT: mega_cat(op, cta, ncta); break;
@@ -707,14 +874,26 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
         m.u.attn.S = (int)op.i[EGR_I_SEQ]; m.u.attn.heads = (int)op.i[EGR_I_HEADS]; m.u.attn.hd = (int)op.i[EGR_I_HEADDIM];
         m.u.attn.B = (int)op.i[EGR_I_BATCH]; m.u.attn.ld = (int)op.i[EGR_I_AUX0];
         m.u.attn.scale = (float)op.f[EGR_F_ALPHA];
-        m.u.attn.qblocks = (m.u.attn.S + 15) / 16;
+        m.u.attn.mma = getenv("EGR_MEGA_ATTN_SIMT") == nullptr ? 1 : 0;
+        if (m.u.attn.mma) {
+          // query tiles of 16 rows per (item, head), split over enough virtual blocks to occupy the SMs; K / V are staged
+          // once per virtual block, so no more splits than needed (a function of the op's geometry and the SM count)
+          const int tiles = (m.u.attn.S + 15) / 16, pairs = m.u.attn.B * m.u.attn.heads;
+          const int sms_ = devinfo().sm_count ? devinfo().sm_count : 148;
+          int qb = (sms_ + pairs - 1) / pairs;
+          const int max_qb = (tiles + MEGA_NW - 1) / MEGA_NW;   // one tile per warp at least
+          if (qb > max_qb) qb = max_qb;
+          m.u.attn.qblocks = qb < 1 ? 1 : qb;
+        } else {
+          m.u.attn.qblocks = (m.u.attn.S + 15) / 16;
+        }
         const int C_ = m.u.attn.heads * m.u.attn.hd;
         auto al16 = [](const void* q) { return reinterpret_cast<uintptr_t>(q) % 16 == 0; };
         if (!m.u.attn.q || !m.u.attn.k || !m.u.attn.v || !m.u.attn.out) return bad("null pointer");
         if (!((m.u.attn.hd == 32 || m.u.attn.hd == 16) && m.u.attn.S <= 512 && C_ % 8 == 0 && al16(m.u.attn.q) && al16(m.u.attn.k) && al16(m.u.attn.v)))
           return bad("attention shape outside the 16/32-dim head, S <= 512 kernel");
         if (m.u.attn.ld != 0 && (m.u.attn.ld < C_ || m.u.attn.ld % 8 != 0)) return bad("bad q/k/v row stride");
-        const size_t need = (size_t)2 * m.u.attn.S * (m.u.attn.hd + 8) * sizeof(__half);
+        const size_t need = (size_t)2 * ((m.u.attn.S + 15) / 16 * 16) * (m.u.attn.hd + 8) * sizeof(__half);
         ring_bytes = need > ring_bytes ? need : ring_bytes;
         break;
       }
@@ -724,6 +903,7 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
         m.u.geglu.out = (__half*)resolve(sp, op.ptr[EGR_P_OUT16]);
         m.u.geglu.rows = op.i[EGR_I_ROWS]; m.u.geglu.D = (int)op.i[EGR_I_COLS];
         if (!m.u.geglu.x || !m.u.geglu.out || m.u.geglu.rows <= 0 || m.u.geglu.D <= 0) return bad("bad arguments");
+        if ((m.u.geglu.D & 3) || reinterpret_cast<uintptr_t>(m.u.geglu.x) % 16 || reinterpret_cast<uintptr_t>(m.u.geglu.out) % 8) return bad("GEGLU width / alignment");
         break;
       }
       case EGR_OP_TIME_EMBED: {
@@ -750,12 +930,18 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
           m.u.cat.ld1 = op.i[EGR_I_AUX1] ? op.i[EGR_I_AUX1] : m.u.cat.C1;
           m.u.cat.o32 = o32; m.u.cat.o16 = o16;
           if (m.u.cat.C1 > 0 && !x1) return bad("null x1");
+          if ((m.u.cat.C0 & 3) || (m.u.cat.C1 & 3) || (m.u.cat.ld0 & 3) || (m.u.cat.ld1 & 3) || reinterpret_cast<uintptr_t>(x0) % 16 ||
+              reinterpret_cast<uintptr_t>(x1) % 16 || reinterpret_cast<uintptr_t>(o32) % 16 || reinterpret_cast<uintptr_t>(o16) % 8)
+            return bad("cast / concat widths or alignment");
         } else if (mode == EGR_ELT_AXPBY || mode == EGR_ELT_SCALE_SHIFT) {
           m.code = MOP_AXPBY;
           m.u.axpby.x = x0; m.u.axpby.y = mode == EGR_ELT_AXPBY ? x1 : nullptr;
           if (mode == EGR_ELT_AXPBY && !x1) return bad("null x1");
           m.u.axpby.a = (float)op.f[EGR_F_A]; m.u.axpby.b = (float)op.f[EGR_F_B];
           m.u.axpby.n = op.i[EGR_I_ROWS];
+          if ((m.u.axpby.n & 3) || reinterpret_cast<uintptr_t>(x0) % 16 || reinterpret_cast<uintptr_t>(x1) % 16 ||
+              reinterpret_cast<uintptr_t>(o32) % 16 || reinterpret_cast<uintptr_t>(o16) % 8)
+            return bad("axpby length / alignment");
           m.u.axpby.o32 = o32; m.u.axpby.o16 = o16;
         } else {
           return bad("eltwise mode");
