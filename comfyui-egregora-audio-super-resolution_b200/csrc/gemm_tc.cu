@@ -187,7 +187,9 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   if (!g.wz_batch && env_int("EGR_TC_NO_SPLITK", 0) == 0) {
     splits = sms / (units > 0 ? units : 1);
     if (splits > MAX_SPLITS) splits = MAX_SPLITS;
-    if (splits > n_outer / 3) splits = n_outer / 3;  // at least three outer steps per split
+    // at least eight outer steps (~1 us of tensor-core issue) per split: a shorter reduction is cheaper left whole than
+    // split and reduced again (the reduction pass costs several microseconds of latency, round-2 trace)
+    if (splits > n_outer / 8) splits = n_outer / 8;
     if (splits < 1) splits = 1;
   }
   if (env_int("EGR_TC_SPLITS", 0) > 0) splits = env_int("EGR_TC_SPLITS", 0) > n_outer ? n_outer : env_int("EGR_TC_SPLITS", 0);

@@ -22,12 +22,16 @@
 
 namespace egr {
 
-enum { MOP_GEMM_TC = 1, MOP_GEMV, MOP_GN_STATS, MOP_GN_APPLY, MOP_LAYERNORM, MOP_ATTN, MOP_GEGLU, MOP_CAT, MOP_AXPBY, MOP_TIME_EMBED, MOP_SPLITK_REDUCE };
+enum { MOP_GEMM_TC = 1, MOP_GEMV, MOP_GN_STATS, MOP_GN_APPLY, MOP_LAYERNORM, MOP_ATTN, MOP_GEGLU, MOP_CAT, MOP_AXPBY, MOP_TIME_EMBED, MOP_SPLITK_REDUCE, MOP_GN_FUSED };
 
 struct __align__(16) MegaOp {
   int code, sync_after, tc, pad;
-  const void* pf_ptr;      // weights of the NEXT weight-reading op: prefetched into L2 while this op runs (static data,
-  long long pf_bytes;      // so always legal) — the layer's first TMA loads then hit L2 instead of paying HBM latency
+  // parameters of the ops that FOLLOW — [0] the weights of the next weight-reading op, [1] [2] the small vectors (bias,
+  // gamma, beta) of the next op — prefetched into L2 while this op runs (static data, so always legal): the layer's
+  // first TMA loads and the epilogue's parameter loads then hit L2 instead of paying HBM latency in their critical path
+  const void* pf_ptr[3];
+  int pf_bytes[3];
+  int pad2;
   union {
     struct { View a; GemmArgs g; int npix; } gemv;
     struct { CatArgs a; const float* gamma; const float* beta; float eps; int silu; float* out32; __half* out16; double* part; int nsl; } gn;
@@ -209,6 +213,103 @@ __device__ __noinline__ void mega_gn_apply(const MegaOp& op, int cta, int ncta, 
       }
     }
     simt_sync();   // stat[] is rewritten by the next unit
+  }
+}
+
+// GroupNorm as ONE op: a CTA owns a whole (item, group) — moments, then normalise (+SiLU) — so no grid barrier sits between
+// the two halves.  Groups of up to 384 x 12 float4 stay in registers between the passes (one trip to L2); larger ones are
+// read twice.  Per-thread partition and reduction order depend on the op's geometry only (batch-invariant, deterministic).
+__device__ __noinline__ void mega_gn_fused(const MegaOp& op, int cta, int ncta, double (*red)[MEGA_NW], float* stat) {
+  constexpr int REG = 12;
+  const CatArgs& a = op.u.gn.a;
+  const int C = a.C0 + a.C1, cpg = C / a.G, q4 = cpg >> 2;
+  const int units = a.B * a.G;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n4 = (int)a.P * q4;
+  const bool inreg = n4 <= MEGA_SIMT * REG;
+  const int silu = op.u.gn.silu;
+  const float* gamma = op.u.gn.gamma;
+  const float* beta = op.u.gn.beta;
+  float* out32 = op.u.gn.out32;
+  __half* out16 = op.u.gn.out16;
+  for (int unit = cta; unit < units; unit += ncta) {
+    const int gi = unit % a.G, b = unit / a.G;
+    float4 xv[REG];
+    float s = 0.f, ss = 0.f;
+    if (inreg) {
+#pragma unroll
+      for (int j = 0; j < REG; ++j) {
+        const int u = tid + j * MEGA_SIMT;
+        if (u < n4) {
+          const int pl = u / q4;
+          xv[j] = ldcg4(gn_src(a, b, pl, gi * cpg + (u - pl * q4) * 4));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < REG; ++j) {
+        if (tid + j * MEGA_SIMT < n4) {
+          const float4 v = xv[j];
+          s += (v.x + v.y) + (v.z + v.w);
+          ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+        }
+      }
+    } else {
+      for (int u = tid; u < n4; u += MEGA_SIMT) {
+        const int pl = u / q4;
+        const float4 v = ldcg4(gn_src(a, b, pl, gi * cpg + (u - pl * q4) * 4));
+        s += (v.x + v.y) + (v.z + v.w);
+        ss = fmaf(v.x, v.x, ss); ss = fmaf(v.y, v.y, ss); ss = fmaf(v.z, v.z, ss); ss = fmaf(v.w, v.w, ss);
+      }
+    }
+    const double ds = warp_sum((double)s), dss = warp_sum((double)ss);
+    if (lane == 0) { red[0][warp] = ds; red[1][warp] = dss; }
+    simt_sync();
+    if (tid == 0) {
+      double t = 0.0, tt = 0.0;
+      for (int w = 0; w < MEGA_NW; ++w) { t += red[0][w]; tt += red[1][w]; }
+      const double cnt = (double)cpg * (double)a.P;
+      const double mean = t / cnt;
+      double var = tt / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stat[0] = (float)mean;
+      stat[1] = (float)(1.0 / sqrt(var + (double)op.u.gn.eps));
+    }
+    simt_sync();
+    const float mean = stat[0], rstd = stat[1];
+    auto emit = [&](int u, const float4 v) {
+      const int pl = u / q4;
+      const int c = gi * cpg + (u - pl * q4) * 4;
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+      float r[4] = {fmaf(v.x, rstd * g4.x, b4.x - mean * (rstd * g4.x)), fmaf(v.y, rstd * g4.y, b4.y - mean * (rstd * g4.y)),
+                    fmaf(v.z, rstd * g4.z, b4.z - mean * (rstd * g4.z)), fmaf(v.w, rstd * g4.w, b4.w - mean * (rstd * g4.w))};
+      if (silu) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = egr_silu(r[k]);
+      }
+      const long long o = ((long long)b * a.P + pl) * C + c;
+      if (out32) *reinterpret_cast<float4*>(out32 + o) = make_float4(r[0], r[1], r[2], r[3]);
+      if (out16) {
+        __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<unsigned*>(&h0);
+        pk.y = *reinterpret_cast<unsigned*>(&h1);
+        *reinterpret_cast<uint2*>(out16 + o) = pk;
+      }
+    };
+    if (inreg) {
+#pragma unroll
+      for (int j = 0; j < REG; ++j) {
+        const int u = tid + j * MEGA_SIMT;
+        if (u < n4) emit(u, xv[j]);
+      }
+    } else {
+      for (int u = tid; u < n4; u += MEGA_SIMT) {
+        const int pl = u / q4;
+        emit(u, ldcg4(gn_src(a, b, pl, gi * cpg + (u - pl * q4) * 4)));
+      }
+    }
+    simt_sync();   // red[] / stat[] are rewritten by the next unit
   }
 }
 
@@ -669,11 +770,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
     if (i + 1 < n_ops) fetch_op(ops, kas, tc_of, i + 1, &s_ops[(i + 1) & 1], &s_kas[(i + 1) & 1]);   // lands while this op runs
     if (tr) tr[4 * i] = clock64();
     const int code = op.code;
-    if (op.pf_bytes > 0) {
-      const long long lines = (op.pf_bytes + 127) >> 7;
-      const char* base = reinterpret_cast<const char*>(op.pf_ptr);
-      for (long long l = (long long)cta * MEGA_THREADS + tid; l < lines; l += (long long)ncta * MEGA_THREADS)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (l << 7)) : "memory");
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr) {
+      if (op.pf_bytes[pr] > 0) {
+        const int lines = (op.pf_bytes[pr] + 127) >> 7;
+        const char* base = reinterpret_cast<const char*>(op.pf_ptr[pr]);
+        for (int l = cta * MEGA_THREADS + tid; l < lines; l += ncta * MEGA_THREADS)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base + ((long long)l << 7)) : "memory");
+      }
     }
     if (code == MOP_GEMM_TC) {
       if (tid == 64) {
@@ -707,6 +811,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
         case MOP_GEMV: mega_gemv(op, cta, ncta); break;
         case MOP_GN_STATS: mega_gn_stats(op, cta, ncta, s_red); break;
         case MOP_GN_APPLY: mega_gn_apply(op, cta, ncta, s_stat); break;
+        case MOP_GN_FUSED: mega_gn_fused(op, cta, ncta, s_red, s_stat); break;
         case MOP_LAYERNORM: mega_layernorm(op, cta, ncta); break;
         case MOP_ATTN:
           if (op.u.attn.mma) {
@@ -841,8 +946,15 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
         m.u.gn.nsl = mega_nsl(a);
         if (!m.u.gn.part) return bad("null stats buffer");
         if (m.u.gn.nsl > 1 + (int)op.i[EGR_I_AUX1]) return bad("stats buffer smaller than the slice partials");
-        if (op.code == EGR_OP_GN_STATS) { m.code = MOP_GN_STATS; break; }
-        m.code = MOP_GN_APPLY;
+        static const bool gn_one_op = getenv("EGR_MEGA_GN_TWO_OPS") == nullptr;
+        if (op.code == EGR_OP_GN_STATS) {
+          // one-op GroupNorm: the moments are computed by the op that applies them (the next plan op, same tensor)
+          if (gn_one_op && i + 1 < last && ops[i + 1].code == EGR_OP_GN_APPLY && a.P * ((a.C0 + a.C1) / a.G) <= 65536) { m.code = 0; break; }
+          m.code = MOP_GN_STATS;
+          break;
+        }
+        m.code = (gn_one_op && i > first && ops[i - 1].code == EGR_OP_GN_STATS && a.P * ((a.C0 + a.C1) / a.G) <= 65536)
+                     ? MOP_GN_FUSED : MOP_GN_APPLY;
         m.u.gn.gamma = (const float*)resolve(sp, op.ptr[EGR_P_GAMMA]);
         m.u.gn.beta = (const float*)resolve(sp, op.ptr[EGR_P_BETA]);
         m.u.gn.out32 = (float*)resolve(sp, op.ptr[EGR_P_OUT32]);
@@ -950,6 +1062,7 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
       }
       default: return bad("op code");
     }
+    if (m.code == 0) continue;   // folded into the next op
     mops.push_back(m);
     if (m.code == MOP_GEMM_TC && kas[m.tc].defer) {   // the grid-wide reduction + epilogue of a split-K layer
       MegaOp rd;
@@ -962,22 +1075,33 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
     }
   }
   if (mops.empty()) return EGR_OK;
-  // weight prefetch chain: op k prefetches the weights the next weight-reading op after it will stream
-  {
+  // prefetch chain: op k prefetches [0] the weights of the next weight-reading op after it, [1] [2] the small parameter
+  // vectors of op k+1
+  if (getenv("EGR_MEGA_NO_PREFETCH") == nullptr) {
     const void* nxt_ptr = nullptr; long long nxt_bytes = 0;
     for (int k = (int)mops.size() - 1; k >= 0; --k) {
-      mops[k].pf_ptr = nxt_ptr; mops[k].pf_bytes = nxt_ptr ? nxt_bytes : 0;
-      if (mops[k].code == MOP_GEMM_TC) {
-        const GemmArgs& g = kas[mops[k].tc].g;
+      MegaOp& m = mops[k];
+      m.pf_ptr[0] = nxt_ptr; m.pf_bytes[0] = nxt_ptr ? (int)(nxt_bytes > (1ll << 30) ? (1ll << 30) : nxt_bytes) : 0;
+      if (k + 1 < (int)mops.size()) {
+        const MegaOp& nx = mops[k + 1];
+        const void* a = nullptr; const void* b = nullptr; long long na = 0, nb = 0;
+        if (nx.code == MOP_GEMM_TC && !kas[nx.tc].defer) { a = kas[nx.tc].g.bias; na = 4ll * kas[nx.tc].g.N; }
+        else if (nx.code == MOP_SPLITK_REDUCE) { a = kas[nx.tc].g.bias; na = 4ll * kas[nx.tc].g.N; }
+        else if (nx.code == MOP_GEMV) { a = nx.u.gemv.g.bias; na = 4ll * nx.u.gemv.g.N; }
+        else if (nx.code == MOP_GN_APPLY || nx.code == MOP_GN_FUSED) { a = nx.u.gn.gamma; b = nx.u.gn.beta; na = nb = 4ll * (nx.u.gn.a.C0 + nx.u.gn.a.C1); }
+        else if (nx.code == MOP_LAYERNORM) { a = nx.u.ln.gamma; b = nx.u.ln.beta; na = nb = 4ll * nx.u.ln.C; }
+        m.pf_ptr[1] = a; m.pf_bytes[1] = a ? (int)na : 0;
+        m.pf_ptr[2] = b; m.pf_bytes[2] = b ? (int)nb : 0;
+      }
+      if (m.code == MOP_GEMM_TC) {
+        const GemmArgs& g = kas[m.tc].g;
         if (!g.wz_batch) { nxt_ptr = g.W; nxt_bytes = (long long)g.ntaps * (g.wstride_z > 0 ? g.wstride_z : g.wstride_n * g.N) * 2; }
-      } else if (mops[k].code == MOP_GEMV) {
-        const GemmArgs& g = mops[k].u.gemv.g;
+      } else if (m.code == MOP_GEMV) {
+        const GemmArgs& g = m.u.gemv.g;
         nxt_ptr = g.W; nxt_bytes = (long long)g.N * g.wstride_n * 4;
       }
-      if (getenv("EGR_MEGA_NO_PREFETCH")) { nxt_ptr = nullptr; nxt_bytes = 0; }
     }
   }
-  mops.back().sync_after = 1;   // the launch ends on a full barrier (nothing of the next kernel may overtake)
   MegaRun* r = new MegaRun();
   r->first = first; r->last = last; r->n_ops = (int)mops.size(); r->n_tc = (int)kas.size();
   for (const MegaOp& m : mops) r->n_sync += m.sync_after;

@@ -36,7 +36,7 @@ stamps = (C.c_ulonglong * (4 * n_ops))()
 codes = (C.c_int * n_ops)()
 lib.egr_debug_mega_trace.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_int), C.c_int]
 n = lib.egr_debug_mega_trace(h, 0, stamps, codes, n_ops)
-NAMES = {1: "gemm_tc", 2: "gemv", 3: "gn_stats", 4: "gn_apply", 5: "layernorm", 6: "attn", 7: "geglu", 8: "cat", 9: "axpby", 10: "time_embed", 11: "splitk_red"}
+NAMES = {1: "gemm_tc", 2: "gemv", 3: "gn_stats", 4: "gn_apply", 5: "layernorm", 6: "attn", 7: "geglu", 8: "cat", 9: "axpby", 10: "time_embed", 11: "splitk_red", 12: "gn_fused"}
 mhz = 1965.0
 agg = collections.OrderedDict()
 flagged = [o.name for o in be.ops if o.flags & 1]
@@ -45,6 +45,8 @@ for k in range(n):   # a deferred split-K layer is two table entries (GEMM, redu
     if codes[k] == 11:
         names.append(names[-1] + " [reduce]")
     else:
+        if codes[k] == 12:   # one-op GroupNorm: the plan's stats op was folded into it
+            fi += 1
         names.append(flagged[fi] if fi < len(flagged) else "?")
         fi += 1
 rows = []
