@@ -527,14 +527,33 @@ def run_b200(args):
         e1.record(es)
         torch.cuda.synchronize(dev)
         t_plan = e0.elapsed_time(e1) / 1e3 / reps
-        achieved = be.tc_flops / t_tc / 1e12
+        # FLOPs of exactly the launches timed above: GEMM ops the library runs inside the persistent UNet kernel
+        # (flagged in the plan, skipped by egr_plan_run_code) are not gemm_tc_kernel launches
+        mega_on = os.environ.get("EGR_NO_MEGA") is None
+        tc_layers = [l for l in be.layer_table if l["kind"] == "tc" and not (mega_on and l.get("mega"))]
+        tc_flops = sum(l["flops"] for l in tc_layers)
+        unet_tc = [l for l in be.layer_table if l["kind"] == "tc" and l.get("mega")]
+        assert len(tc_layers) == n_tc or not mega_on, (len(tc_layers), n_tc)
+        achieved = tc_flops / t_tc / 1e12
+        # the UNet region alone (one persistent launch per diffusion step when EGR_NO_MEGA is unset)
+        flagged = [i for i, o in enumerate(be.ops) if o.flags & 1]
+        t_unet = None
+        if flagged:
+            a_, b_ = flagged[0], flagged[-1] + 1
+            for _ in range(2):
+                _abi.check(lib.egr_plan_run(handle, a_, b_, st))
+            torch.cuda.synchronize(dev)
+            e0.record(es)
+            for _ in range(reps):
+                _abi.check(lib.egr_plan_run(handle, a_, b_, st))
+            e1.record(es)
+            torch.cuda.synchronize(dev)
+            t_unet = e0.elapsed_time(e1) / 1e3 / reps
         # per-launch governing roofline: a layer with few output pixels is bound by streaming its weights, not by the
         # tensor pipe.  ideal = sum over launches of max(FLOP / tensor peak, algorithmic bytes / HBM peak), with
         # algorithmic bytes = f16 activations read once + f16 weights once + f32 output (+ f32 residual) per launch.
         ideal_s, n_hbm, alg_bytes_tc = 0.0, 0, 0.0
-        for l in be.layer_table:
-            if l["kind"] != "tc":
-                continue
+        for l in tc_layers:
             k1 = l["K"] // max(l["taps"], 1)
             byt = 2.0 * l["M"] * k1 + 2.0 * l["N"] * l["K"] + 8.0 * l["M"] * l["N"]
             t_t, t_h = l["flops"] / (pk["bf16_sustained"] * 1e12), byt / (pk["hbm"] * 1e9)
@@ -546,13 +565,20 @@ def run_b200(args):
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long pass)",
                 "traffic": (ncu_traffic("gemm_tc_kernel") or {}).get("bytes_per_launch"),
                 "traffic_note": ncu_traffic("gemm_tc_kernel"),
-                "launches_per_pass": n_tc, "flops_per_pass": be.tc_flops, "avg_launch_us": 1e6 * t_tc / max(n_tc, 1),
+                "launches_per_pass": n_tc, "flops_per_pass": tc_flops, "avg_launch_us": 1e6 * t_tc / max(n_tc, 1),
                 "gemm_share_of_plan": t_tc / t_plan, "plan_ms": 1e3 * t_plan,
                 "algorithmic_bytes_per_launch": alg_bytes_tc / max(n_tc, 1),
                 "layer_table": "roofline/flashsr_layers.json (tools/make_layer_table.py: per-op M/N/K/FLOPs/bytes of this plan, "
                                "cross-checked against forward hooks on the fp32 oracle)",
                 "composite": {"ideal_ms": 1e3 * ideal_s, "frac": ideal_s / t_tc, "hbm_bound_launches": int(n_hbm),
-                              "note": "sum over the GEMM launches of max(FLOP/tensor peak, algorithmic bytes/HBM peak) / measured"}}
+                              "note": "sum over the GEMM launches of max(FLOP/tensor peak, algorithmic bytes/HBM peak) / measured"},
+                "unet_region": None if t_unet is None else {
+                    "kernel": "unet_mega_kernel (persistent: one cooperative launch per diffusion step, grid barriers between ops)"
+                              if mega_on else "one launch per op (EGR_NO_MEGA=1)",
+                    "ms": 1e3 * t_unet, "plan_ops": len(flagged), "gemm_ops": len(unet_tc), "gemm_flops": sum(l["flops"] for l in unet_tc),
+                    "weight_bytes": sum(2.0 * l["N"] * l["K"] for l in unet_tc),
+                    "bound": "hbm (weight streaming) in the limit; measured time is op-to-op latency (see profiles/r2_mega_trace_*.txt)",
+                    "share_of_plan": t_unet / t_plan}}
         # ---- batched throughput (c3's per-GPU share: 33 chunk-channels, 4 steps), extra information
         extra = None
         if os.environ.get("EGR_BENCH_BATCHED", "1") == "1":

@@ -219,7 +219,7 @@ __device__ __noinline__ void mega_gn_apply(const MegaOp& op, int cta, int ncta, 
 // GroupNorm as ONE op: a CTA owns a whole (item, group) — moments, then normalise (+SiLU) — so no grid barrier sits between
 // the two halves.  Groups of up to 384 x 12 float4 stay in registers between the passes (one trip to L2); larger ones are
 // read twice.  Per-thread partition and reduction order depend on the op's geometry only (batch-invariant, deterministic).
-__device__ __noinline__ void mega_gn_fused(const MegaOp& op, int cta, int ncta, double (*red)[MEGA_NW], float* stat) {
+__device__ __noinline__ void mega_gn_fused(const MegaOp& op, int cta, int ncta, double (*red)[MEGA_NW], float* stat, float (*gb)[64]) {
   constexpr int REG = 12;
   const CatArgs& a = op.u.gn.a;
   const int C = a.C0 + a.C1, cpg = C / a.G, q4 = cpg >> 2;
@@ -263,6 +263,9 @@ __device__ __noinline__ void mega_gn_fused(const MegaOp& op, int cta, int ncta, 
     }
     const double ds = warp_sum((double)s), dss = warp_sum((double)ss);
     if (lane == 0) { red[0][warp] = ds; red[1][warp] = dss; }
+    // the group's gamma / beta go through shared memory: parameter loads inside the store loop below would be
+    // serialised behind the stores (the compiler keeps them in program order), one L2 trip per element
+    if (tid < cpg) { gb[0][tid] = __ldg(gamma + gi * cpg + tid); gb[1][tid] = __ldg(beta + gi * cpg + tid); }
     simt_sync();
     if (tid == 0) {
       double t = 0.0, tt = 0.0;
@@ -278,9 +281,10 @@ __device__ __noinline__ void mega_gn_fused(const MegaOp& op, int cta, int ncta, 
     const float mean = stat[0], rstd = stat[1];
     auto emit = [&](int u, const float4 v) {
       const int pl = u / q4;
-      const int c = gi * cpg + (u - pl * q4) * 4;
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const int cl = (u - pl * q4) * 4;
+      const int c = gi * cpg + cl;
+      const float4 g4 = *reinterpret_cast<const float4*>(&gb[0][cl]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&gb[1][cl]);
       float r[4] = {fmaf(v.x, rstd * g4.x, b4.x - mean * (rstd * g4.x)), fmaf(v.y, rstd * g4.y, b4.y - mean * (rstd * g4.y)),
                     fmaf(v.z, rstd * g4.z, b4.z - mean * (rstd * g4.z)), fmaf(v.w, rstd * g4.w, b4.w - mean * (rstd * g4.w))};
       if (silu) {
@@ -733,6 +737,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
   __shared__ __align__(16) TcKernelArgs s_kas[2];
   __shared__ double s_red[2][MEGA_NW];
   __shared__ float s_stat[2];
+  __shared__ __align__(16) float s_gb[2][64];
   __shared__ uint32_t s_tmem, s_last;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -811,7 +816,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) unet_mega_kernel(const MegaOp
         case MOP_GEMV: mega_gemv(op, cta, ncta); break;
         case MOP_GN_STATS: mega_gn_stats(op, cta, ncta, s_red); break;
         case MOP_GN_APPLY: mega_gn_apply(op, cta, ncta, s_stat); break;
-        case MOP_GN_FUSED: mega_gn_fused(op, cta, ncta, s_red, s_stat); break;
+        case MOP_GN_FUSED: mega_gn_fused(op, cta, ncta, s_red, s_stat, s_gb); break;
         case MOP_LAYERNORM: mega_layernorm(op, cta, ncta); break;
         case MOP_ATTN:
           if (op.u.attn.mma) {
@@ -949,11 +954,11 @@ int egr::mega_build(const Spaces& sp, const egr_op* ops, TcPrepared* const* tc, 
         static const bool gn_one_op = getenv("EGR_MEGA_GN_TWO_OPS") == nullptr;
         if (op.code == EGR_OP_GN_STATS) {
           // one-op GroupNorm: the moments are computed by the op that applies them (the next plan op, same tensor)
-          if (gn_one_op && i + 1 < last && ops[i + 1].code == EGR_OP_GN_APPLY && a.P * ((a.C0 + a.C1) / a.G) <= 65536) { m.code = 0; break; }
+          if (gn_one_op && i + 1 < last && ops[i + 1].code == EGR_OP_GN_APPLY && a.P * ((a.C0 + a.C1) / a.G) <= 65536 && (a.C0 + a.C1) / a.G <= 64) { m.code = 0; break; }
           m.code = MOP_GN_STATS;
           break;
         }
-        m.code = (gn_one_op && i > first && ops[i - 1].code == EGR_OP_GN_STATS && a.P * ((a.C0 + a.C1) / a.G) <= 65536)
+        m.code = (gn_one_op && i > first && ops[i - 1].code == EGR_OP_GN_STATS && a.P * ((a.C0 + a.C1) / a.G) <= 65536 && (a.C0 + a.C1) / a.G <= 64)
                      ? MOP_GN_FUSED : MOP_GN_APPLY;
         m.u.gn.gamma = (const float*)resolve(sp, op.ptr[EGR_P_GAMMA]);
         m.u.gn.beta = (const float*)resolve(sp, op.ptr[EGR_P_BETA]);

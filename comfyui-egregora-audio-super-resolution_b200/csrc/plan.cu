@@ -224,10 +224,20 @@ extern "C" int egr_plan_num_launches(const egr_plan* plan, int first, int last) 
   return last > first ? last - first : 0;
 }
 
+// ops that execute inside a persistent-kernel run are not launches of their own: the measurement helpers skip them
+static bool in_mega_run(const egr_plan* plan, int i) {
+  for (const MegaRun* r : plan->runs) {
+    int d[8];
+    mega_describe(r, d);
+    if (i >= d[0] && i < d[1]) return true;
+  }
+  return false;
+}
+
 extern "C" int egr_plan_run_code(egr_plan* plan, int code, void* stream) {
   if (!plan) return fail(EGR_ERR_ARG, "egr_plan_run_code: null plan");
   for (int i = 0; i < (int)plan->ops.size(); ++i) {
-    if (plan->ops[i].code != code) continue;
+    if (plan->ops[i].code != code || in_mega_run(plan, i)) continue;
     int rc = run_op(plan, i, (cudaStream_t)stream);
     if (rc) return rc;
   }
@@ -237,7 +247,7 @@ extern "C" int egr_plan_run_code(egr_plan* plan, int code, void* stream) {
 extern "C" int egr_plan_count_code(const egr_plan* plan, int code) {
   if (!plan) return 0;
   int n = 0;
-  for (const egr_op& op : plan->ops) n += (op.code == code);
+  for (int i = 0; i < (int)plan->ops.size(); ++i) n += (plan->ops[i].code == code && !in_mega_run(plan, i));
   return n;
 }
 

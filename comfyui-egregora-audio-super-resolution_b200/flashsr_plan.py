@@ -326,7 +326,7 @@ class PlanBackend:
         if not simt:
             self.tc_flops += fl
         self.layer_table.append({"name": name, "kind": "simt" if simt else "tc", "M": Bo * Ho * Wo, "N": N, "K": Kdim * ntaps,
-                                 "taps": ntaps, "flops": fl, "block_n": bn})
+                                 "taps": ntaps, "flops": fl, "block_n": bn, "mega": bool(self.mega_region)})
         self.emit(op)
         if out32 and not out16 and not transposed:
             out_pt.producer = op   # f16 copy on demand (same indices as the f32 store)

@@ -216,7 +216,8 @@ int  egr_plan_create(const egr_op* h_ops, int n_ops, void* d_workspace, size_t w
 int  egr_plan_run(egr_plan* plan, int first, int last, void* stream);
 int  egr_plan_num_launches(const egr_plan* plan, int first, int last);
 /* Measurement helpers (bench.py roofline leg): enqueue only the ops whose code == `code` (same shapes and
- * addresses as in a real run; inputs are whatever the workspace holds), and count them. */
+ * addresses as in a real run; inputs are whatever the workspace holds), and count them.  Ops that the library executes
+ * inside a persistent-kernel run (EGR_FLAG_MEGA) are not launches of their own and are skipped by both. */
 int  egr_plan_run_code(egr_plan* plan, int code, void* stream);
 int  egr_plan_count_code(const egr_plan* plan, int code);
 void egr_plan_destroy(egr_plan* plan);

@@ -23,7 +23,7 @@ dev = torch.device("cuda", 0)
 engine = N.get_engine(dev)
 win, hop = N._win_hop()
 x = bench.synth_audio(win, batch).to(dev)
-model = lambda c: engine.infer(c, lowpass=lowpass, steps=steps, seed=4321)  # noqa: E731
+model = lambda c, row0=0: engine.infer(c, lowpass=lowpass, steps=steps, seed=4321, row0=row0)  # noqa: E731
 for _ in range(2):
     N.upscale_48k(x, model)
 torch.cuda.synchronize()
