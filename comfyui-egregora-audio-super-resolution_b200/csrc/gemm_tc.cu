@@ -99,6 +99,59 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------ the CTA-pair kernel
+// cta_group::2: a cluster of two CTAs (one TPC) owns a 256-row x BLOCK_N output tile.  Each CTA stages its own 128 rows
+// of A and HALF of the weight tile (BLOCK_N/2 rows); the leader's tcgen05.mma reads both halves, so a k-step costs each
+// SM 16 KB + BLOCK_N x 64 B of L2 -> shared-memory traffic for 128 x BLOCK_N x 64 MACs — half of what the single-CTA
+// tile moves per FLOP.  That traffic, not the tensor pipe, bounds the big 3x3 layers: ncu (profiles/r2_f_ncu_full_summary)
+// shows ~8 TB/s of TMA loads at 26-40 % tensor-pipe activity, i.e. ~50 B/clk per SM, the rate B300_MICROARCH.md gives
+// for TMA service.  Same warp roles as gemm_tc_kernel (tc_roles<true>): stage barriers live in the leader, commits are
+// multicast to both CTAs, both CTAs' epilogues drain their own TMEM lanes.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ TcKernelArgs ka) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  TcSmemView sv;
+  sv.ringA = smem;
+  sv.ringB = sv.ringA + (size_t)ka.SA * ka.a_stage_bytes;
+  sv.stage_all = reinterpret_cast<float*>(sv.ringB + (size_t)ka.SB * ka.b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sv.stage_all) + 8 * STAGE_BYTES_PER_WARP);
+  sv.fullA = bars;
+  sv.emptyA = sv.fullA + ka.SA;
+  sv.fullB = sv.emptyA + ka.SA;
+  sv.emptyB = sv.fullB + ka.SB;
+  sv.acc_full = sv.emptyB + ka.SB;
+  sv.acc_empty = sv.acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sv.acc_empty + 2);
+  sv.last_flag = tmem_slot + 1;
+  const int warp = threadIdx.x >> 5;
+  const int rank = (int)cluster_ctarank();
+  if (threadIdx.x == 64) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (threadIdx.x == 0) tc_init_barriers(ka, sv);
+  if (warp == 1) {   // both CTAs of the pair, same shared-memory slot offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / TMA completion can reach them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  tc_roles<true>(&tmA, &tmB, ka, sv, tmem_base, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1), nullptr, rank);
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's shared memory and barriers stay alive until the leader's last MMA / commit has landed
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 int egr::tc_global_init() {
   if (g_encode) return EGR_OK;
@@ -109,6 +162,7 @@ int egr::tc_global_init() {
     return fail(EGR_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
   g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
   EGR_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  EGR_CUDA(cudaFuncSetAttribute(gemm_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return EGR_OK;
 }
 
@@ -211,10 +265,10 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
 
   // ---- BLOCK_N and sub-tiles per CTA: cheapest (waves x per-item cycles) under a coarse cost model
   int bn = 0, mt = 1;
+  double best = 1e30;
   if (fold) { bn = fold_bn; mt = 1; }
   else {
     const int cands[] = {256, 192, 160, 128, 96, 80, 64, 48, 32, 16};
-    double best = 1e30;
     for (int c : cands) {
       if (g.N % c) continue;
       for (int m = 1; m <= 2; ++m) {
@@ -238,15 +292,37 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     if (bn == 0) return bail(fail(EGR_ERR_ARG, "%s: no BLOCK_N fits N=%d", op.name, g.N));
   }
   if (!fold && env_int("EGR_TC_BN", 0) > 0 && g.N % env_int("EGR_TC_BN", 0) == 0) { bn = env_int("EGR_TC_BN", 0); if (mt * bn > 256) mt = 1; }
+  // ---- CTA-pair mode (gemm_tc_pair_kernel): big unsplit non-halo layers, same cost model with the pair's traffic (each
+  // SM stages 16 KB of A + BLOCK_N x 64 B of weights per k-step) and MMA pace (128 x BLOCK_N per SM)
+  int pair = 0;
+  if (!fold && !halo && splits == 1 && !g.wz_batch && !(op.flags & EGR_FLAG_MEGA) && tiles1 >= 2 && (sms & 1) == 0 &&
+      env_int("EGR_TC_NO_PAIR", 0) == 0) {
+    int pbn = 0;
+    double pbest = 1e30;
+    for (int c = 256; c >= 32; c -= 32) {
+      if (g.N % c) continue;
+      const long long items = (long long)ceil_div(tiles1, 2) * (g.N / c);
+      const long long waves = (items + sms / 2 - 1) / (sms / 2);
+      const double step_mma = 4.0 * (c > 64 ? c : 64) / 2.0;
+      const double step_mem = ((double)A_BOX_BYTES + c * 64.0) / 48.0;
+      const double step = step_mma > step_mem ? step_mma : step_mem;
+      const double epi = 600.0 + (double)c * 14.0;
+      const double item = (double)n_outer * step + 1500.0;
+      const double cost = (double)waves * (item > epi ? item : epi) + epi;
+      if (cost < pbest) { pbest = cost; pbn = c; }
+    }
+    if (pbn && (pbest < 0.95 * best || env_int("EGR_TC_FORCE_PAIR", 0))) { pair = 1; bn = pbn; mt = 1; }
+  }
   g.block_n = bn;
 
   ka.mt = mt; ka.halo = halo ? 1 : 0; ka.kchunks = kchunks; ka.tmin = tmin;
-  ka.n_iss = (env_int("EGR_TC_ONE_ISSUER", 0) == 0 && (mt == 2 || bn % 32 == 0)) ? 2 : 1;
+  ka.pair = pair;
+  ka.n_iss = (!pair && env_int("EGR_TC_ONE_ISSUER", 0) == 0 && (mt == 2 || bn % 32 == 0)) ? 2 : 1;
   ka.n_outer = n_outer; ka.n_inner = n_inner;
   ka.tiles1 = tiles1;
   ka.tiles_w = halo ? ceil_div(g.Wo, TILE_M * mt) : tiles_w128;
   ka.tiles_h = tiles_h;
-  ka.tiles_m = halo ? ka.tiles_w * tiles_h * tiles_b : ceil_div(tiles1, mt);
+  ka.tiles_m = halo ? ka.tiles_w * tiles_h * tiles_b : (pair ? ceil_div(tiles1, 2) : ceil_div(tiles1, mt));
   ka.tiles_n = g.N / bn;
   ka.splits = splits; ka.outer_per_split = ops;
   ka.fold = fold;
@@ -264,7 +340,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     ka.nboxA = mt;
   }
   ka.a_stage_bytes = ka.nboxA * ka.boxA_bytes;
-  ka.b_stage_bytes = bn * KBLK * 2;
+  ka.b_stage_bytes = (pair ? bn / 2 : bn) * KBLK * 2;   // pair mode: each CTA stages half of the weight rows
   // A map: always rank 5 (missing dims are size 1 with a harmless stride)
   long long dim[5], str[5]; int box[5];
   for (int d = 0; d < 5; ++d) { dim[d] = a.dim[d]; str[d] = a.stride[d]; }
@@ -276,7 +352,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   // B map: [K, N, Z]
   long long bdim[3] = {g.K, g.N, g.wz_batch ? (long long)g.Bo : (long long)g.ntaps};
   long long bstr[3] = {1, g.wstride_n, g.wstride_z > 0 ? g.wstride_z : g.wstride_n * g.N};
-  int bbox[3] = {KBLK, bn, 1};
+  int bbox[3] = {KBLK, pair ? bn / 2 : bn, 1};
   rc = encode_map(&p->tmB, const_cast<void*>(g.W), 3, bdim, bstr, bbox, op.name);
   if (rc) return bail(rc);
 
@@ -295,7 +371,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   ka.SA = SA; ka.SB = SB;
   p->smem_bytes = SA * ka.a_stage_bytes + SB * ka.b_stage_bytes + 8 * STAGE_BYTES_PER_WARP + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
   if (p->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: %d B of shared memory needed", op.name, p->smem_bytes));
-  p->grid = ka.n_work < sms ? ka.n_work : sms;
+  p->grid = pair ? 2 * (ka.n_work < sms / 2 ? ka.n_work : sms / 2) : (ka.n_work < sms ? ka.n_work : sms);
   p->partial_bytes = (splits > 1 && !fold) ? (size_t)ka.tiles_m * ka.tiles_n * splits * mt * TILE_M * bn * sizeof(float) : 0;
   p->n_counters = (splits > 1 && !fold) ? ka.tiles_m * ka.tiles_n : 0;
   // vector epilogue needs 16-byte aligned groups of 4 columns
@@ -345,14 +421,15 @@ int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
     return fail(EGR_ERR_STATE, "%s: split-K scratch not bound", p->name);
   TcKernelArgs ka = p->ka;
   ka.trace = g_trace_dev;
-  gemm_tc_kernel<<<p->grid, 384, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
+  if (ka.pair) gemm_tc_pair_kernel<<<p->grid, 384, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
+  else gemm_tc_kernel<<<p->grid, 384, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
   EGR_CHECK_LAUNCH(p->name);
   return EGR_OK;
 }
 
 void egr::tc_describe(const TcPrepared* p, int* o) {
   o[0] = p->ka.g.block_n; o[1] = p->ka.mt; o[2] = p->ka.splits; o[3] = p->ka.halo; o[4] = p->ka.n_work; o[5] = p->grid;
-  o[6] = p->ka.SA; o[7] = p->ka.SB + 100 * p->ka.fold;
+  o[6] = p->ka.SA; o[7] = p->ka.SB + 100 * p->ka.fold + 1000 * p->ka.pair;
 }
 
 void egr::tc_free(TcPrepared* p) { delete p; }

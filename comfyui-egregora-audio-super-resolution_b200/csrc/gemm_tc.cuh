@@ -40,6 +40,8 @@ struct alignas(16) TcKernelArgs {   // (16-byte multiple: the persistent kernel 
   int tiles1, tiles_w, tiles_h, tiles_m, tiles_n, splits, outer_per_split, n_work;
   FastDiv d_splits, d_tiles_n, d_tiles_w, d_tiles_h, d_kchunks, d_bw, d_bh, d_c4n;
   int acc_cols;  // TMEM columns of one accumulator buffer = mt * block_n (x splits when folded)
+  int pair;      // CTA-pair mode (cta_group::2): a cluster of two CTAs owns a 256-row x BLOCK_N tile — each loads its own
+                 // 128 rows of A and HALF of the weight tile, the leader issues M=256 MMAs that read both halves
   int defer;     // split-K partials are reduced by a separate, grid-wide pass (tc_reduce_distributed: the persistent kernel)
   int fold;      // split-K folded into ONE work item: each split accumulates into its own TMEM region, summed in the epilogue
   int nbuf;      // accumulator buffers in TMEM: 2 when 2 * acc_cols <= 512, else 1
@@ -81,6 +83,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef EGR_TC_GUARD   // bring-up build (make GUARD=1): a wait that never completes traps instead of hanging the GPU
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    if (spins > (1u << 24)) __trap();
+  }
+#else
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
@@ -88,6 +101,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -98,6 +112,45 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants: the barrier that collects a stage's transaction bytes lives in the LEADER CTA
+// (cluster rank 0); both CTAs' producers arrive on it remotely, both CTAs' TMA loads complete on it
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {   // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -193,7 +246,7 @@ struct WorkItem {
   int w0[2], h0[2], b0[2];
 };
 
-__device__ __forceinline__ void decode_work(const TcKernelArgs& ka, int w, WorkItem& wi) {
+__device__ __forceinline__ void decode_work(const TcKernelArgs& ka, int w, WorkItem& wi, int rank = 0) {
   const GemmArgs& g = ka.g;
   int t = w;
   wi.ks = 0;
@@ -215,7 +268,7 @@ __device__ __forceinline__ void decode_work(const TcKernelArgs& ka, int w, WorkI
       wi.w0[m] = (q - q1 * ka.tiles_w) * (TILE_M * ka.mt) + TILE_M * m; q = q1;
       valid = wi.w0[m] < g.Wo;
     } else {
-      q = wi.tm * ka.mt + m;
+      q = ka.pair ? wi.tm * 2 + rank : wi.tm * ka.mt + m;   // pair mode: one 128-row tile per CTA of the pair
       valid = q < ka.tiles1;
       const int q1 = fdiv(q, ka.d_tiles_w);
       wi.w0[m] = (q - q1 * ka.tiles_w) * g.bw; q = q1;
@@ -400,8 +453,9 @@ __device__ __forceinline__ void tc_init_barriers(const TcKernelArgs& ka, const T
   // halo mode: A and B rings advance at different rates and have their own barriers; otherwise the A stage rides
   // on the B barriers (both producers arrive on fullB, one wait and one commit per k-step for the issuers)
   for (int s = 0; s < ka.SA; ++s) { mbar_init(&sv.fullA[s], 1); mbar_init(&sv.emptyA[s], (uint32_t)ka.n_iss); }
-  for (int s = 0; s < ka.SB; ++s) { mbar_init(&sv.fullB[s], ka.halo ? 1u : 2u); mbar_init(&sv.emptyB[s], (uint32_t)ka.n_iss); }
-  for (int s = 0; s < 2; ++s) { mbar_init(&sv.acc_full[s], (uint32_t)ka.n_iss); mbar_init(&sv.acc_empty[s], 8); }
+  // pair mode: four producers (two per CTA) arrive on the leader's stage barrier, sixteen epilogue warps hand a buffer back
+  for (int s = 0; s < ka.SB; ++s) { mbar_init(&sv.fullB[s], ka.pair ? 4u : (ka.halo ? 1u : 2u)); mbar_init(&sv.emptyB[s], (uint32_t)ka.n_iss); }
+  for (int s = 0; s < 2; ++s) { mbar_init(&sv.acc_full[s], (uint32_t)ka.n_iss); mbar_init(&sv.acc_empty[s], ka.pair ? 16u : 8u); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -418,8 +472,10 @@ __device__ __forceinline__ void tc_init_barrier_k(const TcKernelArgs& ka, const 
 
 // All 12 warps of the CTA call this with initialised barriers and allocated TMEM; CTA `cta` of `ncta` takes the work items
 // cta, cta + ncta, ...  Returns when every role has finished its items (no trailing CTA barrier).
+template <bool PAIR = false>
 __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensorMap* tmBp, const TcKernelArgs& ka,
-                                         const TcSmemView& sv, uint32_t tmem_base, int cta, int ncta, unsigned long long* tr) {
+                                         const TcSmemView& sv, uint32_t tmem_base, int cta, int ncta, unsigned long long* tr,
+                                         int rank = 0) {
   const GemmArgs& g = ka.g;
   const int BN = g.block_n;
   uint8_t* const ringA = sv.ringA;
@@ -434,13 +490,15 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
     // ============================================================ A producer (whole warp, one elected lane issues)
     if (tr && lane == 0) tr[5] = clock64();
     const uint32_t ringA_u = smem_u32(ringA);
-    const uint32_t fullA_u = smem_u32(ka.halo ? fullA : fullB), emptyA_u = smem_u32(ka.halo ? emptyA : emptyB);
+    // pair mode: the "full" barrier of a stage is the LEADER's (both CTAs' loads complete on it); "empty" stays local
+    const uint32_t fullA_l = smem_u32(ka.halo ? fullA : fullB);
+    const uint32_t fullA_u = PAIR ? mapa_u32(fullA_l, 0u) : fullA_l, emptyA_u = smem_u32(ka.halo ? emptyA : emptyB);
     int sa = 0;
     uint32_t pa = 0;  // ring phase
     int tcount = 0;
     for (int w = cta; w < ka.n_work; w += ncta) {
       WorkItem wi;
-      decode_work(ka, w, wi);
+      decode_work(ka, w, wi, rank);
       const int nA = ka.halo ? ka.nboxA : wi.mt_eff;
       // per-sub-tile base coordinates, selected without dynamic register indexing
       int cb[2][5];
@@ -458,7 +516,8 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
         const uint32_t dstA = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
         if (elect_one()) {
           if (tr && tcount < 250) tr[16 + 2 * tcount] = clock64();
-          mbar_expect_tx(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
+          if (PAIR) mbar_expect_tx_cluster(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
+          else mbar_expect_tx(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
           if (ka.halo) {
             int c[5];
 #pragma unroll
@@ -477,9 +536,14 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
             t[0] += kc * KBLK;
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-              if (m < nA)
-                tma_load_5d(dstA + (uint32_t)m * A_BOX_BYTES, tmAp, fullA_u + 8 * sa, t[0] + cb[m][0], t[1] + cb[m][1],
-                            t[2] + cb[m][2], t[3] + cb[m][3], t[4] + cb[m][4]);
+              if (m < nA) {
+                if (PAIR)
+                  tma_load_5d_2sm(dstA + (uint32_t)m * A_BOX_BYTES, tmAp, fullA_u + 8 * sa, t[0] + cb[m][0], t[1] + cb[m][1],
+                                  t[2] + cb[m][2], t[3] + cb[m][3], t[4] + cb[m][4]);
+                else
+                  tma_load_5d(dstA + (uint32_t)m * A_BOX_BYTES, tmAp, fullA_u + 8 * sa, t[0] + cb[m][0], t[1] + cb[m][1],
+                              t[2] + cb[m][2], t[3] + cb[m][3], t[4] + cb[m][4]);
+              }
             }
           }
           if (tr && tcount < 250) tr[16 + 2 * tcount + 1] = clock64();
@@ -492,22 +556,28 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
     }
   } else if (warp == 6) {
     // ============================================================ B producer (weights / batch-indexed operand)
-    const uint32_t ringB_u = smem_u32(ringB), fullB_u = smem_u32(fullB), emptyB_u = smem_u32(emptyB);
+    const uint32_t ringB_u = smem_u32(ringB), emptyB_u = smem_u32(emptyB);
+    const uint32_t fullB_u = PAIR ? mapa_u32(smem_u32(fullB), 0u) : smem_u32(fullB);
     int sb = 0;
     uint32_t pb = 0;
     for (int w = cta; w < ka.n_work; w += ncta) {
       WorkItem wi;
-      decode_work(ka, w, wi);
-      const int n0 = wi.tn * BN;
+      decode_work(ka, w, wi, rank);
+      const int n0 = wi.tn * BN + (PAIR ? rank * (BN >> 1) : 0);   // pair mode: this CTA stages its half of the weight rows
       int tap = 0, kc = wi.o_begin;
       if (!ka.halo) { tap = fdiv(wi.o_begin, ka.d_kchunks); kc = wi.o_begin - tap * ka.kchunks; }
       for (int io = wi.o_begin; io < wi.o_end; ++io) {
         for (int ii = 0; ii < ka.n_inner; ++ii) {
           mbar_wait(emptyB_u + 8 * sb, pb ^ 1u);
           if (elect_one()) {
-            mbar_expect_tx(fullB_u + 8 * sb, (uint32_t)ka.b_stage_bytes);
             const int z = g.wz_batch ? wi.b0[0] : (ka.halo ? ii : tap);
-            tma_load_3d(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, tmBp, fullB_u + 8 * sb, kc * KBLK, n0, z);
+            if (PAIR) {
+              mbar_expect_tx_cluster(fullB_u + 8 * sb, (uint32_t)ka.b_stage_bytes);
+              tma_load_3d_2sm(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, tmBp, fullB_u + 8 * sb, kc * KBLK, n0, z);
+            } else {
+              mbar_expect_tx(fullB_u + 8 * sb, (uint32_t)ka.b_stage_bytes);
+              tma_load_3d(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, tmBp, fullB_u + 8 * sb, kc * KBLK, n0, z);
+            }
           }
           __syncwarp();
           if (++sb == ka.SB) { sb = 0; pb ^= 1u; }
@@ -522,7 +592,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
     // tile (a sub-tile when MT = 2, a BLOCK_N/2 column half when MT = 1): disjoint TMEM accumulators, so no ordering
     // between them is needed; stages are released when both have committed (empty barriers count n_iss arrivals).
     const int u = warp == 1 ? 0 : 1;
-    if (u < ka.n_iss) {
+    if (u < ka.n_iss && (!PAIR || rank == 0)) {   // pair mode: only the leader CTA issues (M = 256 across both CTAs)
       const bool split_n = (ka.n_iss == 2 && ka.mt == 1);
       const int NI = split_n ? (BN >> 1) : BN;  // N of one instruction
       const int m_lo = (ka.n_iss == 2 && ka.mt == 2) ? u : 0;
@@ -530,7 +600,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
       const uint32_t b_off = split_n ? (uint32_t)(u * NI * 128) : 0u;  // rows of the B stage owned by this issuer
       const uint32_t c_off = split_n ? (uint32_t)(u * NI) : 0u;          // accumulator columns owned by this issuer
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(NI >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(NI >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TILE_M : TILE_M) >> 4) << 24);
       const uint32_t ringA_u = smem_u32(ringA), ringB_u = smem_u32(ringB);
       const uint32_t fullA_u = smem_u32(fullA), emptyA_u = smem_u32(emptyA), fullB_u = smem_u32(fullB), emptyB_u = smem_u32(emptyB);
       const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
@@ -539,7 +609,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
       int it = 0, tcount = 0;
       for (int w = cta; w < ka.n_work; w += ncta, ++it) {
         WorkItem wi;
-        decode_work(ka, w, wi);
+        decode_work(ka, w, wi, rank);
         const int buf = ka.nbuf == 2 ? (it & 1) : 0;
         const int use = ka.nbuf == 2 ? (it >> 1) : it;
         uint32_t acc = tmem_base + (uint32_t)(buf * ka.acc_cols) + c_off;
@@ -564,19 +634,20 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
               if (tr && u == 0 && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
 #pragma unroll
               for (int m = 0; m < 2; ++m) {
-                if (m >= m_lo && m < m_hi && m < wi.mt_eff) {
+                if (m >= m_lo && m < m_hi && (PAIR ? m == 0 : m < wi.mt_eff)) {
                   const uint64_t adesc = make_smem_desc(aBase + shift + (uint32_t)m * A_BOX_BYTES);
 #pragma unroll
                   for (int k = 0; k < KBLK / 16; ++k) {
                     // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
-                    tc_mma_f16(acc + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                    if (PAIR) tc_mma_f16_2sm(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                    else tc_mma_f16(acc + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
                   }
                 }
               }
-              tc_commit(emptyB_u + 8 * sb);
+              if (PAIR) tc_commit_2sm(emptyB_u + 8 * sb); else tc_commit(emptyB_u + 8 * sb);
               if (lastB) {
                 if (ka.halo) tc_commit(emptyA_u + 8 * sa);
-                if (io == wi.o_end - 1) tc_commit(accF_u + 8 * buf);
+                if (io == wi.o_end - 1) { if (PAIR) tc_commit_2sm(accF_u + 8 * buf); else tc_commit(accF_u + 8 * buf); }
                 if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
               }
             }
@@ -599,7 +670,8 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
     const int ew = eset * 4 + (eset ? warp - 8 : warp - 2);   // 0..7
     const int et = ew * 32 + lane;                             // epilogue thread id 0..255
     float* stg = stage_all + (size_t)ew * (32 * STAGE_LD);
-    const uint32_t accF_u = smem_u32(acc_full), accE_u = smem_u32(acc_empty);
+    // pair mode: the accumulator-drained barrier is the leader's (its MMA warp waits for the epilogues of BOTH CTAs)
+    const uint32_t accF_u = smem_u32(acc_full), accE_u = (PAIR && rank != 0) ? mapa_u32(smem_u32(acc_empty), 0u) : smem_u32(acc_empty);
     const int rsub = lane >> 3, c4 = (lane & 7) * 4;  // vector pass: 4 rows x 8 float4 per instruction
     const int nblk = (BN + 31) >> 5;
     const bool has_resid = g.resid != nullptr, has_bias = g.bias != nullptr, has_out16 = g.out16 != nullptr;
@@ -607,7 +679,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
     int it = 0;
     for (int w = cta; w < ka.n_work; w += ncta, ++it) {
       WorkItem wi;
-      decode_work(ka, w, wi);
+      decode_work(ka, w, wi, rank);
       const int buf = ka.nbuf == 2 ? (it & 1) : 0;
       const int n0 = wi.tn * BN;
       mbar_wait(accF_u + 8 * buf, ((uint32_t)(ka.nbuf == 2 ? (it >> 1) : it)) & 1u);
@@ -621,7 +693,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
       const int last_bi = ntot - 1 - ((ntot - 1 - eset) & 1);  // last block of this set (< eset when it has none)
       if (last_bi < eset) {  // nothing to read for this warp: hand the buffer back right away
         tc_fence_before();
-        if (lane == 0) mbar_arrive(accE_u + 8 * buf);
+        if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_cluster(accE_u + 8 * buf); else mbar_arrive(accE_u + 8 * buf); }
       }
       // NOTE: r[] and the other per-block arrays must only be indexed by compile-time constants (fully unrolled
       // loops): one dynamic index sends the whole array to local memory.
@@ -712,7 +784,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
         tc_wait_ld();
         if (bi == last_bi) {  // last TMEM read of this buffer by this warp: hand it back to the MMA warps
           tc_fence_before();
-          if (lane == 0) mbar_arrive(accE_u + 8 * buf);
+          if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_cluster(accE_u + 8 * buf); else mbar_arrive(accE_u + 8 * buf); }
         }
         if (!any_ok) continue;
         if (g.transposed && !part) {
