@@ -301,6 +301,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     double pbest = 1e30;
     for (int c = 256; c >= 32; c -= 32) {
       if (g.N % c) continue;
+      if (env_int("EGR_TC_PAIR_BN", 0) > 0 && c != env_int("EGR_TC_PAIR_BN", 0)) continue;
       const long long items = (long long)ceil_div(tiles1, 2) * (g.N / c);
       const long long waves = (items + sms / 2 - 1) / (sms / 2);
       const double step_mma = 4.0 * (c > 64 ? c : 64) / 2.0;
@@ -317,7 +318,9 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
 
   ka.mt = mt; ka.halo = halo ? 1 : 0; ka.kchunks = kchunks; ka.tmin = tmin;
   ka.pair = pair;
-  ka.n_iss = (!pair && env_int("EGR_TC_ONE_ISSUER", 0) == 0 && (mt == 2 || bn % 32 == 0)) ? 2 : 1;
+  // two issuers: each owns a sub-tile (MT = 2) or a column half (MT = 1; in pair mode the halves must be whole 32-column
+  // blocks per CTA half: BLOCK_N a multiple of 128)
+  ka.n_iss = (env_int("EGR_TC_ONE_ISSUER", 0) == 0 && (pair ? bn % 128 == 0 : (mt == 2 || bn % 32 == 0))) ? 2 : 1;
   ka.n_outer = n_outer; ka.n_inner = n_inner;
   ka.tiles1 = tiles1;
   ka.tiles_w = halo ? ceil_div(g.Wo, TILE_M * mt) : tiles_w128;
@@ -368,6 +371,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     SA = budget / (ka.a_stage_bytes + ka.b_stage_bytes); if (SA > 10) SA = 10; if (SA < 2) SA = 2;
     SB = SA;
   }
+  if (env_int("EGR_TC_STAGES", 0) >= 2 && !halo) { SA = SA < env_int("EGR_TC_STAGES", 0) ? SA : env_int("EGR_TC_STAGES", 0); SB = SA; }
   ka.SA = SA; ka.SB = SB;
   p->smem_bytes = SA * ka.a_stage_bytes + SB * ka.b_stage_bytes + 8 * STAGE_BYTES_PER_WARP + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
   if (p->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: %d B of shared memory needed", op.name, p->smem_bytes));

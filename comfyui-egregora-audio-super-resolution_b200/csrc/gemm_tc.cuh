@@ -453,8 +453,8 @@ __device__ __forceinline__ void tc_init_barriers(const TcKernelArgs& ka, const T
   // halo mode: A and B rings advance at different rates and have their own barriers; otherwise the A stage rides
   // on the B barriers (both producers arrive on fullB, one wait and one commit per k-step for the issuers)
   for (int s = 0; s < ka.SA; ++s) { mbar_init(&sv.fullA[s], 1); mbar_init(&sv.emptyA[s], (uint32_t)ka.n_iss); }
-  // pair mode: four producers (two per CTA) arrive on the leader's stage barrier, sixteen epilogue warps hand a buffer back
-  for (int s = 0; s < ka.SB; ++s) { mbar_init(&sv.fullB[s], ka.pair ? 4u : (ka.halo ? 1u : 2u)); mbar_init(&sv.emptyB[s], (uint32_t)ka.n_iss); }
+  // pair mode: the leader's two producers arrive on its stage barrier (expecting both CTAs' bytes), sixteen epilogue warps hand a buffer back
+  for (int s = 0; s < ka.SB; ++s) { mbar_init(&sv.fullB[s], ka.halo ? 1u : 2u); mbar_init(&sv.emptyB[s], (uint32_t)ka.n_iss); }
   for (int s = 0; s < 2; ++s) { mbar_init(&sv.acc_full[s], (uint32_t)ka.n_iss); mbar_init(&sv.acc_empty[s], ka.pair ? 16u : 8u); }
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -516,8 +516,17 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
         const uint32_t dstA = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
         if (elect_one()) {
           if (tr && tcount < 250) tr[16 + 2 * tcount] = clock64();
-          if (PAIR) mbar_expect_tx_cluster(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
-          else mbar_expect_tx(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
+          if (PAIR) {
+            // only the LEADER arrives, expecting the bytes of both CTAs (the peer's loads complete on the leader's barrier
+            // too).  A remote release-arrive per stage from the peer throttled the whole pair to one k-step per ~1500
+            // cycles whatever the tile width or ring depth (round-2 probe: 474 / 777 / 1517 us at BLOCK_N 256 / 128 / 64).
+            if (rank == 0) {
+              const int peer_ok = (wi.tm * 2 + 1 < ka.tiles1) ? 1 : 0;
+              mbar_expect_tx(fullA_l + 8 * sa, (uint32_t)((nA + peer_ok) * ka.boxA_bytes));
+            }
+          } else {
+            mbar_expect_tx(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
+          }
           if (ka.halo) {
             int c[5];
 #pragma unroll
@@ -572,7 +581,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
           if (elect_one()) {
             const int z = g.wz_batch ? wi.b0[0] : (ka.halo ? ii : tap);
             if (PAIR) {
-              mbar_expect_tx_cluster(fullB_u + 8 * sb, (uint32_t)ka.b_stage_bytes);
+              if (rank == 0) mbar_expect_tx(smem_u32(fullB) + 8 * sb, 2u * (uint32_t)ka.b_stage_bytes);   // both halves
               tma_load_3d_2sm(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, tmBp, fullB_u + 8 * sb, kc * KBLK, n0, z);
             } else {
               mbar_expect_tx(fullB_u + 8 * sb, (uint32_t)ka.b_stage_bytes);
@@ -597,7 +606,10 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
       const int NI = split_n ? (BN >> 1) : BN;  // N of one instruction
       const int m_lo = (ka.n_iss == 2 && ka.mt == 2) ? u : 0;
       const int m_hi = (ka.n_iss == 2 && ka.mt == 2) ? u + 1 : ka.mt;
-      const uint32_t b_off = split_n ? (uint32_t)(u * NI * 128) : 0u;  // rows of the B stage owned by this issuer
+      // rows of the B stage owned by this issuer.  Pair mode: an instruction of width NI takes NI/2 weight rows from EACH
+      // CTA's stage, so issuer u starts at local row u*NI/2 (its accumulator columns then hold the leader's rows
+      // u*NI/2.. first and the peer's rows u*NI/2.. second: the epilogue maps columns back, see `nb` there)
+      const uint32_t b_off = split_n ? (uint32_t)((PAIR ? u * (NI >> 1) : u * NI) * 128) : 0u;
       const uint32_t c_off = split_n ? (uint32_t)(u * NI) : 0u;          // accumulator columns owned by this issuer
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(NI >> 3) << 17) | ((uint32_t)((PAIR ? 2 * TILE_M : TILE_M) >> 4) << 24);
@@ -743,7 +755,12 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
             }
           }
         }
-        const int nb = n0 + cb;
+        int nb = n0 + cb;
+        if (PAIR && ka.n_iss == 2) {   // two issuers in pair mode: column block -> (issuer, CTA half, row) -> output column
+          const int NI = BN >> 1, q = NI >> 1;
+          const int iu = cb / NI, r = cb - iu * NI, hf = r / q;
+          nb = n0 + hf * (BN >> 1) + iu * q + (r - hf * q);
+        }
         const int n = nb + c4;
         const bool col_ok = c4 < ncols && n < g.N;
         // bias / residual loads of the vector path are issued under the TMEM load
