@@ -297,20 +297,23 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   int pair = 0;
   if (!fold && !halo && splits == 1 && !g.wz_batch && !(op.flags & EGR_FLAG_MEGA) && tiles1 >= 2 && (sms & 1) == 0 &&
       env_int("EGR_TC_NO_PAIR", 0) == 0) {
+    // Measured (round-2 probes, tools/gemm_probe.py, batch 8): a pair k-step costs ~520 + 2.3 * BLOCK_N cycles (a 2-CTA
+    // MMA has a ~160-190 cycle floor whatever its N, and wait + commit are not hidden behind the MMAs), so only the
+    // 256-wide tile pays: 1090 / 1060 / 1150 TF/s against 935 / 940 / 1010 single-CTA on the 1024-, 256- and 512-channel
+    // 3x3 layers, while BLOCK_N = 128 pairs lose (670 against 820).  Rule: pair mode iff a 256-wide tile divides N
+    // and the pair items fill at least 80 % of their waves (a function of the launch only: results do not depend on it).
     int pbn = 0;
     double pbest = 1e30;
     for (int c = 256; c >= 32; c -= 32) {
       if (g.N % c) continue;
       if (env_int("EGR_TC_PAIR_BN", 0) > 0 && c != env_int("EGR_TC_PAIR_BN", 0)) continue;
+      if (env_int("EGR_TC_PAIR_BN", 0) == 0 && c != 256) continue;
       const long long items = (long long)ceil_div(tiles1, 2) * (g.N / c);
       const long long waves = (items + sms / 2 - 1) / (sms / 2);
-      const double step_mma = 4.0 * (c > 64 ? c : 64) / 2.0;
-      const double step_mem = ((double)A_BOX_BYTES + c * 64.0) / 48.0;
-      const double step = step_mma > step_mem ? step_mma : step_mem;
-      const double epi = 600.0 + (double)c * 14.0;
-      const double item = (double)n_outer * step + 1500.0;
-      const double cost = (double)waves * (item > epi ? item : epi) + epi;
-      if (cost < pbest) { pbest = cost; pbn = c; }
+      const double fill = (double)items / (double)(waves * (sms / 2));
+      if (fill < 0.8 && env_int("EGR_TC_FORCE_PAIR", 0) == 0) continue;
+      pbest = 0.0; pbn = c;
+      break;
     }
     if (pbn && (pbest < 0.95 * best || env_int("EGR_TC_FORCE_PAIR", 0))) { pair = 1; bn = pbn; mt = 1; }
   }
@@ -320,7 +323,10 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   ka.pair = pair;
   // two issuers: each owns a sub-tile (MT = 2) or a column half (MT = 1; in pair mode the halves must be whole 32-column
   // blocks per CTA half: BLOCK_N a multiple of 128)
-  ka.n_iss = (env_int("EGR_TC_ONE_ISSUER", 0) == 0 && (pair ? bn % 128 == 0 : (mt == 2 || bn % 32 == 0))) ? 2 : 1;
+  // (pair mode: ONE issuer — two issuers on column halves double the number of 2-CTA MMAs, each with its ~170-cycle floor:
+  //  950 against 1090 TF/s measured; EGR_TC_PAIR_TWO_ISSUERS=1 keeps the variant reachable)
+  ka.n_iss = (env_int("EGR_TC_ONE_ISSUER", 0) == 0 &&
+              (pair ? (bn % 128 == 0 && env_int("EGR_TC_PAIR_TWO_ISSUERS", 0)) : (mt == 2 || bn % 32 == 0))) ? 2 : 1;
   ka.n_outer = n_outer; ka.n_inner = n_inner;
   ka.tiles1 = tiles1;
   ka.tiles_w = halo ? ceil_div(g.Wo, TILE_M * mt) : tiles_w128;
