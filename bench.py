@@ -597,7 +597,7 @@ def run_b200(args):
                 e1.record()
                 torch.cuda.synchronize(dev)
                 tb = e0.elapsed_time(e1) / 1e3
-                extra = {"workload": "c3 per-GPU share: 33 chunk-channels x 5.12 s, 4 diffusion steps, sub-batches of <= 8",
+                extra = {"workload": f"c3 per-GPU share: 33 chunk-channels x 5.12 s, 4 diffusion steps, sub-batches of <= {engine.max_batch}",
                          "chunk_channels_per_s": nb / tb, "rtf_mono_equiv": nb * win / N.REQ_SR / tb, "seconds": tb}
             except Exception as e:  # pragma: no cover
                 extra = {"error": str(e)[:200]}

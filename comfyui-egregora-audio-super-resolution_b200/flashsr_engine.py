@@ -28,7 +28,10 @@ class FlashSREngine:
         self.spec = spec or M.default_spec()
         # No checkpoint exists in this environment: seeded random weights of the spec'd architecture.
         self.weights = weights if weights is not None else M.init_weights(self.spec, seed)
-        self.max_batch = int(max_batch or os.environ.get("EGREGORA_FLASHSR_BATCH", "8"))
+        # chunk-channels per plan launch.  The UNet's time barely grows with the batch (latency-bound: 4.5 ms at 1, 6.7 ms at
+        # 8, 9.7 ms at 16 per step) while VAE / vocoder scale linearly, so larger sub-batches amortise it: c3 on one GPU
+        # 192 -> 204 -> 208 x real-time at 8 / 12 / 16 (round-2 measurement); the workspace is 5.2 GB at 16.
+        self.max_batch = int(max_batch or os.environ.get("EGREGORA_FLASHSR_BATCH", "16"))
         self.debug = debug
         self.blob = WeightBlob()
         # one dry walk (batch 1, lowpass on) packs every weight/constant the graph can touch
