@@ -304,7 +304,15 @@ def upscale_48k(x: torch.Tensor, chunk_model, *, shard: bool = True, device: Opt
     if hi > lo:
         # only the samples this rank's spans cover cross PCIe (1/world of the clip plus one overlap)
         s0, s1 = mine[0][0], mine[-1][0] + mine[-1][1]
-        x_dev = x[:, s0:s1].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if x.is_cuda:
+            x_dev = x[:, s0:s1].to(torch.float32).contiguous()
+        else:
+            # channel by channel: each row slice of the (pinned) host clip is contiguous, so each copy is one DMA at
+            # PCIe speed; the 2-D slice as a whole is strided and torch would stage it through a pageable temporary
+            # (round 2, N=2: 56 ms for 115 MB instead of 2.3 ms)
+            x_dev = torch.empty((C, s1 - s0), dtype=torch.float32, device=dev)
+            for c in range(C):
+                x_dev[c].copy_(x[c, s0:s1], non_blocking=True)
         _mark(marks, "h2d")
         chunks = gather_chunks(x_dev, [(s - s0, L) for s, L in mine], win)
         _mark(marks, "gather")

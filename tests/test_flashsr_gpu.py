@@ -94,7 +94,7 @@ def full(cuda_dev):
     from egregora_b200.flashsr_engine import FlashSREngine
     spec = M.default_spec()
     W = M.init_weights(spec, 0)
-    return spec, W, FlashSREngine(cuda_dev, spec, W, max_batch=8)
+    return spec, W, FlashSREngine(cuda_dev, spec, W, max_batch=16)
 
 
 def _bench_audio(spec, B):
@@ -147,15 +147,16 @@ def test_c3_subbatch_full_spec_vs_oracle(full, cuda_dev):
 
 def test_full_spec_rows_are_bit_identical_alone_and_batched(full, cuda_dev):
     """split-K is a per-layer constant, noise is keyed by global row -> a chunk-channel's output does not
-    depend on the batch it ran in (1, 7 or 8 rows), nor on the sub-batch split (9 rows -> 5 + 4)."""
+    depend on the batch it ran in (1, 7, 8 or 16 rows), nor on the sub-batch split (18 rows -> 9 + 9)."""
     spec, W, eng = full
-    wav = _bench_audio(spec, 9).to(cuda_dev)
-    y9 = eng.infer(wav, lowpass=True, steps=1, seed=4321)            # sub-batches 5 + 4
+    wav = _bench_audio(spec, 18).to(cuda_dev)
+    y18 = eng.infer(wav, lowpass=True, steps=1, seed=4321)           # sub-batches 9 + 9
+    y16 = eng.infer(wav[:16], lowpass=True, steps=1, seed=4321)      # one launch of 16 (the engine's default sub-batch)
     y7 = eng.infer(wav[:7], lowpass=True, steps=1, seed=4321)
     y8 = eng.infer(wav[:8], lowpass=True, steps=1, seed=4321)
     y1 = eng.infer(wav[6:7], lowpass=True, steps=1, seed=4321, row0=6)
-    assert torch.equal(y9[:7], y7) and torch.equal(y8[:7], y7)
+    assert torch.equal(y18[:16], y16) and torch.equal(y16[:8], y8) and torch.equal(y8[:7], y7)
     assert torch.equal(y1, y7[6:7]), float((y1 - y7[6:7]).abs().max())
-    # a sharded run: "rank 1" owns rows 5..8 and numbers its noise from row0 = 5
-    assert torch.equal(eng.infer(wav[5:], lowpass=True, steps=1, seed=4321, row0=5), y9[5:])
-    assert 0.005 < float(y9.pow(2).mean().sqrt()) < 0.9
+    # a sharded run: "rank 1" owns rows 10..17 and numbers its noise from row0 = 10
+    assert torch.equal(eng.infer(wav[10:], lowpass=True, steps=1, seed=4321, row0=10), y18[10:])
+    assert 0.005 < float(y18.pow(2).mean().sqrt()) < 0.9
