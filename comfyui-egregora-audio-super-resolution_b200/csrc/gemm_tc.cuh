@@ -46,6 +46,7 @@ struct alignas(16) TcKernelArgs {   // (16-byte multiple: the persistent kernel 
   int fold;      // split-K folded into ONE work item: each split accumulates into its own TMEM region, summed in the epilogue
   int nbuf;      // accumulator buffers in TMEM: 2 when 2 * acc_cols <= 512, else 1
   int vec_ok, need_crop, epi_plain;
+  int dbg;       // timing experiments only (EGR_TC_DBG_SKIP): bit 0 = no A loads, bit 1 = no B loads (results are garbage)
   float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
   unsigned int* counters;  // one per output tile, zero between launches
   unsigned long long* trace;  // debug: clock64() stamps of CTA 0 when non-null
@@ -522,12 +523,13 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
             // cycles whatever the tile width or ring depth (round-2 probe: 474 / 777 / 1517 us at BLOCK_N 256 / 128 / 64).
             if (rank == 0) {
               const int peer_ok = (wi.tm * 2 + 1 < ka.tiles1) ? 1 : 0;
-              mbar_expect_tx(fullA_l + 8 * sa, (uint32_t)((nA + peer_ok) * ka.boxA_bytes));
+              mbar_expect_tx(fullA_l + 8 * sa, (ka.dbg & 1) ? 0u : (uint32_t)((nA + peer_ok) * ka.boxA_bytes));
             }
           } else {
-            mbar_expect_tx(fullA_u + 8 * sa, (uint32_t)(nA * ka.boxA_bytes));
+            mbar_expect_tx(fullA_u + 8 * sa, (ka.dbg & 1) ? 0u : (uint32_t)(nA * ka.boxA_bytes));
           }
-          if (ka.halo) {
+          if (ka.dbg & 1) {
+          } else if (ka.halo) {
             int c[5];
 #pragma unroll
             for (int d = 0; d < 5; ++d) c[d] = cb[0][d] + (g.dimW == d ? ka.tmin : 0);
@@ -581,11 +583,11 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
           if (elect_one()) {
             const int z = g.wz_batch ? wi.b0[0] : (ka.halo ? ii : tap);
             if (PAIR) {
-              if (rank == 0) mbar_expect_tx(smem_u32(fullB) + 8 * sb, 2u * (uint32_t)ka.b_stage_bytes);   // both halves
-              tma_load_3d_2sm(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, tmBp, fullB_u + 8 * sb, kc * KBLK, n0, z);
+              if (rank == 0) mbar_expect_tx(smem_u32(fullB) + 8 * sb, (ka.dbg & 2) ? 0u : 2u * (uint32_t)ka.b_stage_bytes);   // both halves
+              if (!(ka.dbg & 2)) tma_load_3d_2sm(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, tmBp, fullB_u + 8 * sb, kc * KBLK, n0, z);
             } else {
-              mbar_expect_tx(fullB_u + 8 * sb, (uint32_t)ka.b_stage_bytes);
-              tma_load_3d(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, tmBp, fullB_u + 8 * sb, kc * KBLK, n0, z);
+              mbar_expect_tx(fullB_u + 8 * sb, (ka.dbg & 2) ? 0u : (uint32_t)ka.b_stage_bytes);
+              if (!(ka.dbg & 2)) tma_load_3d(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes, tmBp, fullB_u + 8 * sb, kc * KBLK, n0, z);
             }
           }
           __syncwarp();
