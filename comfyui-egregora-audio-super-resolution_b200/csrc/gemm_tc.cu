@@ -380,6 +380,10 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   if (env_int("EGR_TC_STAGES", 0) >= 2 && !halo) { SA = SA < env_int("EGR_TC_STAGES", 0) ? SA : env_int("EGR_TC_STAGES", 0); SB = SA; }
   ka.SA = SA; ka.SB = SB;
   ka.dbg = env_int("EGR_TC_DBG_SKIP", 0);
+  ka.gmax = halo ? env_int("EGR_TC_GMAX_HALO", 1) : env_int("EGR_TC_GMAX", TC_GMAX);
+  if (ka.gmax > TC_GMAX) ka.gmax = TC_GMAX;
+  if (ka.gmax > SB) ka.gmax = SB;
+  if (ka.gmax < 1) ka.gmax = 1;
   p->smem_bytes = SA * ka.a_stage_bytes + SB * ka.b_stage_bytes + 8 * STAGE_BYTES_PER_WARP + (2 * SA + 2 * SB + 4) * 8 + 16 + 1024;
   if (p->smem_bytes > 227 * 1024) return bail(fail(EGR_ERR_UNSUPPORTED, "%s: %d B of shared memory needed", op.name, p->smem_bytes));
   p->grid = pair ? 2 * (ka.n_work < sms / 2 ? ka.n_work : sms / 2) : (ka.n_work < sms ? ka.n_work : sms);

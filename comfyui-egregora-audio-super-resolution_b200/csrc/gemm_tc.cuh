@@ -12,6 +12,7 @@ static constexpr int TILE_M = 128;
 static constexpr int KBLK = 64;  // f16 elements per smem row = 128 B = one swizzle span
 static constexpr int A_BOX_BYTES = TILE_M * KBLK * 2;
 static constexpr int HALO_BOX_ROWS = 64;
+static constexpr int TC_GMAX = 4;    // weight slots one barrier round of the MMA issuers may cover (TcKernelArgs::gmax <= this)
 static constexpr int STAGE_LD = 36;  // floats per row of the epilogue staging tile (16-byte aligned, conflict-free)
 static constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_LD * 4;
 static constexpr int MAX_SPLITS = 16;
@@ -46,6 +47,7 @@ struct alignas(16) TcKernelArgs {   // (16-byte multiple: the persistent kernel 
   int fold;      // split-K folded into ONE work item: each split accumulates into its own TMEM region, summed in the epilogue
   int nbuf;      // accumulator buffers in TMEM: 2 when 2 * acc_cols <= 512, else 1
   int vec_ok, need_crop, epi_plain;
+  int gmax;      // weight slots per barrier round of the MMA issuers (1 = one round per slot; <= TC_GMAX, <= SB)
   int dbg;       // timing experiments only (EGR_TC_DBG_SKIP): bit 0 = no A loads, bit 1 = no B loads (results are garbage)
   float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
   unsigned int* counters;  // one per output tile, zero between launches
@@ -103,6 +105,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 #endif
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {   // non-blocking: has this phase completed?
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile(
@@ -621,6 +631,13 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it = 0, tcount = 0;
+      // One barrier ROUND covers up to ka.gmax consecutive weight slots.  Measured on B200 (tools/micro/mma_rate.cu): the
+      // tensor pipe retires a 128 x 256 x 16 MMA every 128 cycles from a free-running issuer, but every wait -> elect ->
+      // descriptor -> issue sequence leaves it idle for 170-480 cycles (the issuing thread cannot run ahead of a barrier
+      // it has not seen), so one round per 64-deep k-step ran the pipe at ~50 %.  A round blocks on its first slot only,
+      // takes the following ones if their barriers have ALREADY completed (test_wait, never blocking: a starved ring
+      // degrades to one slot per round).
+      const int gcap = ka.gmax;
       for (int w = cta; w < ka.n_work; w += ncta, ++it) {
         WorkItem wi;
         decode_work(ka, w, wi, rank);
@@ -631,46 +648,123 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
         tc_fence_after();
         uint32_t first = 0;  // 0 until the first MMA of this item (of this split when folded) has been issued
         int in_split = 0;    // folded split-K: outer steps issued into the current split's accumulator
-        for (int io = wi.o_begin; io < wi.o_end; ++io) {
-          if (ka.fold && in_split == ka.outer_per_split) {   // next split: its own TMEM region, accumulation restarts
-            in_split = 0; first = 0; acc += (uint32_t)(ka.mt * BN);
+        if (gcap <= 1) {
+          // one round per weight slot: the tap loop of the halo layers (ptxas unrolls it; multi-slot rounds measured slower there)
+          for (int io = wi.o_begin; io < wi.o_end; ++io) {
+            if (ka.fold && in_split == ka.outer_per_split) {   // next split: its own TMEM region, accumulation restarts
+              in_split = 0; first = 0; acc += (uint32_t)(ka.mt * BN);
+            }
+            ++in_split;
+            if (ka.halo) mbar_wait(fullA_u + 8 * sa, pa);  // otherwise A rides on the B barriers (same stage index)
+            const uint32_t aBase = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
+            for (int ii = 0; ii < ka.n_inner; ++ii) {
+              mbar_wait(fullB_u + 8 * sb, pb);
+              tc_fence_after();
+              const uint64_t bdesc = make_smem_desc(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes + b_off);
+              const uint32_t shift = ka.halo ? (uint32_t)((ka.tapw[ii] - ka.tmin) * 128) : 0u;
+              const bool lastB = (ii == ka.n_inner - 1);
+              if (elect_one()) {
+                if (tr && u == 0 && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
+  #pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                  if (m >= m_lo && m < m_hi && (PAIR ? m == 0 : m < wi.mt_eff)) {
+                    const uint64_t adesc = make_smem_desc(aBase + shift + (uint32_t)m * A_BOX_BYTES);
+  #pragma unroll
+                    for (int k = 0; k < KBLK / 16; ++k) {
+                      // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
+                      if (PAIR) tc_mma_f16_2sm(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                      else tc_mma_f16(acc + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                    }
+                  }
+                }
+                if (PAIR) tc_commit_2sm(emptyB_u + 8 * sb); else tc_commit(emptyB_u + 8 * sb);
+                if (lastB) {
+                  if (ka.halo) tc_commit(emptyA_u + 8 * sa);
+                  if (io == wi.o_end - 1) { if (PAIR) tc_commit_2sm(accF_u + 8 * buf); else tc_commit(accF_u + 8 * buf); }
+                  if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
+                }
+              }
+              __syncwarp();
+              first = 1;
+              if (++sb == ka.SB) { sb = 0; pb ^= 1u; }
+            }
+            ++tcount;
+            if (++sa == ka.SA) { sa = 0; pa ^= 1u; }
           }
-          ++in_split;
-          if (ka.halo) mbar_wait(fullA_u + 8 * sa, pa);  // otherwise A rides on the B barriers (same stage index)
-          const uint32_t aBase = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
-          for (int ii = 0; ii < ka.n_inner; ++ii) {
+        } else {
+          int io = wi.o_begin, ii = 0;
+          while (io < wi.o_end) {
+            if (ka.fold && (!ka.halo || ii == 0) && in_split == ka.outer_per_split) {   // next split: its own TMEM region
+              in_split = 0; first = 0; acc += (uint32_t)(ka.mt * BN);
+            }
+            int gmax;
+            if (ka.halo) {
+              if (ii == 0) ++in_split;
+              gmax = min(gcap, ka.n_inner - ii);                 // taps of one channel chunk share its A stage
+            } else {
+              gmax = min(gcap, wi.o_end - io);
+              if (ka.fold) gmax = min(gmax, ka.outer_per_split - in_split);
+            }
+            if (ka.halo && ii == 0) mbar_wait(fullA_u + 8 * sa, pa);
             mbar_wait(fullB_u + 8 * sb, pb);
+            int n = 1;
+  #pragma unroll
+            for (int j = 1; j < TC_GMAX; ++j) {
+              if (j == n && j < gmax) {
+                int s = sb + j;
+                uint32_t par = pb;
+                if (s >= ka.SB) { s -= ka.SB; par ^= 1u; }
+                if (__all_sync(0xffffffffu, mbar_test(fullB_u + 8 * s, par))) n = j + 1;
+              }
+            }
             tc_fence_after();
-            const uint64_t bdesc = make_smem_desc(ringB_u + (uint32_t)sb * (uint32_t)ka.b_stage_bytes + b_off);
-            const uint32_t shift = ka.halo ? (uint32_t)((ka.tapw[ii] - ka.tmin) * 128) : 0u;
-            const bool lastB = (ii == ka.n_inner - 1);
             if (elect_one()) {
-              if (tr && u == 0 && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
-#pragma unroll
-              for (int m = 0; m < 2; ++m) {
-                if (m >= m_lo && m < m_hi && (PAIR ? m == 0 : m < wi.mt_eff)) {
-                  const uint64_t adesc = make_smem_desc(aBase + shift + (uint32_t)m * A_BOX_BYTES);
-#pragma unroll
-                  for (int k = 0; k < KBLK / 16; ++k) {
-                    // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
-                    if (PAIR) tc_mma_f16_2sm(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
-                    else tc_mma_f16(acc + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+              if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount] = clock64();
+  #pragma unroll
+              for (int j = 0; j < TC_GMAX; ++j) {
+                if (j < n) {
+                  int s = sb + j;
+                  if (s >= ka.SB) s -= ka.SB;
+                  // descriptors of slot j are formed here, behind the MMAs of slot j-1 already in the pipe's queue
+                  const uint64_t bdj = make_smem_desc(ringB_u + (uint32_t)s * (uint32_t)ka.b_stage_bytes + b_off);
+                  const uint32_t aB = ka.halo ? ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes + (uint32_t)((ka.tapw[ii + j] - ka.tmin) * 128)
+                                              : ringA_u + (uint32_t)s * (uint32_t)ka.a_stage_bytes;   // A rides on the B barriers (same slot)
+  #pragma unroll
+                  for (int m = 0; m < 2; ++m) {
+                    if (m >= m_lo && m < m_hi && (PAIR ? m == 0 : m < wi.mt_eff)) {
+                      const uint64_t adj = make_smem_desc(aB + (uint32_t)m * A_BOX_BYTES);
+  #pragma unroll
+                      for (int k = 0; k < KBLK / 16; ++k) {
+                        // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
+                        const uint32_t accum = (j ? 1u : first) | (uint32_t)k;
+                        if (PAIR) tc_mma_f16_2sm(acc, adj + (uint64_t)(2 * k), bdj + (uint64_t)(2 * k), idesc, accum);
+                        else tc_mma_f16(acc + (uint32_t)(m * BN), adj + (uint64_t)(2 * k), bdj + (uint64_t)(2 * k), idesc, accum);
+                      }
+                    }
+                  }
+                  if (PAIR) tc_commit_2sm(emptyB_u + 8 * s); else tc_commit(emptyB_u + 8 * s);
+                  const bool last_of_io = ka.halo ? (ii + j == ka.n_inner - 1) : true;
+                  if (last_of_io) {
+                    if (ka.halo) tc_commit(emptyA_u + 8 * sa);
+                    if ((ka.halo ? io : io + j) == wi.o_end - 1) { if (PAIR) tc_commit_2sm(accF_u + 8 * buf); else tc_commit(accF_u + 8 * buf); }
                   }
                 }
               }
-              if (PAIR) tc_commit_2sm(emptyB_u + 8 * sb); else tc_commit(emptyB_u + 8 * sb);
-              if (lastB) {
-                if (ka.halo) tc_commit(emptyA_u + 8 * sa);
-                if (io == wi.o_end - 1) { if (PAIR) tc_commit_2sm(accF_u + 8 * buf); else tc_commit(accF_u + 8 * buf); }
-                if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
-              }
+              if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
             }
             __syncwarp();
             first = 1;
-            if (++sb == ka.SB) { sb = 0; pb ^= 1u; }
-          }
-          ++tcount;
-          if (++sa == ka.SA) { sa = 0; pa ^= 1u; }
+            ++tcount;
+            sb += n;
+            if (sb >= ka.SB) { sb -= ka.SB; pb ^= 1u; }
+            if (ka.halo) {
+              ii += n;
+              if (ii == ka.n_inner) { ii = 0; ++io; if (++sa == ka.SA) { sa = 0; pa ^= 1u; } }
+            } else {
+              io += n;
+              in_split += n;
+            }
+        }
         }
       }
     }
