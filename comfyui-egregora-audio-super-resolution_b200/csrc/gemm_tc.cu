@@ -381,6 +381,10 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   ka.SA = SA; ka.SB = SB;
   ka.dbg = env_int("EGR_TC_DBG_SKIP", 0);
   ka.gmax = halo ? env_int("EGR_TC_GMAX_HALO", 1) : env_int("EGR_TC_GMAX", TC_GMAX);
+  ka.hgroup = (halo && !pair) ? env_int("EGR_TC_HGROUP", 1) : 1;
+  if (ka.hgroup > TC_GMAX) ka.hgroup = TC_GMAX;
+  if (ka.hgroup > SB - 1) ka.hgroup = SB - 1;
+  if (ka.hgroup < 1) ka.hgroup = 1;
   if (ka.gmax > TC_GMAX) ka.gmax = TC_GMAX;
   if (ka.gmax > SB) ka.gmax = SB;
   if (ka.gmax < 1) ka.gmax = 1;
@@ -404,7 +408,7 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
     ka.need_crop = (g.out_lo > 0 || g.out_hi < (long long)(g.Ho - 1) * g.out_h_stride + (long long)g.Wo * g.out_pix_stride + g.out_offset + g.N) ? 1 : 0;
   }
   ka.vec_ok = vec ? 1 : 0;
-  ka.epi_plain = (vec && g.out32 && g.post == 1.0f && g.act == EGR_ACT_NONE && !g.rowbias && !ka.need_crop) ? 1 : 0;
+  ka.epi_plain = (vec && g.out32 && g.post == 1.0f && g.act == EGR_ACT_NONE && !g.rowbias) ? 1 : 0;   // cropped edge rows: decided per warp
   *out = p;
   return EGR_OK;
 }

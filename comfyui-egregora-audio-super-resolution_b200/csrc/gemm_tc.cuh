@@ -47,6 +47,7 @@ struct alignas(16) TcKernelArgs {   // (16-byte multiple: the persistent kernel 
   int fold;      // split-K folded into ONE work item: each split accumulates into its own TMEM region, summed in the epilogue
   int nbuf;      // accumulator buffers in TMEM: 2 when 2 * acc_cols <= 512, else 1
   int vec_ok, need_crop, epi_plain;
+  int hgroup;    // halo mode: taps per barrier round of the MMA issuers (1 = the per-tap loop)
   int gmax;      // weight slots per barrier round of the MMA issuers (1 = one round per slot; <= TC_GMAX, <= SB)
   int dbg;       // timing experiments only (EGR_TC_DBG_SKIP): bit 0 = no A loads, bit 1 = no B loads (results are garbage)
   float* partial;          // split-K workspace: [tile][split][mt*128][block_n] f32
@@ -648,7 +649,66 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
         tc_fence_after();
         uint32_t first = 0;  // 0 until the first MMA of this item (of this split when folded) has been issued
         int in_split = 0;    // folded split-K: outer steps issued into the current split's accumulator
-        if (gcap <= 1) {
+        if (ka.halo && ka.hgroup > 1) {
+          // halo layers, taps in fixed groups: every weight slot of the group is waited for (blocking, in ring order), then
+          // the elected lane issues the MMAs of all of them back to back — one wait -> elect -> issue sequence per group
+          for (int io = wi.o_begin; io < wi.o_end; ++io) {
+            if (ka.fold && in_split == ka.outer_per_split) { in_split = 0; first = 0; acc += (uint32_t)(ka.mt * BN); }
+            ++in_split;
+            mbar_wait(fullA_u + 8 * sa, pa);
+            const uint32_t aBase = ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes;
+            for (int ii = 0; ii < ka.n_inner; ii += ka.hgroup) {
+              const int g = min(ka.hgroup, ka.n_inner - ii);
+              uint64_t bdesc[TC_GMAX];
+              uint32_t shift[TC_GMAX], eB[TC_GMAX];
+              {
+                int s = sb;
+                uint32_t par = pb;
+#pragma unroll
+                for (int j = 0; j < TC_GMAX; ++j) {
+                  bdesc[j] = 0; shift[j] = 0; eB[j] = 0;
+                  if (j < g) {
+                    mbar_wait(fullB_u + 8 * s, par);
+                    bdesc[j] = make_smem_desc(ringB_u + (uint32_t)s * (uint32_t)ka.b_stage_bytes + b_off);
+                    shift[j] = (uint32_t)((ka.tapw[ii + j] - ka.tmin) * 128);
+                    eB[j] = emptyB_u + 8 * s;
+                    if (++s == ka.SB) { s = 0; par ^= 1u; }
+                  }
+                }
+                sb = s; pb = par;
+              }
+              tc_fence_after();
+              const bool lastG = (ii + g == ka.n_inner);
+              if (elect_one()) {
+                if (tr && u == 0 && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
+#pragma unroll
+                for (int j = 0; j < TC_GMAX; ++j) {
+                  if (j < g) {
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) {
+                      if (m >= m_lo && m < m_hi && m < wi.mt_eff) {
+                        const uint64_t adesc = make_smem_desc(aBase + shift[j] + (uint32_t)m * A_BOX_BYTES);
+#pragma unroll
+                        for (int k = 0; k < KBLK / 16; ++k)
+                          tc_mma_f16(acc + (uint32_t)(m * BN), adesc + (uint64_t)(2 * k), bdesc[j] + (uint64_t)(2 * k), idesc, (j ? 1u : first) | (uint32_t)k);
+                      }
+                    }
+                    tc_commit(eB[j]);
+                  }
+                }
+                if (lastG) {
+                  tc_commit(emptyA_u + 8 * sa);
+                  if (io == wi.o_end - 1) tc_commit(accF_u + 8 * buf);
+                  if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount + 1] = clock64();
+                }
+              }
+              __syncwarp();
+              first = 1;
+            }
+            ++tcount;
+            if (++sa == ka.SA) { sa = 0; pa ^= 1u; }
+          }
+        } else if (gcap <= 1) {
           // one round per weight slot: the tap loop of the halo layers (ptxas unrolls it; multi-slot rounds measured slower there)
           for (int io = wi.o_begin; io < wi.o_end; ++io) {
             if (ka.fold && in_split == ka.outer_per_split) {   // next split: its own TMEM region, accumulation restarts
@@ -665,11 +725,11 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
               const bool lastB = (ii == ka.n_inner - 1);
               if (elect_one()) {
                 if (tr && u == 0 && tcount < 250 && ii == 0) tr[528 + 2 * tcount] = clock64();
-  #pragma unroll
+#pragma unroll
                 for (int m = 0; m < 2; ++m) {
                   if (m >= m_lo && m < m_hi && (PAIR ? m == 0 : m < wi.mt_eff)) {
                     const uint64_t adesc = make_smem_desc(aBase + shift + (uint32_t)m * A_BOX_BYTES);
-  #pragma unroll
+#pragma unroll
                     for (int k = 0; k < KBLK / 16; ++k) {
                       // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
                       if (PAIR) tc_mma_f16_2sm(acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
@@ -708,7 +768,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
             if (ka.halo && ii == 0) mbar_wait(fullA_u + 8 * sa, pa);
             mbar_wait(fullB_u + 8 * sb, pb);
             int n = 1;
-  #pragma unroll
+#pragma unroll
             for (int j = 1; j < TC_GMAX; ++j) {
               if (j == n && j < gmax) {
                 int s = sb + j;
@@ -720,7 +780,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
             tc_fence_after();
             if (elect_one()) {
               if (tr && u == 0 && tcount < 250) tr[528 + 2 * tcount] = clock64();
-  #pragma unroll
+#pragma unroll
               for (int j = 0; j < TC_GMAX; ++j) {
                 if (j < n) {
                   int s = sb + j;
@@ -729,11 +789,11 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
                   const uint64_t bdj = make_smem_desc(ringB_u + (uint32_t)s * (uint32_t)ka.b_stage_bytes + b_off);
                   const uint32_t aB = ka.halo ? ringA_u + (uint32_t)sa * (uint32_t)ka.a_stage_bytes + (uint32_t)((ka.tapw[ii + j] - ka.tmin) * 128)
                                               : ringA_u + (uint32_t)s * (uint32_t)ka.a_stage_bytes;   // A rides on the B barriers (same slot)
-  #pragma unroll
+#pragma unroll
                   for (int m = 0; m < 2; ++m) {
                     if (m >= m_lo && m < m_hi && (PAIR ? m == 0 : m < wi.mt_eff)) {
                       const uint64_t adj = make_smem_desc(aB + (uint32_t)m * A_BOX_BYTES);
-  #pragma unroll
+#pragma unroll
                       for (int k = 0; k < KBLK / 16; ++k) {
                         // advance 16 f16 = 32 B inside the 128 B swizzle span: +2 in the (addr >> 4) field
                         const uint32_t accum = (j ? 1u : first) | (uint32_t)k;
@@ -808,6 +868,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
       int m_prev = -1;
       RowInfo ri;
       uint32_t any_ok = 0;
+      bool crop_here = false;
       long long base_l0 = 0, flat_l0 = 0;
       int roff = 0, foff = 0;
       int off[8];
@@ -818,6 +879,9 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
           m_prev = m;
           ri = row_info(ka, wi, m, lg * 32 + lane);  // this thread's own row
           any_ok = __ballot_sync(0xffffffffu, ri.ok);
+          // cropped outputs (transposed-conv margins): only the rows at a clip's edges reach outside [out_lo, out_hi) — a
+          // warp whose 32 rows all lie inside takes the same branch-free store passes as an uncropped layer
+          crop_here = ka.need_crop && __any_sync(0xffffffffu, ri.ok && (ri.flat0 < g.out_lo || ri.flat0 + (long long)g.N > g.out_hi));
           base_l0 = __shfl_sync(0xffffffffu, ri.base, 0);
           flat_l0 = __shfl_sync(0xffffffffu, ri.flat0, 0);
           roff = (int)(ri.base - base_l0);   // row offsets inside the tile (host checked: fit 32 bits)
@@ -867,7 +931,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
         if (vecpath && any_ok) {
           if (col_ok && has_bias) bias4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
           if (has_resid) {
-            if (!ka.need_crop) {  // predicated loads, no per-cell branches
+            if (!crop_here) {  // predicated loads, no per-cell branches
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (col_ok && off[i] >= 0) rv[i] = __ldg(reinterpret_cast<const float4*>(g.resid + base_l0 + off[i] + n));
@@ -930,7 +994,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
           }
         } else if (vecpath) {
           // 4 rows x 128 contiguous bytes per store instruction
-          if (ka.epi_plain) {
+          if (ka.epi_plain && !crop_here) {
             // plain f32 output (+bias, +residual): branch-free passes, only the store is predicated, so the passes
             // interleave (the general variant below serialises on its per-pass uniform branches)
 #pragma unroll
@@ -963,7 +1027,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
               const int fo = __shfl_sync(0xffffffffu, foff, rr);   // convergent: before any per-lane skip
               const int bb = __shfl_sync(0xffffffffu, ri.b, rr);
               bool ok = col_ok && off[i] >= 0;
-              if (ka.need_crop) {
+              if (crop_here) {
                 const long long fl = flat_l0 + fo + n;
                 ok = ok && fl >= g.out_lo && fl < g.out_hi;
               }

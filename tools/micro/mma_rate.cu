@@ -48,10 +48,12 @@ struct P { int N, issuers, stages, commit_each, ksteps, kper, pollers, ring, nof
 
 template <int CG>
 __global__ void __launch_bounds__(384, 1) k(P p, unsigned long long* out) {
+  long long* stamps = reinterpret_cast<long long*>(out + 148 * 4);
   extern __shared__ uint8_t raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bars[12];
   __shared__ uint64_t full[8], empty[8], never, never2;
+  __shared__ unsigned flag[8];
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5;
   uint32_t rank = 0;
@@ -59,6 +61,7 @@ __global__ void __launch_bounds__(384, 1) k(P p, unsigned long long* out) {
   // operand slots: A 16 KB, B (N/CG)*128 B each, per stage
   const int a_bytes = 16384, b_bytes = (p.N / CG) * 128;
   for (int i = threadIdx.x; i < p.stages * (a_bytes + b_bytes) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0x3c003c00u;  // f16 1.0
+  if (threadIdx.x < 8) flag[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 12; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bars[i])), "r"(1));
     for (int i = 0; i < 8; ++i) {
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(384, 1) k(P p, unsigned long long* out) {
     t0 = clock64();
     int s = 0;
     unsigned long long rounds = 0;
+    long long ph[7] = {0, 0, 0, 0, 0, 0, 0}, cend = 0, c0 = clock64(); int elected = 0;
     if (p.ring == 2) {
       int ks = 0;
       while (ks < p.ksteps) {
@@ -131,9 +135,16 @@ __global__ void __launch_bounds__(384, 1) k(P p, unsigned long long* out) {
       const uint32_t aB = sm_u + s * (a_bytes + b_bytes);
       const uint32_t bB = aB + a_bytes + (uint32_t)(u * (NI / CG) * 128);
       const uint64_t ad = make_desc(aB), bd = make_desc(bB);
-      if (p.ring && !p.nowait) {
+      const long long cw0 = clock64();
+      if (p.ring && !p.nowait && (p.wmode != 5 || ks == 0)) {
         const uint32_t par = (uint32_t)((ks / p.stages) & 1);
-        if (p.wmode == 0) mbar_wait(smem_u32(&full[s]), par);
+        if (p.wmode == 0 || p.wmode == 5) mbar_wait(smem_u32(&full[s]), par);
+        else if (p.wmode == 6) {
+          asm volatile("{\n\t.reg .pred q;\n\tWL6:\n\tmbarrier.try_wait.parity.relaxed.cta.shared::cta.b64 q, [%0], %1;\n\t@q bra DN6;\n\tbra WL6;\n\tDN6:\n\t}" ::"r"(smem_u32(&full[s])), "r"(par) : "memory");
+        } else if (p.wmode == 7) {   // plain volatile load poll of the barrier word's phase bit? not portable: poll a flag the producer writes
+          volatile unsigned* f = (volatile unsigned*)&flag[s];
+          while (*f != (unsigned)(ks / p.stages + 1)) { }
+        }
         else if (p.wmode == 1) {
           uint32_t ok = 0;
           while (!ok) asm volatile("{\n\t.reg .pred q;\n\tmbarrier.test_wait.parity.shared::cta.b64 q, [%1], %2;\n\tselp.b32 %0, 1, 0, q;\n\t}" : "=r"(ok) : "r"(smem_u32(&full[s])), "r"(par) : "memory");
@@ -146,13 +157,24 @@ __global__ void __launch_bounds__(384, 1) k(P p, unsigned long long* out) {
         }
       }
       if (p.ring && !p.nofence) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const long long c1 = clock64();
+      if (u == 0 && blockIdx.x == 0 && ks >= 200 && ks < 216 && (threadIdx.x & 31) == 0) { stamps[(ks - 200) * 5 + 0] = cw0; stamps[(ks - 200) * 5 + 1] = c1; }
       if (elect_one()) {
+        const long long c2 = clock64();
+        mma<CG>(tm + (uint32_t)(u * NI), ad, bd, idesc, ks ? 1u : 0u);
+        const long long c3 = clock64();
 #pragma unroll 4
-        for (int kk = 0; kk < p.kper; ++kk)
-          mma<CG>(tm + (uint32_t)(u * NI), ad + (uint64_t)(2 * (kk & 3)), bd + (uint64_t)(2 * (kk & 3)), idesc, (ks | kk) ? 1u : 0u);
+        for (int kk = 1; kk < p.kper; ++kk)
+          mma<CG>(tm + (uint32_t)(u * NI), ad + (uint64_t)(2 * (kk & 3)), bd + (uint64_t)(2 * (kk & 3)), idesc, 1u);
+        const long long c4 = clock64();
+        if (p.wmode == 5 && ks + 1 < p.ksteps) { const int s1 = (s + 1 == p.stages) ? 0 : s + 1; mbar_wait(smem_u32(&full[s1]), (uint32_t)(((ks + 1) / p.stages) & 1)); }
         if (p.ring) commit<CG>(smem_u32(&empty[s])); else if (p.commit_each) commit<CG>(bar_step);
+        const long long c5 = clock64();
+        if (u == 0 && blockIdx.x == 0 && ks >= 200 && ks < 216) stamps[(ks - 200) * 5 + 2] = c5;
+        ph[1] += c2 - c1; ph[2] += c3 - c2; ph[3] += c4 - c3; ph[4] += c5 - c4; cend = c5; elected = 1;
       }
       __syncwarp();
+      { const long long c6 = clock64(); if (elected) ph[5] += c6 - cend; ph[0] += c1 - c0; ph[6] += c6 - c0; c0 = c6; }
       if (++s == p.stages) s = 0;
     }
     if (elect_one()) commit<CG>(bar_done);
@@ -160,13 +182,17 @@ __global__ void __launch_bounds__(384, 1) k(P p, unsigned long long* out) {
     mbar_wait(bar_done, 0);
     t1 = clock64();
     if (threadIdx.x % 32 == 0) { out[(blockIdx.x * 2 + u) * 2] = t0; out[(blockIdx.x * 2 + u) * 2 + 1] = t1; if (blockIdx.x == 0 && u == 0) out[148 * 4 - 1] = rounds; }
+    if (elected && blockIdx.x == 0 && u == 0) for (int i = 0; i < 7; ++i) out[148 * 4 - 9 + i] = (unsigned long long)ph[i];
     if (u == 0 && threadIdx.x == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&never)) : "memory");
   } else if (warp == 2 && p.ring && rank == 0) {
     // producer stand-in: hands every stage back as soon as the MMAs that read it have completed (no loads)
     int s = 0;
     for (int ks = 0; ks < p.ksteps; ++ks) {
       mbar_wait(smem_u32(&empty[s]), (uint32_t)(((ks / p.stages) & 1) ^ 1));
+      const long long pw = clock64();
+      if ((threadIdx.x & 31) == 0) { ((volatile unsigned*)flag)[s] = (unsigned)(ks / p.stages + 1); }
       if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&full[s])) : "memory");
+      if (blockIdx.x == 0 && ks >= 200 && ks < 216 && (threadIdx.x & 31) == 0) { stamps[(ks - 200) * 5 + 3] = pw; stamps[(ks - 200) * 5 + 4] = clock64(); }
       __syncwarp();
       if (++s == p.stages) s = 0;
     }
@@ -185,8 +211,8 @@ __global__ void __launch_bounds__(384, 1) k(P p, unsigned long long* out) {
 template <int CG>
 static void run(P p, int grid, const char* tag) {
   unsigned long long* d;
-  cudaMalloc(&d, 148 * 4 * 8);
-  cudaMemset(d, 0, 148 * 4 * 8);
+  cudaMalloc(&d, 148 * 4 * 8 + 80 * 8);
+  cudaMemset(d, 0, 148 * 4 * 8 + 80 * 8);
   const int smem = p.stages * (16384 + (p.N / CG) * 128) + 2048;
   cudaFuncSetAttribute(k<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaEvent_t e0, e1;
@@ -218,6 +244,10 @@ static void run(P p, int grid, const char* tag) {
   printf("%-34s N=%3d iss=%d stages=%d ring=%d pollers=%d commit_each=%d : %7.1f clk per k-step(%d MMAs/issuer)  %6.1f clk/MMA  floor %5.1f   chip %7.1f TF/s (%.3f ms)\n",
          tag, p.N, p.issuers, p.stages, p.ring, p.pollers, p.commit_each, cyc / p.ksteps, p.kper, cyc / n_mma,
          128.0 * (p.N / p.issuers) / 256.0, flops / best / 1e9, best);
+  if (p.ring != 2) printf("      per round: top-of-loop+wait %.0f | ->elected %.0f | 1st MMA %.0f | rest MMAs %.0f | commit %.0f | ->reconverged %.0f | total %.0f\n",
+         (double)h[148*4-9] / p.ksteps, (double)h[148*4-8] / p.ksteps, (double)h[148*4-7] / p.ksteps, (double)h[148*4-6] / p.ksteps, (double)h[148*4-5] / p.ksteps, (double)h[148*4-4] / p.ksteps, (double)h[148*4-3] / p.ksteps);
+  if (p.ring == 1) { long long st[80]; cudaMemcpy(st, d + 148 * 4, sizeof(st), cudaMemcpyDeviceToHost); long long b = st[0];
+    for (int r = 0; r < 16; ++r) printf("      r%02d issuer: at wait %6lld, passed %6lld, committed %6lld | producer for this round: woke %6lld, armed %6lld\n", r, st[r*5]-b, st[r*5+1]-b, st[r*5+2]-b, st[r*5+3]-b, st[r*5+4]-b); }
   if (p.ring == 2) printf("      adaptive: %.2f k-steps per round\n", (double)p.ksteps / (double)h[148 * 4 - 1]);
   cudaFree(d);
 }
@@ -225,14 +255,10 @@ static void run(P p, int grid, const char* tag) {
 int main() {
   const int KS = 4000;
   const int grid = 148;
-  run<1>({256, 1, 3, 1, KS, 4, 0, 1, 0, 0, 0, 1}, grid, "ring 4/round (reference)");
-  for (int G : {1, 2, 3}) run<1>({256, 1, 3, 1, KS, 4, 0, 2, 0, 0, 0, G}, grid, "cg1 adaptive S=3");
-  for (int G : {1, 2, 3}) run<1>({256, 2, 3, 1, KS, 4, 0, 2, 0, 0, 0, G}, grid, "cg1 2 iss adaptive S=3");
-  for (int G : {2, 4}) run<2>({256, 1, 5, 1, KS, 4, 0, 2, 0, 0, 0, G}, grid, "cg2 adaptive S=5");
-  for (int G : {2, 4}) run<1>({192, 1, 4, 1, KS, 4, 0, 2, 0, 0, 0, G}, grid, "N=192 adaptive S=4");
-  for (int G : {2, 4}) run<1>({192, 2, 4, 1, KS, 4, 0, 2, 0, 0, 0, G}, grid, "N=192 2 iss adaptive S=4");
-  for (int G : {2, 4}) run<1>({128, 2, 6, 1, KS, 4, 0, 2, 0, 0, 0, G}, grid, "N=128 2 iss adaptive S=6");
-  for (int G : {2, 4}) run<1>({96, 2, 8, 1, KS, 4, 0, 2, 0, 0, 0, G}, grid, "N=96 2 iss adaptive S=8");
-  for (int G : {2, 4}) run<1>({48, 1, 8, 1, KS, 4, 0, 2, 0, 0, 0, G}, grid, "N=48 adaptive S=8");
+  run<1>({96, 1, 3, 1, KS, 4, 0, 1, 0, 0, 0, 1}, grid, "ring N=96 acquire try_wait");
+  run<1>({96, 1, 3, 1, KS, 4, 0, 1, 0, 0, 6, 1}, grid, "ring N=96 relaxed try_wait");
+  run<1>({96, 1, 3, 1, KS, 4, 0, 1, 0, 0, 7, 1}, grid, "ring N=96 flag poll (ld.volatile)");
+  run<1>({256, 1, 3, 1, KS, 4, 0, 1, 0, 0, 6, 1}, grid, "ring N=256 relaxed try_wait");
+  run<1>({256, 1, 3, 1, KS, 4, 0, 1, 0, 0, 7, 1}, grid, "ring N=256 flag poll");
   return 0;
 }
