@@ -124,17 +124,21 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def ncu_traffic(kernel: str):
-    """Per-launch DRAM bytes of `kernel` from the committed ncu pass of one c2 step (tools/gpu_ncu2.sh writes
-    profiles/*_traffic_c2_b1.json: dram__bytes_read.sum + dram__bytes_write.sum over every launch)."""
+def ncu_traffic(kernels):
+    """Per-launch DRAM bytes of the named kernel(s) from the committed ncu pass of one c2 step (tools/traffic_summary.py
+    writes profiles/*_traffic_c2_b1.json: dram__bytes_read.sum + dram__bytes_write.sum over every launch).  The tap-GEMM
+    has two entry points (gemm_tc_kernel and its CTA-pair variant): their launches are pooled."""
     cands = sorted((ROOT / "profiles").glob("*_traffic_c2_b1.json"))
     if not cands:
         return None
-    d = json.loads(cands[-1].read_text()).get(kernel)
-    if not d or not d.get("launches"):
+    js = json.loads(cands[-1].read_text())
+    ds = [js[k] for k in ((kernels,) if isinstance(kernels, str) else kernels) if js.get(k) and js[k].get("launches")]
+    if not ds:
         return None
-    return {"bytes_per_launch": (d["dram_read_bytes"] + d["dram_write_bytes"]) / d["launches"], "source": cands[-1].name,
-            "tensor_pipe_pct": d.get("tensor_pipe_pct_time_weighted")}
+    n = sum(d["launches"] for d in ds)
+    us = sum(d["us"] for d in ds)
+    return {"bytes_per_launch": sum(d["dram_read_bytes"] + d["dram_write_bytes"] for d in ds) / n, "source": cands[-1].name, "launches": n,
+            "tensor_pipe_pct": sum(d["us"] * d.get("tensor_pipe_pct_time_weighted", 0.0) for d in ds) / us if us else None}
 
 
 def peaks() -> dict:
@@ -564,11 +568,11 @@ def run_b200(args):
             ideal_s += max(t_t, t_h)
             alg_bytes_tc += byt
             n_hbm += t_h > t_t
-        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05 tap-GEMM, f16 operands, f32 TMEM accumulate)",
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel + gemm_tc_pair_kernel (tcgen05 tap-GEMM, f16 operands, f32 TMEM accumulate; the pair variant is cta_group::2)",
                 "achieved": achieved, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long pass)",
-                "traffic": (ncu_traffic("gemm_tc_kernel") or {}).get("bytes_per_launch"),
-                "traffic_note": ncu_traffic("gemm_tc_kernel"),
+                "traffic": (ncu_traffic(("gemm_tc_kernel", "gemm_tc_pair_kernel")) or {}).get("bytes_per_launch"),
+                "traffic_note": ncu_traffic(("gemm_tc_kernel", "gemm_tc_pair_kernel")),
                 "launches_per_pass": n_tc, "flops_per_pass": tc_flops, "avg_launch_us": 1e6 * t_tc / max(n_tc, 1),
                 "gemm_share_of_plan": t_tc / t_plan, "plan_ms": 1e3 * t_plan,
                 "algorithmic_bytes_per_launch": alg_bytes_tc / max(n_tc, 1),
@@ -583,6 +587,46 @@ def run_b200(args):
                     "weight_bytes": sum(2.0 * l["N"] * l["K"] for l in unet_tc),
                     "bound": "hbm (weight streaming) in the limit; measured time is op-to-op latency (see profiles/r2_mega_trace_*.txt)",
                     "share_of_plan": t_unet / t_plan}}
+        # ---- the same GEMM-only measurement on a batch of 8 chunk-channels (one sub-batch of c3 / c5): M grows 8x, so the
+        # layers that are short of output tiles at batch 1 fill the 148 SMs; reported beside the c2 figure, not instead of it
+        roof_b8 = None
+        try:
+            be8, h8 = engine.plan(8, 1, True)
+            engine.infer(x_dev[:, :win].expand(8, win).contiguous(), lowpass=True, steps=1)
+            be8, h8 = engine.plan(8, 1, True)
+            for _ in range(2):
+                _abi.check(lib.egr_plan_run_code(h8, K["EGR_OP_GEMM_TC"], st))
+            torch.cuda.synchronize(dev)
+            e0.record(es)
+            for _ in range(3):
+                _abi.check(lib.egr_plan_run_code(h8, K["EGR_OP_GEMM_TC"], st))
+            e1.record(es)
+            torch.cuda.synchronize(dev)
+            t8 = e0.elapsed_time(e1) / 1e3 / 3
+            for _ in range(2):
+                _abi.check(lib.egr_plan_run(h8, 0, -1, st))
+            torch.cuda.synchronize(dev)
+            e0.record(es)
+            for _ in range(3):
+                _abi.check(lib.egr_plan_run(h8, 0, -1, st))
+            e1.record(es)
+            torch.cuda.synchronize(dev)
+            tp8 = e0.elapsed_time(e1) / 1e3 / 3
+            tc8 = [l for l in be8.layer_table if l["kind"] == "tc" and not (mega_on and l.get("mega"))]
+            fl8 = sum(l["flops"] for l in tc8)
+            ideal8 = 0.0
+            for l in tc8:
+                k1 = l["K"] // max(l["taps"], 1)
+                byt = 2.0 * l["M"] * k1 + 2.0 * l["N"] * l["K"] + 8.0 * l["M"] * l["N"]
+                ideal8 += max(l["flops"] / (pk["bf16_sustained"] * 1e12), byt / (pk["hbm"] * 1e9))
+            roof_b8 = {"workload": "one pass over 8 chunk-channels (1 diffusion step, low-pass on)", "bound": "tensor",
+                       "achieved": fl8 / t8 / 1e12, "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": fl8 / t8 / 1e12 / pk["bf16_sustained"],
+                       "launches_per_pass": len(tc8), "flops_per_pass": fl8, "gemm_ms": 1e3 * t8, "plan_ms": 1e3 * tp8,
+                       "ms_per_chunk_channel": 1e3 * tp8 / 8, "composite_frac": ideal8 / t8}
+            be, handle = engine.plan(1, 1, True)
+        except Exception as e:  # pragma: no cover
+            roof_b8 = {"error": repr(e)[:300]}
+        roof["batch8"] = roof_b8
         # ---- batched throughput (c3's per-GPU share: 33 chunk-channels, 4 steps), extra information
         extra = None
         if os.environ.get("EGR_BENCH_BATCHED", "1") == "1":

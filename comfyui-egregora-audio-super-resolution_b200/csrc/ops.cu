@@ -1100,7 +1100,9 @@ int egr::launch_eltwise(const Spaces& s, const egr_op& op, cudaStream_t st) {
 
 // sin with an exact two-constant range reduction to [-pi, pi] followed by the SFU approximation (abs err ~4e-7)
 __device__ __forceinline__ float snake_sin(float a) {
-  const float k = rintf(a * 0.15915494309189535f);
+  // round-to-nearest by the 1.5 * 2^23 trick (two FMA-pipe instructions): rintf() is an FRND on the 16-lane XU pipe, which the
+  // two MUFU.SIN per output already keep busy — the XU pipe, not instruction issue, was this kernel's limiter
+  const float k = fmaf(a, 0.15915494309189535f, 12582912.0f) - 12582912.0f;
   a = fmaf(k, -6.2831854820251465f, a);
   a = fmaf(k, 1.7484555e-7f, a);
   return __sinf(a);
