@@ -241,9 +241,11 @@ int egr::tc_prepare(const Spaces& s, const egr_op& op, TcPrepared** out) {
   if (!g.wz_batch && env_int("EGR_TC_NO_SPLITK", 0) == 0) {
     splits = sms / (units > 0 ? units : 1);
     if (splits > MAX_SPLITS) splits = MAX_SPLITS;
-    // at least eight outer steps (~1 us of tensor-core issue) per split: a shorter reduction is cheaper left whole than
-    // split and reduced again (the reduction pass costs several microseconds of latency, round-2 trace)
-    if (splits > n_outer / 8) splits = n_outer / 8;
+    // at least sixteen outer steps per split: a shorter reduction is cheaper left whole than split and reduced again (the
+    // reduction pass costs several microseconds of latency; swept 8 ... 32 in the plan: batch-8 UNet 6.6 -> 6.1 ms at 16,
+    // batch 1 flat)
+    static const int split_min = env_int("EGR_TC_SPLIT_MIN", 16) > 0 ? env_int("EGR_TC_SPLIT_MIN", 16) : 16;   // outer steps a split keeps (A/B knob)
+    if (splits > n_outer / split_min) splits = n_outer / split_min;
     if (splits < 1) splits = 1;
   }
   if (env_int("EGR_TC_SPLITS", 0) > 0) splits = env_int("EGR_TC_SPLITS", 0) > n_outer ? n_outer : env_int("EGR_TC_SPLITS", 0);

@@ -234,6 +234,33 @@ def test_groupnorm_cluster_sizes(C, H, W, B, cuda_dev):
         assert torch.equal(mp1.read(y1), got[:1])
 
 
+@pytest.mark.parametrize("C0,C1,H,W,B,silu", [(128, 0, 96, 64, 2, True), (64, 64, 83, 53, 1, False), (256, 128, 70, 61, 2, True), (32, 0, 211, 97, 3, True)])
+def test_groupnorm_large_maps(C0, C1, H, W, B, silu, cuda_dev):
+    """Maps above 4096 pixels take the slab path (gn_stats + gn_finalize + gn_apply): slab tails, pixel counts that are
+    not multiples of the unrolled load groups, a virtual concat, and batch items that must not influence each other."""
+    Cc = C0 + C1
+    Wt = {"n.weight": 1 + 0.1 * _x((Cc,), 1), "n.bias": 0.1 * _x((Cc,), 2)}
+    a = _x((B, C0, H, W), 3) * 2 + 0.7
+
+    def build(a_, b_):
+        mp = MiniPlan(Wt)
+        t = mp.input(a_)
+        if b_ is not None:
+            t = mp.be.concat(t, mp.input(b_))
+        y = mp.be.groupnorm(t, "n", Cc, 32, 1e-6, silu=silu)
+        mp.run_gpu()
+        return mp.read(y)
+
+    b = (_x((B, C1, H, W), 4) - 0.5) if C1 else None
+    x = torch.cat([a, b], 1) if C1 else a
+    got = build(a, b)
+    ref = F.group_norm(x, 32, Wt["n.weight"], Wt["n.bias"], 1e-6)
+    ref = F.silu(ref) if silu else ref
+    assert rel_err(got, ref) < 1e-3  # f16 output rounding
+    if B > 1:
+        assert torch.equal(build(a[:1], b[:1] if C1 else None), got[:1])
+
+
 def test_layernorm_geglu_softmax_cast_upsample(cuda_dev):
     Cc = 96
     Wt = {"n.weight": 1 + 0.1 * _x((Cc,), 1), "n.bias": 0.1 * _x((Cc,), 2)}
