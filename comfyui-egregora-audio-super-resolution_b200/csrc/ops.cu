@@ -398,28 +398,28 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(CatArgs a, double* __rest
     if (q < C4) {
       const float* base; int cc, Cx;
       if (c < a.C0) { base = a.x0; cc = c; Cx = a.C0; } else { base = a.x1; cc = c - a.C0; Cx = a.C1; }
-      // four rows per iteration, loads first: same additions in the same order as the one-row loop (p ascending)
+      // eight rows per iteration, all loads issued first (rows past the slab read as zeros, which leave the sums
+      // unchanged): same additions in the same order as a one-row loop (p ascending).  With four loads in flight per
+      // thread a 111-row slab was five dependent HBM round trips and the pass ran at ~45 % of the HBM rate.
       const float* rowp = base + ((long long)b * a.P + p_lo + ty) * Cx + cc;
       const long long rstride = 8ll * Cx;
-      long long p = p_lo + ty;
-      for (; p + 24 < p_hi; p += 32, rowp += 4 * rstride) {
-        float4 v[4];
+      for (long long p = p_lo + ty; p < p_hi; p += 64, rowp += 8 * rstride) {
+        float4 v[8];
+        // unconditional loads (a row past the slab re-reads the first one and is zeroed afterwards): predicated loads
+        // were scheduled two at a time by ptxas
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(rowp + k * rstride));
+        for (int k = 0; k < 8; ++k)
+          v[k] = __ldg(reinterpret_cast<const float4*>(p + 8 * k < p_hi ? rowp + k * rstride : rowp));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < 8; ++k)
+          if (p + 8 * k >= p_hi) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
           s[0] += v[k].x; ss[0] = fmaf(v[k].x, v[k].x, ss[0]);
           s[1] += v[k].y; ss[1] = fmaf(v[k].y, v[k].y, ss[1]);
           s[2] += v[k].z; ss[2] = fmaf(v[k].z, v[k].z, ss[2]);
           s[3] += v[k].w; ss[3] = fmaf(v[k].w, v[k].w, ss[3]);
         }
-      }
-      for (; p < p_hi; p += 8, rowp += rstride) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(rowp));
-        s[0] += v.x; ss[0] = fmaf(v.x, v.x, ss[0]);
-        s[1] += v.y; ss[1] = fmaf(v.y, v.y, ss[1]);
-        s[2] += v.z; ss[2] = fmaf(v.z, v.z, ss[2]);
-        s[3] += v.w; ss[3] = fmaf(v.w, v.w, ss[3]);
       }
     }
     // warps add their partials into sh in warp order (each lane owns its 4 channels: no conflicts)
@@ -450,6 +450,15 @@ __global__ void gn_finalize_kernel(const double* __restrict__ partials, double* 
   const double* p = partials + (long long)b * nslabs * G2 + i;
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int sl = y;
+  // sixteen loads in flight, added in the order of the four-load loop below (same bits): at ~1184 slabs the four-load
+  // form was 18 dependent L2 round trips, 11 us for 600 KB
+  for (; sl + 240 < nslabs; sl += 256) {
+    double v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = p[(long long)(sl + 16 * k) * G2];
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) { a0 += v[k]; a1 += v[k + 1]; a2 += v[k + 2]; a3 += v[k + 3]; }
+  }
   for (; sl + 48 < nslabs; sl += 64) {
     a0 += p[(long long)sl * G2]; a1 += p[(long long)(sl + 16) * G2];
     a2 += p[(long long)(sl + 32) * G2]; a3 += p[(long long)(sl + 48) * G2];
@@ -464,6 +473,7 @@ __global__ void gn_finalize_kernel(const double* __restrict__ partials, double* 
   }
 }
 
+template <bool CAT>   // CAT: the input is a virtual concat of two tensors (per-unit source select, 4 units in flight)
 __global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* __restrict__ stats,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int silu, float* __restrict__ out32,
@@ -486,13 +496,51 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* 
   }
   __syncthreads();
   const long long p_lo = (long long)blockIdx.x * slab, p_hi = min(p_lo + slab, a.P);
+  if (p_lo >= p_hi) return;
   const int total = (int)(p_hi - p_lo) * C4;  // float4 units of this slab (slab <= a few thousand pixels)
   const long long row0 = (long long)b * a.P + p_lo;
   // (pixel, channel-quad) of unit i advance by a fixed step per iteration: one division per thread, none per element.
-  // Four units per thread and iteration, all four loads issued before the first use (one load in flight per thread left
-  // this kernel at ~40 % of the HBM rate on the 131072 x 128 maps).
   const int step_p = (int)blockDim.x / C4, step_q = (int)blockDim.x - step_p * C4;
   int pl = (int)threadIdx.x / C4, q = (int)threadIdx.x - pl * C4;
+  auto finish = [&](float4 v, int c, long long o) {
+    const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
+    float r[4] = {fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)};
+    if (silu) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = egr_silu(r[u]);
+    }
+    if (out32) *reinterpret_cast<float4*>(out32 + o) = make_float4(r[0], r[1], r[2], r[3]);
+    if (out16) {
+      __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<unsigned*>(&h0);
+      pk.y = *reinterpret_cast<unsigned*>(&h1);
+      *reinterpret_cast<uint2*>(out16 + o) = pk;
+    }
+  };
+  if (!CAT) {
+    // one tensor: the slab is one contiguous run of float4 units, unit i at base + 4 i; only the channel quad needs
+    // tracking.  Eight loads per thread are issued before the first use (one load in flight per thread left this kernel
+    // at ~40 % of the HBM rate on the 131072 x 128 maps, four at ~55 %).
+    const float4* src = reinterpret_cast<const float4*>(a.x0 + row0 * C);
+    const long long obase = row0 * C;
+    for (int i = threadIdx.x; i < total; i += 8 * blockDim.x) {
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int u = i + k * (int)blockDim.x;
+        v[k] = __ldg(src + (u < total ? u : i));   // unconditional: ptxas keeps all eight in flight
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int u = i + k * (int)blockDim.x;
+        if (u < total) finish(v[k], q << 2, obase + 4ll * u);
+        q += step_q;
+        if (q >= C4) q -= C4;
+      }
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < total; i += 4 * blockDim.x) {
     float4 v[4];
     int cq[4];
@@ -512,24 +560,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* 
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (i + k * (int)blockDim.x < total) {
-        const int c = cq[k];
-        const float4 sc = *reinterpret_cast<const float4*>(scale + c), sh = *reinterpret_cast<const float4*>(shift + c);
-        float r[4] = {fmaf(v[k].x, sc.x, sh.x), fmaf(v[k].y, sc.y, sh.y), fmaf(v[k].z, sc.z, sh.z), fmaf(v[k].w, sc.w, sh.w)};
-        if (silu) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) r[u] = egr_silu(r[u]);
-        }
-        const long long o = pp[k] * C + c;
-        if (out32) *reinterpret_cast<float4*>(out32 + o) = make_float4(r[0], r[1], r[2], r[3]);
-        if (out16) {
-          __half2 h0 = __floats2half2_rn(r[0], r[1]), h1 = __floats2half2_rn(r[2], r[3]);
-          uint2 pk;
-          pk.x = *reinterpret_cast<unsigned*>(&h0);
-          pk.y = *reinterpret_cast<unsigned*>(&h1);
-          *reinterpret_cast<uint2*>(out16 + o) = pk;
-        }
-      }
+      if (i + k * (int)blockDim.x < total) finish(v[k], cq[k], pp[k] * C + cq[k]);
     }
   }
 }
@@ -635,8 +666,9 @@ static bool gn_use_fused(const CatArgs& a) {
 }
 
 static int slab_for(long long P, int* nslabs) {
-  // ~1184 slabs for the largest maps (8 per SM at batch 1); a function of P only, so results do not depend on B
-  long long slab = (P + 1183) / 1184;
+  // ~592 slabs for the largest maps (one wave of 4 CTAs per SM at batch 1; the finalize pass reads every slab's partials
+  // in one CTA per item, so fewer, longer slabs are cheaper); a function of P only, so results do not depend on B
+  long long slab = (P + 591) / 592;
   if (slab < 16) slab = 16;
   if (slab > P) slab = P;
   *nslabs = (int)((P + slab - 1) / slab);
@@ -689,10 +721,27 @@ int egr::launch_gn_apply(const Spaces& s, const egr_op& op, cudaStream_t st) {
     EGR_CHECK_LAUNCH(op.name);
     return EGR_OK;
   }
-  int ns; int slab = slab_for(a.P, &ns);
+  // The apply pass is element-wise, so its partition is free (the statistics keep theirs: it fixes their summation
+  // order): one wave of row blocks per batch item, sized from the kernel's real occupancy.
   const int C = a.C0 + a.C1;
-  gn_apply_kernel<<<dim3(ns, a.B), 256, 2 * C * sizeof(float), st>>>(a, stats, gamma, beta, (float)op.f[EGR_F_EPS],
-                                                                     (int)op.i[EGR_I_MODE], o32, o16, slab);
+  const bool cat = a.C1 > 0;
+  static int resident[2] = {0, 0};
+  if (!resident[cat]) {
+    int per_sm = 0;
+    if (cat) EGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_apply_kernel<true>, 256, 2 * C * sizeof(float)));
+    else EGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_apply_kernel<false>, 256, 2 * C * sizeof(float)));
+    resident[cat] = (per_sm > 0 ? per_sm : 4) * (devinfo().sm_count ? devinfo().sm_count : 148);
+  }
+  long long slab = (a.P + resident[cat] - 1) / resident[cat];
+  if (slab < 16) slab = 16;
+  if (slab > a.P) slab = a.P;
+  const int ns = (int)((a.P + slab - 1) / slab);
+  if (cat)
+    gn_apply_kernel<true><<<dim3(ns, a.B), 256, 2 * C * sizeof(float), st>>>(a, stats, gamma, beta, (float)op.f[EGR_F_EPS],
+                                                                             (int)op.i[EGR_I_MODE], o32, o16, (int)slab);
+  else
+    gn_apply_kernel<false><<<dim3(ns, a.B), 256, 2 * C * sizeof(float), st>>>(a, stats, gamma, beta, (float)op.f[EGR_F_EPS],
+                                                                              (int)op.i[EGR_I_MODE], o32, o16, (int)slab);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }
@@ -1136,76 +1185,113 @@ int egr::launch_eltwise(const Spaces& s, const egr_op& op, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 #define SNAKE_TT 64
 
-// sin with an exact two-constant range reduction to [-pi, pi] followed by the SFU approximation (abs err ~4e-7)
-__device__ __forceinline__ float snake_sin(float a) {
-  // round-to-nearest by the 1.5 * 2^23 trick (two FMA-pipe instructions): rintf() is an FRND on the 16-lane XU pipe, which the
-  // two MUFU.SIN per output already keep busy — the XU pipe, not instruction issue, was this kernel's limiter
-  const float k = fmaf(a, 0.15915494309189535f, 12582912.0f) - 12582912.0f;
-  a = fmaf(k, -6.2831854820251465f, a);
-  a = fmaf(k, 1.7484555e-7f, a);
-  return __sinf(a);
-}
-__device__ __forceinline__ float snake_eval(float u, float alpha, float inv_beta) {
-  const float sn = snake_sin(u * alpha);
-  return fmaf(inv_beta * sn, sn, u);
+// The kernel is written once over a lane type V: float (one channel per thread) or float2 (two adjacent channels per
+// thread, every arithmetic instruction a packed FFMA2 / FMUL2 / FADD2 — same IEEE result per lane, half the issue slots;
+// the scalar kernel sat at 74 cycles per warp-output = its 38 FMA-pipe instructions at one per two cycles).
+template <typename V> struct SnakeLane;
+template <> struct SnakeLane<float> {
+  static constexpr int W = 1;
+  static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ float bc(float a) { return a; }
+  static __device__ __forceinline__ float fma(float a, float b, float c) { return fmaf(a, b, c); }
+  static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+  static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+  static __device__ __forceinline__ float sfu_sin(float a) { return __sinf(a); }
+  static __device__ __forceinline__ float expv(float a) { return __expf(a); }
+  static __device__ __forceinline__ float inv_eps(float a) { return 1.0f / (a + 1e-9f); }
+  static __device__ __forceinline__ void st32(float* p, float v) { *p = v; }
+  static __device__ __forceinline__ void st16(__half* p, float v) { *p = __float2half_rn(v); }
+};
+template <> struct SnakeLane<float2> {
+  static constexpr int W = 2;
+  static __device__ __forceinline__ float2 ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+  static __device__ __forceinline__ float2 bc(float a) { return make_float2(a, a); }
+  static __device__ __forceinline__ float2 fma(float2 a, float2 b, float2 c) { return egr_fma2(a, b, c); }
+  static __device__ __forceinline__ float2 mul(float2 a, float2 b) { return egr_mul2(a, b); }
+  static __device__ __forceinline__ float2 add(float2 a, float2 b) { return egr_add2(a, b); }
+  static __device__ __forceinline__ float2 sfu_sin(float2 a) { return make_float2(__sinf(a.x), __sinf(a.y)); }
+  static __device__ __forceinline__ float2 expv(float2 a) { return make_float2(__expf(a.x), __expf(a.y)); }
+  static __device__ __forceinline__ float2 inv_eps(float2 a) { return make_float2(1.0f / (a.x + 1e-9f), 1.0f / (a.y + 1e-9f)); }
+  static __device__ __forceinline__ void st32(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+  static __device__ __forceinline__ void st16(__half* p, float2 v) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v.x, v.y); }
+};
+
+// s = U + sin^2(alpha U) / beta, U = the up-sampled sample (the up-sampler's gain of 2 is folded into its taps: doubling
+// is exact, so U carries the bits of 2 * sum).  sin is the SFU approximation on the raw phase: MUFU.SIN works on
+// phase / 2 pi, whose float32 rounding is |phase| * 1e-8 rad — 3e-6 rad at 50 rad, two orders of magnitude below the f16
+// rounding of the value this feeds — so the explicit reduction to [-pi, pi] this kernel used to carry (four more FMA-pipe
+// instructions per evaluation, in a kernel that is bound by that pipe) bought nothing measurable.
+template <typename V>
+__device__ __forceinline__ V snake_eval(V U, V alpha, V inv_beta) {
+  using L = SnakeLane<V>;
+  const V sn = L::sfu_sin(L::mul(U, alpha));
+  return L::fma(L::mul(inv_beta, sn), sn, U);
 }
 
-// Thread = (channel, run of SNAKE_TT outputs), linear over (run, channel) so every lane is busy for any C and
-// consecutive lanes read consecutive channels (coalesced).  Both the 6-sample input window and the 12-sample
+// Thread = (W adjacent channels, run of tt outputs), linear over (run, channel group) so every lane is busy for any C
+// and consecutive lanes read consecutive channels (coalesced).  Both the 6-sample input window and the 12-sample
 // activated window slide in registers: per output 1 load, 12 FMAs (two up-sampling phases), 2 snake evaluations,
 // 12 FMAs (down-sampling), 1 store.
-template <bool O32, bool O16>   // which outputs exist: compile-time, so the per-sample stores carry no branches
-__global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__ x, int T, int C, int nruns, int tt,
+// MB = resident CTAs per SM the register allocation aims at.
+template <typename V, int MB, bool O32, bool O16>   // which outputs exist: compile-time, so the per-sample stores carry no branches
+__global__ void __launch_bounds__(128, MB) snake_aa_kernel(const float* __restrict__ x, int T, int C, int nruns, int tt,
                                                         const float* __restrict__ log_alpha,
                                                         const float* __restrict__ log_beta,
                                                         const float* __restrict__ filt, float* __restrict__ o32,
                                                         __half* __restrict__ o16) {
+  using L = SnakeLane<V>;
+  const int CG = C / L::W;   // channel groups
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)nruns * C) return;
-  const int c = (int)(idx % C);
-  const int t0 = (int)(idx / C) * tt;
+  if (idx >= (long long)nruns * CG) return;
+  const int c = (int)(idx % CG) * L::W;
+  const int t0 = (int)(idx / CG) * tt;
   const int b = blockIdx.y;
-  const float alpha = __expf(log_alpha[c]);
-  const float inv_beta = 1.0f / (__expf(log_beta[c]) + 1e-9f);
+  const V alpha = L::expv(L::ld(log_alpha + c));
+  const V inv_beta = L::inv_eps(L::expv(L::ld(log_beta + c)));
   const float* xb = x + (long long)b * T * C + c;
-  float f[12];
+  V f[12], f2[12];   // down-sampling taps, up-sampling taps (x2); uniform registers in the compiled kernel
 #pragma unroll
-  for (int j = 0; j < 12; ++j) f[j] = __ldg(filt + j);
+  for (int j = 0; j < 12; ++j) {
+    const float fj = __ldg(filt + j);
+    f[j] = L::bc(fj);
+    f2[j] = L::bc(2.0f * fj);
+  }
+  const V zero = L::bc(0.f);
   const int n_last = 2 * T - 1;
-  auto xat = [&](int m) { m = m < 0 ? 0 : (m >= T ? T - 1 : m); return __ldg(xb + (long long)m * C); };
+  auto xat = [&](int m) { m = m < 0 ? 0 : (m >= T ? T - 1 : m); return L::ld(xb + (long long)m * C); };
   auto s_at = [&](int n) {  // activated up-sampled sample n (clamped = replicate padding of s); warm-up only
     n = n < 0 ? 0 : (n > n_last ? n_last : n);
     const int m = n >> 1;
-    float u = 0.f;
+    V u = zero;
     if (n & 1) {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) u = fmaf(xat(m - 2 + r), f[10 - 2 * r], u);
+      for (int r = 0; r < 6; ++r) u = L::fma(xat(m - 2 + r), f2[10 - 2 * r], u);
     } else {
 #pragma unroll
-      for (int r = 0; r < 6; ++r) u = fmaf(xat(m - 3 + r), f[11 - 2 * r], u);
+      for (int r = 0; r < 6; ++r) u = L::fma(xat(m - 3 + r), f2[11 - 2 * r], u);
     }
-    return snake_eval(2.0f * u, alpha, inv_beta);
+    return snake_eval<V>(u, alpha, inv_beta);
   };
-  float sw[12];
-  float xw[6];
+  V sw[12];
+  V xw[6];
   if (t0 >= 5 && 2 * t0 + 4 <= n_last && t0 + 4 < T) {
     // interior run: the ten warm-up samples s[2t0-5 .. 2t0+4] only need x[t0-5 .. t0+4] — ten independent loads
     // issued together instead of sixty dependent-latency ones
-    float xr[10];
+    V xr[10];
 #pragma unroll
-    for (int i = 0; i < 10; ++i) xr[i] = __ldg(xb + (long long)(t0 - 5 + i) * C);
+    for (int i = 0; i < 10; ++i) xr[i] = L::ld(xb + (long long)(t0 - 5 + i) * C);
 #pragma unroll
     for (int j = 0; j < 10; ++j) {
       // n = 2 t0 - 5 + j ; odd n (j even): m = t0 - 3 + j/2, taps x[m-2 .. m+3] ; even n (j odd): m = t0 - 2 + (j-1)/2, x[m-3 .. m+2]
-      float u = 0.f;
+      V u = zero;
       if ((j & 1) == 0) {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) u = fmaf(xr[(j >> 1) + r], f[10 - 2 * r], u);
+        for (int r = 0; r < 6; ++r) u = L::fma(xr[(j >> 1) + r], f2[10 - 2 * r], u);
       } else {
 #pragma unroll
-        for (int r = 0; r < 6; ++r) u = fmaf(xr[((j - 1) >> 1) + r], f[11 - 2 * r], u);
+        for (int r = 0; r < 6; ++r) u = L::fma(xr[((j - 1) >> 1) + r], f2[11 - 2 * r], u);
       }
-      sw[j + 2] = snake_eval(2.0f * u, alpha, inv_beta);
+      sw[j + 2] = snake_eval<V>(u, alpha, inv_beta);
     }
 #pragma unroll
     for (int r = 0; r < 5; ++r) xw[r + 1] = xr[5 + r];  // slots 1..5 hold x[t0 .. t0+4]
@@ -1216,52 +1302,53 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
     for (int r = 0; r < 5; ++r) xw[r + 1] = xat(t0 + r);
   }
   const int t_end = min(T, t0 + tt);
-  if (t0 >= 5 && t0 + tt + 13 <= T && (tt & 7) == 0) {
+  if (t0 >= 5 && t0 + tt + 13 <= T && tt % (L::W == 2 ? 6 : 8) == 0) {
     // Interior run (all but the first / last runs of a signal): every index is in range, so the clamps, the end-of-
     // signal selects and the per-output bounds test disappear and addresses advance by pointer increments — the
     // clamped form spends more instructions on integer index math than on the filter itself.
     const float* px = xb + (long long)(t0 + 5) * C;   // next input sample to enter the window
+    constexpr int PF = L::W == 2 ? 6 : 8;             // outputs per load group; 6 = one full rotation of both register windows
     float* p32 = O32 ? o32 + ((long long)b * T + t0) * C + c : nullptr;
     __half* p16 = O16 ? o16 + ((long long)b * T + t0) * C + c : nullptr;
-    float xn[8];
+    V xn[PF];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { xn[i] = __ldg(px); px += C; }
-    for (int tb = t0; tb < t_end; tb += 8) {
-      float xnext[8];
+    for (int i = 0; i < PF; ++i) { xn[i] = L::ld(px); px += C; }
+    for (int tb = t0; tb < t_end; tb += PF) {
+      V xnext[PF];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { xnext[i] = __ldg(px); px += C; }  // one group ahead (in range by the run test)
+      for (int i = 0; i < PF; ++i) { xnext[i] = L::ld(px); px += C; }  // one group ahead (in range by the run test)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < PF; ++i) {
 #pragma unroll
         for (int j = 0; j < 10; ++j) sw[j] = sw[j + 2];
 #pragma unroll
         for (int r = 0; r < 5; ++r) xw[r] = xw[r + 1];
         xw[5] = xn[i];
-        float uo = 0.f, ue = 0.f;
+        V uo = zero, ue = zero;
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-          uo = fmaf(xw[r], f[10 - 2 * r], uo);
-          ue = fmaf(xw[r], f[11 - 2 * r], ue);
+          uo = L::fma(xw[r], f2[10 - 2 * r], uo);
+          ue = L::fma(xw[r], f2[11 - 2 * r], ue);
         }
-        sw[10] = snake_eval(2.0f * uo, alpha, inv_beta);
-        sw[11] = snake_eval(2.0f * ue, alpha, inv_beta);
-        float y = 0.f;
+        sw[10] = snake_eval<V>(uo, alpha, inv_beta);
+        sw[11] = snake_eval<V>(ue, alpha, inv_beta);
+        V y = zero;
 #pragma unroll
-        for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
-        if (O32) { *p32 = y; p32 += C; }
-        if (O16) { *p16 = __float2half_rn(y); p16 += C; }
+        for (int j = 0; j < 12; ++j) y = L::fma(sw[j], f[j], y);
+        if (O32) { L::st32(p32, y); p32 += C; }
+        if (O16) { L::st16(p16, y); p16 += C; }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xn[i] = xnext[i];
+      for (int i = 0; i < PF; ++i) xn[i] = xnext[i];
     }
     return;
   }
   // boundary runs: clamped indices (replicate padding of the input and of the activated signal)
-  float xn[8];
+  V xn[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) xn[i] = xat(t0 + i + 5);
   for (int tb = t0; tb < t_end; tb += 8) {
-    float xnext[8];
+    V xnext[8];
     if (tb + 8 < t_end) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) xnext[i] = xat(tb + 8 + i + 5);
@@ -1276,25 +1363,59 @@ __global__ void __launch_bounds__(128) snake_aa_kernel(const float* __restrict__
       for (int r = 0; r < 5; ++r) xw[r] = xw[r + 1];
       xw[5] = xn[i];
       // s[2t+5] (odd phase of m = t+2) and s[2t+6] (even phase of m = t+3) both read x[t .. t+5]
-      float uo = 0.f, ue = 0.f;
+      V uo = zero, ue = zero;
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
-        uo = fmaf(xw[r], f[10 - 2 * r], uo);
-        ue = fmaf(xw[r], f[11 - 2 * r], ue);
+        uo = L::fma(xw[r], f2[10 - 2 * r], uo);
+        ue = L::fma(xw[r], f2[11 - 2 * r], ue);
       }
-      const float so = snake_eval(2.0f * uo, alpha, inv_beta), se = snake_eval(2.0f * ue, alpha, inv_beta);
+      const V so = snake_eval<V>(uo, alpha, inv_beta), se = snake_eval<V>(ue, alpha, inv_beta);
       sw[10] = (2 * t + 5 <= n_last) ? so : sw[9];
       sw[11] = (2 * t + 6 <= n_last) ? se : sw[10];
-      float y = 0.f;
+      V y = zero;
 #pragma unroll
-      for (int j = 0; j < 12; ++j) y = fmaf(sw[j], f[j], y);
+      for (int j = 0; j < 12; ++j) y = L::fma(sw[j], f[j], y);
       const long long o = ((long long)b * T + t) * C + c;
-      if (O32) o32[o] = y;
-      if (O16) o16[o] = __float2half_rn(y);
+      if (O32) L::st32(o32 + o, y);
+      if (O16) L::st16(o16 + o, y);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) xn[i] = xnext[i];
   }
+}
+
+template <typename V, int MB>
+static int snake_aa_launch(const char* name, const float* x, int B, int T, int C, const float* la, const float* lb,
+                           const float* filt, float* o32, __half* o16, cudaStream_t st) {
+  constexpr int W = SnakeLane<V>::W;
+  // Outputs per thread: every run pays ~10 warm-up evaluations of the activation, and a grid slightly larger than
+  // what the GPU holds at once costs a whole extra wave — pick the run length (multiple of the unroll) that minimises
+  // waves x (run + warm-up) for this tensor.
+  static int resident = 0;
+  if (!resident) {
+    int per_sm = 0;
+    EGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snake_aa_kernel<V, MB, false, true>, 128, 0));
+    resident = (per_sm > 0 ? per_sm : 8) * (egr::devinfo().sm_count ? egr::devinfo().sm_count : 148);
+  }
+  const int CG = C / W;
+  int tt = SNAKE_TT;
+  {
+    double best = 1e30;
+    constexpr int unit = W == 2 ? 6 : 8;   // the interior loop's unroll
+    for (int cand = 2 * unit; cand <= 128; cand += unit) {
+      const long long blocks = (((long long)((T + cand - 1) / cand) * CG + 127) / 128) * B;
+      const long long waves = (blocks + resident - 1) / resident;
+      const double cost = (double)waves * (cand + 10);
+      if (cost < best) { best = cost; tt = cand; }
+    }
+  }
+  const int nruns = (T + tt - 1) / tt;
+  dim3 grid((unsigned)(((long long)nruns * CG + 127) / 128), B);
+  if (o32 && o16) snake_aa_kernel<V, MB, true, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
+  else if (o16) snake_aa_kernel<V, MB, false, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
+  else snake_aa_kernel<V, MB, true, false><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
+  EGR_CHECK_LAUNCH(name);
+  return EGR_OK;
 }
 
 int egr::launch_snake_aa(const Spaces& s, const egr_op& op, cudaStream_t st) {
@@ -1307,32 +1428,14 @@ int egr::launch_snake_aa(const Spaces& s, const egr_op& op, cudaStream_t st) {
   const int B = (int)op.i[EGR_I_BATCH], T = (int)op.i[EGR_I_ROWS], C = (int)op.i[EGR_I_COLS];
   if (!x || !la || !lb || !filt || (!o32 && !o16) || B <= 0 || T <= 0 || C <= 0) return fail(EGR_ERR_ARG, "%s: bad arguments", op.name);
   if (op.i[EGR_I_AUX0] != 12) return fail(EGR_ERR_UNSUPPORTED, "%s: only the 12-tap anti-alias filter is built", op.name);
-  // Outputs per thread: every run pays ~10 warm-up evaluations of the activation, and a grid slightly larger than
-  // what the GPU holds at once costs a whole extra wave — pick the run length (multiple of 8) that minimises
-  // waves x (run + warm-up) for this tensor.
-  static int resident = 0;
-  if (!resident) {
-    int per_sm = 0;
-    EGR_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, snake_aa_kernel<false, true>, 128, 0));
-    resident = (per_sm > 0 ? per_sm : 8) * (devinfo().sm_count ? devinfo().sm_count : 148);
-  }
-  int tt = SNAKE_TT;
-  {
-    double best = 1e30;
-    for (int cand = 16; cand <= 128; cand += 8) {
-      const long long blocks = (((long long)((T + cand - 1) / cand) * C + 127) / 128) * B;
-      const long long waves = (blocks + resident - 1) / resident;
-      const double cost = (double)waves * (cand + 10);
-      if (cost < best) { best = cost; tt = cand; }
-    }
-  }
-  const int nruns = (T + tt - 1) / tt;
-  dim3 grid((unsigned)(((long long)nruns * C + 127) / 128), B);
-  if (o32 && o16) snake_aa_kernel<true, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
-  else if (o16) snake_aa_kernel<false, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
-  else snake_aa_kernel<true, false><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
-  EGR_CHECK_LAUNCH(op.name);
-  return EGR_OK;
+  // two channels per thread (packed f32x2 arithmetic) whenever the channel pairs are 8-byte aligned everywhere
+  const bool no_pack = getenv("EGR_SNAKE_SCALAR") != nullptr;   // read per launch: the op test compares the two paths bit for bit
+  const bool pack = !no_pack && (C & 1) == 0 && (((uintptr_t)x | (uintptr_t)la | (uintptr_t)lb | (uintptr_t)o32) & 7) == 0 &&
+                    ((uintptr_t)o16 & 3) == 0;
+  // register targets swept on B200 (tools/snake_sweep.py, c2 pass, 91 ops): packed at 4 / 5 / 6 / 7 / 8 CTAs per SM
+  // 2031 / 2224 / 2223 / 2437 / 2347 us, scalar 2352 us — the kernel is bound by the FMA pipe, not by latency
+  if (pack) return snake_aa_launch<float2, 4>(op.name, x, B, T, C, la, lb, filt, o32, o16, st);
+  return snake_aa_launch<float, 6>(op.name, x, B, T, C, la, lb, filt, o32, o16, st);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -114,7 +114,7 @@ def tile_geometry(Wo: int, Ho: int, Bo: int) -> Tuple[int, int, int]:
 def gn_slabs(P: int) -> Tuple[int, int]:
     """(slab, n_slabs) of the GroupNorm reduction — must match slab_for() in csrc/ops.cu; a function of the pixel
     count only, so results are bit-identical for any batch size."""
-    slab = min(max((P + 1183) // 1184, 16), P)
+    slab = min(max((P + 591) // 592, 16), P)
     return slab, (P + slab - 1) // slab
 
 
@@ -245,14 +245,17 @@ class PlanBackend:
         """Return a PT whose .f16 holds x (concats and f32-only tensors go through one CAST16 pass)."""
         if x.f16 is not None and x.parts is None and not x.f16_transposed and x.ld == x.C:
             return x
-        prod = x.producer
-        if (x.f16 is None and x.parts is None and x.ld == x.C and x.coff == 0 and prod is not None and prod.index >= 0
-                and "OUT16" not in prod.ptr):
-            # the op that produced the f32 tensor writes the f16 copy in its own epilogue: no separate cast pass
+        prods = x.producer if isinstance(x.producer, list) else ([x.producer] if x.producer is not None else [])
+        if (x.f16 is None and x.parts is None and x.ld == x.C and x.coff == 0 and prods
+                and all(pr.index >= 0 and "OUT16" not in pr.ptr for pr in prods)):
+            # the op(s) that produced the f32 tensor write the f16 copy in their own epilogue (same element indices as the
+            # f32 store, so the four interleaved phase GEMMs of an up-sampling conv fill one buffer): no separate cast pass
             buf = self.buf(x.B * x.P * x.C * 2, tag + ".f16", persistent=self.debug)
-            buf.first = buf.last = prod.index
-            prod.ptr["OUT16"] = ("ws", buf, 0)
-            prod.writes.append(buf)
+            buf.first = min(pr.index for pr in prods)
+            buf.last = max(pr.index for pr in prods)
+            for pr in prods:
+                pr.ptr["OUT16"] = ("ws", buf, 0)
+                pr.writes.append(buf)
             x.f16 = buf
             return x
         parts = x.parts if x.parts else (x, None)
@@ -393,6 +396,7 @@ class PlanBackend:
         w = self.Wt[name + ".weight"].float()           # [cout, cin, 3, 3]
         groups = {0: [(-1, [0]), (0, [1, 2])], 1: [(0, [0, 1]), (1, [2])]}   # phase -> [(source offset, kernel rows/cols)]
         dims, strides = [cin, W, H, B], [1, cin, W * cin, H * W * cin]
+        phase_ops = []
         for a in (0, 1):
             for b in (0, 1):
                 taps, mats = [], []
@@ -402,11 +406,11 @@ class PlanBackend:
                         mats.append(sum(w[:, :, ky, kx] for ky in kys for kx in kxs))   # [cout, cin]
                 pk = torch.stack(mats, 0).contiguous()
                 w_off = self.blob.put(f"f16:{name}.weight:up{a}{b}", pk.numpy().astype(np.float16))
-                self._gemm(f"{name}.p{a}{b}", x, (xa.f16, 0, dims, strides), taps, cin, cout, w_off, simt=False, dimW=1, dimH=2,
+                phase_ops.append(self._gemm(f"{name}.p{a}{b}", x, (xa.f16, 0, dims, strides), taps, cin, cout, w_off, simt=False, dimW=1, dimH=2,
                            dimB=3, Wo=W, Ho=H, Bo=B, out_pt=o, out16=False, out32=True, bias_off=self.w_bias(name),
                            out_pix_stride=2 * cout, out_h_stride=4 * W * cout, out_batch_stride=4 * H * W * cout,
-                           out_offset=(a * 2 * W + b) * cout, out_lo=0, out_hi=4 * H * W * cout)
-        o.producer = None   # four writers: an f16 copy would need all of them
+                           out_offset=(a * 2 * W + b) * cout, out_lo=0, out_hi=4 * H * W * cout))
+        o.producer = phase_ops   # four writers: an f16 copy on demand is written by all of them (_materialize16)
         return o
 
     def linear(self, x: PT, name, cin, cout, bias=True, small=False, act=None, out=None, add=None):

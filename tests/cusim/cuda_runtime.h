@@ -205,6 +205,7 @@ inline float __fdiv_rn(float a, float b) { return a / b; }
 inline float __fsqrt_rn(float a) { return sqrtf(a); }
 inline float __expf(float a) { return expf(a); }
 inline float __sinf(float a) { return sinf(a); }
+inline float __fdividef(float a, float b) { return a / b; }
 inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}

@@ -2,6 +2,7 @@
 egr_plan_create / egr_plan_run, i.e. the C ABI).  Tolerances: CUDA-core f32 paths 1e-5 relative; tensor-core
 paths round operands to f16 (11-bit mantissa) and accumulate in f32 -> 2e-3 relative RMS."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -318,7 +319,7 @@ def test_attention_gemm_path(S, Cc, cuda_dev):
     assert rel_err(mp.read(o).flatten(2).permute(0, 2, 1), ref) < 4e-3
 
 
-@pytest.mark.parametrize("Cc,T", [(48, 1000), (24, 77), (96, 4096), (8, 13)])
+@pytest.mark.parametrize("Cc,T", [(48, 1000), (24, 77), (96, 4096), (8, 13), (7, 50)])
 def test_snake_aa(Cc, T, cuda_dev):
     from oracle.flashsr_oracle import TorchBackend
     from egregora_b200 import flashsr_model as M
@@ -328,7 +329,19 @@ def test_snake_aa(Cc, T, cuda_dev):
     y = mp.be.snake_aa(mp.input(x), "a", Cc)
     mp.run_gpu()
     ref = TorchBackend(M.tiny_spec(), Wt).snake_aa(x[:, :, 0], "a", Cc)
-    assert rel_err(mp.read(y)[:, :, 0], ref) < 1e-3
+    got = mp.read(y)
+    assert rel_err(got[:, :, 0], ref) < 1e-3
+    if Cc % 2 == 0:
+        # even channel counts take the two-channels-per-thread kernel (packed f32x2 arithmetic): every lane must round
+        # exactly like the one-channel kernel
+        os.environ["EGR_SNAKE_SCALAR"] = "1"
+        try:
+            mp2 = MiniPlan(Wt)
+            y2 = mp2.be.snake_aa(mp2.input(x), "a", Cc)
+            mp2.run_gpu()
+            assert torch.equal(mp2.read(y2), got)
+        finally:
+            del os.environ["EGR_SNAKE_SCALAR"]
 
 
 @pytest.mark.parametrize("spec_name", ["tiny", "full"])
