@@ -258,6 +258,112 @@ __global__ void __launch_bounds__(256) conv_smalln8_kernel(View a, GemmArgs g, T
   }
 }
 
+// One-output-channel convolutions over an f16 map (vae.decoder.conv_out 128 -> 1 3x3, vocoder.conv_post 48 -> 1 k=7),
+// input-stationary: a CTA owns TW output pixels of one row.  Phase 1: a thread loads ONE input pixel (all K channels, once,
+// into registers) and forms its dot product with every tap that reads that input row, into shared memory; phase 2: an
+// output is the sum over taps of the dot products of the inputs it sees.  The output-stationary kernel above spends one
+// bounds test + address computation + load per (pixel, tap, 8-channel slice) — ~60 instructions around 8 FMAs; here every
+// input element is loaded and converted once per CTA and the FMAs dominate (98 -> ~12 us on the c2 pass per layer).
+struct RowTaps {
+  int ntaps, nrows, min_dw, span;   // span = max_dw - min_dw
+  int dh[4];                        // input-row offsets (distinct values of the taps' H offset)
+  signed char row_of[EGR_MAX_TAPS]; // tap -> index into dh
+  short dw[EGR_MAX_TAPS];
+};
+
+template <int K8>
+__global__ void __launch_bounds__(256) conv_n1_rows_kernel(View a, GemmArgs g, RowTaps rt, int TW) {
+  extern __shared__ float wsm[];  // weights [ntaps][K], then dots [ntaps][TW + span]
+  constexpr int K = K8 * 8;
+  const int IW = TW + rt.span;
+  float* dots = wsm + rt.ntaps * K;
+  const float* W = reinterpret_cast<const float*>(g.W);
+  for (int i = threadIdx.x; i < rt.ntaps * K; i += blockDim.x) {
+    const int tap = i / K, k = i - tap * K;
+    wsm[i] = W[(long long)tap * g.wstride_z + k];
+  }
+  __syncthreads();
+  const int w0 = blockIdx.x * TW, h = blockIdx.y, b = blockIdx.z;
+  for (int it = threadIdx.x; it < rt.nrows * IW; it += blockDim.x) {
+    const int r = it / IW, j = it - r * IW;
+    const long long wi = (long long)w0 + rt.min_dw + j, hi = (long long)h + rt.dh[r];
+    const bool inb = wi >= 0 && wi < a.dim[g.dimW] && hi >= 0 && hi < a.dim[g.dimH];
+    float x[K];
+    if (inb) {
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.p) + wi * a.stride[g.dimW] +
+                                                        hi * a.stride[g.dimH] + (long long)b * a.stride[g.dimB]);
+      uint4 raw[K8];
+#pragma unroll
+      for (int i = 0; i < K8; ++i) raw[i] = __ldg(src + i);
+#pragma unroll
+      for (int i = 0; i < K8; ++i) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].y));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].z));
+        const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].w));
+        x[8 * i] = f0.x; x[8 * i + 1] = f0.y; x[8 * i + 2] = f1.x; x[8 * i + 3] = f1.y;
+        x[8 * i + 4] = f2.x; x[8 * i + 5] = f2.y; x[8 * i + 6] = f3.x; x[8 * i + 7] = f3.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) x[k] = 0.f;   // zero padding
+    }
+    for (int t = 0; t < rt.ntaps; ++t) {
+      if (rt.row_of[t] != r) continue;
+      const float* wt = wsm + t * K;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};   // four interleaved partial sums (k mod 4), added pairwise at the end
+#pragma unroll
+      for (int k = 0; k < K; k += 4) {
+        const float4 wv = *reinterpret_cast<const float4*>(wt + k);
+        acc[0] = fmaf(x[k], wv.x, acc[0]); acc[1] = fmaf(x[k + 1], wv.y, acc[1]);
+        acc[2] = fmaf(x[k + 2], wv.z, acc[2]); acc[3] = fmaf(x[k + 3], wv.w, acc[3]);
+      }
+      dots[t * IW + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    }
+  }
+  __syncthreads();
+  for (int jo = threadIdx.x; jo < TW; jo += blockDim.x) {
+    const int w = w0 + jo;
+    if (w >= g.Wo) break;
+    float sum = 0.f;
+    for (int t = 0; t < rt.ntaps; ++t) sum += dots[t * IW + jo + rt.dw[t] - rt.min_dw];   // tap order
+    epilogue_store(g, b, (long long)h * g.Wo + w, 0, sum);
+  }
+}
+
+// host side: does the op have the shape conv_n1_rows_kernel handles?  Fills rt / TW / K8.
+static bool conv_n1_rows_match(const View& a, const GemmArgs& g, const Taps& taps, RowTaps* rt, int* TW) {
+  if (g.N != 1 || a.elem != 1 || a.stride[0] != 1 || g.K != a.dim[0] || (g.K & 7) != 0 || g.K > 128) return false;
+  if (g.Wo != a.dim[g.dimW] || g.Ho != a.dim[g.dimH] || g.Bo != a.dim[g.dimB]) return false;   // stride-1, same size
+  if (g.dimW == g.dimH || g.dimW == g.dimB || g.dimH == g.dimB) return false;
+  if (((uintptr_t)a.p & 15) != 0) return false;
+  for (int d = 1; d < 5; ++d)
+    if ((a.stride[d] & 7) != 0) return false;   // 16-byte pixel rows
+  if (g.Ho > 65535 || g.Bo > 65535) return false;
+  rt->ntaps = g.ntaps; rt->nrows = 0;
+  int lo = 1 << 30, hi = -(1 << 30);
+  for (int t = 0; t < g.ntaps; ++t) {
+    for (int d = 0; d < 5; ++d)
+      if (d != g.dimW && d != g.dimH && taps.t[t][d] != 0) return false;   // channel / batch offsets: not this kernel
+    const int dh = taps.t[t][g.dimH], dw = taps.t[t][g.dimW];
+    int r = -1;
+    for (int i = 0; i < rt->nrows; ++i)
+      if (rt->dh[i] == dh) r = i;
+    if (r < 0) {
+      if (rt->nrows == 4) return false;
+      r = rt->nrows++;
+      rt->dh[r] = dh;
+    }
+    rt->row_of[t] = (signed char)r;
+    rt->dw[t] = (short)dw;
+    lo = dw < lo ? dw : lo; hi = dw > hi ? dw : hi;
+  }
+  rt->min_dw = lo; rt->span = hi - lo;
+  if (rt->span > 64) return false;
+  *TW = rt->nrows == 1 ? 256 - rt->span : 128;   // one row: exactly one 256-thread pass over the inputs
+  return true;
+}
+
 // Convolutions with a tiny reduction (1-channel inputs: vae.encoder.conv_in, vocoder.wave_pre; taps*K <= 64): a CTA
 // owns 64 pixels.  Phase 1 gathers the 64 x R input patch into shared memory (the tap bounds / address math runs
 // once per patch value, not once per output); phase 2: 4 threads per pixel sweep the output channels as float4
@@ -308,8 +414,7 @@ __global__ void __launch_bounds__(256) conv_smallk_kernel(View a, GemmArgs g, Ta
       const float4 wv = *reinterpret_cast<const float4*>(wsm + (size_t)r * g.N + n);
       acc[0] = fmaf(x, wv.x, acc[0]); acc[1] = fmaf(x, wv.y, acc[1]); acc[2] = fmaf(x, wv.z, acc[2]); acc[3] = fmaf(x, wv.w, acc[3]);
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) epilogue_store(g, b, pix, n + u, acc[u]);
+    epilogue_store4(g, b, pix, n, acc);
   }
 }
 
@@ -349,9 +454,26 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
   bool zero_taps = true;
   for (int t = 0; t < g.ntaps; ++t)
     for (int d = 0; d < 5; ++d) zero_taps = zero_taps && taps.t[t][d] == 0;
+  RowTaps rt;
+  int TW = 0;
   if (npix <= 8 && g.ntaps == 1 && zero_taps && a.elem == 0 && a.stride[0] == 1 && g.K <= a.dim[0] && al16(a.p) && al16(g.W) &&
       (g.wstride_n & 3) == 0 && (a.stride[g.dimW] & 3) == 0 && (a.stride[g.dimH] & 3) == 0 && (a.stride[g.dimB] & 3) == 0) {
     gemm_simt_gemv_kernel<<<(unsigned)((g.N + 7) / 8), 256, 0, st>>>(a, g, (int)npix);
+  } else if (conv_n1_rows_match(a, g, taps, &rt, &TW) && getenv("EGR_NO_CONV_N1_ROWS") == nullptr && [&] {
+               switch (g.K / 8) { case 1: case 2: case 3: case 4: case 6: case 8: case 12: case 16: return true; default: return false; }
+             }()) {
+    const dim3 grid((unsigned)((g.Wo + TW - 1) / TW), (unsigned)g.Ho, (unsigned)g.Bo);
+    const size_t smem = ((size_t)g.ntaps * g.K + (size_t)g.ntaps * (TW + rt.span)) * sizeof(float);
+    switch (g.K / 8) {
+      case 1: conv_n1_rows_kernel<1><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
+      case 2: conv_n1_rows_kernel<2><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
+      case 3: conv_n1_rows_kernel<3><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
+      case 4: conv_n1_rows_kernel<4><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
+      case 6: conv_n1_rows_kernel<6><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
+      case 8: conv_n1_rows_kernel<8><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
+      case 12: conv_n1_rows_kernel<12><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
+      default: conv_n1_rows_kernel<16><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
+    }
   } else if (g.K <= 4 && g.ntaps * g.K <= 64 && (g.N & 3) == 0 && (size_t)g.ntaps * g.K * (g.N + SMK_PIX) * sizeof(float) <= 48 * 1024) {
     conv_smallk_kernel<<<(unsigned)((npix + SMK_PIX - 1) / SMK_PIX), 256, (size_t)g.ntaps * g.K * (g.N + SMK_PIX) * sizeof(float), st>>>(a, g, taps);
   } else if (g.N <= 4 && (g.K & 7) == 0 && (a.dim[0] & 7) == 0 && a.stride[0] == 1 && al16(a.p) &&
@@ -385,59 +507,54 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
 
 // Deterministic (no atomics, fixed summation order) and independent of the batch size: block (slab, b) reduces its
 // slab of pixels to per-group f64 partial sums; gn_finalize_kernel adds the slabs in index order.
+// Thread mapping: QW threads across the channel quads of a pixel row (coalesced float4 loads), RP = 256 / QW row phases;
+// a thread sums rows p_lo + rp, + RP, ... in ascending order, eight loads in flight.  The phases meet through shared
+// memory after ONE barrier and are added in phase order.  (The first version put all eight warps on the same 32 quads and
+// walked wider rows in serial 32-quad passes with eight barriers each: 22 us for a 16 MB map of 8192 x 512.)
 __global__ void __launch_bounds__(256) gn_stats_kernel(CatArgs a, double* __restrict__ partials, int slab, int nslabs) {
-  extern __shared__ double sh[];  // [C][2]
-  const int C = a.C0 + a.C1, C4 = C >> 2, cpg = C / a.G;
+  extern __shared__ double sh[];  // [RP][C][2]
+  const int C = a.C0 + a.C1, Q = C >> 2, cpg = C / a.G;
+  int QW = 1;
+  while (QW * 2 <= Q && QW * 2 <= 256) QW *= 2;
+  const int RP = 256 / QW;
+  const int qi = threadIdx.x & (QW - 1), rp = threadIdx.x / QW;
   const int b = blockIdx.y;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const long long p_lo = (long long)blockIdx.x * slab, p_hi = min(p_lo + slab, a.P);
-  for (int q0 = 0; q0 < C4; q0 += 32) {
-    const int q = q0 + tx;
+  for (int q = qi; q < Q; q += QW) {
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
     const int c = q << 2;
-    if (q < C4) {
-      const float* base; int cc, Cx;
-      if (c < a.C0) { base = a.x0; cc = c; Cx = a.C0; } else { base = a.x1; cc = c - a.C0; Cx = a.C1; }
-      // eight rows per iteration, all loads issued first (rows past the slab read as zeros, which leave the sums
-      // unchanged): same additions in the same order as a one-row loop (p ascending).  With four loads in flight per
-      // thread a 111-row slab was five dependent HBM round trips and the pass ran at ~45 % of the HBM rate.
-      const float* rowp = base + ((long long)b * a.P + p_lo + ty) * Cx + cc;
-      const long long rstride = 8ll * Cx;
-      for (long long p = p_lo + ty; p < p_hi; p += 64, rowp += 8 * rstride) {
-        float4 v[8];
-        // unconditional loads (a row past the slab re-reads the first one and is zeroed afterwards): predicated loads
-        // were scheduled two at a time by ptxas
+    const float* base; int cc, Cx;
+    if (c < a.C0) { base = a.x0; cc = c; Cx = a.C0; } else { base = a.x1; cc = c - a.C0; Cx = a.C1; }
+    const float* rowp = base + ((long long)b * a.P + p_lo + rp) * Cx + cc;
+    const long long rstride = (long long)RP * Cx;
+    for (long long p = p_lo + rp; p < p_hi; p += 8 * RP, rowp += 8 * rstride) {
+      float4 v[8];
+      // unconditional loads (a row past the slab re-reads the first one and is zeroed afterwards, which leaves the sums
+      // unchanged): predicated loads were scheduled two at a time by ptxas
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          v[k] = __ldg(reinterpret_cast<const float4*>(p + 8 * k < p_hi ? rowp + k * rstride : rowp));
+      for (int k = 0; k < 8; ++k)
+        v[k] = __ldg(reinterpret_cast<const float4*>(p + (long long)k * RP < p_hi ? rowp + k * rstride : rowp));
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (p + 8 * k >= p_hi) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < 8; ++k)
+        if (p + (long long)k * RP >= p_hi) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          s[0] += v[k].x; ss[0] = fmaf(v[k].x, v[k].x, ss[0]);
-          s[1] += v[k].y; ss[1] = fmaf(v[k].y, v[k].y, ss[1]);
-          s[2] += v[k].z; ss[2] = fmaf(v[k].z, v[k].z, ss[2]);
-          s[3] += v[k].w; ss[3] = fmaf(v[k].w, v[k].w, ss[3]);
-        }
+      for (int k = 0; k < 8; ++k) {
+        s[0] += v[k].x; ss[0] = fmaf(v[k].x, v[k].x, ss[0]);
+        s[1] += v[k].y; ss[1] = fmaf(v[k].y, v[k].y, ss[1]);
+        s[2] += v[k].z; ss[2] = fmaf(v[k].z, v[k].z, ss[2]);
+        s[3] += v[k].w; ss[3] = fmaf(v[k].w, v[k].w, ss[3]);
       }
     }
-    // warps add their partials into sh in warp order (each lane owns its 4 channels: no conflicts)
-    for (int w = 0; w < 8; ++w) {
-      if (ty == w && q < C4) {
+    double* dst = sh + ((size_t)rp * C + c) * 2;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (w == 0) { sh[2 * (c + u)] = (double)s[u]; sh[2 * (c + u) + 1] = (double)ss[u]; }
-          else { sh[2 * (c + u)] += (double)s[u]; sh[2 * (c + u) + 1] += (double)ss[u]; }
-        }
-      }
-      __syncthreads();
-    }
+    for (int u = 0; u < 4; ++u) { dst[2 * u] = (double)s[u]; dst[2 * u + 1] = (double)ss[u]; }
   }
+  __syncthreads();
   for (int i = threadIdx.x; i < 2 * a.G; i += blockDim.x) {
     const int gi = i >> 1, st = i & 1;
     double acc = 0.0;
-    for (int cc = 0; cc < cpg; ++cc) acc += sh[2 * (gi * cpg + cc) + st];
+    for (int r = 0; r < RP; ++r)
+      for (int cc = 0; cc < cpg; ++cc) acc += sh[((size_t)r * C + gi * cpg + cc) * 2 + st];
     partials[(((long long)b * nslabs + blockIdx.x) * a.G + gi) * 2 + st] = acc;
   }
 }
@@ -686,7 +803,9 @@ int egr::launch_gn_stats(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (op.i[EGR_I_AUX1] != ns) return fail(EGR_ERR_ARG, "%s: plan was built for %lld slabs, kernel wants %d", op.name, (long long)op.i[EGR_I_AUX1], ns);
   const int C = a.C0 + a.C1, G2 = 2 * a.G;
   double* partials = stats + (long long)a.B * G2;
-  const size_t smem = (size_t)C * 2 * sizeof(double);
+  int QW = 1;
+  while (QW * 2 <= (C >> 2) && QW * 2 <= 256) QW *= 2;
+  const size_t smem = (size_t)(256 / QW) * C * 2 * sizeof(double);   // [RP][C][2] as the kernel lays it out (< 32 KB up to C = 1024)
   if (smem > 48 * 1024) return fail(EGR_ERR_UNSUPPORTED, "%s: C=%d too wide for the GroupNorm reduction", op.name, C);
   if (G2 > 64) return fail(EGR_ERR_UNSUPPORTED, "%s: at most 32 groups", op.name);
   gn_stats_kernel<<<dim3(ns, a.B), 256, smem, st>>>(a, partials, slab, ns);

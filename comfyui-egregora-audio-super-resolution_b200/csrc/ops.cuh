@@ -108,6 +108,48 @@ __device__ __forceinline__ void epilogue_store(const egr::GemmArgs& g, int b, lo
   if (g.out16) g.out16[idx] = __float2half_rn(v);
 }
 
+// four consecutive output channels n .. n+3 of one pixel: one 16-byte store (and one 8-byte f16 store) when the output is
+// dense in n, aligned and inside the crop; the scalar path otherwise.  Same arithmetic per element as epilogue_store.
+__device__ __forceinline__ void epilogue_store4(const egr::GemmArgs& g, int b, long long pix, int n, const float (&acc)[4]) {
+  const long long flat = pix * g.out_pix_stride + g.out_offset + n;
+  const long long idx = (long long)b * g.out_batch_stride + flat;
+  const bool vec = !g.transposed && (idx & 3) == 0 && flat >= g.out_lo && flat + 3 < g.out_hi && n + 3 < g.N &&
+                   (reinterpret_cast<uintptr_t>(g.out32) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.out16) & 7) == 0 &&
+                   (!g.resid || (reinterpret_cast<uintptr_t>(g.resid) & 15) == 0) &&
+                   (!g.resid2 || (reinterpret_cast<uintptr_t>(g.resid2) & 15) == 0);
+  if (!vec) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (n + u < g.N) epilogue_store(g, b, pix, n + u, acc[u]);
+    return;
+  }
+  float v[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    v[u] = acc[u] * g.alpha;
+    if (g.bias) v[u] += g.bias[n + u];
+    if (g.rowbias) v[u] += g.rowbias[(long long)b * g.rowbias_stride + n + u];
+    v[u] = egr_apply_act(v[u], g.act);
+  }
+  if (g.resid) {
+    const float4 r = *reinterpret_cast<const float4*>(g.resid + idx);
+    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+  }
+  if (g.resid2) {
+    const float4 r = *reinterpret_cast<const float4*>(g.resid2 + idx);
+    v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) v[u] *= g.post;
+  if (g.out32) *reinterpret_cast<float4*>(g.out32 + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  if (g.out16) {
+    __half2 h0 = __floats2half2_rn(v[0], v[1]), h1 = __floats2half2_rn(v[2], v[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<unsigned*>(&h0);
+    pk.y = *reinterpret_cast<unsigned*>(&h1);
+    *reinterpret_cast<uint2*>(g.out16 + idx) = pk;
+  }
+}
 
 // GroupNorm input: a virtual channel-concat of x0 (C0 channels) and x1 (C1 channels), f32, channels innermost
 struct CatArgs {

@@ -141,6 +141,38 @@ def test_conv2d_simt(cin, cout, cuda_dev):
     assert rel_err(mp.read(y), F.conv2d(x, Wt["c.weight"], Wt["c.bias"], padding=1)) < F32_TOL
 
 
+@pytest.mark.parametrize("cin,H,W,B", [(128, 20, 37, 2), (32, 9, 300, 1), (64, 3, 129, 3)])
+def test_conv2d_one_output_channel_f16_input(cin, H, W, B, cuda_dev):
+    """vae.decoder.conv_out as the plan runs it: GroupNorm + SiLU (f16 out) -> 3x3 conv to ONE channel (the input-stationary
+    kernel: row tiles with ragged ends, zero padding on all four borders, batch items)."""
+    Wt = {"n.weight": 1 + 0.1 * _x((cin,), 1), "n.bias": 0.1 * _x((cin,), 2),
+          "c.weight": _w((1, cin, 3, 3), 3), "c.bias": _x((1,), 4) * 0.1}
+    x = _x((B, cin, H, W), 5)
+    mp = MiniPlan(Wt)
+    hmid = mp.be.groupnorm(mp.input(x), "n", cin, 32, 1e-6, silu=True)
+    y = mp.be.conv2d(hmid, "c", cin, 1, 3)
+    assert mp.be.ops[-1].code == 2
+    mp.run_gpu()
+    mid = mp.read(hmid)     # the f16 values the conv actually consumed
+    assert rel_err(mp.read(y), F.conv2d(mid, Wt["c.weight"], Wt["c.bias"], padding=1)) < F32_TOL
+
+
+@pytest.mark.parametrize("cin,k,T,B", [(48, 7, 1000, 2), (16, 7, 250, 1), (24, 3, 777, 1), (96, 11, 260, 2)])
+def test_conv1d_one_output_channel_f16_input(cin, k, T, B, cuda_dev):
+    """vocoder.conv_post as the plan runs it: anti-aliased SnakeBeta (f16 out) -> k-tap conv to ONE channel + tanh."""
+    Wt = {"a.act.alpha": 0.2 * _x((cin,), 1), "a.act.beta": 0.2 * _x((cin,), 2),
+          "c.weight": _w((1, cin, k), 3), "c.bias": _x((1,), 4) * 0.1}
+    x = _x((B, cin, 1, T), 5)
+    mp = MiniPlan(Wt)
+    hmid = mp.be.snake_aa(mp.input(x), "a", cin)
+    y = mp.be.conv1d(hmid, "c", cin, 1, k, act="tanh")
+    assert mp.be.ops[-1].code == 2
+    mp.run_gpu()
+    mid = mp.read(hmid)[:, :, 0]
+    ref = torch.tanh(F.conv1d(mid, Wt["c.weight"], Wt["c.bias"], padding=k // 2))
+    assert rel_err(mp.read(y)[:, :, 0], ref) < F32_TOL
+
+
 def test_conv2d_f16_transposed_and_rowbias(cuda_dev):
     cin, cout = 64, 128
     Wt = {"c.weight": _w((cout, cin, 1, 1), 1), "c.bias": _x((cout,), 2) * 0.1,
