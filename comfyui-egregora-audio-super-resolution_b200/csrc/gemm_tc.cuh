@@ -894,6 +894,8 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
           }
         }
         uint32_t r[32];
+        const bool stamp = tr && threadIdx.x == 64 && it == 1 && bi < 32;   // trace build: stamps of this warp's blocks of item 1
+        if (stamp) tr[800 + 5 * (bi >> 1)] = clock64();
         const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(buf * ka.acc_cols + m * BN + cb);
         const int ncols = min(32, BN - cb);  // BN is a multiple of 16
         if (ncols == 32) tc_ld32(taddr, r); else tc_ld16(taddr, r);
@@ -959,6 +961,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
           }
         }
         tc_wait_ld();
+        if (stamp) tr[800 + 5 * (bi >> 1) + 1] = clock64();
         if (bi == last_bi) {  // last TMEM read of this buffer by this warp: hand it back to the MMA warps
           tc_fence_before();
           if (lane == 0) { if (PAIR && rank != 0) mbar_arrive_cluster(accE_u + 8 * buf); else mbar_arrive(accE_u + 8 * buf); }
@@ -981,6 +984,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
             *reinterpret_cast<float4*>(stg + lane * STAGE_LD + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
                                                                                __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
         __syncwarp();
+        if (stamp) { tr[800 + 5 * (bi >> 1) + 2] = clock64(); tr[800 + 5 * (bi >> 1) + 3] = (unsigned long long)(__float_as_uint(rv[0].x) & 1u) + clock64(); }
         if (part) {
           // raw partial sums, row-major [mt*128][BN]
           if (c4 < ncols) {
@@ -1072,6 +1076,7 @@ __device__ __forceinline__ void tc_roles(const CUtensorMap* tmAp, const CUtensor
           }
         }
         __syncwarp();
+        if (stamp) tr[800 + 5 * (bi >> 1) + 4] = clock64();
       }
       if (part && !ka.defer) {
         // split-K: the last CTA to finish this output tile reduces all partials in split order

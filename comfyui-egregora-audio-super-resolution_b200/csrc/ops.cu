@@ -271,10 +271,12 @@ struct RowTaps {
   short dw[EGR_MAX_TAPS];
 };
 
-template <int K8>
+template <int CH>   // 8-channel groups per register chunk (CH * 8 channels live at a time: 165 registers and one CTA per SM
+                    // with all 128 channels of conv_out in registers, 63 and four CTAs with 32)
 __global__ void __launch_bounds__(256) conv_n1_rows_kernel(View a, GemmArgs g, RowTaps rt, int TW) {
   extern __shared__ float wsm[];  // weights [ntaps][K], then dots [ntaps][TW + span]
-  constexpr int K = K8 * 8;
+  constexpr int KC = CH * 8;
+  const int K = g.K, nchunks = K / KC;
   const int IW = TW + rt.span;
   float* dots = wsm + rt.ntaps * K;
   const float* W = reinterpret_cast<const float*>(g.W);
@@ -288,15 +290,20 @@ __global__ void __launch_bounds__(256) conv_n1_rows_kernel(View a, GemmArgs g, R
     const int r = it / IW, j = it - r * IW;
     const long long wi = (long long)w0 + rt.min_dw + j, hi = (long long)h + rt.dh[r];
     const bool inb = wi >= 0 && wi < a.dim[g.dimW] && hi >= 0 && hi < a.dim[g.dimH];
-    float x[K];
-    if (inb) {
-      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.p) + wi * a.stride[g.dimW] +
-                                                        hi * a.stride[g.dimH] + (long long)b * a.stride[g.dimB]);
-      uint4 raw[K8];
+    if (!inb) {   // zero padding
+      for (int t = 0; t < rt.ntaps; ++t)
+        if (rt.row_of[t] == r) dots[t * IW + j] = 0.f;
+      continue;
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(a.p) + wi * a.stride[g.dimW] +
+                                                      hi * a.stride[g.dimH] + (long long)b * a.stride[g.dimB]);
+    for (int c = 0; c < nchunks; ++c) {
+      uint4 raw[CH];
 #pragma unroll
-      for (int i = 0; i < K8; ++i) raw[i] = __ldg(src + i);
+      for (int i = 0; i < CH; ++i) raw[i] = __ldg(src + c * CH + i);
+      float x[KC];
 #pragma unroll
-      for (int i = 0; i < K8; ++i) {
+      for (int i = 0; i < CH; ++i) {
         const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].x));
         const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].y));
         const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&raw[i].z));
@@ -304,21 +311,20 @@ __global__ void __launch_bounds__(256) conv_n1_rows_kernel(View a, GemmArgs g, R
         x[8 * i] = f0.x; x[8 * i + 1] = f0.y; x[8 * i + 2] = f1.x; x[8 * i + 3] = f1.y;
         x[8 * i + 4] = f2.x; x[8 * i + 5] = f2.y; x[8 * i + 6] = f3.x; x[8 * i + 7] = f3.y;
       }
-    } else {
+      for (int t = 0; t < rt.ntaps; ++t) {
+        if (rt.row_of[t] != r) continue;
+        const float* wt = wsm + t * K + c * KC;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};   // four interleaved partial sums (k mod 4), added pairwise at the end
 #pragma unroll
-      for (int k = 0; k < K; ++k) x[k] = 0.f;   // zero padding
-    }
-    for (int t = 0; t < rt.ntaps; ++t) {
-      if (rt.row_of[t] != r) continue;
-      const float* wt = wsm + t * K;
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};   // four interleaved partial sums (k mod 4), added pairwise at the end
-#pragma unroll
-      for (int k = 0; k < K; k += 4) {
-        const float4 wv = *reinterpret_cast<const float4*>(wt + k);
-        acc[0] = fmaf(x[k], wv.x, acc[0]); acc[1] = fmaf(x[k + 1], wv.y, acc[1]);
-        acc[2] = fmaf(x[k + 2], wv.z, acc[2]); acc[3] = fmaf(x[k + 3], wv.w, acc[3]);
+        for (int k = 0; k < KC; k += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(wt + k);
+          acc[0] = fmaf(x[k], wv.x, acc[0]); acc[1] = fmaf(x[k + 1], wv.y, acc[1]);
+          acc[2] = fmaf(x[k + 2], wv.z, acc[2]); acc[3] = fmaf(x[k + 3], wv.w, acc[3]);
+        }
+        const float part = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+        float* d = dots + t * IW + j;          // chunk partials are added in chunk order (this thread owns the slot)
+        *d = c == 0 ? part : *d + part;
       }
-      dots[t * IW + j] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
     }
   }
   __syncthreads();
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(256) conv_n1_rows_kernel(View a, GemmArgs g, R
 
 // host side: does the op have the shape conv_n1_rows_kernel handles?  Fills rt / TW / K8.
 static bool conv_n1_rows_match(const View& a, const GemmArgs& g, const Taps& taps, RowTaps* rt, int* TW) {
-  if (g.N != 1 || a.elem != 1 || a.stride[0] != 1 || g.K != a.dim[0] || (g.K & 7) != 0 || g.K > 128) return false;
+  if (g.N != 1 || a.elem != 1 || a.stride[0] != 1 || g.K != a.dim[0] || (g.K & 7) != 0 || g.K > 1024) return false;
   if (g.Wo != a.dim[g.dimW] || g.Ho != a.dim[g.dimH] || g.Bo != a.dim[g.dimB]) return false;   // stride-1, same size
   if (g.dimW == g.dimH || g.dimW == g.dimB || g.dimH == g.dimB) return false;
   if (((uintptr_t)a.p & 15) != 0) return false;
@@ -459,21 +465,14 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (npix <= 8 && g.ntaps == 1 && zero_taps && a.elem == 0 && a.stride[0] == 1 && g.K <= a.dim[0] && al16(a.p) && al16(g.W) &&
       (g.wstride_n & 3) == 0 && (a.stride[g.dimW] & 3) == 0 && (a.stride[g.dimH] & 3) == 0 && (a.stride[g.dimB] & 3) == 0) {
     gemm_simt_gemv_kernel<<<(unsigned)((g.N + 7) / 8), 256, 0, st>>>(a, g, (int)npix);
-  } else if (conv_n1_rows_match(a, g, taps, &rt, &TW) && getenv("EGR_NO_CONV_N1_ROWS") == nullptr && [&] {
-               switch (g.K / 8) { case 1: case 2: case 3: case 4: case 6: case 8: case 12: case 16: return true; default: return false; }
-             }()) {
+  } else if (conv_n1_rows_match(a, g, taps, &rt, &TW) && getenv("EGR_NO_CONV_N1_ROWS") == nullptr) {
     const dim3 grid((unsigned)((g.Wo + TW - 1) / TW), (unsigned)g.Ho, (unsigned)g.Bo);
     const size_t smem = ((size_t)g.ntaps * g.K + (size_t)g.ntaps * (TW + rt.span)) * sizeof(float);
-    switch (g.K / 8) {
-      case 1: conv_n1_rows_kernel<1><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
-      case 2: conv_n1_rows_kernel<2><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
-      case 3: conv_n1_rows_kernel<3><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
-      case 4: conv_n1_rows_kernel<4><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
-      case 6: conv_n1_rows_kernel<6><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
-      case 8: conv_n1_rows_kernel<8><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
-      case 12: conv_n1_rows_kernel<12><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
-      default: conv_n1_rows_kernel<16><<<grid, 256, smem, st>>>(a, g, rt, TW); break;
-    }
+    const int k8 = g.K / 8;   // channels per register chunk: the largest of 32 / 24 / 16 / 8 that divides K
+    if (k8 % 4 == 0) conv_n1_rows_kernel<4><<<grid, 256, smem, st>>>(a, g, rt, TW);
+    else if (k8 % 3 == 0) conv_n1_rows_kernel<3><<<grid, 256, smem, st>>>(a, g, rt, TW);
+    else if (k8 % 2 == 0) conv_n1_rows_kernel<2><<<grid, 256, smem, st>>>(a, g, rt, TW);
+    else conv_n1_rows_kernel<1><<<grid, 256, smem, st>>>(a, g, rt, TW);
   } else if (g.K <= 4 && g.ntaps * g.K <= 64 && (g.N & 3) == 0 && (size_t)g.ntaps * g.K * (g.N + SMK_PIX) * sizeof(float) <= 48 * 1024) {
     conv_smallk_kernel<<<(unsigned)((npix + SMK_PIX - 1) / SMK_PIX), 256, (size_t)g.ntaps * g.K * (g.N + SMK_PIX) * sizeof(float), st>>>(a, g, taps);
   } else if (g.N <= 4 && (g.K & 7) == 0 && (a.dim[0] & 7) == 0 && a.stride[0] == 1 && al16(a.p) &&

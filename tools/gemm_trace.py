@@ -45,8 +45,8 @@ def main():
             print(f"   k-step period {per:.0f} clk; producer-issue -> mma-issue lag {lag:.0f} clk; CTA0 {cyc_total} clk in {ns_cta0} ns = {1e3 * cyc_total / max(ns_cta0, 1):.0f} MHz")
         if brief:
             continue
-        ep = [tuple(t[800 + 5 * i + j] - t[800 + 5 * i] for j in range(1, 5)) for i in range(16) if t[800 + 5 * i]]
-        print("   epilogue blocks of item 1 (+tmem ld, +next loads issued, +smem staged, +computed/stored):", ep[:10])
+        ep = [(rel(t[800 + 5 * i]),) + tuple(t[800 + 5 * i + j] - t[800 + 5 * i] for j in range(1, 5)) for i in range(16) if t[800 + 5 * i]]
+        print("   epilogue blocks of item 1 (start; +tmem ld done, +smem staged, +residual arrived, +stored):", ep[:10])
         print("   producer warp: role entry", rel(t[5]), "decoded", rel(t[6]), "first wait passed", rel(t[7]))
         prod = [(rel(t[16 + 2 * i]), rel(t[17 + 2 * i])) for i in range(250) if t[16 + 2 * i]]
         mma = [(rel(t[528 + 2 * i]), rel(t[529 + 2 * i])) for i in range(250) if t[528 + 2 * i]]
