@@ -4,8 +4,14 @@ tile), EGR_FFT_MAXR (radix cap), EGR_FL_ROW_T / EGR_FL_COL_T (threads per CTA), 
     python tools/fl_sweep.py [quick]"""
 cfgs = [
     {},
+    {"EGR_FFT_MAXR": "12"},
+    {"EGR_FFT_MAXR": "10"},
+    {"EGR_FFT_MAXR": "9"},
+    {"EGR_FFT_MAXR": "10", "EGR_FL_MINB": "3"},
     {"EGR_FL_MINB": "3"},
-    {"EGR_FL_MINB": "2", "EGR_FFT_CW": "4"},
+    {"EGR_FFT_R1": "2100"},
+    {"EGR_FFT_R1": "1800"},
+    {"EGR_FFT_R1": "2520"},
 ]
 for cfg in cfgs:
     env = dict(os.environ)
