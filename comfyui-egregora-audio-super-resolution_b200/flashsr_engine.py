@@ -28,10 +28,11 @@ class FlashSREngine:
         self.spec = spec or M.default_spec()
         # No checkpoint exists in this environment: seeded random weights of the spec'd architecture.
         self.weights = weights if weights is not None else M.init_weights(self.spec, seed)
-        # chunk-channels per plan launch.  The UNet's time barely grows with the batch (latency-bound: 4.5 ms at 1, 6.7 ms at
-        # 8, 9.7 ms at 16 per step) while VAE / vocoder scale linearly, so larger sub-batches amortise it: c3 on one GPU
-        # 192 -> 204 -> 208 x real-time at 8 / 12 / 16 (round-2 measurement); the workspace is 5.2 GB at 16.
-        self.max_batch = int(max_batch or os.environ.get("EGREGORA_FLASHSR_BATCH", "16"))
+        # chunk-channels per plan launch.  The UNet's time grows slowly with the batch (latency-bound: 4.3 ms at 1, 6.2 ms at
+        # 8, 8.2 at 16, 12.4 at 32, 16.9 at 48 per step) while VAE / vocoder scale linearly, so larger sub-batches amortise it:
+        # c3 on one GPU 192 -> 204 -> 208 x real-time at 8 / 12 / 16, and on the final round-2 kernels 237 -> 250 -> 257 x at
+        # 16 / 32 / 48 (tools/gpu_r2_nn.sh).  The workspace is ~0.33 GB per chunk-channel (16 GB at 48) of the 180 GB.
+        self.max_batch = int(max_batch or os.environ.get("EGREGORA_FLASHSR_BATCH", "48"))
         self.debug = debug
         self.blob = WeightBlob()
         # one dry walk (batch 1, lowpass on) packs every weight/constant the graph can touch

@@ -160,3 +160,11 @@ def test_full_spec_rows_are_bit_identical_alone_and_batched(full, cuda_dev):
     # a sharded run: "rank 1" owns rows 10..17 and numbers its noise from row0 = 10
     assert torch.equal(eng.infer(wav[10:], lowpass=True, steps=1, seed=4321, row0=10), y18[10:])
     assert 0.005 < float(y18.pow(2).mean().sqrt()) < 0.9
+    # the engine's default sub-batch is 48: one launch of 18 rows (different fold / pair-tile decisions of the launch, same
+    # per-layer split count) must give the bits of the 9 + 9 run
+    from egregora_b200.flashsr_engine import FlashSREngine
+    eng48 = FlashSREngine(cuda_dev, spec, W, max_batch=48)
+    try:
+        assert torch.equal(eng48.infer(wav, lowpass=True, steps=1, seed=4321), y18)
+    finally:
+        eng48.close()
