@@ -48,6 +48,25 @@ DeviceInfo& devinfo();
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (EGR_PDL=1): a kernel launched through launch_pdl() may be scheduled while its predecessor in
+// the stream is still draining — its CTAs take the SM slots the predecessor's last CTAs free, run their set-up (barrier
+// init, TMEM allocation, descriptor prefetch) and block in egr_pdl_wait() until the predecessor has completed and its
+// writes are visible.  Every kernel launched that way calls egr_pdl_wait() before its first global-memory access (reads AND
+// writes: workspace buffers are recycled) and egr_pdl_trigger() right after it, so at most one kernel runs ahead.
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 // resolved pointers of a plan
 struct Spaces {
   char* ws = nullptr;
@@ -69,6 +88,18 @@ inline void* resolve(const Spaces& s, uint64_t addr) {
 }  // namespace egr
 
 // ---------------------------------------------------------------- device helpers
+// no-ops when the kernel was not launched as a programmatic dependent (and under the CPU emulator)
+__device__ __forceinline__ void egr_pdl_wait() {
+#ifdef __CUDACC__
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void egr_pdl_trigger() {
+#ifdef __CUDACC__
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void egr_pdl_sync() { egr_pdl_wait(); egr_pdl_trigger(); }
 // x * sigmoid(x) as FMUL + MUFU.EX2 + FADD + MUFU.RCP + FMUL (2 ulp): the IEEE division this replaces was ~20 instructions
 // per element (Newton steps + a range check with a slow-path call) and made the GroupNorm apply pass issue bound
 __device__ __forceinline__ float egr_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }

@@ -1,4 +1,5 @@
 // core.cu — lifecycle, error reporting, small utility kernels (absmax, PCM-16 wire format).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace egr {
@@ -14,6 +15,15 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(err_buf(), 1024, fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+#ifdef __CUDACC__
+  static const int on = [] { const char* e = getenv("EGR_PDL"); return e ? atoi(e) : 0; }();
+  return on != 0;
+#else
+  return false;
+#endif
 }
 
 unsigned long long& launch_count() {

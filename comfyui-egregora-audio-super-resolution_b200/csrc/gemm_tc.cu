@@ -83,6 +83,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tc_kernel(const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tr && threadIdx.x == 0) tr[1] = clock64();
+  // programmatic dependent launch: everything above (barriers, TMEM, descriptor prefetch) touched no global memory and may
+  // have run while the previous kernel of the stream was draining; from here on its results are needed
+  egr_pdl_sync();
 
   tc_roles(&tmA, &tmB, ka, sv, tmem_base, (int)blockIdx.x, (int)gridDim.x, tr);
 
@@ -141,6 +144,7 @@ gemm_tc_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / TMA completion can reach them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  egr_pdl_sync();   // launched as a cluster, never as a programmatic dependent itself: only the trigger matters here
 
   tc_roles<true>(&tmA, &tmB, ka, sv, tmem_base, (int)(blockIdx.x >> 1), (int)(gridDim.x >> 1), nullptr, rank);
 
@@ -443,6 +447,7 @@ int egr::tc_launch(const TcPrepared* p, cudaStream_t st) {
   TcKernelArgs ka = p->ka;
   ka.trace = g_trace_dev;
   if (ka.pair) gemm_tc_pair_kernel<<<p->grid, 384, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
+  else if (egr::pdl_enabled()) EGR_CUDA(egr::launch_pdl(gemm_tc_kernel, dim3(p->grid), dim3(384), (size_t)p->smem_bytes, st, p->tmA, p->tmB, ka));
   else gemm_tc_kernel<<<p->grid, 384, p->smem_bytes, st>>>(p->tmA, p->tmB, ka);
   EGR_CHECK_LAUNCH(p->name);
   return EGR_OK;

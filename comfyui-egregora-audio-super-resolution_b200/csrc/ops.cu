@@ -274,6 +274,7 @@ struct RowTaps {
 template <int CH>   // 8-channel groups per register chunk (CH * 8 channels live at a time: 165 registers and one CTA per SM
                     // with all 128 channels of conv_out in registers, 63 and four CTAs with 32)
 __global__ void __launch_bounds__(256) conv_n1_rows_kernel(View a, GemmArgs g, RowTaps rt, int TW) {
+  egr_pdl_sync();
   extern __shared__ float wsm[];  // weights [ntaps][K], then dots [ntaps][TW + span]
   constexpr int KC = CH * 8;
   const int K = g.K, nchunks = K / KC;
@@ -465,7 +466,8 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (npix <= 8 && g.ntaps == 1 && zero_taps && a.elem == 0 && a.stride[0] == 1 && g.K <= a.dim[0] && al16(a.p) && al16(g.W) &&
       (g.wstride_n & 3) == 0 && (a.stride[g.dimW] & 3) == 0 && (a.stride[g.dimH] & 3) == 0 && (a.stride[g.dimB] & 3) == 0) {
     gemm_simt_gemv_kernel<<<(unsigned)((g.N + 7) / 8), 256, 0, st>>>(a, g, (int)npix);
-  } else if (conv_n1_rows_match(a, g, taps, &rt, &TW) && getenv("EGR_NO_CONV_N1_ROWS") == nullptr) {
+  } else if (conv_n1_rows_match(a, g, taps, &rt, &TW) && getenv("EGR_NO_CONV_N1_ROWS") == nullptr &&
+             ((size_t)g.ntaps * g.K + (size_t)g.ntaps * (TW + rt.span)) * sizeof(float) <= 48 * 1024) {
     const dim3 grid((unsigned)((g.Wo + TW - 1) / TW), (unsigned)g.Ho, (unsigned)g.Bo);
     const size_t smem = ((size_t)g.ntaps * g.K + (size_t)g.ntaps * (TW + rt.span)) * sizeof(float);
     const int k8 = g.K / 8;   // channels per register chunk: the largest of 32 / 24 / 16 / 8 that divides K
@@ -511,6 +513,7 @@ int egr::launch_gemm_simt(const Spaces& s, const egr_op& op, cudaStream_t st) {
 // memory after ONE barrier and are added in phase order.  (The first version put all eight warps on the same 32 quads and
 // walked wider rows in serial 32-quad passes with eight barriers each: 22 us for a 16 MB map of 8192 x 512.)
 __global__ void __launch_bounds__(256) gn_stats_kernel(CatArgs a, double* __restrict__ partials, int slab, int nslabs) {
+  egr_pdl_sync();
   extern __shared__ double sh[];  // [RP][C][2]
   const int C = a.C0 + a.C1, Q = C >> 2, cpg = C / a.G;
   int QW = 1;
@@ -561,6 +564,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(CatArgs a, double* __rest
 // stats[b][g][2] = sum over slabs in a fixed order (16 strided rows x 4 interleaved accumulators, then row order):
 // 64 slab loads per thread would be one long L2-latency chain, so four independent chains run at once
 __global__ void gn_finalize_kernel(const double* __restrict__ partials, double* __restrict__ stats, int G2, int nslabs) {
+  egr_pdl_sync();
   extern __shared__ double shf64[];  // [16][G2]
   const int b = blockIdx.x, i = threadIdx.x, y = threadIdx.y;
   const double* p = partials + (long long)b * nslabs * G2 + i;
@@ -594,6 +598,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(CatArgs a, const double* 
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, int silu, float* __restrict__ out32,
                                                         __half* __restrict__ out16, int slab) {
+  egr_pdl_sync();
   extern __shared__ float shf[];  // scale[C], shift[C]
   const int C = a.C0 + a.C1, C4 = C >> 2, cpg = C / a.G;
   const int b = blockIdx.y;
@@ -807,9 +812,17 @@ int egr::launch_gn_stats(const Spaces& s, const egr_op& op, cudaStream_t st) {
   const size_t smem = (size_t)(256 / QW) * C * 2 * sizeof(double);   // [RP][C][2] as the kernel lays it out (< 32 KB up to C = 1024)
   if (smem > 48 * 1024) return fail(EGR_ERR_UNSUPPORTED, "%s: C=%d too wide for the GroupNorm reduction", op.name, C);
   if (G2 > 64) return fail(EGR_ERR_UNSUPPORTED, "%s: at most 32 groups", op.name);
-  gn_stats_kernel<<<dim3(ns, a.B), 256, smem, st>>>(a, partials, slab, ns);
+  if (egr::pdl_enabled()) {
+#ifdef __CUDACC__
+    EGR_CUDA(egr::launch_pdl(gn_stats_kernel, dim3(ns, a.B), dim3(256), smem, st, a, partials, slab, ns));
+#endif
+  } else gn_stats_kernel<<<dim3(ns, a.B), 256, smem, st>>>(a, partials, slab, ns);
   EGR_CHECK_LAUNCH(op.name);
-  gn_finalize_kernel<<<a.B, dim3(G2, 16), (size_t)16 * G2 * sizeof(double), st>>>(partials, stats, G2, ns);
+  if (egr::pdl_enabled()) {
+#ifdef __CUDACC__
+    EGR_CUDA(egr::launch_pdl(gn_finalize_kernel, dim3(a.B), dim3(G2, 16), (size_t)16 * G2 * sizeof(double), st, partials, stats, G2, ns));
+#endif
+  } else gn_finalize_kernel<<<a.B, dim3(G2, 16), (size_t)16 * G2 * sizeof(double), st>>>(partials, stats, G2, ns);
   EGR_CHECK_LAUNCH(op.name);
   return EGR_OK;
 }
@@ -854,7 +867,14 @@ int egr::launch_gn_apply(const Spaces& s, const egr_op& op, cudaStream_t st) {
   if (slab < 16) slab = 16;
   if (slab > a.P) slab = a.P;
   const int ns = (int)((a.P + slab - 1) / slab);
-  if (cat)
+  if (egr::pdl_enabled()) {
+#ifdef __CUDACC__
+    if (cat) EGR_CUDA(egr::launch_pdl(gn_apply_kernel<true>, dim3(ns, a.B), dim3(256), 2 * C * sizeof(float), st, a, stats, gamma, beta,
+                                      (float)op.f[EGR_F_EPS], (int)op.i[EGR_I_MODE], o32, o16, (int)slab));
+    else EGR_CUDA(egr::launch_pdl(gn_apply_kernel<false>, dim3(ns, a.B), dim3(256), 2 * C * sizeof(float), st, a, stats, gamma, beta,
+                                  (float)op.f[EGR_F_EPS], (int)op.i[EGR_I_MODE], o32, o16, (int)slab));
+#endif
+  } else if (cat)
     gn_apply_kernel<true><<<dim3(ns, a.B), 256, 2 * C * sizeof(float), st>>>(a, stats, gamma, beta, (float)op.f[EGR_F_EPS],
                                                                              (int)op.i[EGR_I_MODE], o32, o16, (int)slab);
   else
@@ -1214,6 +1234,7 @@ __global__ void __launch_bounds__(256) elt_axpby_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) elt_sum3_kernel(const float4* __restrict__ x, const float4* __restrict__ y,
                                                         const float4* __restrict__ z, float a, long long n4,
                                                         float4* __restrict__ o32, uint2* __restrict__ o16) {
+  egr_pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 p = __ldg(x + i), q = __ldg(y + i), r = __ldg(z + i);
     const float4 v = make_float4(((p.x + q.x) + r.x) * a, ((p.y + q.y) + r.y) * a, ((p.z + q.z) + r.z) * a, ((p.w + q.w) + r.w) * a);
@@ -1357,6 +1378,7 @@ __global__ void __launch_bounds__(128, MB) snake_aa_kernel(const float* __restri
                                                         const float* __restrict__ log_beta,
                                                         const float* __restrict__ filt, float* __restrict__ o32,
                                                         __half* __restrict__ o16) {
+  egr_pdl_sync();
   using L = SnakeLane<V>;
   const int CG = C / L::W;   // channel groups
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1529,7 +1551,13 @@ static int snake_aa_launch(const char* name, const float* x, int B, int T, int C
   }
   const int nruns = (T + tt - 1) / tt;
   dim3 grid((unsigned)(((long long)nruns * CG + 127) / 128), B);
-  if (o32 && o16) snake_aa_kernel<V, MB, true, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
+  if (egr::pdl_enabled()) {
+#ifdef __CUDACC__
+    if (o32 && o16) EGR_CUDA(egr::launch_pdl(snake_aa_kernel<V, MB, true, true>, grid, dim3(128), 0, st, x, T, C, nruns, tt, la, lb, filt, o32, o16));
+    else if (o16) EGR_CUDA(egr::launch_pdl(snake_aa_kernel<V, MB, false, true>, grid, dim3(128), 0, st, x, T, C, nruns, tt, la, lb, filt, o32, o16));
+    else EGR_CUDA(egr::launch_pdl(snake_aa_kernel<V, MB, true, false>, grid, dim3(128), 0, st, x, T, C, nruns, tt, la, lb, filt, o32, o16));
+#endif
+  } else if (o32 && o16) snake_aa_kernel<V, MB, true, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
   else if (o16) snake_aa_kernel<V, MB, false, true><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
   else snake_aa_kernel<V, MB, true, false><<<grid, 128, 0, st>>>(x, T, C, nruns, tt, la, lb, filt, o32, o16);
   EGR_CHECK_LAUNCH(name);
