@@ -97,3 +97,35 @@ def test_committed_layer_table_matches_the_plan():
         assert row["flops"] == l["flops"]
     assert tab["totals"]["tc_flops"] == be.tc_flops
     assert tab["reconciliation"]["relative_difference"] < 1e-4
+
+
+def test_upsampling_conv_writes_the_f16_copy_for_the_following_shortcut_conv():
+    """The four phase GEMMs of an up-sampling conv write the f16 copy that the next block's 1x1 shortcut conv consumes
+    (same element indices as their interleaved f32 stores), so the c2 plan holds no separate f32 -> f16 pass over the VAE
+    decoder's largest maps (three cast passes, 170 us of a c2 pass, before)."""
+    spec = M.default_spec()
+    be = P.build_plan(spec, M.init_weights(spec, 0), P.WeightBlob(), 1, 1, True)
+    names = [o.name for o in be.ops]
+    assert not any(n.startswith("vae.decoder.up.") and n.endswith("nin_shortcut.in16") for n in names)
+    n_checked = 0
+    for lvl in (1, 2, 3):
+        phases = [o for o in be.ops if o.name.startswith(f"vae.decoder.up.{lvl}.upsample.conv.p")]
+        assert len(phases) == 4
+        shortcut = [o for o in be.ops if o.name == f"vae.decoder.up.{lvl - 1}.block.0.nin_shortcut"]
+        if not shortcut:
+            continue
+        bufs = {id(o.ptr["OUT16"][1]) for o in phases}
+        assert len(bufs) == 1 and all("OUT32" in o.ptr for o in phases)      # one shared f16 buffer next to the f32 output
+        f16 = phases[0].ptr["OUT16"][1]
+        assert shortcut[0].x0[0] is f16                                      # ... which is the shortcut conv's A operand
+        assert f16.first == min(o.index for o in phases) and f16.last >= shortcut[0].index
+        n_checked += 1
+    assert n_checked == 3
+
+
+def test_groupnorm_slab_count_is_a_function_of_the_pixel_count_only():
+    """gn_slabs() must match slab_for() in csrc/ops.cu (the plan sizes the partial-sum buffer with it and the kernel
+    refuses a mismatch); the batch size does not enter, so a chunk-channel's statistics are summed in the same order in any
+    batch."""
+    for P_, want in ((131072, (222, 591)), (32768, (56, 586)), (8192, (16, 512)), (4097, (16, 257)), (20, (16, 2)), (7, (7, 1))):
+        assert P.gn_slabs(P_) == want, (P_, P.gn_slabs(P_))
