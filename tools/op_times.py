@@ -1,5 +1,5 @@
 """Warm device time of every op of the FlashSR plan, one op at a time (egr_plan_run(h, i, i+1), back to back).
-    python tools/op_times.py [batch] > ops.tsv        (EGREGORA_B200_LIB picks the library build)"""
+    python tools/op_times.py [batch] [name filter] > ops.tsv        (EGREGORA_B200_LIB picks the library build)"""
 import os, sys
 from pathlib import Path
 import torch
@@ -20,8 +20,9 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 lt = {l["name"]: l for l in be.layer_table}
 mega = [i for i, o in enumerate(be.ops) if o.flags & 1]
 lo, hi = (mega[0], mega[-1] + 1) if mega else (0, 0)
+flt = sys.argv[2] if len(sys.argv) > 2 else ""   # optional substring filter on the op name
 for i, o in enumerate(be.ops):
-    if lo <= i < hi:
+    if lo <= i < hi or (flt and flt not in o.name):
         continue
     for _ in range(2): _abi.check(lib.egr_plan_run(h, i, i + 1, st))
     torch.cuda.synchronize()
